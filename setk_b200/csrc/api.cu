@@ -1,0 +1,340 @@
+// api.cu -- the C-ABI of libsetk_b200.so (include/setk_b200.h): argument
+// checking, plan / workspace management and dispatch to the kernels.
+#include "common.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+namespace setk {
+
+std::atomic<long long> g_launch_count{0};
+
+// --- launchers implemented in the other translation units ---
+cudaError_t run_stft_generic(const setk_plan*, const float*, const int*, int, int, int, float2*, void*);
+cudaError_t run_cov_generic(const float2*, const float*, unsigned, int, int, int, int, float2*, void*);
+cudaError_t run_apply_generic(const float2*, const void*, int, const float*, int, int, int, int, float2*, void*);
+cudaError_t run_istft_generic(const setk_plan*, const float2*, int, int, int, int, float*, float*, unsigned*, void*);
+cudaError_t run_peak_scale(float*, int, int, const float*, const unsigned*, void*);
+cudaError_t run_float_to_pcm16(const float*, long long, int16_t*, void*);
+cudaError_t run_pcm16_to_float(const int16_t*, long long, float*, void*);
+
+bool stft_cov_fused_supported(const Geometry&);
+size_t stft_cov_partial_floats(const Geometry&);
+int stft_cov_pick_chunks(const setk_plan*, int, int);
+cudaError_t run_stft_cov_fused(setk_plan*, const float*, const int*, int, int, int, const float*,
+                               const float*, unsigned, int, float*, unsigned*, float2*, float2*, float*,
+                               void*);
+bool apply_istft_fused_supported(const Geometry&);
+cudaError_t run_apply_istft_fused(setk_plan*, const float*, const int*, int, int, int, const void*, int,
+                                  const float*, int, int, float*, unsigned*, void*);
+
+struct WeightsArgs;
+cudaError_t weights_run(int kind, double beta, int ref_channel, int rank1, int ban, const void* Rs,
+                        const void* Rn, const void* Ry, int r_dtype, int B, int F, int C, void* w,
+                        int w_dtype, unsigned* status, int* ref_used, void* stream);
+cudaError_t maxabs_generic(const float* audio, const int* n_samples, int B, int C, int N,
+                           unsigned* bits, float* out, void* stream);
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
+  return (int)e;
+}
+
+// grow-only device workspace
+template <class T>
+static cudaError_t ensure(T** ptr, size_t* have, size_t want) {
+  if (*have >= want && *ptr) return cudaSuccess;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr; *have = 0;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(ptr), want);
+  if (e == cudaSuccess) *have = want;
+  return e;
+}
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+}  // namespace setk
+
+using namespace setk;
+
+extern "C" {
+
+int setk_version(void) { return SETK_VERSION; }
+const char* setk_last_error_string(void) { return g_err; }
+int64_t setk_launch_count(void) { return (int64_t)g_launch_count.load(); }
+
+int setk_plan_create(const setk_config_t* cfg, setk_plan_t** plan_out) {
+  if (!cfg || !plan_out) return fail(SETK_EINVAL, "setk_plan_create: null argument");
+  *plan_out = nullptr;
+  if (cfg->num_channels < 1 || cfg->num_channels > SETK_MAX_CHANNELS)
+    return fail(SETK_EINVAL, "num_channels %d outside [1, %d]", cfg->num_channels, SETK_MAX_CHANNELS);
+  if (cfg->frame_len < 1 || cfg->frame_hop < 1)
+    return fail(SETK_EINVAL, "frame_len %d / frame_hop %d must be positive", cfg->frame_len, cfg->frame_hop);
+  if (cfg->n_fft < cfg->frame_len)
+    return fail(SETK_EINVAL, "n_fft %d smaller than frame_len %d", cfg->n_fft, cfg->frame_len);
+  if (!is_pow2(cfg->n_fft) || cfg->n_fft < 32 || cfg->n_fft > 4096)
+    return fail(SETK_EUNSUPPORTED, "n_fft %d: only powers of two in [32, 4096] are supported", cfg->n_fft);
+  if (!cfg->window_host) return fail(SETK_EINVAL, "window_host is null");
+  if (cfg->max_batch < 1 || cfg->max_samples < 1)
+    return fail(SETK_EINVAL, "max_batch / max_samples must be positive");
+
+  setk_plan* pl = static_cast<setk_plan*>(calloc(1, sizeof(setk_plan)));
+  if (!pl) return fail(SETK_ENOMEM, "out of host memory");
+  pl->cfg = *cfg;
+  pl->cfg.window_host = nullptr;
+  Geometry& g = pl->geo;
+  g.C = cfg->num_channels;
+  g.n_fft = cfg->n_fft;
+  g.log2n = 0;
+  while ((1 << g.log2n) < g.n_fft) ++g.log2n;
+  g.hop = cfg->frame_hop;
+  g.pad = cfg->center ? g.n_fft / 2 : 0;
+  g.F = g.n_fft / 2 + 1;
+
+  // librosa.util.pad_center: left pad (n_fft - frame_len) // 2
+  std::vector<float> win(g.n_fft, 0.f), wsq(g.n_fft, 0.f);
+  const int lpad = (g.n_fft - cfg->frame_len) / 2;
+  for (int i = 0; i < cfg->frame_len; ++i) {
+    const double w = cfg->window_host[i];
+    win[lpad + i] = (float)w;
+    wsq[lpad + i] = (float)(w * w);
+  }
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&pl->d_window), sizeof(float) * g.n_fft);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&pl->d_wsq), sizeof(float) * g.n_fft);
+  if (e == cudaSuccess) e = cudaMemcpy(pl->d_window, win.data(), sizeof(float) * g.n_fft, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(pl->d_wsq, wsq.data(), sizeof(float) * g.n_fft, cudaMemcpyHostToDevice);
+  int dev = 0;
+  if (e == cudaSuccess) e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&pl->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) {
+    setk_plan_destroy(pl);
+    return cuda_fail(e, "setk_plan_create");
+  }
+  *plan_out = pl;
+  return SETK_OK;
+}
+
+int setk_plan_destroy(setk_plan_t* pl) {
+  if (!pl) return SETK_OK;
+  if (pl->d_window) cudaFree(pl->d_window);
+  if (pl->d_wsq) cudaFree(pl->d_wsq);
+  if (pl->d_partials) cudaFree(pl->d_partials);
+  if (pl->d_stft_ws) cudaFree(pl->d_stft_ws);
+  if (pl->d_enh_ws) cudaFree(pl->d_enh_ws);
+  if (pl->d_frames_ws) cudaFree(pl->d_frames_ws);
+  if (pl->d_peak) cudaFree(pl->d_peak);
+  free(pl);
+  return SETK_OK;
+}
+
+int setk_num_frames(const setk_plan_t* pl, int32_t n_samples) {
+  if (!pl) return fail(SETK_EINVAL, "null plan");
+  const int T = frames_of(n_samples, pl->geo.n_fft, pl->geo.hop, pl->geo.pad);
+  return T > 0 ? T : -1;
+}
+
+int setk_istft_length(const setk_plan_t* pl, int32_t num_frames) {
+  if (!pl) return fail(SETK_EINVAL, "null plan");
+  if (num_frames < 1) return -1;
+  return pl->geo.hop * (num_frames - 1) + pl->geo.n_fft - 2 * pl->geo.pad;
+}
+
+int setk_num_bins(const setk_plan_t* pl) { return pl ? pl->geo.F : fail(SETK_EINVAL, "null plan"); }
+
+static int check_batch(const setk_plan_t* pl, int B, int N, const char* who) {
+  if (!pl) return fail(SETK_EINVAL, "%s: null plan", who);
+  if (B < 1 || B > pl->cfg.max_batch) return fail(SETK_ESHAPE, "%s: batch %d outside [1, max_batch=%d]", who, B, pl->cfg.max_batch);
+  if (N < 1 || N > pl->cfg.max_samples) return fail(SETK_ESHAPE, "%s: N=%d outside [1, max_samples=%d]", who, N, pl->cfg.max_samples);
+  if (frames_of(N, pl->geo.n_fft, pl->geo.hop, pl->geo.pad) < 1)
+    return fail(SETK_ESHAPE, "%s: N=%d too short for n_fft=%d", who, N, pl->geo.n_fft);
+  return SETK_OK;
+}
+
+int setk_stft(setk_plan_t* pl, const float* audio, const int32_t* n_samples, int32_t B, int32_t N,
+              void* stft_out, void* stream) {
+  int rc = check_batch(pl, B, N, "setk_stft");
+  if (rc) return rc;
+  if (!audio || !stft_out) return fail(SETK_EINVAL, "setk_stft: null buffer");
+  const int T = frames_of(N, pl->geo.n_fft, pl->geo.hop, pl->geo.pad);
+  cudaError_t e = run_stft_generic(pl, audio, n_samples, B, N, T, static_cast<float2*>(stft_out), stream);
+  return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_stft");
+}
+
+int setk_cov(const void* stft, const float* mask, uint32_t flags, int32_t B, int32_t C, int32_t F,
+             int32_t T, void* R, void* stream) {
+  if (!stft || !mask || !R) return fail(SETK_EINVAL, "setk_cov: null buffer");
+  if (B < 1 || F < 1 || T < 1 || C < 1 || C > SETK_MAX_CHANNELS)
+    return fail(SETK_ESHAPE, "setk_cov: bad shape B=%d C=%d F=%d T=%d", B, C, F, T);
+  if (B > 65535) return fail(SETK_ESHAPE, "setk_cov: batch %d > 65535", B);
+  cudaError_t e = run_cov_generic(static_cast<const float2*>(stft), mask, flags, B, C, F, T,
+                                  static_cast<float2*>(R), stream);
+  return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_cov");
+}
+
+int setk_stft_cov(setk_plan_t* pl, const float* audio, const int32_t* n_samples, int32_t B, int32_t N,
+                  const float* mask_s, const float* mask_n, uint32_t flags, void* Rs, void* Rn,
+                  float* maxabs, void* stream) {
+  int rc = check_batch(pl, B, N, "setk_stft_cov");
+  if (rc) return rc;
+  if (!audio || !mask_s || !Rs || !Rn) return fail(SETK_EINVAL, "setk_stft_cov: null buffer");
+  const Geometry& g = pl->geo;
+  const int T = frames_of(N, g.n_fft, g.hop, g.pad);
+  cudaError_t e = ensure(&pl->d_peak, &pl->peak_bytes, sizeof(unsigned) * 2 * (size_t)pl->cfg.max_batch);
+  if (e != cudaSuccess) return cuda_fail(e, "setk_stft_cov(workspace)");
+  unsigned* maxabs_bits = nullptr;
+  if (maxabs) {
+    maxabs_bits = pl->d_peak + pl->cfg.max_batch;   // second half: audio max|x|
+    e = cudaMemsetAsync(maxabs_bits, 0, sizeof(unsigned) * B, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "setk_stft_cov(memset)");
+  }
+  if (stft_cov_fused_supported(g)) {
+    const int n_chunks = stft_cov_pick_chunks(pl, B, T);
+    const size_t want = sizeof(float) * stft_cov_partial_floats(g) * (size_t)n_chunks * B;
+    e = ensure(&pl->d_partials, &pl->partials_bytes, want);
+    if (e != cudaSuccess) return cuda_fail(e, "setk_stft_cov(workspace)");
+    e = run_stft_cov_fused(pl, audio, n_samples, B, N, T, mask_s, mask_n, flags, n_chunks,
+                           pl->d_partials, maxabs_bits, static_cast<float2*>(Rs),
+                           static_cast<float2*>(Rn), maxabs, stream);
+    return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_stft_cov");
+  }
+  // shape-generic route: explicit STFT in workspace, then two covariance passes
+  const size_t want = sizeof(float2) * (size_t)B * g.C * g.F * T;
+  e = ensure(&pl->d_stft_ws, &pl->stft_ws_bytes, want);
+  if (e != cudaSuccess) return cuda_fail(e, "setk_stft_cov(workspace)");
+  e = run_stft_generic(pl, audio, n_samples, B, N, T, pl->d_stft_ws, stream);
+  if (e == cudaSuccess)
+    e = run_cov_generic(pl->d_stft_ws, mask_s, flags, B, g.C, g.F, T, static_cast<float2*>(Rs), stream);
+  if (e == cudaSuccess) {
+    if (mask_n)
+      e = run_cov_generic(pl->d_stft_ws, mask_n, flags & ~SETK_F_CLIP_MASK, B, g.C, g.F, T,
+                          static_cast<float2*>(Rn), stream);
+    else
+      e = run_cov_generic(pl->d_stft_ws, mask_s, flags | SETK_F_ONE_MINUS_INTERNAL, B, g.C, g.F, T,
+                          static_cast<float2*>(Rn), stream);
+  }
+  if (e == cudaSuccess && maxabs)
+    e = maxabs_generic(audio, n_samples, B, g.C, N, maxabs_bits, maxabs, stream);
+  return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_stft_cov(generic)");
+}
+
+int setk_weights(int32_t kind, double beta, int32_t ref_channel, int32_t rank1, int32_t ban,
+                 const void* Rs, const void* Rn, const void* Ry, int32_t r_dtype, int32_t B, int32_t F,
+                 int32_t C, void* w, int32_t w_dtype, uint32_t* status, int32_t* ref_used, void* stream) {
+  if (!Rs || !w || !status) return fail(SETK_EINVAL, "setk_weights: null buffer");
+  if (B < 1 || F < 1 || C < 1 || C > SETK_MAX_CHANNELS)
+    return fail(SETK_ESHAPE, "setk_weights: bad shape B=%d F=%d C=%d", B, F, C);
+  if (kind < SETK_BF_MVDR || kind > SETK_BF_PEVD) return fail(SETK_EINVAL, "setk_weights: unknown kind %d", kind);
+  if ((r_dtype != SETK_C64 && r_dtype != SETK_C128) || (w_dtype != SETK_C64 && w_dtype != SETK_C128))
+    return fail(SETK_EINVAL, "setk_weights: bad dtype");
+  const bool need_rn = kind == SETK_BF_MVDR || kind == SETK_BF_MPDR_WHITEN || kind == SETK_BF_GEVD ||
+                       kind == SETK_BF_PMWF;
+  if (need_rn && !Rn) return fail(SETK_EINVAL, "setk_weights: Rn required for kind %d", kind);
+  if ((kind == SETK_BF_MPDR || kind == SETK_BF_MPDR_WHITEN) && !Ry)
+    return fail(SETK_EINVAL, "setk_weights: Ry required for MPDR");
+  if (ban && !Rn) return fail(SETK_EINVAL, "setk_weights: BAN needs Rn");
+  if (rank1 < SETK_RANK1_NONE || rank1 > SETK_RANK1_GEV) return fail(SETK_EINVAL, "setk_weights: bad rank1 %d", rank1);
+  cudaError_t e = weights_run(kind, beta, ref_channel, rank1, ban, Rs, Rn, Ry, r_dtype, B, F, C, w, w_dtype,
+                              status, ref_used, stream);
+  return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_weights");
+}
+
+int setk_apply(const void* stft, const void* w, int32_t w_dtype, const float* post_mask, int32_t B,
+               int32_t C, int32_t F, int32_t T, void* enh, void* stream) {
+  if (!stft || !w || !enh) return fail(SETK_EINVAL, "setk_apply: null buffer");
+  if (B < 1 || F < 1 || T < 1 || C < 1 || C > SETK_MAX_CHANNELS)
+    return fail(SETK_ESHAPE, "setk_apply: bad shape B=%d C=%d F=%d T=%d", B, C, F, T);
+  cudaError_t e = run_apply_generic(static_cast<const float2*>(stft), w, w_dtype, post_mask, B, C, F, T,
+                                    static_cast<float2*>(enh), stream);
+  return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_apply");
+}
+
+static int T_used_for(const Geometry& g, int T, int n_out) {
+  const int cap = (n_out + 2 * g.pad + g.hop - 1) / g.hop;
+  return T < cap ? T : cap;
+}
+
+int setk_istft(setk_plan_t* pl, const void* enh, int32_t B, int32_t T, int32_t n_out, const float* norm,
+               float* wave, void* stream) {
+  if (!pl || !enh || !wave) return fail(SETK_EINVAL, "setk_istft: null argument");
+  if (B < 1 || B > pl->cfg.max_batch || T < 1 || n_out < 1)
+    return fail(SETK_ESHAPE, "setk_istft: bad shape B=%d T=%d n_out=%d", B, T, n_out);
+  const Geometry& g = pl->geo;
+  const int T_used = T_used_for(g, T, n_out);
+  cudaError_t e = ensure(&pl->d_frames_ws, &pl->frames_ws_bytes, sizeof(float) * (size_t)B * T_used * g.n_fft);
+  if (e == cudaSuccess) e = ensure(&pl->d_peak, &pl->peak_bytes, sizeof(unsigned) * 2 * (size_t)pl->cfg.max_batch);
+  if (e != cudaSuccess) return cuda_fail(e, "setk_istft(workspace)");
+  unsigned* peak = norm ? pl->d_peak : nullptr;
+  if (peak) {
+    e = cudaMemsetAsync(peak, 0, sizeof(unsigned) * B, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "setk_istft(memset)");
+  }
+  e = run_istft_generic(pl, static_cast<const float2*>(enh), B, T, T_used, n_out, pl->d_frames_ws, wave,
+                        peak, stream);
+  if (e == cudaSuccess && norm) e = run_peak_scale(wave, B, n_out, norm, peak, stream);
+  return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_istft");
+}
+
+int setk_apply_istft(setk_plan_t* pl, const float* audio, const int32_t* n_samples, int32_t B, int32_t N,
+                     const void* w, int32_t w_dtype, const float* post_mask, int32_t n_out,
+                     const float* norm, float* wave, void* stream) {
+  int rc = check_batch(pl, B, N, "setk_apply_istft");
+  if (rc) return rc;
+  if (!audio || !w || !wave) return fail(SETK_EINVAL, "setk_apply_istft: null buffer");
+  if (n_out < 1) return fail(SETK_ESHAPE, "setk_apply_istft: n_out=%d", n_out);
+  const Geometry& g = pl->geo;
+  const int T = frames_of(N, g.n_fft, g.hop, g.pad);
+  cudaError_t e = ensure(&pl->d_peak, &pl->peak_bytes, sizeof(unsigned) * 2 * (size_t)pl->cfg.max_batch);
+  if (e != cudaSuccess) return cuda_fail(e, "setk_apply_istft(workspace)");
+  unsigned* peak = norm ? pl->d_peak : nullptr;
+  if (peak) {
+    e = cudaMemsetAsync(peak, 0, sizeof(unsigned) * B, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "setk_apply_istft(memset)");
+  }
+  if (apply_istft_fused_supported(g)) {
+    const int n_chunks = stft_cov_pick_chunks(pl, B, T);
+    e = run_apply_istft_fused(pl, audio, n_samples, B, N, T, w, w_dtype, post_mask, n_out, n_chunks,
+                              wave, peak, stream);
+  } else {
+    const int T_used = T_used_for(g, T, n_out);
+    e = ensure(&pl->d_stft_ws, &pl->stft_ws_bytes, sizeof(float2) * (size_t)B * g.C * g.F * T);
+    if (e == cudaSuccess) e = ensure(&pl->d_enh_ws, &pl->enh_ws_bytes, sizeof(float2) * (size_t)B * g.F * T);
+    if (e == cudaSuccess)
+      e = ensure(&pl->d_frames_ws, &pl->frames_ws_bytes, sizeof(float) * (size_t)B * T_used * g.n_fft);
+    if (e == cudaSuccess) e = run_stft_generic(pl, audio, n_samples, B, N, T, pl->d_stft_ws, stream);
+    if (e == cudaSuccess)
+      e = run_apply_generic(pl->d_stft_ws, w, w_dtype, post_mask, B, g.C, g.F, T, pl->d_enh_ws, stream);
+    if (e == cudaSuccess)
+      e = run_istft_generic(pl, pl->d_enh_ws, B, T, T_used, n_out, pl->d_frames_ws, wave, peak, stream);
+  }
+  if (e == cudaSuccess && norm) e = run_peak_scale(wave, B, n_out, norm, peak, stream);
+  return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_apply_istft");
+}
+
+int setk_float_to_pcm16(const float* wave, int64_t n, int16_t* pcm, void* stream) {
+  if (!wave || !pcm || n < 0) return fail(SETK_EINVAL, "setk_float_to_pcm16: bad argument");
+  if (n == 0) return SETK_OK;
+  cudaError_t e = run_float_to_pcm16(wave, n, pcm, stream);
+  return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_float_to_pcm16");
+}
+
+int setk_pcm16_to_float(const int16_t* pcm, int64_t n, float* wave, void* stream) {
+  if (!wave || !pcm || n < 0) return fail(SETK_EINVAL, "setk_pcm16_to_float: bad argument");
+  if (n == 0) return SETK_OK;
+  cudaError_t e = run_pcm16_to_float(pcm, n, wave, stream);
+  return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_pcm16_to_float");
+}
+
+}  // extern "C"

@@ -1,0 +1,275 @@
+// apply_istft_fused.cu -- beamform apply fused with the inverse STFT, driven
+// from the multichannel AUDIO: the STFT is recomputed on chip (same tile code as
+// the covariance pass), so neither the C-channel STFT nor the enhanced STFT
+// ever exists in HBM.
+//
+// Replaces (scripts/sptk): Beamformer.beamform (libs/beamformer.py:220-234),
+// the optional post-mask (apply_adaptive_beamformer.py:174-175) and
+// inverse_stft (libs/utils.py:142-173 -> librosa.istft: irfft, x window,
+// overlap-add, / window-sum-square, trim) up to the peak of |y| needed by the
+// `norm` rescale (utils.py:166-168), which peak_scale_kernel then applies.
+// C++ twin: Beamform (include/beamformer.cc:215-230) + InverseShortTimeFT
+// (include/stft.cc:154-198).
+//
+// Per tile of <= TT frames (288 threads):
+//   stage + forward FFT          (stft_tile.cuh)
+//   apply   item (frame, k<=128): split Z -> X_c[k], X_c[256-k]; y = w^H x for
+//           both bins; inverse split -> half-size spectrum Zi[k], Zi[256-k]
+//   iFFT    one half-warp per frame: conj . FFT256 . conj, x synthesis window
+//   flush   gather overlap-add of the tile's frames + carry from the previous
+//           tile; positions no later frame can touch are divided by the
+//           window-sum-square, trimmed and written (16-byte coalesced rows),
+//           the rest becomes the next carry.  Deterministic: no atomics on data.
+// A CTA owns the output positions of its own frames; the <= ceil(n_fft/hop)-1
+// frames before its first frame are recomputed as a halo tile.
+// Algorithmic bytes per utterance: 4*C*N (audio) + 8*F*C (w) + 4*n_out (wave)
+// (+ 4*T*F with a post-mask).
+#include "common.cuh"
+#include "stft_tile.cuh"
+
+namespace setk {
+
+struct ApplyIstftArgs {
+  Geometry g;
+  const float* audio; const int* n_samples; int N;
+  const void* w; int w_dtype;
+  const float* post_mask; int T;   // mask leading dimension (frames of N samples)
+  int frames_per_chunk, n_chunks;
+  const float* window;  // [n_fft] analysis == synthesis window
+  const float* wsq;     // [n_fft]
+  int n_out;
+  float* wave;          // [B][n_out]
+  unsigned* peak;       // [B] or null
+};
+
+template <int C, int TT>
+__global__ void __launch_bounds__(288, 2) apply_istft_kernel(ApplyIstftArgs a) {
+  constexpr int F = kBins;
+  constexpr int NPAIR = kM / 2 + 1;     // 129 bin pairs (k, 256-k)
+  SETK_DYN_SMEM(float, smem);
+  const int hop = a.g.hop, pad = a.g.pad;
+  TileSmem<C, TT> sm;
+  sm.carve(smem, hop);
+  const int carry_len = kNfft - hop;
+  float2* s_w = reinterpret_cast<float2*>(sm.end());          // [F][C]
+  float2* s_zi = s_w + F * C;                                 // [TT][SETK_ZSLOT]
+  float* s_frames = reinterpret_cast<float*>(s_zi + TT * SETK_ZSLOT);   // [TT][512]
+  float* s_wsyn = s_frames + TT * kNfft;                      // [512] window / 512
+  float* s_wsq = s_wsyn + kNfft;                              // [512]
+  float* s_carry = s_wsq + kNfft;                             // [2][512]
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int lane16 = lane & 15, half = lane >> 4;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int nb = a.n_samples ? a.n_samples[b] : a.N;
+  const int Tb = frames_of(nb, kNfft, hop, pad);
+  // frames librosa.istft would use for this output length
+  const int T_cap = (a.n_out + 2 * pad + hop - 1) / hop;
+  const int T_used = imin(Tb, T_cap);
+  const int t_begin = chunk * a.frames_per_chunk;
+  const int t_end = imin(t_begin + a.frames_per_chunk, T_used);
+  const int expected = T_used > 0 ? kNfft + hop * (T_used - 1) : 0;   // padded signal length
+  float* yb = a.wave + (long long)b * a.n_out;
+  float peak = 0.f;
+
+  for (int n = tid; n < kNfft; n += blockDim.x) {
+    const float w = a.window[n];
+    sm.win[n] = 0.5f * w;
+    s_wsyn[n] = w * (1.0f / 512.0f);
+    s_wsq[n] = a.wsq[n];
+    s_carry[n] = 0.f;
+    s_carry[kNfft + n] = 0.f;
+  }
+  for (int e = tid; e < F * C; e += blockDim.x) {
+    const long long wi = (long long)b * F * C + e;
+    float2 v;
+    if (a.w_dtype == SETK_C128) {
+      const double* p = reinterpret_cast<const double*>(a.w) + 2 * wi;
+      v = make_float2((float)p[0], (float)p[1]);
+    } else {
+      const float* p = reinterpret_cast<const float*>(a.w) + 2 * wi;
+      v = make_float2(p[0], p[1]);
+    }
+    s_w[e] = v;
+  }
+
+  float w1s, w1c;
+  sincospif((float)lane16 / 128.0f, &w1s, &w1c);
+  const float2 w1 = make_float2(w1c, -w1s);
+  const float* xb = a.audio + (long long)b * C * a.N;
+  const bool vec_ok = ((a.N & 3) == 0) && ((hop & 3) == 0) && ((pad & 3) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(a.audio) & 15) == 0);
+
+  const int R = (kNfft + hop - 1) / hop - 1;       // frames before t that overlap frame t
+  int cur = 0;                                     // which carry buffer is the input
+  int t0 = imax(0, t_begin - R);
+  if (t_begin >= t_end) t0 = t_end;                // nothing to do for this chunk
+  while (t0 < t_end) {
+    const int nt = (t0 < t_begin) ? (t_begin - t0) : imin(TT, t_end - t0);
+    __syncthreads();
+    stage_tile<C, TT>(sm, xb, a.N, nb, t0, nt, hop, pad, vec_ok, 0.f);
+    __syncthreads();
+    if (warp < 8) fft_tile<C, TT>(sm, nt, hop, w1);
+    __syncthreads();
+    // ---- apply + inverse split ----
+    for (int it = tid; it < nt * NPAIR; it += blockDim.x) {
+      const int j = it / NPAIR, k = it - j * NPAIR;
+      const int km = kM - k;                              // mirrored bin 256-k
+      const float2 tw = split_twiddle(k);
+      float2 yk = make_float2(0.f, 0.f), ym = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float2* z = sm.z + (j * C + c) * SETK_ZSLOT;
+        float2 xk, xm;
+        split_pair(z[k & (kM - 1)], z[km & (kM - 1)], tw, xk, xm);
+        if (k == 0) { xk.y = 0.f; xm.y = 0.f; }
+        const float2 wk = s_w[k * C + c], wm = s_w[km * C + c];
+        // conj(w) * x
+        yk.x += wk.x * xk.x + wk.y * xk.y;  yk.y += wk.x * xk.y - wk.y * xk.x;
+        ym.x += wm.x * xm.x + wm.y * xm.y;  ym.y += wm.x * xm.y - wm.y * xm.x;
+      }
+      if (a.post_mask) {
+        const float* pm = a.post_mask + ((long long)b * a.T + (t0 + j)) * F;
+        const float mk = pm[k], mm = pm[km];
+        yk.x *= mk; yk.y *= mk; ym.x *= mm; ym.y *= mm;
+      }
+      float2* zi = s_zi + j * SETK_ZSLOT;
+      if (k == 0) {
+        // irfft ignores Im Y[0], Im Y[256]
+        zi[0] = make_float2(yk.x + ym.x, yk.x - ym.x);
+      } else {
+        // Zi[k]   = (Yk + conj(Ym)) + conj(tw) (Yk - conj(Ym))
+        const float er = yk.x + ym.x, ei = yk.y - ym.y;
+        const float dr = yk.x - ym.x, di = yk.y + ym.y;
+        // conj(tw) * D = (tw.x dr + tw.y di, tw.x di - tw.y dr)
+        zi[k] = make_float2(er + tw.x * dr + tw.y * di, ei + tw.x * di - tw.y * dr);
+        if (k != kM / 2) {
+          // Zi[256-k] = (Ym + conj(Yk)) + tw (Ym - conj(Yk))
+          const float er2 = er, ei2 = -ei;            // Ym + conj(Yk) = conj(E)
+          const float dr2 = -dr, di2 = di;            // Ym - conj(Yk) = -conj(D)
+          zi[km] = make_float2(er2 + tw.x * dr2 - tw.y * di2, ei2 + tw.x * di2 + tw.y * dr2);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- inverse FFT: one half-warp per frame ----
+    if (warp * 2 < TT) {
+      const int job = warp * 2 + half;
+      float2 v[16];
+      const float2* zi = s_zi + job * SETK_ZSLOT;
+#pragma unroll
+      for (int m1 = 0; m1 < 16; ++m1) {
+        float2 x = make_float2(0.f, 0.f);
+        if (job < nt) { x = zi[16 * m1 + lane16]; x.y = -x.y; }
+        v[m1] = x;
+      }
+      halfwarp_fft256(v, sm.z + job * SETK_ZSLOT, lane16, w1);
+      float* fr = s_frames + job * kNfft;
+#pragma unroll
+      for (int s = 0; s < 16; ++s) {
+        const int m = lane16 + 16 * kof(s);
+        const float2 ws = *reinterpret_cast<const float2*>(s_wsyn + 2 * m);
+        *reinterpret_cast<float2*>(fr + 2 * m) = make_float2(v[s].x * ws.x, -v[s].y * ws.y);
+      }
+    }
+    __syncthreads();
+    // ---- flush: gather overlap-add, normalise, trim, write ----
+    {
+      const int p_tile = t0 * hop;
+      const bool last_tile = (t0 + nt == T_used);
+      const int final_len = last_tile ? (nt - 1) * hop + kNfft : nt * hop;
+      const int span = (nt - 1) * hop + kNfft;
+      const float* cin = s_carry + cur * kNfft;
+      float* cout = s_carry + (cur ^ 1) * kNfft;
+      for (int rel = tid; rel < span; rel += blockDim.x) {
+        float val = rel < carry_len ? cin[rel] : 0.f;
+        const int j_hi = imin(nt - 1, rel / hop);
+        const int j_lo = (rel >= kNfft) ? (rel - kNfft) / hop + 1 : 0;
+        for (int j = j_lo; j <= j_hi; ++j) val += s_frames[j * kNfft + rel - j * hop];
+        if (rel < final_len) {
+          const int p = p_tile + rel;
+          const int q = p - pad;
+          if (p >= t_begin * hop && q >= 0 && q < a.n_out) {
+            const int tl = (p >= kNfft) ? (p - kNfft) / hop + 1 : 0;
+            const int th = imin(T_used - 1, p / hop);
+            float wss = 0.f;
+            for (int t = tl; t <= th; ++t) wss += s_wsq[p - t * hop];
+            if (wss > SETK_TINY32) val /= wss;
+            yb[q] = val;
+            peak = fmaxf(peak, fabsf(val));
+          }
+        } else {
+          cout[rel - nt * hop] = val;
+        }
+      }
+      cur ^= 1;
+    }
+    t0 += nt;
+  }
+
+  // zero-fill what no frame reaches (fix_length padding / too-short input)
+  if (chunk == a.n_chunks - 1) {
+    const int q0 = imax(expected - pad, 0);
+    for (int q = q0 + tid; q < a.n_out; q += blockDim.x) yb[q] = 0.f;
+  }
+  if (a.peak) {
+    for (int o = 16; o > 0; o >>= 1) peak = fmaxf(peak, __shfl_xor_sync(0xffffffffu, peak, o));
+    if (lane == 0 && peak > 0.f) atomicMax(a.peak + b, __float_as_uint(peak));
+  }
+}
+
+template <int C, int TT>
+static size_t apply_istft_smem_bytes(int hop) {
+  size_t fl = TileSmem<C, TT>::floats(hop);
+  fl += 2 * (size_t)kBins * C;            // s_w
+  fl += 2 * (size_t)TT * SETK_ZSLOT;      // s_zi
+  fl += (size_t)TT * kNfft;               // s_frames
+  fl += 2 * (size_t)kNfft;                // s_wsyn, s_wsq
+  fl += 2 * (size_t)kNfft;                // carry x2
+  return fl * sizeof(float);
+}
+
+template <int C, int TT>
+static cudaError_t run_apply_istft_t(const ApplyIstftArgs& a, int B, void* stream) {
+  const size_t smem = apply_istft_smem_bytes<C, TT>(a.g.hop);
+  cudaError_t e = cudaFuncSetAttribute(apply_istft_kernel<C, TT>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return launch(apply_istft_kernel<C, TT>, dim3(a.n_chunks, B), dim3(288), smem, stream, false, a);
+}
+
+bool apply_istft_fused_supported(const Geometry& g) {
+  if (g.n_fft != 512) return false;
+  if (g.C < 1 || g.C > 4) return false;
+  if (g.hop < 128 || g.hop > 512 || (g.hop & 1)) return false;   // halo <= TT frames
+  return true;
+}
+
+cudaError_t run_apply_istft_fused(setk_plan* pl, const float* audio, const int* n_samples, int B, int N,
+                                  int T, const void* w, int w_dtype, const float* post_mask, int n_out,
+                                  int n_chunks, float* wave, unsigned* peak, void* stream) {
+  constexpr int TT = 4;
+  ApplyIstftArgs a;
+  a.g = pl->geo;
+  a.audio = audio; a.n_samples = n_samples; a.N = N;
+  a.w = w; a.w_dtype = w_dtype;
+  a.post_mask = post_mask; a.T = T;
+  a.n_chunks = n_chunks;
+  int fpc = (T + n_chunks - 1) / n_chunks;
+  a.frames_per_chunk = ((fpc + TT - 1) / TT) * TT;
+  a.window = pl->d_window;
+  a.wsq = pl->d_wsq;
+  a.n_out = n_out;
+  a.wave = wave;
+  a.peak = peak;
+  switch (pl->geo.C) {
+    case 1: return run_apply_istft_t<1, TT>(a, B, stream);
+    case 2: return run_apply_istft_t<2, TT>(a, B, stream);
+    case 3: return run_apply_istft_t<3, TT>(a, B, stream);
+    case 4: return run_apply_istft_t<4, TT>(a, B, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace setk

@@ -1,0 +1,131 @@
+// stft_tile.cuh -- the on-chip STFT of one tile of TT frames x C channels,
+// shared by the two fused kernels (stft_cov_fused.cu, apply_istft_fused.cu).
+//
+//   stage_tile : audio (global, f32 [C][N]) -> shared, with librosa's
+//                center=True reflect padding resolved per sample
+//                (np.pad(y, n_fft//2, "reflect"))
+//   fft_tile   : 512-point real FFT of every (frame, channel) as a 256-point
+//                complex FFT on one half-warp (fft16.cuh); the *unsplit*
+//                half-size spectrum Z stays in shared memory
+//   split_bin  : X[k] (and X[256-k]) from Z[k], Z[256-k] with the bin's
+//                constant twiddle
+#pragma once
+#include "common.cuh"
+#include "fft16.cuh"
+
+namespace setk {
+
+constexpr int kNfft = 512;      // frame size of the fused kernels
+constexpr int kM = 256;         // half-size complex transform
+constexpr int kBins = 257;
+
+// Shared-memory carve-up common to both fused kernels.
+template <int C, int TT>
+struct TileSmem {
+  int Lp;            // staged samples per channel (padded to a multiple of 4)
+  float* win;        // [512]  analysis window x 0.5
+  float* audio;      // [C][Lp]
+  float2* z;         // [TT*C][SETK_ZSLOT]
+  SETK_HD static int staged_len(int hop) { return ((TT - 1) * hop + kNfft + 3) & ~3; }
+  SETK_HD static size_t floats(int hop) {
+    return (size_t)kNfft + (size_t)C * staged_len(hop) + 2 * (size_t)TT * C * SETK_ZSLOT;
+  }
+  __device__ void carve(float* base, int hop) {
+    Lp = staged_len(hop);
+    win = base;
+    audio = win + kNfft;
+    z = reinterpret_cast<float2*>(audio + C * Lp);
+  }
+  __device__ float* end() { return reinterpret_cast<float*>(z + TT * C * SETK_ZSLOT); }
+};
+
+// Stage the samples of frames [t0, t0+nt) of every channel.  Returns the
+// running max |sample| seen by this thread.
+template <int C, int TT>
+__device__ __forceinline__ float stage_tile(const TileSmem<C, TT>& sm, const float* __restrict__ xb,
+                                            int N, int nb, int t0, int nt, int hop, int pad,
+                                            bool vec_ok, float amax) {
+  const int tid = threadIdx.x;
+  const int p0 = t0 * hop;                      // first padded position of the tile
+  const int need = (nt - 1) * hop + kNfft;      // samples actually used
+  const int i0 = p0 - pad;
+  if (vec_ok && i0 >= 0 && i0 + need <= nb) {
+    const int nv = need >> 2;                   // hop % 4 == 0 here
+    for (int e = tid; e < C * nv; e += blockDim.x) {
+      const int c = e / nv, q = e - c * nv;
+      const float4 v = *reinterpret_cast<const float4*>(xb + (long long)c * N + i0 + 4 * q);
+      *reinterpret_cast<float4*>(sm.audio + c * sm.Lp + 4 * q) = v;
+      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+  } else {
+    for (int e = tid; e < C * need; e += blockDim.x) {
+      const int c = e / need, q = e - c * need;
+      const int i = pad ? reflect_index(p0 + q, pad, nb) : (p0 + q);
+      const float v = xb[(long long)c * N + i];
+      sm.audio[c * sm.Lp + q] = v;
+      amax = fmaxf(amax, fabsf(v));
+    }
+  }
+  return amax;
+}
+
+// Forward FFT of every (frame, channel) of the tile by warps 0..7.
+// All threads of warps 0..7 must call it; hop must be even.
+template <int C, int TT>
+__device__ __forceinline__ void fft_tile(const TileSmem<C, TT>& sm, int nt, int hop, float2 w1) {
+  constexpr int JOBS = TT * C;
+  static_assert(JOBS % 2 == 0, "half-warp jobs must pair up per warp");
+  constexpr int ROUNDS = (JOBS + 15) / 16;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane16 = lane & 15, half = lane >> 4;
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const int job = r * 16 + warp * 2 + half;
+    if (job - half < JOBS) {                    // warp-uniform
+      const int fr = job / C, ch = job - fr * C;
+      float2 v[16];
+      const float* src = sm.audio + ch * sm.Lp + fr * hop + 2 * lane16;
+      const float* wsrc = sm.win + 2 * lane16;
+      const bool live = fr < nt;
+#pragma unroll
+      for (int m1 = 0; m1 < 16; ++m1) {
+        float2 x = make_float2(0.f, 0.f);
+        if (live) {
+          const float2 s = *reinterpret_cast<const float2*>(src + 32 * m1);
+          const float2 w = *reinterpret_cast<const float2*>(wsrc + 32 * m1);
+          x = make_float2(s.x * w.x, s.y * w.y);
+        }
+        v[m1] = x;
+      }
+      float2* zs = sm.z + job * SETK_ZSLOT;
+      halfwarp_fft256(v, zs, lane16, w1);
+#pragma unroll
+      for (int s = 0; s < 16; ++s) zs[lane16 + 16 * kof(s)] = v[s];
+    }
+  }
+}
+
+// Twiddle of bin k for the real-FFT split: -i W512^k = (-sin t, -cos t), t = 2 pi k / 512.
+__device__ __forceinline__ float2 split_twiddle(int k) {
+  float s, c;
+  sincospif((float)k / 256.0f, &s, &c);
+  return make_float2(-s, -c);
+}
+
+// X[k] from the half-size spectrum (Z was computed from samples x 0.5):
+//   X[k] = (Zk + conj(Zn)) + (-i W^k)(Zk - conj(Zn)),  Zn = Z[(256-k) & 255]
+__device__ __forceinline__ float2 split_bin(float2 zk, float2 zn, float2 tw) {
+  const float er = zk.x + zn.x, ei = zk.y - zn.y;
+  const float dr = zk.x - zn.x, di = zk.y + zn.y;
+  return make_float2(er + tw.x * dr - tw.y * di, ei + tw.x * di + tw.y * dr);
+}
+// the mirrored bin from the same pair: X[256-k] = conj(E - P), P = (-iW^k) D
+__device__ __forceinline__ void split_pair(float2 zk, float2 zn, float2 tw, float2& xk, float2& xm) {
+  const float er = zk.x + zn.x, ei = zk.y - zn.y;
+  const float dr = zk.x - zn.x, di = zk.y + zn.y;
+  const float pr = tw.x * dr - tw.y * di, pi = tw.x * di + tw.y * dr;
+  xk = make_float2(er + pr, ei + pi);
+  xm = make_float2(er - pr, -(ei - pi));
+}
+
+}  // namespace setk
