@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""
+bench.py -- utterances/second of the mask-based MVDR beamformer hot path.
+
+Workload (BASELINE.json configs[1], "metric"): 4-channel MVDR, oracle IRM mask,
+16 kHz, 10 s utterances (N = 160000), 512-point STFT / hop 256 / hann /
+center, batch = 256 utterances per GPU per step.  A "step" is one pass of the
+hot path over one resident batch:
+
+    setk_stft_cov (fused STFT + Rs/Rn) -> setk_weights (fp64 MVDR) ->
+    setk_apply_istft (fused beamform + iSTFT + peak normalisation)
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 is launched by torch.distributed.run, one rank per GPU; utterances shard
+across ranks with no data-path collective ("scaling": "weak"); the timed region
+ends with ONE NCCL gather of the last batch's enhanced audio to rank 0.
+
+Prints one JSON line (rank 0).  Keys beyond the base contract:
+  roofline      the dominant kernel (fused STFT+covariance): algorithmic bytes
+                per launch / CUDA-event time of that call, vs MEASURED_PEAKS.json
+  cpu_baseline  the oracle's numpy restatement of the reference path timed on
+                this box's host cores (bounded sample), beside the GPU number
+  e2e           same metric through the public API with HOST (pinned) buffers:
+                H2D of audio+mask and D2H of the enhanced audio inside the
+                timed region
+`--impl reference` times the reference's CPU implementation of the path (the
+oracle port: /root/reference does not exist on the GPU box) with all host
+cores, and prints the same JSON line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "utts/sec 4-ch MVDR 10s@16kHz"
+UNIT = "utts/s"
+C, N, FRAME_LEN, HOP, NFFT = 4, 160000, 512, 256, 512
+BATCH = 256
+F = NFFT // 2 + 1
+T = 1 + N // HOP            # center=True
+
+
+def algorithmic_bytes_stft_cov(c=C, n=N, t=T, f=F):
+    """audio f32 + mask f32 + Rs,Rn c64, per utterance."""
+    return 4 * c * n + 4 * t * f + 2 * 8 * f * c * c
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6),
+                                  ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU arm ---
+def run_cpu_arm(n_utts_per_worker, workers, seed=20240923):
+    """Reference CPU path (oracle port) on `workers` processes; returns utts/s."""
+    from oracle import cpu_bench
+    return cpu_bench.throughput(C, N, n_utts_per_worker, workers, seed)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = max(cores, 8)                       # utterances per "step" sample
+    t0 = time.time()
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        run_cpu_arm(1, cores)
+    vals = []
+    for _ in range(max(1, min(args.steps, 3))):
+        vals.append(run_cpu_arm(max(1, per_step // cores), cores))
+    val = sum(vals) / len(vals)
+    sample = (f"{len(vals)} steps x {max(1, per_step // cores) * cores} utterances of the "
+              f"workload, {cores} worker processes, compute only")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * BATCH / val, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg2: 4-ch MVDR, IRM mask, 16 kHz x 10 s, 512/256 hann center, "
+                               "batch 256 per GPU", "cpu": cpu_model()},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.time() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for ln in fh:
+                if ln.startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+# ------------------------------------------------------------------ GPU arm ---
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from setk_b200 import _lib, synth
+    from setk_b200.engine import BeamformPipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    # CPU baseline first (rank 0, N=1 only): before the GPU gets busy
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        per_worker = max(1, args.cpu_utts // cores)
+        v = run_cpu_arm(per_worker, cores)
+        cpu_base = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"{per_worker * cores} utterances of the same synthetic workload "
+                              f"({cores} processes x {per_worker}), oracle numpy path, compute only",
+                    "cpu": cpu_model()}
+
+    B = args.batch
+    pipe = BeamformPipeline(C, "mvdr", frame_len=FRAME_LEN, frame_hop=HOP, center=True,
+                            window="hann", max_batch=B, max_samples=N, device=dev)
+    # distinct synthetic utterances per rank; a few unique ones tiled to the batch
+    uniq = min(B, args.unique)
+    a_u, m_u = synth.make_batch(uniq, C, N, device=dev, first=rank * uniq)
+    reps = (B + uniq - 1) // uniq
+    audio = a_u.repeat(reps, 1, 1)[:B].contiguous()
+    mask = m_u.repeat(reps, 1, 1)[:B].contiguous()
+    del a_u, m_u
+    torch.cuda.synchronize()
+
+    def step():
+        return pipe.run(audio, mask)
+
+    for _ in range(args.warmup):
+        wave, status = step()
+    torch.cuda.synchronize()
+    assert int(status.abs().sum()) == 0, "solver reported failures on the synthetic batch"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        wave, status = step()
+    gathered = None
+    if world > 1:
+        gathered = [torch.empty_like(wave) for _ in range(world)] if rank == 0 else None
+        dist.gather(wave, gathered, dst=0)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count() - launches0
+    if sampler:
+        sampler.stop()
+    t_ms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    value = world * B * args.steps / (ms / 1000.0)
+
+    # ---- roofline of the dominant kernel: fused STFT+cov, timed alone ----
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(2):
+        pipe.covariances(audio, mask)
+    torch.cuda.synchronize()
+    reps_k = max(5, args.steps)
+    e0.record()
+    for _ in range(reps_k):
+        pipe.covariances(audio, mask)
+    e1.record()
+    torch.cuda.synchronize()
+    k_ms = e0.elapsed_time(e1) / reps_k
+    peak, peak_src = measured_peaks()
+    alg = algorithmic_bytes_stft_cov() * B
+    achieved = alg / (k_ms * 1e-3) / 1e9
+
+    # ---- stage split (CUDA events, informational) ----
+    Rs, Rn, mx = pipe.covariances(audio, mask)
+    w = pipe.solve(Rs, Rn)[0]
+    stage = {}
+    for name, fn in (("weights", lambda: pipe.solve(Rs, Rn)),
+                     ("apply_istft", lambda: pipe.plan.apply_istft(audio, w, norm=mx))):
+        fn(); torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(5):
+            fn()
+        s1.record(); torch.cuda.synchronize()
+        stage[name + "_ms"] = s0.elapsed_time(s1) / 5
+    stage["stft_cov_ms"] = k_ms
+
+    # ---- e2e: host pinned buffers in, enhanced audio out, every step ----
+    h_audio = torch.empty(audio.shape, dtype=audio.dtype, pin_memory=True)
+    h_mask = torch.empty(mask.shape, dtype=mask.dtype, pin_memory=True)
+    h_audio.copy_(audio); h_mask.copy_(mask)
+    h_out = torch.empty(wave.shape, dtype=wave.dtype, pin_memory=True)
+    d_audio, d_mask = torch.empty_like(audio), torch.empty_like(mask)
+
+    def e2e_step():
+        d_audio.copy_(h_audio, non_blocking=True)
+        d_mask.copy_(h_mask, non_blocking=True)
+        wv, st = pipe.run(d_audio, d_mask)
+        h_out.copy_(wv, non_blocking=True)
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step(); torch.cuda.synchronize()
+    barrier()
+    x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    x0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    x1.record()
+    barrier()
+    e_ms = torch.tensor([x0.elapsed_time(x1)], device=dev)
+    if world > 1:
+        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+    e2e_val = world * B * e2e_steps / (float(e_ms.item()) / 1000.0)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (STFT/cov/apply), f64 (per-bin weight solve)", "data": "synthetic",
+            "config": {"workload": "cfg2: 4-ch MVDR, IRM mask, 16 kHz x 10 s, 512/256 hann center",
+                       "batch_per_gpu": B, "global_batch": B * world,
+                       "parallelism": f"utterance-sharded x{world}, no data-path collective; one "
+                                      f"NCCL gather of the last batch inside the timed region",
+                       "l2": f"inputs {(audio.numel() + mask.numel()) * 4 / 1e6:.0f} MB per step "
+                             f"exceed the 126 MB L2 (no flush needed)",
+                       "unique_utterances_per_gpu": uniq},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "setk_stft_cov (stft_cov_kernel<4,4> + finalize)",
+                         "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms},
+            "cpu_baseline": cpu_base,
+            "e2e": {"value": e2e_val, "unit": UNIT,
+                    "h2d_bytes_per_step": (audio.numel() + mask.numel()) * 4,
+                    "d2h_bytes_per_step": wave.numel() * 4, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "stages": stage,
+            "clocks": sampler.summary() if sampler else None,
+            "library": _lib.library_path(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--unique", type=int, default=32,
+                    help="distinct synthetic utterances per GPU (tiled to the batch)")
+    ap.add_argument("--cpu-utts", type=int, default=0,
+                    help="utterances for the cpu_baseline sample (0 = 16 per core)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.cpu_utts <= 0:
+        args.cpu_utts = 16 * (os.cpu_count() or 1)
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

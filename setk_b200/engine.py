@@ -1,0 +1,117 @@
+"""
+setk_b200.engine -- the batched utterance pipeline (the benchmarked hot path).
+
+One call = the per-utterance loop body of the reference's
+scripts/sptk/apply_adaptive_beamformer.py:130-177 for a whole batch:
+
+    SpectrogramReader._load + beamformer.run (covariances)  -> setk_stft_cov   (K1+K2 fused)
+    beamformer.weight (+ do_ban / rank-1)                    -> setk_weights    (K3, fp64)
+    beamformer.beamform + post-mask + inverse_stft(norm=)    -> setk_apply_istft (K4+K5 fused)
+
+Three kernel launches of substance per batch; the STFT never exists in HBM.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .plan import StftPlan, weights
+
+BEAMFORMERS = ["mvdr", "mpdr", "mpdr-whiten", "gevd", "pmwf-0", "pmwf-1"]
+_KIND = {
+    "mvdr": _lib.BF_MVDR, "mpdr": _lib.BF_MPDR, "mpdr-whiten": _lib.BF_MPDR_WHITEN,
+    "gevd": _lib.BF_GEVD, "pmwf-0": _lib.BF_PMWF, "pmwf-1": _lib.BF_PMWF,
+}
+_RANK1 = {"": _lib.RANK1_NONE, "none": _lib.RANK1_NONE, "eig": _lib.RANK1_EIG,
+          "gev": _lib.RANK1_GEV}
+
+
+def status_message(st):
+    parts = []
+    if st & _lib.ST_SINGULAR:
+        parts.append("Singular matrix")
+    if st & _lib.ST_NOT_PD:
+        parts.append("noise covariance not positive definite")
+    if st & _lib.ST_NO_CONVERGE:
+        parts.append("eigen-iteration did not converge")
+    if st & _lib.ST_NONFINITE:
+        parts.append("non-finite weights")
+    if st & _lib.ST_BAD_REF:
+        parts.append("reference channel exceeds total channels")
+    return ", ".join(parts)
+
+
+class BeamformPipeline(object):
+    """
+    Mask-based adaptive beamformer over a batch of equal-capacity utterances.
+
+    Arguments mirror the CLI flags of apply_adaptive_beamformer.py:183-259 and
+    StftParser (libs/opts.py:21-49).
+    """
+
+    def __init__(self, num_channels, beamformer="mvdr", frame_len=512, frame_hop=256,
+                 center=True, round_power_of_two=True, window="hann", ban=False,
+                 pmwf_ref=-1, rank1_appro="", post_masking=False, max_batch=256,
+                 max_samples=160000, device=None):
+        if beamformer not in BEAMFORMERS:
+            raise ValueError(f"Unknown beamformer {beamformer}, choose from {BEAMFORMERS}")
+        if rank1_appro not in _RANK1:
+            raise ValueError(f"Unknown rank1 approximation {rank1_appro}")
+        self.beamformer = beamformer
+        self.ban = bool(ban)
+        self.pmwf_ref = int(pmwf_ref)
+        self.rank1 = _RANK1[rank1_appro]
+        self.post_masking = bool(post_masking)
+        self.plan = StftPlan(num_channels, frame_len=frame_len, frame_hop=frame_hop,
+                             center=center, round_power_of_two=round_power_of_two,
+                             window=window, max_batch=max_batch, max_samples=max_samples,
+                             device=device)
+        self.device = self.plan.device
+        self._ones = None
+
+    def covariances(self, audio, mask_s, mask_n=None, n_samples=None, clip_mask=None):
+        if clip_mask is None:
+            clip_mask = mask_n is None     # apply_adaptive_beamformer.py:141-143
+        return self.plan.stft_cov(audio, mask_s, mask_n, n_samples=n_samples,
+                                  clip_mask=clip_mask)
+
+    def solve(self, Rs, Rn, Ry=None):
+        beta = 1.0 if self.beamformer == "pmwf-1" else 0.0
+        return weights(_KIND[self.beamformer], Rs, Rn=Rn, Ry=Ry, beta=beta,
+                       ref_channel=self.pmwf_ref, rank1=self.rank1, ban=self.ban,
+                       out_dtype=torch.complex64)
+
+    def run(self, audio, mask_s, mask_n=None, n_samples=None, clip_mask=None,
+            normalize=True, n_out=None):
+        """
+        audio (B,C,N) f32, mask_s (B,T,F) f32 [, mask_n].  Returns
+        (wave (B,N_out) f32, status (B,) int32 device tensor).  `normalize`
+        applies inverse_stft's norm=max|x| rescale (CLI behaviour).
+        """
+        Rs, Rn, maxabs = self.covariances(audio, mask_s, mask_n, n_samples, clip_mask)
+        Ry = None
+        if self.beamformer in ("mpdr", "mpdr-whiten"):
+            if self._ones is None or self._ones.shape != mask_s.shape:
+                self._ones = torch.ones_like(torch.as_tensor(mask_s, device=self.device),
+                                             dtype=torch.float32)
+            Ry, _, _ = self.plan.stft_cov(audio, self._ones, None, n_samples=n_samples,
+                                          want_maxabs=False)
+        w, status, _ = self.solve(Rs, Rn, Ry)
+        post = None
+        if self.post_masking:
+            post = torch.as_tensor(mask_s, device=self.device)
+            if clip_mask or (clip_mask is None and mask_n is None):
+                post = torch.clamp(post, max=1.0)
+        wave = self.plan.apply_istft(audio, w, post_mask=post, n_out=n_out,
+                                     norm=maxabs if normalize else None,
+                                     n_samples=n_samples)
+        return wave, status
+
+    @staticmethod
+    def raise_for_status(status, keys=None):
+        """Map per-utterance status words to numpy.linalg.LinAlgError (first failure)."""
+        st = status.detach().cpu().numpy()
+        bad = np.nonzero(st)[0]
+        if bad.size:
+            i = int(bad[0])
+            key = keys[i] if keys is not None else i
+            raise np.linalg.LinAlgError(f"utterance {key}: {status_message(int(st[i]))}")

@@ -1,0 +1,285 @@
+"""
+Shared parity checks: the CUDA path (through the C-ABI via setk_b200.plan)
+against the CPU oracle on the same seeded inputs.  The same functions run
+
+  * in the CPU tier against tests/emu/libsetk_b200_emu.so (the kernels' sources
+    under the CPU execution model) at tiny sizes, and
+  * in the GPU tier against libsetk_b200.so on a B200.
+
+Tolerances (float path; integer bookkeeping is asserted exactly):
+  STFT / covariance / iSTFT  fp32 kernels vs float64 oracle : rel-inf <= 2e-5
+                             (observed ~3e-7; c64 storage alone is 6e-8)
+  weights                    fp64 kernel vs LAPACK           : rel-inf <= 1e-9 after
+                             per-bin phase alignment (observed 1e-13)
+  end-to-end MVDR wave       north_star's bound              : rel-inf <= 1e-4 after
+                             per-bin phase alignment of the weights
+"""
+import numpy as np
+import torch
+
+from oracle import beamformer_oracle as bo
+from oracle import stft_oracle as so
+from setk_b200 import _lib
+from setk_b200 import plan as P
+
+TOL_F32 = 2e-5
+TOL_W = 1e-9
+TOL_E2E = 1e-4
+
+
+def rng_audio(rng, B, C, N, scale=0.1):
+    return (rng.standard_normal((B, C, N)) * scale).astype(np.float32)
+
+
+def stft_kwargs(frame_len, hop, center, window):
+    return dict(frame_len=frame_len, frame_hop=hop, center=center, window=window,
+                transpose=False)
+
+
+def oracle_stft(x, frame_len, hop, center, window, dtype=np.complex128):
+    return so.multichannel_stft(x, round_power_of_two=True, out_dtype=dtype,
+                                **stft_kwargs(frame_len, hop, center, window))
+
+
+def check_bookkeeping(device, frame_len, hop, center, lengths):
+    """Frame counts / iSTFT lengths are integer work: bit-exact vs the oracle."""
+    pl = P.StftPlan(1, frame_len, hop, center, True, "hann", 1, max(lengths), device)
+    n_fft = so.nextpow2(frame_len)
+    for n in lengths:
+        T = so.num_frames(n, n_fft, hop, center)
+        assert pl.num_frames(n) == T
+        assert pl.istft_length(T) == so.istft_length(T, n_fft, hop, center)
+    pl.close()
+
+
+def check_stft(device, rng, B, C, N, frame_len=512, hop=256, center=True, window="hann",
+               n_samples=None):
+    x = rng_audio(rng, B, C, N)
+    pl = P.StftPlan(C, frame_len, hop, center, True, window, B, N, device)
+    S = pl.stft(torch.from_numpy(x).to(device), n_samples=n_samples).cpu().numpy()
+    assert S.dtype == np.complex64
+    for b in range(B):
+        nb = N if n_samples is None else int(n_samples[b])
+        So = oracle_stft(x[b, :, :nb], frame_len, hop, center, window)
+        Tb = So.shape[-1]
+        assert S.shape[1:3] == So.shape[0:2]
+        err = bo.rel_inf(S[b, :, :, :Tb], So)
+        assert err <= TOL_F32, f"stft rel-inf {err}"
+        assert np.all(S[b, :, :, Tb:] == 0)
+    pl.close()
+    return err
+
+
+def check_stft_cov(device, rng, B, C, N, frame_len=512, hop=256, center=True, window="hann",
+                   with_mask_n=False, n_samples=None, clip=False, mask_ft=False):
+    x = rng_audio(rng, B, C, N)
+    pl = P.StftPlan(C, frame_len, hop, center, True, window, B, N, device)
+    T, F = pl.num_frames(N), pl.num_bins
+    hi = 1.3 if clip else 1.0
+    ms = rng.uniform(0, hi, (B, T, F)).astype(np.float32)
+    mn = rng.uniform(0, 1, (B, T, F)).astype(np.float32) if with_mask_n else None
+    tms = torch.from_numpy(ms.transpose(0, 2, 1).copy() if mask_ft else ms).to(device)
+    tmn = None if mn is None else torch.from_numpy(
+        mn.transpose(0, 2, 1).copy() if mask_ft else mn).to(device)
+    Rs, Rn, mx = pl.stft_cov(torch.from_numpy(x).to(device), tms, tmn, n_samples=n_samples,
+                             clip_mask=clip, mask_ft=mask_ft)
+    Rs, Rn, mx = Rs.cpu().numpy(), Rn.cpu().numpy(), mx.cpu().numpy()
+    worst = 0.0
+    for b in range(B):
+        nb = N if n_samples is None else int(n_samples[b])
+        So = oracle_stft(x[b, :, :nb], frame_len, hop, center, window)
+        Tb = So.shape[-1]
+        m_s = ms[b, :Tb].astype(np.float64)
+        if clip:
+            m_s = np.minimum(m_s, 1)
+        m_n = (1 - m_s) if mn is None else mn[b, :Tb].astype(np.float64)
+        Rs_o = bo.compute_covar(So, m_s)
+        Rn_o = bo.compute_covar(So, m_n)
+        es, en = bo.rel_inf(Rs[b], Rs_o), bo.rel_inf(Rn[b], Rn_o)
+        assert es <= TOL_F32 and en <= TOL_F32, f"covariance rel-inf {es} {en}"
+        # exactly Hermitian, real diagonal (the reference's only asserted property,
+        # test/test-beamformer.cc:45)
+        assert np.array_equal(Rs[b], np.conj(np.swapaxes(Rs[b], -1, -2)))
+        assert mx[b] == np.float32(np.max(np.abs(x[b, :, :nb])))
+        worst = max(worst, es, en)
+    pl.close()
+    return worst
+
+
+def check_cov_generic(device, rng, B, C, F, T):
+    X = (rng.standard_normal((B, C, F, T)) + 1j * rng.standard_normal((B, C, F, T))).astype(
+        np.complex64)
+    m = rng.uniform(0, 1, (B, T, F)).astype(np.float32)
+    R = P.covariance(torch.from_numpy(X).to(device), torch.from_numpy(m).to(device)).cpu().numpy()
+    for b in range(B):
+        Ro = bo.compute_covar(X[b].astype(np.complex128), m[b].astype(np.float64))
+        assert bo.rel_inf(R[b], Ro) <= TOL_F32
+
+
+def random_hpd(rng, F, C, cond=50.0):
+    A = rng.standard_normal((F, C, C + 4)) + 1j * rng.standard_normal((F, C, C + 4))
+    R = A @ np.conj(np.swapaxes(A, -1, -2)) / (C + 4)
+    return R + np.eye(C)[None] * (np.trace(R, axis1=-1, axis2=-2).real[:, None, None] / C / cond)
+
+
+def random_rank1_plus(rng, F, C):
+    """Rs with a clearly dominant eigenvector in every bin (eigen-gap >= ~5)."""
+    d = rng.standard_normal((F, C)) + 1j * rng.standard_normal((F, C))
+    return 6.0 * d[:, :, None] * np.conj(d[:, None, :]) + 0.3 * random_hpd(rng, F, C)
+
+
+def check_weights(device, rng, B, F, C, dtype=np.complex128):
+    """Every beamformer kind against the oracle (= the reference's LAPACK calls)."""
+    Rs = np.stack([random_rank1_plus(rng, F, C) for _ in range(B)]).astype(dtype)
+    Rn = np.stack([random_hpd(rng, F, C) for _ in range(B)]).astype(dtype)
+    Ry = (Rs + Rn).astype(dtype)
+    tRs, tRn, tRy = (torch.from_numpy(a).to(device) for a in (Rs, Rn, Ry))
+    tol = TOL_W if dtype == np.complex128 else 5e-4
+    Rs64, Rn64, Ry64 = Rs.astype(np.complex128), Rn.astype(np.complex128), Ry.astype(np.complex128)
+
+    def cmp(w, wo, align=True):
+        w = w.cpu().numpy().astype(np.complex128)
+        worst = 0.0
+        for b in range(B):
+            wa = bo.align_phase(w[b], wo[b])[0] if align else w[b]
+            worst = max(worst, bo.rel_inf(wa, wo[b]))
+        assert worst <= tol, f"weights rel-inf {worst}"
+
+    out = {}
+    w, st, _ = P.weights(_lib.BF_PEVD, tRs)
+    cmp(w, [bo.solve_pevd(Rs64[b]) for b in range(B)])
+    wn = w.cpu().numpy()
+    assert np.allclose(np.linalg.norm(wn, axis=-1), 1, atol=1e-5)
+    assert np.all(np.abs(wn[..., 0].imag) <= 1e-7) and np.all(wn[..., 0].real >= 0)
+    w, st1, _ = P.weights(_lib.BF_PEVD, tRs, tRn)
+    cmp(w, [bo.solve_pevd(Rs64[b], Rn64[b]) for b in range(B)])
+    w, st2, _ = P.weights(_lib.BF_MVDR, tRs, tRn)
+    cmp(w, [bo.mvdr_weight(Rs64[b], Rn64[b]) for b in range(B)])
+    out["mvdr"] = w
+    w, st3, _ = P.weights(_lib.BF_MVDR, tRs, tRn, ban=True)
+    cmp(w, [bo.do_ban(bo.mvdr_weight(Rs64[b], Rn64[b]), Rn64[b]) for b in range(B)])
+    w, st4, _ = P.weights(_lib.BF_GEVD, tRs, tRn)
+    cmp(w, [bo.gevd_weight(Rs64[b], Rn64[b]) for b in range(B)])
+    w, st5, _ = P.weights(_lib.BF_MPDR, tRs, None, tRy)
+    cmp(w, [bo.mpdr_weight(Rs64[b], Ry64[b]) for b in range(B)])
+    w, st6, _ = P.weights(_lib.BF_MPDR_WHITEN, tRs, tRn, tRy)
+    cmp(w, [bo.mpdr_weight(Rs64[b], Ry64[b], Rn=Rn64[b]) for b in range(B)])
+    for beta in (0.0, 1.0):
+        for r1, r1name in ((_lib.RANK1_NONE, ""), (_lib.RANK1_EIG, "eig"), (_lib.RANK1_GEV, "gev")):
+            for ref in (-1, C - 1):
+                w, st7, used = P.weights(_lib.BF_PMWF, tRs, tRn, beta=beta, ref_channel=ref, rank1=r1)
+                exp = [bo.pmwf_weight(Rs64[b], Rn64[b], beta=beta, ref_channel=ref,
+                                      rank1_appro=r1name) for b in range(B)]
+                cmp(w, [e[0] for e in exp], align=False)   # PMWF is phase invariant
+                assert [int(u) for u in used.cpu()] == [e[1] for e in exp]
+                assert int(st7.abs().sum()) == 0
+    for st in (st, st1, st2, st3, st4, st5, st6):
+        assert int(st.abs().sum()) == 0
+    # MVDR is distortionless: w^H d = 1
+    d = np.stack([bo.solve_pevd(Rs64[b]) for b in range(B)])
+    wd = np.sum(np.conj(out["mvdr"].cpu().numpy().astype(np.complex128)) * d, axis=-1)
+    assert np.allclose(np.abs(wd), 1, atol=1e-6 if dtype == np.complex128 else 1e-3)
+
+
+def check_weights_status(device):
+    """Singular / non-PD inputs set status bits instead of failing the call."""
+    F, C = 3, 3
+    Rs = np.tile(np.eye(C, dtype=np.complex128), (1, F, 1, 1))
+    Rn = np.zeros((1, F, C, C), dtype=np.complex128)          # exactly singular
+    w, st, _ = P.weights(_lib.BF_MVDR, torch.from_numpy(Rs).to(device),
+                         torch.from_numpy(Rn).to(device))
+    assert int(st[0]) & _lib.ST_SINGULAR
+    Rn2 = np.tile(np.diag([1.0, -1.0, 1.0]).astype(np.complex128), (1, F, 1, 1))
+    w, st, _ = P.weights(_lib.BF_GEVD, torch.from_numpy(Rs).to(device),
+                         torch.from_numpy(Rn2).to(device))
+    assert int(st[0]) & _lib.ST_NOT_PD
+    w, st, _ = P.weights(_lib.BF_PMWF, torch.from_numpy(Rs).to(device),
+                         torch.from_numpy(Rs.copy()).to(device), ref_channel=C + 2)
+    assert int(st[0]) & _lib.ST_BAD_REF
+
+
+def check_apply_istft(device, rng, B, C, N, frame_len=512, hop=256, center=True, window="hann",
+                      post_mask=False, norm=True, n_out=None, n_samples=None):
+    x = rng_audio(rng, B, C, N)
+    pl = P.StftPlan(C, frame_len, hop, center, True, window, B, N, device)
+    T, F = pl.num_frames(N), pl.num_bins
+    w = (rng.standard_normal((B, F, C)) + 1j * rng.standard_normal((B, F, C))).astype(np.complex64)
+    pm = rng.uniform(0, 1, (B, T, F)).astype(np.float32)
+    nm = np.abs(x).max(axis=(1, 2)).astype(np.float32)
+    y = pl.apply_istft(torch.from_numpy(x).to(device), torch.from_numpy(w).to(device),
+                       post_mask=torch.from_numpy(pm).to(device) if post_mask else None,
+                       n_out=n_out, norm=torch.from_numpy(nm).to(device) if norm else None,
+                       n_samples=n_samples).cpu().numpy()
+    kw = stft_kwargs(frame_len, hop, center, window)
+    worst = 0.0
+    for b in range(B):
+        nb = N if n_samples is None else int(n_samples[b])
+        So = oracle_stft(x[b, :, :nb], frame_len, hop, center, window)
+        Tb = So.shape[-1]
+        enh = bo.beamform(w[b].astype(np.complex128), So)
+        if post_mask:
+            enh = enh * pm[b, :Tb].T
+        want = n_out
+        if want is None and n_samples is not None:
+            want = y.shape[1]
+        yo = so.inverse_stft(enh, norm=float(nm[b]) if norm else None, nsamps=want, **kw)
+        assert yo.shape[0] == y.shape[1], (yo.shape, y.shape)      # integer bookkeeping
+        err = bo.rel_inf(y[b], yo)
+        assert err <= TOL_F32, f"apply+istft rel-inf {err}"
+        worst = max(worst, err)
+    pl.close()
+    return worst
+
+
+def check_generic_chain(device, rng, B, C, N, frame_len, hop, center, window):
+    """setk_stft -> setk_apply -> setk_istft (explicit STFT route) vs the oracle."""
+    x = rng_audio(rng, B, C, N)
+    pl = P.StftPlan(C, frame_len, hop, center, True, window, B, N, device)
+    T, F = pl.num_frames(N), pl.num_bins
+    w = (rng.standard_normal((B, F, C)) + 1j * rng.standard_normal((B, F, C))).astype(np.complex128)
+    S = pl.stft(torch.from_numpy(x).to(device))
+    enh = P.apply_weights(S, torch.from_numpy(w).to(device))
+    nm = np.abs(x).max(axis=(1, 2)).astype(np.float32)
+    y = pl.istft(enh, norm=torch.from_numpy(nm).to(device)).cpu().numpy()
+    kw = stft_kwargs(frame_len, hop, center, window)
+    for b in range(B):
+        So = oracle_stft(x[b], frame_len, hop, center, window)
+        yo = so.inverse_stft(bo.beamform(w[b], So), norm=float(nm[b]), **kw)
+        assert yo.shape[0] == y.shape[1]
+        assert bo.rel_inf(y[b], yo) <= TOL_F32
+    pl.close()
+
+
+def mvdr_end_to_end(device, x, mask, kind="mvdr", frame_len=512, hop=256, center=True,
+                    window="hann", **bf_kwargs):
+    """
+    Whole pipeline on one batch vs the oracle's enhance_utterance, with the
+    oracle's weights phase-aligned per bin to ours (the reference's sign is
+    LAPACK-defined, SURVEY.md finding 4) before the oracle's own
+    beamform + iSTFT.  Returns the worst global rel-inf over the batch.
+    """
+    from setk_b200.engine import BeamformPipeline
+    B, C, N = x.shape
+    name = {"pmwf": "pmwf-0"}.get(kind, kind)
+    pipe = BeamformPipeline(C, beamformer=name, frame_len=frame_len, frame_hop=hop, center=center,
+                            window=window, max_batch=B, max_samples=N, device=device, **bf_kwargs)
+    tx, tm = torch.from_numpy(x).to(device), torch.from_numpy(mask).to(device)
+    y, status = pipe.run(tx, tm)
+    assert int(status.abs().sum()) == 0
+    Rs, Rn, _ = pipe.covariances(tx, tm)
+    w_ours = pipe.solve(Rs, Rn)[0].cpu().numpy().astype(np.complex128)
+    y = y.cpu().numpy()
+    kw = stft_kwargs(frame_len, hop, center, window)
+    worst = 0.0
+    for b in range(B):
+        So = oracle_stft(x[b], frame_len, hop, center, window)
+        ms = np.minimum(mask[b].astype(np.float64), 1)
+        okind = "pmwf" if kind.startswith("pmwf") else kind
+        _, w_o, _, _ = bo.run_supervised(okind, ms, So, ban=bf_kwargs.get("ban", False),
+                                         ref_channel=bf_kwargs.get("pmwf_ref", -1),
+                                         rank1_appro=bf_kwargs.get("rank1_appro", ""),
+                                         return_all=True)
+        w_al, _ = bo.align_phase(w_o, w_ours[b])
+        yo = so.inverse_stft(bo.beamform(w_al, So), norm=float(np.max(np.abs(x[b]))), **kw)
+        worst = max(worst, bo.rel_inf(y[b], yo))
+    return worst

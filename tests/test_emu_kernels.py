@@ -1,0 +1,120 @@
+"""
+CPU tier: the kernel sources of setk_b200/csrc compiled for the CPU execution
+model (tests/emu) and driven through the same C-ABI / ctypes / plan code as the
+product, checked against the oracle at small sizes.  Catches index
+bookkeeping, staging, barrier-structure and argument-checking defects before a
+GPU is involved.  (The sm_100a library itself is exercised by test_gpu_*.py.)
+"""
+import numpy as np
+import pytest
+import torch
+
+import parity_cases as pc
+
+
+def test_bookkeeping_bit_exact(emu):
+    for fl, hop, center in [(512, 256, True), (512, 256, False), (400, 160, True),
+                            (1024, 256, True), (256, 64, False)]:
+        pc.check_bookkeeping(emu, fl, hop, center, [1025, 2048, 4099, 16000, 94010, 160000])
+
+
+@pytest.mark.parametrize("C,N,fl,hop,center,window", [
+    (1, 1500, 512, 256, True, "hann"),
+    (3, 1300, 256, 128, False, "hamming"),
+    (2, 2100, 1024, 256, True, "sqrthann"),
+    (2, 1200, 400, 160, True, "hann"),
+])
+def test_stft_generic(emu, C, N, fl, hop, center, window):
+    pc.check_stft(emu, np.random.default_rng(1), 1, C, N, fl, hop, center, window)
+
+
+def test_stft_generic_ragged(emu):
+    ns = torch.tensor([1500, 900], dtype=torch.int32)
+    pc.check_stft(emu, np.random.default_rng(2), 2, 2, 1500, n_samples=ns)
+
+
+@pytest.mark.parametrize("C,N,hop,center,with_mn,clip,mask_ft", [
+    (4, 3000, 256, True, False, False, False),     # the config-2 geometry, fused kernel
+    (4, 2900, 256, False, True, False, False),
+    (2, 2600, 128, True, False, True, False),
+    (3, 2000, 384, True, True, False, True),
+    (1, 1800, 256, True, False, False, False),
+])
+def test_stft_cov_fused(emu, C, N, hop, center, with_mn, clip, mask_ft):
+    pc.check_stft_cov(emu, np.random.default_rng(3), 2, C, N, 512, hop, center, "hann",
+                      with_mask_n=with_mn, clip=clip, mask_ft=mask_ft)
+
+
+def test_stft_cov_fused_ragged(emu):
+    ns = torch.tensor([3000, 1701, 2048], dtype=torch.int32)
+    pc.check_stft_cov(emu, np.random.default_rng(4), 3, 4, 3000, n_samples=ns)
+
+
+def test_stft_cov_generic_route(emu):
+    # C = 5 and n_fft = 256 have no fused instantiation: explicit STFT + covariance
+    pc.check_stft_cov(emu, np.random.default_rng(5), 1, 5, 1500, 512, 256, True, "hann")
+    pc.check_stft_cov(emu, np.random.default_rng(6), 1, 2, 900, 256, 64, True, "hann",
+                      with_mask_n=True)
+
+
+def test_cov_generic(emu):
+    pc.check_cov_generic(emu, np.random.default_rng(7), 2, 6, 9, 70)
+
+
+@pytest.mark.parametrize("C", [1, 2, 4, 5, 8])
+def test_weights_all_kinds(emu, C):
+    pc.check_weights(emu, np.random.default_rng(10 + C), 2, 7, C)
+
+
+def test_weights_c64_and_status(emu):
+    pc.check_weights(emu, np.random.default_rng(20), 1, 5, 4, dtype=np.complex64)
+    pc.check_weights_status(emu)
+
+
+@pytest.mark.parametrize("C,N,hop,center,pm,norm", [
+    (4, 3000, 256, True, False, True),
+    (4, 2500, 256, False, True, True),
+    (2, 3100, 128, True, False, False),
+    (3, 2000, 384, True, True, True),
+])
+def test_apply_istft_fused(emu, C, N, hop, center, pm, norm):
+    pc.check_apply_istft(emu, np.random.default_rng(30), 2, C, N, 512, hop, center, "hann",
+                         post_mask=pm, norm=norm)
+
+
+def test_apply_istft_nsamps_and_ragged(emu):
+    rng = np.random.default_rng(31)
+    pc.check_apply_istft(emu, rng, 1, 4, 3000, n_out=3000)           # fix_length: pad
+    pc.check_apply_istft(emu, rng, 1, 4, 3000, n_out=2000)           # fix_length: crop
+    ns = torch.tensor([3000, 1900], dtype=torch.int32)
+    pc.check_apply_istft(emu, rng, 2, 4, 3000, n_samples=ns)
+
+
+def test_generic_chain(emu):
+    rng = np.random.default_rng(32)
+    pc.check_generic_chain(emu, rng, 1, 5, 1500, 512, 256, True, "hann")
+    pc.check_generic_chain(emu, rng, 1, 2, 1000, 256, 64, False, "hamming")
+    pc.check_apply_istft(emu, rng, 1, 2, 1100, 256, 128, True, "hann")   # generic apply_istft route
+
+
+def test_pipeline_end_to_end_small(emu):
+    from setk_b200 import synth
+    x, m = synth.make_batch(1, 4, 4000, device="cpu")
+    for kind in ("mvdr", "gevd", "pmwf-0"):
+        err = pc.mvdr_end_to_end(emu, x.numpy(), m.numpy(), kind=kind)
+        assert err <= pc.TOL_E2E, (kind, err)
+
+
+def test_argument_errors(emu):
+    from setk_b200 import _lib, plan as P
+    with pytest.raises(_lib.SetkError):
+        P.StftPlan(4, 300, 100, True, False, "hann", 1, 1000, emu)      # n_fft=300 not a power of two
+    pl = P.StftPlan(4, 512, 256, True, True, "hann", 1, 2000, emu)
+    with pytest.raises(ValueError):
+        pl.stft(torch.zeros(1, 3, 2000))                                # wrong channel count
+    with pytest.raises(_lib.SetkError):
+        pl.stft(torch.zeros(2, 4, 2000))                                # batch > max_batch
+    with pytest.raises(ValueError):
+        pl.stft_cov(torch.zeros(1, 4, 2000), torch.zeros(1, 3, 257))    # wrong mask shape
+    with pytest.raises(ValueError):
+        pl.num_frames(100)

@@ -1,0 +1,221 @@
+"""
+GPU tier: libsetk_b200.so (sm_100a) through the C-ABI against the CPU oracle
+and the golden fixtures generated from the reference's own code.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import parity_cases as pc
+from oracle import beamformer_oracle as bo
+from oracle import stft_oracle as so
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_native_library_is_loaded(cuda):
+    from setk_b200 import _lib
+    assert _lib.library_path().endswith("setk_b200/libsetk_b200.so")
+    with open("/proc/self/maps") as f:
+        assert "libsetk_b200.so" in f.read()
+
+
+def test_bookkeeping_bit_exact(cuda):
+    for fl, hop, center in [(512, 256, True), (512, 256, False), (400, 160, True),
+                            (1024, 256, True), (256, 64, False)]:
+        pc.check_bookkeeping(cuda, fl, hop, center, [1025, 2048, 4099, 16000, 94010, 160000])
+
+
+@pytest.mark.parametrize("C,N,fl,hop,center,window", [
+    (1, 16000, 512, 256, True, "hann"),
+    (3, 9000, 256, 128, False, "hamming"),
+    (8, 12000, 1024, 256, True, "sqrthann"),
+    (5, 7000, 400, 160, True, "hann"),
+    (2, 30000, 2048, 512, True, "blackman"),
+])
+def test_stft_generic(cuda, C, N, fl, hop, center, window):
+    pc.check_stft(cuda, np.random.default_rng(1), 2, C, N, fl, hop, center, window)
+
+
+def test_stft_generic_ragged(cuda):
+    ns = torch.tensor([16000, 9000, 700], dtype=torch.int32)
+    pc.check_stft(cuda, np.random.default_rng(2), 3, 2, 16000, n_samples=ns)
+
+
+@pytest.mark.parametrize("C,N,hop,center,with_mn,clip,mask_ft", [
+    (4, 32000, 256, True, False, False, False),
+    (4, 31000, 256, False, True, False, False),
+    (2, 20000, 128, True, False, True, False),
+    (3, 20000, 384, True, True, False, True),
+    (1, 16000, 256, True, False, False, False),
+    (4, 160000, 256, True, False, True, False),    # config-2 utterance length
+])
+def test_stft_cov_fused(cuda, C, N, hop, center, with_mn, clip, mask_ft):
+    pc.check_stft_cov(cuda, np.random.default_rng(3), 3, C, N, 512, hop, center, "hann",
+                      with_mask_n=with_mn, clip=clip, mask_ft=mask_ft)
+
+
+def test_stft_cov_fused_ragged(cuda):
+    ns = torch.tensor([30000, 17001, 20480, 600], dtype=torch.int32)
+    pc.check_stft_cov(cuda, np.random.default_rng(4), 4, 4, 30000, n_samples=ns)
+
+
+def test_stft_cov_generic_route(cuda):
+    pc.check_stft_cov(cuda, np.random.default_rng(5), 2, 8, 16000, 1024, 256, True, "hann")   # config-3 geometry
+    pc.check_stft_cov(cuda, np.random.default_rng(6), 2, 6, 9000, 512, 256, True, "hann",
+                      with_mask_n=True)                                                        # config-4 channels
+    pc.check_stft_cov(cuda, np.random.default_rng(7), 1, 16, 8000, 512, 256, True, "hann")
+
+
+def test_cov_generic(cuda):
+    pc.check_cov_generic(cuda, np.random.default_rng(7), 2, 6, 33, 300)
+
+
+@pytest.mark.parametrize("C", [1, 2, 3, 4, 5, 6, 8, 16])
+def test_weights_all_kinds(cuda, C):
+    pc.check_weights(cuda, np.random.default_rng(10 + C), 2, 64, C)
+
+
+def test_weights_c64_and_status(cuda):
+    pc.check_weights(cuda, np.random.default_rng(20), 2, 64, 4, dtype=np.complex64)
+    pc.check_weights_status(cuda)
+
+
+@pytest.mark.parametrize("C,N,hop,center,pm,norm", [
+    (4, 32000, 256, True, False, True),
+    (4, 25000, 256, False, True, True),
+    (2, 31000, 128, True, False, False),
+    (3, 20000, 384, True, True, True),
+    (4, 160000, 256, True, False, True),
+])
+def test_apply_istft_fused(cuda, C, N, hop, center, pm, norm):
+    pc.check_apply_istft(cuda, np.random.default_rng(30), 2, C, N, 512, hop, center, "hann",
+                         post_mask=pm, norm=norm)
+
+
+def test_apply_istft_nsamps_and_ragged(cuda):
+    rng = np.random.default_rng(31)
+    pc.check_apply_istft(cuda, rng, 1, 4, 30000, n_out=30000)
+    pc.check_apply_istft(cuda, rng, 1, 4, 30000, n_out=20000)
+    ns = torch.tensor([30000, 19000, 1000], dtype=torch.int32)
+    pc.check_apply_istft(cuda, rng, 3, 4, 30000, n_samples=ns)
+
+
+def test_generic_chain(cuda):
+    rng = np.random.default_rng(32)
+    pc.check_generic_chain(cuda, rng, 2, 5, 15000, 512, 256, True, "hann")
+    pc.check_generic_chain(cuda, rng, 1, 2, 10000, 256, 64, False, "hamming")
+    pc.check_generic_chain(cuda, rng, 1, 8, 12000, 1024, 256, True, "hann")
+    pc.check_apply_istft(cuda, rng, 1, 8, 12000, 1024, 256, True, "hann")
+
+
+@pytest.mark.parametrize("kind,kw", [
+    ("mvdr", {}), ("mvdr", {"ban": True}), ("gevd", {}), ("gevd", {"ban": True}),
+    ("pmwf-0", {}), ("pmwf-1", {"pmwf_ref": 1}), ("pmwf-0", {"rank1_appro": "eig"}),
+    ("pmwf-0", {"rank1_appro": "gev"}),
+])
+def test_pipeline_end_to_end(cuda, kind, kw):
+    """north_star bound: MVDR output within 1e-4 rel-inf of the reference path."""
+    from setk_b200 import synth
+    x, m = synth.make_batch(3, 4, 48000, device=cuda)
+    err = pc.mvdr_end_to_end(cuda, x.cpu().numpy(), m.cpu().numpy(), kind=kind, **kw)
+    assert err <= pc.TOL_E2E, (kind, kw, err)
+
+
+# ----------------------------------------------------------------- golden ----
+def test_golden_small_cases_from_reference(cuda):
+    """
+    tests/golden/ref_small.npz: outputs of the reference's own forward_stft /
+    compute_covar / *.weight / beamform / inverse_stft (oracle/make_golden.py).
+    """
+    from setk_b200 import _lib, plan as P
+    g = np.load(os.path.join(GOLD, "ref_small.npz"))
+    for name in ("c4_512", "c5_400", "c2_256nc", "c8_1024"):
+        C, N, fl, hop, center = [int(v) for v in g[name + "/cfg"]]
+        window = str(g[name + "/window"])
+        mix, mask = g[name + "/mix"], g[name + "/mask"]
+        pl = P.StftPlan(C, fl, hop, bool(center), True, window, 1, N, cuda)
+        Rs, Rn, mx = pl.stft_cov(torch.from_numpy(mix[None]).to(cuda),
+                                 torch.from_numpy(mask[None]).to(cuda))
+        assert bo.rel_inf(Rs[0].cpu().numpy(), g[name + "/Rs"]) <= pc.TOL_F32
+        assert bo.rel_inf(Rn[0].cpu().numpy(), g[name + "/Rn"]) <= pc.TOL_F32
+        tRs = torch.from_numpy(g[name + "/Rs"][None]).to(cuda)
+        tRn = torch.from_numpy(g[name + "/Rn"][None]).to(cuda)
+        for kind, key in ((_lib.BF_MVDR, "w_mvdr"), (_lib.BF_GEVD, "w_gev")):
+            w = P.weights(kind, tRs, tRn)[0][0].cpu().numpy()
+            wa = bo.align_phase(w, g[name + "/" + key])[0]
+            assert bo.rel_inf(wa, g[name + "/" + key]) <= pc.TOL_W * 100
+        w = P.weights(_lib.BF_PMWF, tRs, tRn, beta=1.0, ref_channel=0)[0][0].cpu().numpy()
+        assert bo.rel_inf(w, g[name + "/w_pmwf1_ref0"]) <= pc.TOL_W * 100
+        # reference's MVDR weights -> our apply + iSTFT == reference's waveform
+        y = pl.apply_istft(torch.from_numpy(mix[None]).to(cuda),
+                           torch.from_numpy(g[name + "/w_mvdr"][None]).to(cuda),
+                           norm=mx)[0].cpu().numpy()
+        yr = g[name + "/y_mvdr"]
+        assert y.shape == yr.shape
+        assert bo.rel_inf(y, yr) <= pc.TOL_F32
+        pl.close()
+
+
+def test_golden_doc_vectors_pmwf_chain(cuda):
+    """
+    The reference's shipped example (doc/adaptive_beamformer/asset): egs.wav +
+    CGMM mask -> pmwf-0 / pmwf-0-eig / pmwf-0-gev .wav.  PMWF is phase
+    invariant, so the shipped PCM-16 vectors pin the whole chain: our output
+    must agree to <= 1 LSB on >= 95 % of samples and never differ by more than
+    2 LSB (the reference's own c64 replay differs from the shipped file in up
+    to 2.8 % of samples by 1 LSB: tests/golden/PINNING.json).
+    """
+    from setk_b200.engine import BeamformPipeline
+    from setk_b200 import plan as P
+    g = np.load(os.path.join(GOLD, "doc_adaptive_beamformer.npz"))
+    pcm = torch.from_numpy(g["egs_pcm16"]).to(cuda)                 # (5, 94010) int16
+    audio = P.pcm16_to_float(pcm)[None]
+    mask = torch.from_numpy(g["mask"]).to(cuda)[None]
+    for name, r1 in (("pmwf-0", ""), ("pmwf-0-eig", "eig"), ("pmwf-0-gev", "gev")):
+        pipe = BeamformPipeline(5, "pmwf-0", rank1_appro=r1, max_batch=1,
+                                max_samples=audio.shape[-1], device=cuda)
+        wave, status = pipe.run(audio, mask)
+        assert int(status[0]) == 0
+        out = P.float_to_pcm16(wave)[0].cpu().numpy().astype(np.int64)
+        shipped = g["shipped/" + name].astype(np.int64)
+        assert out.shape == shipped.shape == (93952,)
+        d = np.abs(out - shipped)
+        assert d.max() <= 2, (name, d.max())
+        assert np.mean(d > 0) <= 0.05, (name, float(np.mean(d > 0)))
+
+
+def test_golden_doc_vectors_gevd_sign_fit(cuda):
+    """
+    gevd.wav is a golden vector modulo one sign per bin (scipy's hegvd chooses
+    it): fit the 257 signs in the time domain (iSTFT is linear) and compare.
+    """
+    from setk_b200.engine import BeamformPipeline
+    from setk_b200 import plan as P
+    g = np.load(os.path.join(GOLD, "doc_adaptive_beamformer.npz"))
+    audio = P.pcm16_to_float(torch.from_numpy(g["egs_pcm16"]).to(cuda))[None]
+    mask = torch.from_numpy(g["mask"]).to(cuda)[None]
+    N = audio.shape[-1]
+    pipe = BeamformPipeline(5, "gevd", max_batch=1, max_samples=N, device=cuda)
+    Rs, Rn, mx = pipe.covariances(audio, mask)
+    w = pipe.solve(Rs, Rn)[0]
+    shipped = g["shipped/gevd"].astype(np.float64) / 32768.0
+    F = w.shape[1]
+    stft = pipe.plan.stft(audio)
+    enh = P.apply_weights(stft, w)[0]                                # (F, T)
+    per_bin = torch.zeros((F, F, enh.shape[-1]), dtype=torch.complex64, device=cuda)
+    idx = torch.arange(F, device=cuda)
+    per_bin[idx, idx] = enh
+    pl1 = P.StftPlan(1, 512, 256, True, True, "hann", F, N, cuda)
+    contrib = pl1.istft(per_bin).cpu().numpy().astype(np.float64)    # (F, n_out)
+    signs = np.sign(contrib @ shipped)
+    signs[signs == 0] = 1
+    y = (signs[:, None] * contrib).sum(axis=0)
+    y = y * float(mx[0]) / (np.max(np.abs(y)) + so.EPSILON)
+    out = so.pcm16_from_float(y).astype(np.int64)
+    d = np.abs(out - g["shipped/gevd"].astype(np.int64))
+    assert d.max() <= 2, d.max()
+    assert np.mean(d > 0) <= 0.05
