@@ -121,7 +121,8 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    from oracle.cpu_bench import usable_cores
+    cores = usable_cores()
     per_step = max(cores, 8)                       # utterances per "step" sample
     t0 = time.time()
     for _ in range(args.warmup if args.warmup < 2 else 1):
@@ -178,7 +179,10 @@ def gpu_arm(args):
     # CPU baseline first (rank 0, N=1 only): before the GPU gets busy
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        from oracle.cpu_bench import usable_cores
+        cores = usable_cores()
+        if args.cpu_utts <= 0:
+            args.cpu_utts = 16 * cores
         per_worker = max(1, args.cpu_utts // cores)
         v = run_cpu_arm(per_worker, cores)
         cpu_base = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
@@ -339,8 +343,6 @@ def main():
                     help="utterances for the cpu_baseline sample (0 = 16 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.cpu_utts <= 0:
-        args.cpu_utts = 16 * (os.cpu_count() or 1)
     if args.impl == "reference":
         reference_arm(args)
     else:

@@ -60,6 +60,19 @@ def _worker(args):
     return time.perf_counter() - t0
 
 
+def usable_cores():
+    """Cores this process may actually use: affinity mask and cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as fh:
+            quota, period = fh.read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def throughput(C, N, n_utts_per_worker, workers, seed=20240923):
     """utterances / second over `workers` concurrent single-threaded processes."""
     ctx = mp.get_context("spawn")

@@ -276,6 +276,7 @@ def mvdr_end_to_end(device, x, mask, kind="mvdr", frame_len=512, hop=256, center
         ms = np.minimum(mask[b].astype(np.float64), 1)
         okind = "pmwf" if kind.startswith("pmwf") else kind
         _, w_o, _, _ = bo.run_supervised(okind, ms, So, ban=bf_kwargs.get("ban", False),
+                                         beta=1 if kind == "pmwf-1" else 0,
                                          ref_channel=bf_kwargs.get("pmwf_ref", -1),
                                          rank1_appro=bf_kwargs.get("rank1_appro", ""),
                                          return_all=True)
