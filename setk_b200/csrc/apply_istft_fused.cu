@@ -11,15 +11,16 @@
 // C++ twin: Beamform (include/beamformer.cc:215-230) + InverseShortTimeFT
 // (include/stft.cc:154-198).
 //
-// Per tile of <= TT frames (288 threads):
-//   stage + forward FFT          (stft_tile.cuh)
+// Per tile of <= TT frames (288 threads), audio streamed one tile ahead by TMA
+// bulk copies (stft_tile.cuh):
+//   forward FFT  (stft_tile.cuh)
 //   apply   item (frame, k<=128): split Z -> X_c[k], X_c[256-k]; y = w^H x for
 //           both bins; inverse split -> half-size spectrum Zi[k], Zi[256-k]
 //   iFFT    one half-warp per frame: conj . FFT256 . conj, x synthesis window
 //   flush   gather overlap-add of the tile's frames + carry from the previous
 //           tile; positions no later frame can touch are divided by the
-//           window-sum-square, trimmed and written (16-byte coalesced rows),
-//           the rest becomes the next carry.  Deterministic: no atomics on data.
+//           window-sum-square, trimmed and written (coalesced rows), the rest
+//           becomes the next carry.  Deterministic: no atomics on data.
 // A CTA owns the output positions of its own frames; the <= ceil(n_fft/hop)-1
 // frames before its first frame are recomputed as a halo tile.
 // Algorithmic bytes per utterance: 4*C*N (audio) + 8*F*C (w) + 4*n_out (wave)
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(288, 2) apply_istft_kernel(ApplyIstftArgs a) {
     s_carry[n] = 0.f;
     s_carry[kNfft + n] = 0.f;
   }
+  if (tid == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); }
   for (int e = tid; e < F * C; e += blockDim.x) {
     const long long wi = (long long)b * F * C + e;
     float2 v;
@@ -103,14 +105,27 @@ __global__ void __launch_bounds__(288, 2) apply_istft_kernel(ApplyIstftArgs a) {
 
   const int R = (kNfft + hop - 1) / hop - 1;       // frames before t that overlap frame t
   int cur = 0;                                     // which carry buffer is the input
+  // tile sequence: an optional halo tile [t_begin-R, t_begin), then full tiles
   int t0 = imax(0, t_begin - R);
   if (t_begin >= t_end) t0 = t_end;                // nothing to do for this chunk
+  int nt = (t0 < t_begin) ? (t_begin - t0) : imin(TT, t_end - t0);
+  unsigned par = 0;
+  float amax_unused = 0.f;
+  bool async_cur = false;
+  if (t0 < t_end) async_cur = stage_tile_begin<C, TT>(sm, 0, xb, a.N, nb, t0, nt, hop, pad, vec_ok);
+  int buf = 0;
   while (t0 < t_end) {
-    const int nt = (t0 < t_begin) ? (t_begin - t0) : imin(TT, t_end - t0);
-    __syncthreads();
-    stage_tile<C, TT>(sm, xb, a.N, nb, t0, nt, hop, pad, vec_ok, 0.f);
-    __syncthreads();
-    if (warp < 8) fft_tile<C, TT>(sm, nt, hop, w1);
+    const int t_next = t0 + nt;
+    const int nt_next = imin(TT, t_end - t_next);
+    __syncthreads();   // previous tile fully consumed (sm.z, s_frames, audio[buf^1])
+    bool async_next = false;
+    if (t_next < t_end)
+      async_next = stage_tile_begin<C, TT>(sm, buf ^ 1, xb, a.N, nb, t_next, nt_next, hop, pad, vec_ok);
+    if (async_cur) {
+      mbar_wait(&sm.bar[buf], (par >> buf) & 1u);
+      par ^= 1u << buf;
+    }
+    if (warp < 8) fft_tile<C, TT>(sm, buf, nt, hop, w1, amax_unused);
     __syncthreads();
     // ---- apply + inverse split ----
     for (int it = tid; it < nt * NPAIR; it += blockDim.x) {
@@ -142,13 +157,10 @@ __global__ void __launch_bounds__(288, 2) apply_istft_kernel(ApplyIstftArgs a) {
         // Zi[k]   = (Yk + conj(Ym)) + conj(tw) (Yk - conj(Ym))
         const float er = yk.x + ym.x, ei = yk.y - ym.y;
         const float dr = yk.x - ym.x, di = yk.y + ym.y;
-        // conj(tw) * D = (tw.x dr + tw.y di, tw.x di - tw.y dr)
         zi[k] = make_float2(er + tw.x * dr + tw.y * di, ei + tw.x * di - tw.y * dr);
         if (k != kM / 2) {
-          // Zi[256-k] = (Ym + conj(Yk)) + tw (Ym - conj(Yk))
-          const float er2 = er, ei2 = -ei;            // Ym + conj(Yk) = conj(E)
-          const float dr2 = -dr, di2 = di;            // Ym - conj(Yk) = -conj(D)
-          zi[km] = make_float2(er2 + tw.x * dr2 - tw.y * di2, ei2 + tw.x * di2 + tw.y * dr2);
+          // Zi[256-k] = (Ym + conj(Yk)) + tw (Ym - conj(Yk)) = conj(E) - tw conj(D)
+          zi[km] = make_float2(er - tw.x * dr - tw.y * di, -ei + tw.x * di - tw.y * dr);
         }
       }
     }
@@ -177,35 +189,43 @@ __global__ void __launch_bounds__(288, 2) apply_istft_kernel(ApplyIstftArgs a) {
     // ---- flush: gather overlap-add, normalise, trim, write ----
     {
       const int p_tile = t0 * hop;
-      const bool last_tile = (t0 + nt == T_used);
-      const int final_len = last_tile ? (nt - 1) * hop + kNfft : nt * hop;
-      const int span = (nt - 1) * hop + kNfft;
+      const bool last_tile = (t_next == T_used);
+      const int span = (nt - 1) * hop + kNfft;           // positions touched by this tile
+      const int final_len = last_tile ? span : nt * hop;
       const float* cin = s_carry + cur * kNfft;
       float* cout = s_carry + (cur ^ 1) * kNfft;
-      for (int rel = tid; rel < span; rel += blockDim.x) {
-        float val = rel < carry_len ? cin[rel] : 0.f;
-        const int j_hi = imin(nt - 1, rel / hop);
-        const int j_lo = (rel >= kNfft) ? (rel - kNfft) / hop + 1 : 0;
-        for (int j = j_lo; j <= j_hi; ++j) val += s_frames[j * kNfft + rel - j * hop];
-        if (rel < final_len) {
-          const int p = p_tile + rel;
-          const int q = p - pad;
-          if (p >= t_begin * hop && q >= 0 && q < a.n_out) {
-            const int tl = (p >= kNfft) ? (p - kNfft) / hop + 1 : 0;
-            const int th = imin(T_used - 1, p / hop);
-            float wss = 0.f;
-            for (int t = tl; t <= th; ++t) wss += s_wsq[p - t * hop];
-            if (wss > SETK_TINY32) val /= wss;
-            yb[q] = val;
-            peak = fmaxf(peak, fabsf(val));
+      for (int jj = 0; jj * hop < span; ++jj) {          // hop-sized rows of positions
+        const int rmax = imin(hop, span - jj * hop);
+        for (int r = tid; r < rmax; r += blockDim.x) {
+          const int rel = jj * hop + r;
+          float val = rel < carry_len ? cin[rel] : 0.f;
+          float wss = 0.f;
+          // frames t = (t0 + jj) - d overlap position p at sample n = r + d*hop
+          for (int d = 0, n = r; n < kNfft; ++d, n += hop) {
+            const int j = jj - d;                        // index inside this tile
+            const int t = t0 + j;                        // absolute frame
+            if (j >= 0 && j < nt) val += s_frames[j * kNfft + n];
+            if (t >= 0 && t < T_used) wss += s_wsq[n];
           }
-        } else {
-          cout[rel - nt * hop] = val;
+          if (rel < final_len) {
+            const int p = p_tile + rel;
+            const int q = p - pad;
+            if (p >= t_begin * hop && q >= 0 && q < a.n_out) {
+              if (wss > SETK_TINY32) val /= wss;
+              yb[q] = val;
+              peak = fmaxf(peak, fabsf(val));
+            }
+          } else {
+            cout[rel - nt * hop] = val;
+          }
         }
       }
       cur ^= 1;
     }
-    t0 += nt;
+    t0 = t_next;
+    nt = nt_next;
+    async_cur = async_next;
+    buf ^= 1;
   }
 
   // zero-fill what no frame reaches (fix_length padding / too-short input)

@@ -1,5 +1,6 @@
 #!/bin/bash
 # Build libsetk_b200.so for sm_100a (B200) in-tree.  No GPU needed (nvcc cross-compiles).
+# Objects are rebuilt only when their .cu or any header is newer.
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
 ROOT="$(cd "$HERE/../.." && pwd)"
@@ -8,13 +9,27 @@ OBJ="$HERE/obj"
 mkdir -p "$OBJ"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -I$ROOT/include ${SETK_NVCC_EXTRA}"
+# headers each translation unit depends on
+declare -A DEPS
+DEPS[api]="common.cuh compat.cuh"
+DEPS[generic]="common.cuh compat.cuh"
+DEPS[weights]="common.cuh compat.cuh hermitian_solve.cuh"
+DEPS[stft_cov_fused]="common.cuh compat.cuh stft_tile.cuh fft16.cuh async_copy.cuh"
+DEPS[apply_istft_fused]="common.cuh compat.cuh stft_tile.cuh fft16.cuh async_copy.cuh"
 pids=()
 for f in api generic weights stft_cov_fused apply_istft_fused; do
-  $NVCC $FLAGS -Xptxas -v -c "$HERE/$f.cu" -o "$OBJ/$f.o" > "$OBJ/$f.log" 2>&1 &
-  pids+=($!)
+  stale=0
+  [ -f "$OBJ/$f.o" ] || stale=1
+  for d in "$f.cu" ${DEPS[$f]} ../../include/setk_b200.h build.sh; do
+    [ "$HERE/$d" -nt "$OBJ/$f.o" ] && stale=1
+  done
+  if [ $stale -eq 1 ]; then
+    ( $NVCC $FLAGS -Xptxas -v -c "$HERE/$f.cu" -o "$OBJ/$f.o.tmp" > "$OBJ/$f.log" 2>&1 && mv "$OBJ/$f.o.tmp" "$OBJ/$f.o" ) &
+    pids+=($!)
+  fi
 done
 rc=0
 for p in "${pids[@]}"; do wait $p || rc=1; done
 if [ $rc -ne 0 ]; then cat "$OBJ"/*.log | grep -v "^ptxas info" | head -100; exit 1; fi
-$NVCC -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT" "$OBJ"/*.o
+$NVCC -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT" "$OBJ"/api.o "$OBJ"/generic.o "$OBJ"/weights.o "$OBJ"/stft_cov_fused.o "$OBJ"/apply_istft_fused.o
 echo "built $OUT"

@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(288, 2) stft_cov_kernel(StftCovArgs a) {
   const int t_end = imin(t_begin + a.frames_per_chunk, Tb);
 
   for (int n = tid; n < kNfft; n += blockDim.x) sm.win[n] = 0.5f * a.window[n];
+  if (tid == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); }
 
   // thread constants
   float w1s, w1c;
@@ -83,7 +84,15 @@ __global__ void __launch_bounds__(288, 2) stft_cov_kernel(StftCovArgs a) {
   const bool vec_ok = ((a.N & 3) == 0) && ((hop & 3) == 0) && ((pad & 3) == 0) &&
                       ((reinterpret_cast<uintptr_t>(a.audio) & 15) == 0);
 
-  for (int t0 = t_begin; t0 < t_end; t0 += TT) {
+  // software pipeline: tile i+1 streams into the other audio buffer while tile i
+  // is transformed and accumulated
+  unsigned par = 0;                 // mbarrier phase parity per buffer (bit b)
+  bool async_cur = false;
+  if (t_begin < t_end)
+    async_cur = stage_tile_begin<C, TT>(sm, 0, xb, a.N, nb, t_begin, imin(TT, t_end - t_begin), hop,
+                                        pad, vec_ok);
+  int buf = 0;
+  for (int t0 = t_begin; t0 < t_end; t0 += TT, buf ^= 1) {
     const int nt = imin(TT, t_end - t0);
     // ---- masks for this tile: issue the global loads early ----
     float ms[TT], mn[TT];
@@ -100,10 +109,17 @@ __global__ void __launch_bounds__(288, 2) stft_cov_kernel(StftCovArgs a) {
         mn[j] = a.mask_n ? a.mask_n[mi] : 1.0f - m;
       }
     }
-    __syncthreads();   // previous tile's readers of sm.z / sm.audio are done
-    amax = stage_tile<C, TT>(sm, xb, a.N, nb, t0, nt, hop, pad, vec_ok, amax);
-    __syncthreads();
-    if (warp < 8) fft_tile<C, TT>(sm, nt, hop, w1);
+    __syncthreads();   // tile i-1 fully consumed: sm.z and audio[buf^1] are free
+    bool async_next = false;
+    if (t0 + TT < t_end)
+      async_next = stage_tile_begin<C, TT>(sm, buf ^ 1, xb, a.N, nb, t0 + TT,
+                                           imin(TT, t_end - t0 - TT), hop, pad, vec_ok);
+    if (async_cur) {
+      mbar_wait(&sm.bar[buf], (par >> buf) & 1u);
+      par ^= 1u << buf;
+    }
+    if (warp < 8) fft_tile<C, TT>(sm, buf, nt, hop, w1, amax);
+    async_cur = async_next;
     __syncthreads();
     // ---- covariance: thread per bin ----
     if (cov_thread) {

@@ -1,15 +1,19 @@
 // stft_tile.cuh -- the on-chip STFT of one tile of TT frames x C channels,
 // shared by the two fused kernels (stft_cov_fused.cu, apply_istft_fused.cu).
 //
-//   stage_tile : audio (global, f32 [C][N]) -> shared, with librosa's
-//                center=True reflect padding resolved per sample
-//                (np.pad(y, n_fft//2, "reflect"))
+//   stage_tile_begin : audio (global, f32 [C][N]) -> shared.  Interior tiles are
+//                streamed by TMA 1-D bulk copies (one elected thread, completion
+//                on an mbarrier) into one of two buffers, one tile ahead of the
+//                math; tiles that touch librosa's center=True reflect padding
+//                (np.pad(y, n_fft//2, "reflect")) or a
+//                ragged end are written element-wise.
 //   fft_tile   : 512-point real FFT of every (frame, channel) as a 256-point
 //                complex FFT on one half-warp (fft16.cuh); the *unsplit*
 //                half-size spectrum Z stays in shared memory
 //   split_bin  : X[k] (and X[256-k]) from Z[k], Z[256-k] with the bin's
 //                constant twiddle
 #pragma once
+#include "async_copy.cuh"
 #include "common.cuh"
 #include "fft16.cuh"
 
@@ -23,56 +27,65 @@ constexpr int kBins = 257;
 template <int C, int TT>
 struct TileSmem {
   int Lp;            // staged samples per channel (padded to a multiple of 4)
+  MBar* bar;         // [2] one per audio buffer
   float* win;        // [512]  analysis window x 0.5
-  float* audio;      // [C][Lp]
+  float* audio[2];   // [C][Lp] double buffered
   float2* z;         // [TT*C][SETK_ZSLOT]
   SETK_HD static int staged_len(int hop) { return ((TT - 1) * hop + kNfft + 3) & ~3; }
   SETK_HD static size_t floats(int hop) {
-    return (size_t)kNfft + (size_t)C * staged_len(hop) + 2 * (size_t)TT * C * SETK_ZSLOT;
+    return 4 + (size_t)kNfft + 2 * (size_t)C * staged_len(hop) + 2 * (size_t)TT * C * SETK_ZSLOT;
   }
   __device__ void carve(float* base, int hop) {
     Lp = staged_len(hop);
-    win = base;
-    audio = win + kNfft;
-    z = reinterpret_cast<float2*>(audio + C * Lp);
+    bar = reinterpret_cast<MBar*>(base);
+    win = base + 4;
+    audio[0] = win + kNfft;
+    audio[1] = audio[0] + C * Lp;
+    z = reinterpret_cast<float2*>(audio[1] + C * Lp);
   }
   __device__ float* end() { return reinterpret_cast<float*>(z + TT * C * SETK_ZSLOT); }
 };
 
-// Stage the samples of frames [t0, t0+nt) of every channel.  Returns the
-// running max |sample| seen by this thread.
+// Begin staging the samples of frames [t0, t0+nt) of every channel into
+// audio[buf].  Called by ALL threads (uniform).  Returns true when the tile is
+// delivered asynchronously (consumers must mbar_wait on bar[buf]); false when
+// it was written with ordinary stores (visible after the next __syncthreads).
 template <int C, int TT>
-__device__ __forceinline__ float stage_tile(const TileSmem<C, TT>& sm, const float* __restrict__ xb,
-                                            int N, int nb, int t0, int nt, int hop, int pad,
-                                            bool vec_ok, float amax) {
-  const int tid = threadIdx.x;
+__device__ __forceinline__ bool stage_tile_begin(const TileSmem<C, TT>& sm, int buf,
+                                                 const float* __restrict__ xb, int N, int nb, int t0,
+                                                 int nt, int hop, int pad, bool vec_ok) {
   const int p0 = t0 * hop;                      // first padded position of the tile
   const int need = (nt - 1) * hop + kNfft;      // samples actually used
   const int i0 = p0 - pad;
+  float* dst = sm.audio[buf];
   if (vec_ok && i0 >= 0 && i0 + need <= nb) {
-    const int nv = need >> 2;                   // hop % 4 == 0 here
-    for (int e = tid; e < C * nv; e += blockDim.x) {
-      const int c = e / nv, q = e - c * nv;
-      const float4 v = *reinterpret_cast<const float4*>(xb + (long long)c * N + i0 + 4 * q);
-      *reinterpret_cast<float4*>(sm.audio + c * sm.Lp + 4 * q) = v;
-      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    if (threadIdx.x == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(&sm.bar[buf], (unsigned)(C * need * sizeof(float)));
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        bulk_g2s(dst + c * sm.Lp, xb + (long long)c * N + i0, (unsigned)(need * sizeof(float)),
+                 &sm.bar[buf]);
     }
-  } else {
-    for (int e = tid; e < C * need; e += blockDim.x) {
-      const int c = e / need, q = e - c * need;
+    return true;
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float* src = xb + (long long)c * N;
+    for (int q = threadIdx.x; q < need; q += blockDim.x) {
       const int i = pad ? reflect_index(p0 + q, pad, nb) : (p0 + q);
-      const float v = xb[(long long)c * N + i];
-      sm.audio[c * sm.Lp + q] = v;
-      amax = fmaxf(amax, fabsf(v));
+      dst[c * sm.Lp + q] = src[i];
     }
   }
-  return amax;
+  return false;
 }
 
-// Forward FFT of every (frame, channel) of the tile by warps 0..7.
-// All threads of warps 0..7 must call it; hop must be even.
+// Forward FFT of every (frame, channel) of the tile by warps 0..7, reading
+// audio[buf].  All threads of warps 0..7 must call it; hop must be even.
+// amax accumulates max |sample| of everything the tile reads.
 template <int C, int TT>
-__device__ __forceinline__ void fft_tile(const TileSmem<C, TT>& sm, int nt, int hop, float2 w1) {
+__device__ __forceinline__ void fft_tile(const TileSmem<C, TT>& sm, int buf, int nt, int hop,
+                                         float2 w1, float& amax) {
   constexpr int JOBS = TT * C;
   static_assert(JOBS % 2 == 0, "half-warp jobs must pair up per warp");
   constexpr int ROUNDS = (JOBS + 15) / 16;
@@ -84,7 +97,7 @@ __device__ __forceinline__ void fft_tile(const TileSmem<C, TT>& sm, int nt, int 
     if (job - half < JOBS) {                    // warp-uniform
       const int fr = job / C, ch = job - fr * C;
       float2 v[16];
-      const float* src = sm.audio + ch * sm.Lp + fr * hop + 2 * lane16;
+      const float* src = sm.audio[buf] + ch * sm.Lp + fr * hop + 2 * lane16;
       const float* wsrc = sm.win + 2 * lane16;
       const bool live = fr < nt;
 #pragma unroll
@@ -93,6 +106,7 @@ __device__ __forceinline__ void fft_tile(const TileSmem<C, TT>& sm, int nt, int 
         if (live) {
           const float2 s = *reinterpret_cast<const float2*>(src + 32 * m1);
           const float2 w = *reinterpret_cast<const float2*>(wsrc + 32 * m1);
+          amax = fmaxf(amax, fmaxf(fabsf(s.x), fabsf(s.y)));
           x = make_float2(s.x * w.x, s.y * w.y);
         }
         v[m1] = x;

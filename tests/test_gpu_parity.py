@@ -184,8 +184,16 @@ def test_golden_doc_vectors_pmwf_chain(cuda):
         shipped = g["shipped/" + name].astype(np.int64)
         assert out.shape == shipped.shape == (93952,)
         d = np.abs(out - shipped)
+        # the shipped file is the reference's complex64 path, itself ~1e-4 rel
+        # (about 1 LSB at this level) from the exact answer (SURVEY.md finding 5)
         assert d.max() <= 2, (name, d.max())
-        assert np.mean(d > 0) <= 0.05, (name, float(np.mean(d > 0)))
+        assert d.mean() <= 0.5, (name, float(d.mean()))
+        # against the float64 oracle of the same chain: at most the odd LSB
+        samps = so.float_from_pcm16(g["egs_pcm16"])
+        y_o, _, _ = bo.enhance_utterance(samps, g["mask"], kind="pmwf", beta=0, rank1_appro=r1)
+        d64 = np.abs(out - so.pcm16_from_float(y_o).astype(np.int64))
+        assert d64.max() <= 1, (name, d64.max())
+        assert np.mean(d64 > 0) <= 0.01, (name, float(np.mean(d64 > 0)))
 
 
 def test_golden_doc_vectors_gevd_sign_fit(cuda):
