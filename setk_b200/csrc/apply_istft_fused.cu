@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(288, 2) apply_istft_kernel(ApplyIstftArgs a) {
   float* s_wsyn = s_frames + TT * kNfft;                      // [512] window / 512
   float* s_wsq = s_wsyn + kNfft;                              // [512]
   float* s_carry = s_wsq + kNfft;                             // [2][512]
+  float2* s_tw = reinterpret_cast<float2*>(s_carry + 2 * kNfft);   // [129] split twiddles
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(288, 2) apply_istft_kernel(ApplyIstftArgs a) {
     s_carry[kNfft + n] = 0.f;
   }
   if (tid == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); }
+  for (int k = tid; k < NPAIR; k += blockDim.x) s_tw[k] = split_twiddle(k);
   for (int e = tid; e < F * C; e += blockDim.x) {
     const long long wi = (long long)b * F * C + e;
     float2 v;
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(288, 2) apply_istft_kernel(ApplyIstftArgs a) {
     for (int it = tid; it < nt * NPAIR; it += blockDim.x) {
       const int j = it / NPAIR, k = it - j * NPAIR;
       const int km = kM - k;                              // mirrored bin 256-k
-      const float2 tw = split_twiddle(k);
+      const float2 tw = s_tw[k];
       float2 yk = make_float2(0.f, 0.f), ym = make_float2(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < C; ++c) {
@@ -247,6 +249,7 @@ static size_t apply_istft_smem_bytes(int hop) {
   fl += (size_t)TT * kNfft;               // s_frames
   fl += 2 * (size_t)kNfft;                // s_wsyn, s_wsq
   fl += 2 * (size_t)kNfft;                // carry x2
+  fl += 2 * (size_t)(kM / 2 + 1) + 2;     // split twiddles
   return fl * sizeof(float);
 }
 

@@ -91,22 +91,39 @@ __global__ void __launch_bounds__(288, 2) stft_cov_kernel(StftCovArgs a) {
   if (t_begin < t_end)
     async_cur = stage_tile_begin<C, TT>(sm, 0, xb, a.N, nb, t_begin, imin(TT, t_end - t_begin), hop,
                                         pad, vec_ok);
+  // mask rows: this thread's bin, one frame per step of `mstride`; the raw values
+  // of tile i+1 are requested while tile i is processed (a full tile of latency
+  // hiding) and only touched (clip, 1-m) when that tile is consumed
+  const bool has_mn = a.mask_n != nullptr;
+  const bool clip = (a.flags & SETK_F_CLIP_MASK) != 0;
+  const long long mstride = (a.flags & SETK_F_MASK_FT) ? 1 : F;
+  const long long mbase = (a.flags & SETK_F_MASK_FT) ? ((long long)b * F + (cov_thread ? bin : 0)) * a.T
+                                                     : (long long)b * a.T * F + (cov_thread ? bin : 0);
+  const float* mps = a.mask_s + mbase + (long long)t_begin * mstride;
+  const float* mpn = has_mn ? a.mask_n + mbase + (long long)t_begin * mstride : nullptr;
+  float ms_raw[TT], mn_raw[TT];
+#pragma unroll
+  for (int j = 0; j < TT; ++j) {
+    ms_raw[j] = 0.f; mn_raw[j] = 0.f;
+    if (cov_thread && t_begin + j < t_end) {
+      ms_raw[j] = mps[j * mstride];
+      if (has_mn) mn_raw[j] = mpn[j * mstride];
+    }
+  }
   int buf = 0;
   for (int t0 = t_begin; t0 < t_end; t0 += TT, buf ^= 1) {
     const int nt = imin(TT, t_end - t0);
-    // ---- masks for this tile: issue the global loads early ----
     float ms[TT], mn[TT];
 #pragma unroll
+    for (int j = 0; j < TT; ++j) { ms[j] = ms_raw[j]; mn[j] = mn_raw[j]; }
+    // ---- request the masks of the next tile ----
+    mps += TT * mstride;
+    if (has_mn) mpn += TT * mstride;
+#pragma unroll
     for (int j = 0; j < TT; ++j) {
-      ms[j] = 0.f; mn[j] = 0.f;
-      if (cov_thread && j < nt) {
-        const long long mi = (a.flags & SETK_F_MASK_FT)
-                                 ? ((long long)b * F + bin) * a.T + (t0 + j)
-                                 : ((long long)b * a.T + (t0 + j)) * F + bin;
-        float m = a.mask_s[mi];
-        if (a.flags & SETK_F_CLIP_MASK) m = fminf(m, 1.0f);
-        ms[j] = m;
-        mn[j] = a.mask_n ? a.mask_n[mi] : 1.0f - m;
+      if (cov_thread && t0 + TT + j < t_end) {
+        ms_raw[j] = mps[j * mstride];
+        if (has_mn) mn_raw[j] = mpn[j * mstride];
       }
     }
     __syncthreads();   // tile i-1 fully consumed: sm.z and audio[buf^1] are free
@@ -136,7 +153,8 @@ __global__ void __launch_bounds__(288, 2) stft_cov_kernel(StftCovArgs a) {
 #pragma unroll
             for (int c = 0; c < C; ++c) x[c].y = 0.f;               // DC / Nyquist are real
           }
-          const float m_s = ms[j], m_n = mn[j];
+          const float m_s = clip ? fminf(ms[j], 1.0f) : ms[j];
+          const float m_n = has_mn ? mn[j] : 1.0f - m_s;
           sum_s += m_s; sum_n += m_n;
           int o = C;
 #pragma unroll

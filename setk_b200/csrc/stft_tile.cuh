@@ -29,7 +29,8 @@ struct TileSmem {
   int Lp;            // staged samples per channel (padded to a multiple of 4)
   MBar* bar;         // [2] one per audio buffer
   float* win;        // [512]  analysis window x 0.5
-  float* audio[2];   // [C][Lp] double buffered
+  float* audio0;     // [2][C][Lp] double buffered (kept as base + offset so the
+                     // compiler keeps shared-memory addressing, LDS not LD)
   float2* z;         // [TT*C][SETK_ZSLOT]
   SETK_HD static int staged_len(int hop) { return ((TT - 1) * hop + kNfft + 3) & ~3; }
   SETK_HD static size_t floats(int hop) {
@@ -39,10 +40,10 @@ struct TileSmem {
     Lp = staged_len(hop);
     bar = reinterpret_cast<MBar*>(base);
     win = base + 4;
-    audio[0] = win + kNfft;
-    audio[1] = audio[0] + C * Lp;
-    z = reinterpret_cast<float2*>(audio[1] + C * Lp);
+    audio0 = win + kNfft;
+    z = reinterpret_cast<float2*>(audio0 + 2 * C * Lp);
   }
+  __device__ float* abuf(int buf) const { return audio0 + buf * (C * Lp); }
   __device__ float* end() { return reinterpret_cast<float*>(z + TT * C * SETK_ZSLOT); }
 };
 
@@ -57,7 +58,7 @@ __device__ __forceinline__ bool stage_tile_begin(const TileSmem<C, TT>& sm, int 
   const int p0 = t0 * hop;                      // first padded position of the tile
   const int need = (nt - 1) * hop + kNfft;      // samples actually used
   const int i0 = p0 - pad;
-  float* dst = sm.audio[buf];
+  float* dst = sm.abuf(buf);
   if (vec_ok && i0 >= 0 && i0 + need <= nb) {
     if (threadIdx.x == 0) {
       fence_proxy_async();
@@ -97,7 +98,7 @@ __device__ __forceinline__ void fft_tile(const TileSmem<C, TT>& sm, int buf, int
     if (job - half < JOBS) {                    // warp-uniform
       const int fr = job / C, ch = job - fr * C;
       float2 v[16];
-      const float* src = sm.audio[buf] + ch * sm.Lp + fr * hop + 2 * lane16;
+      const float* src = sm.abuf(buf) + ch * sm.Lp + fr * hop + 2 * lane16;
       const float* wsrc = sm.win + 2 * lane16;
       const bool live = fr < nt;
 #pragma unroll
