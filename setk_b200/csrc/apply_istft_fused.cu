@@ -44,7 +44,7 @@ struct ApplyIstftArgs {
 };
 
 template <int C, int TT>
-__global__ void __launch_bounds__(288, 2) apply_istft_kernel(ApplyIstftArgs a) {
+__global__ void __maxnreg__(112) apply_istft_kernel(ApplyIstftArgs a) {
   constexpr int F = kBins;
   constexpr int NPAIR = kM / 2 + 1;     // 129 bin pairs (k, 256-k)
   SETK_DYN_SMEM(float, smem);

@@ -33,6 +33,9 @@ __device__ inline void mbar_wait(MBar* b, unsigned parity) {
   while ((((__atomic_load_n(&b->v, __ATOMIC_SEQ_CST)) >> 32) & 1ull) == (unsigned long long)parity)
     std::this_thread::yield();
 }
+// 4-byte cp.async (LDGSTS): global -> shared without a register round trip
+__device__ inline void cp_async_f32(float* dst, const float* src) { *dst = *src; }
+__device__ inline void cp_async_wait_all() {}
 
 #else
 
@@ -70,6 +73,14 @@ __device__ __forceinline__ void mbar_wait(MBar* b, unsigned parity) {
       "}" ::"r"(smem_u32(b)),
       "r"(parity)
       : "memory");
+}
+
+// 4-byte cp.async (LDGSTS): global -> shared without a register round trip
+__device__ __forceinline__ void cp_async_f32(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
 #endif

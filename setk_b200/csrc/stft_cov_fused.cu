@@ -46,7 +46,7 @@ struct StftCovArgs {
 };
 
 template <int C, int TT>
-__global__ void __launch_bounds__(288, 2) stft_cov_kernel(StftCovArgs a) {
+__global__ void __maxnreg__(112) stft_cov_kernel(StftCovArgs a) {
   constexpr int NACC = CovAcc<C>::NACC;
   constexpr int F = kBins;
   SETK_DYN_SMEM(float, smem);
@@ -91,9 +91,10 @@ __global__ void __launch_bounds__(288, 2) stft_cov_kernel(StftCovArgs a) {
   if (t_begin < t_end)
     async_cur = stage_tile_begin<C, TT>(sm, 0, xb, a.N, nb, t_begin, imin(TT, t_end - t_begin), hop,
                                         pad, vec_ok);
-  // mask rows: this thread's bin, one frame per step of `mstride`; the raw values
-  // of tile i+1 are requested while tile i is processed (a full tile of latency
-  // hiding) and only touched (clip, 1-m) when that tile is consumed
+  // mask rows of this thread's bin: one frame per step of `mstride`.  They are
+  // fetched with 4-byte cp.async straight into shared memory at the top of the
+  // tile and first touched after the FFT phase, so their latency costs neither
+  // registers nor issue slots
   const bool has_mn = a.mask_n != nullptr;
   const bool clip = (a.flags & SETK_F_CLIP_MASK) != 0;
   const long long mstride = (a.flags & SETK_F_MASK_FT) ? 1 : F;
@@ -101,42 +102,34 @@ __global__ void __launch_bounds__(288, 2) stft_cov_kernel(StftCovArgs a) {
                                                      : (long long)b * a.T * F + (cov_thread ? bin : 0);
   const float* mps = a.mask_s + mbase + (long long)t_begin * mstride;
   const float* mpn = has_mn ? a.mask_n + mbase + (long long)t_begin * mstride : nullptr;
-  float ms_raw[TT], mn_raw[TT];
-#pragma unroll
-  for (int j = 0; j < TT; ++j) {
-    ms_raw[j] = 0.f; mn_raw[j] = 0.f;
-    if (cov_thread && t_begin + j < t_end) {
-      ms_raw[j] = mps[j * mstride];
-      if (has_mn) mn_raw[j] = mpn[j * mstride];
-    }
-  }
+  float* s_mask = sm.end();                        // [TT][2][MPITCH]
+  constexpr int MPITCH = 260;
   int buf = 0;
   for (int t0 = t_begin; t0 < t_end; t0 += TT, buf ^= 1) {
     const int nt = imin(TT, t_end - t0);
-    float ms[TT], mn[TT];
-#pragma unroll
-    for (int j = 0; j < TT; ++j) { ms[j] = ms_raw[j]; mn[j] = mn_raw[j]; }
-    // ---- request the masks of the next tile ----
-    mps += TT * mstride;
-    if (has_mn) mpn += TT * mstride;
-#pragma unroll
-    for (int j = 0; j < TT; ++j) {
-      if (cov_thread && t0 + TT + j < t_end) {
-        ms_raw[j] = mps[j * mstride];
-        if (has_mn) mn_raw[j] = mpn[j * mstride];
-      }
-    }
     __syncthreads();   // tile i-1 fully consumed: sm.z and audio[buf^1] are free
     bool async_next = false;
     if (t0 + TT < t_end)
       async_next = stage_tile_begin<C, TT>(sm, buf ^ 1, xb, a.N, nb, t0 + TT,
                                            imin(TT, t_end - t0 - TT), hop, pad, vec_ok);
+    if (cov_thread) {
+#pragma unroll
+      for (int j = 0; j < TT; ++j) {
+        if (j < nt) {
+          cp_async_f32(s_mask + (2 * j) * MPITCH + bin, mps + j * mstride);
+          if (has_mn) cp_async_f32(s_mask + (2 * j + 1) * MPITCH + bin, mpn + j * mstride);
+        }
+      }
+      mps += TT * mstride;
+      if (has_mn) mpn += TT * mstride;
+    }
     if (async_cur) {
       mbar_wait(&sm.bar[buf], (par >> buf) & 1u);
       par ^= 1u << buf;
     }
     if (warp < 8) fft_tile<C, TT>(sm, buf, nt, hop, w1, amax);
     async_cur = async_next;
+    cp_async_wait_all();
     __syncthreads();
     // ---- covariance: thread per bin ----
     if (cov_thread) {
@@ -153,8 +146,9 @@ __global__ void __launch_bounds__(288, 2) stft_cov_kernel(StftCovArgs a) {
 #pragma unroll
             for (int c = 0; c < C; ++c) x[c].y = 0.f;               // DC / Nyquist are real
           }
-          const float m_s = clip ? fminf(ms[j], 1.0f) : ms[j];
-          const float m_n = has_mn ? mn[j] : 1.0f - m_s;
+          const float m_raw = s_mask[(2 * j) * MPITCH + bin];
+          const float m_s = clip ? fminf(m_raw, 1.0f) : m_raw;
+          const float m_n = has_mn ? s_mask[(2 * j + 1) * MPITCH + bin] : 1.0f - m_s;
           sum_s += m_s; sum_n += m_n;
           int o = C;
 #pragma unroll
@@ -240,7 +234,7 @@ cudaError_t run_bits_to_float(const unsigned* bits, int n, float* out, void* str
 
 template <int C, int TT>
 static size_t stft_cov_smem_bytes(int hop) {
-  return sizeof(float) * TileSmem<C, TT>::floats(hop);
+  return sizeof(float) * (TileSmem<C, TT>::floats(hop) + (size_t)TT * 2 * 260);
 }
 
 template <int C, int TT>

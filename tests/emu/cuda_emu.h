@@ -50,6 +50,7 @@ static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 #define __noinline__ __attribute__((noinline))
 #define __restrict__ __restrict
 #define __launch_bounds__(...)
+#define __maxnreg__(...)
 #define __shared__ static
 #define __constant__ static
 #define __align__(n) alignas(n)
