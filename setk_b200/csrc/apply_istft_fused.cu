@@ -11,18 +11,21 @@
 // C++ twin: Beamform (include/beamformer.cc:215-230) + InverseShortTimeFT
 // (include/stft.cc:154-198).
 //
-// Per tile of <= TT frames (288 threads), audio streamed one tile ahead by TMA
-// bulk copies (stft_tile.cuh):
-//   forward FFT  (stft_tile.cuh)
-//   apply   item (frame, k<=128): split Z -> X_c[k], X_c[256-k]; y = w^H x for
-//           both bins; inverse split -> half-size spectrum Zi[k], Zi[256-k]
-//   iFFT    one half-warp per frame: conj . FFT256 . conj, x synthesis window
-//   flush   gather overlap-add of the tile's frames + carry from the previous
-//           tile; positions no later frame can touch are divided by the
-//           window-sum-square, trimmed and written (coalesced rows), the rest
-//           becomes the next carry.  Deterministic: no atomics on data.
-// A CTA owns the output positions of its own frames; the <= ceil(n_fft/hop)-1
-// frames before its first frame are recomputed as a halo tile.
+// 320 threads, two barriers per tile of <= TT frames, audio streamed one tile
+// ahead by TMA bulk copies (stft_tile.cuh).  Software pipeline over tiles:
+//   phase A(i)  warps 0-7 : forward FFT of tile i            (Z_i in smem)
+//               warps 8-9 : inverse FFT of tile i-1 (one half-warp per frame:
+//                           conj . FFT256 . conj) x synthesis window -> frames
+//   phase B(i)  all       : apply items (frame, k<=128) of tile i: split Z ->
+//                           X_c[k], X_c[256-k]; y = w^H x for both bins;
+//                           inverse split -> half-size spectrum Zi[k], Zi[256-k]
+//                           flush tile i-1: gather overlap-add of its frames +
+//                           carry; positions no later frame can touch are
+//                           divided by the window-sum-square, trimmed and
+//                           written (coalesced rows); the rest is the next carry
+// Deterministic: no atomics on data.  A CTA owns the output positions of its
+// own frames; the <= ceil(n_fft/hop)-1 frames before its first frame are
+// recomputed as a halo tile.
 // Algorithmic bytes per utterance: 4*C*N (audio) + 8*F*C (w) + 4*n_out (wave)
 // (+ 4*T*F with a post-mask).
 #include "common.cuh"
@@ -43,8 +46,12 @@ struct ApplyIstftArgs {
   unsigned* peak;       // [B] or null
 };
 
+constexpr int kApplyThreads = 320;
+constexpr int kWPitch = 260;          // float2 pitch of the per-channel weight rows
+
 template <int C, int TT>
-__global__ void __maxnreg__(112) apply_istft_kernel(ApplyIstftArgs a) {
+__global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
+  static_assert(TT == 4, "two inverse-FFT warps serve exactly four frames");
   constexpr int F = kBins;
   constexpr int NPAIR = kM / 2 + 1;     // 129 bin pairs (k, 256-k)
   SETK_DYN_SMEM(float, smem);
@@ -52,13 +59,14 @@ __global__ void __maxnreg__(112) apply_istft_kernel(ApplyIstftArgs a) {
   TileSmem<C, TT> sm;
   sm.carve(smem, hop);
   const int carry_len = kNfft - hop;
-  float2* s_w = reinterpret_cast<float2*>(sm.end());          // [F][C]
-  float2* s_zi = s_w + F * C;                                 // [TT][SETK_ZSLOT]
-  float* s_frames = reinterpret_cast<float*>(s_zi + TT * SETK_ZSLOT);   // [TT][512]
+  float2* s_w = reinterpret_cast<float2*>(sm.end());          // [C][kWPitch]
+  float2* s_zi = s_w + C * kWPitch;                           // [TT][SETK_ZSLOT]
+  float2* s_tw = s_zi + TT * SETK_ZSLOT;                      // [130] split twiddles
+  float* s_frames = reinterpret_cast<float*>(s_tw + NPAIR + 1);   // [TT][512]
   float* s_wsyn = s_frames + TT * kNfft;                      // [512] window / 512
   float* s_wsq = s_wsyn + kNfft;                              // [512]
-  float* s_carry = s_wsq + kNfft;                             // [2][512]
-  float2* s_tw = reinterpret_cast<float2*>(s_carry + 2 * kNfft);   // [129] split twiddles
+  float* s_rw = s_wsq + kNfft;                                // [256] 1 / (wsq[r] + wsq[r+256])
+  float* s_carry = s_rw + kM;                                 // [2][carry_len]
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -72,6 +80,7 @@ __global__ void __maxnreg__(112) apply_istft_kernel(ApplyIstftArgs a) {
   const int t_begin = chunk * a.frames_per_chunk;
   const int t_end = imin(t_begin + a.frames_per_chunk, T_used);
   const int expected = T_used > 0 ? kNfft + hop * (T_used - 1) : 0;   // padded signal length
+  const int own_begin = t_begin * hop;
   float* yb = a.wave + (long long)b * a.n_out;
   float peak = 0.f;
 
@@ -80,12 +89,16 @@ __global__ void __maxnreg__(112) apply_istft_kernel(ApplyIstftArgs a) {
     sm.win[n] = 0.5f * w;
     s_wsyn[n] = w * (1.0f / 512.0f);
     s_wsq[n] = a.wsq[n];
-    s_carry[n] = 0.f;
-    s_carry[kNfft + n] = 0.f;
   }
+  for (int n = tid; n < kM; n += blockDim.x) {
+    const float s = a.wsq[n] + a.wsq[n + kM];
+    s_rw[n] = s > SETK_TINY32 ? 1.0f / s : 1.0f;
+  }
+  for (int n = tid; n < 2 * carry_len; n += blockDim.x) s_carry[n] = 0.f;
   if (tid == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); }
   for (int k = tid; k < NPAIR; k += blockDim.x) s_tw[k] = split_twiddle(k);
   for (int e = tid; e < F * C; e += blockDim.x) {
+    const int k = e / C, c = e - k * C;
     const long long wi = (long long)b * F * C + e;
     float2 v;
     if (a.w_dtype == SETK_C128) {
@@ -95,7 +108,7 @@ __global__ void __maxnreg__(112) apply_istft_kernel(ApplyIstftArgs a) {
       const float* p = reinterpret_cast<const float*>(a.w) + 2 * wi;
       v = make_float2(p[0], p[1]);
     }
-    s_w[e] = v;
+    s_w[c * kWPitch + k] = v;
   }
 
   float w1s, w1c;
@@ -104,9 +117,95 @@ __global__ void __maxnreg__(112) apply_istft_kernel(ApplyIstftArgs a) {
   const float* xb = a.audio + (long long)b * C * a.N;
   const bool vec_ok = ((a.N & 3) == 0) && ((hop & 3) == 0) && ((pad & 3) == 0) &&
                       ((reinterpret_cast<uintptr_t>(a.audio) & 15) == 0);
+  const bool fast_hop = (hop == kM);               // 50 % overlap: every position has two frames
+
+  // ---- inverse FFT of the frames of the pending tile (warps 8, 9) ----
+  auto ifft_tile = [&](int p_nt) {
+    const int job = (warp - 8) * 2 + half;         // frame inside the tile
+    float2 v[16];
+    float2* zi = s_zi + job * SETK_ZSLOT;
+#pragma unroll
+    for (int m1 = 0; m1 < 16; ++m1) {
+      float2 x = make_float2(0.f, 0.f);
+      if (job < p_nt) { x = zi[16 * m1 + lane16]; x.y = -x.y; }
+      v[m1] = x;
+    }
+    __syncwarp();                                  // slot is free: reuse it as the exchange tile
+    halfwarp_fft256(v, zi, lane16, w1);
+    float* fr = s_frames + job * kNfft;
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+      const int m = lane16 + 16 * kof(s);
+      const float2 ws = *reinterpret_cast<const float2*>(s_wsyn + 2 * m);
+      *reinterpret_cast<float2*>(fr + 2 * m) = make_float2(v[s].x * ws.x, -v[s].y * ws.y);
+    }
+  };
+
+  // ---- flush of a finished tile: overlap-add, normalise, trim, write ----
+  int cur = 0;                                     // which carry buffer is the input
+  auto flush_tile = [&](int p_t0, int p_nt) {
+    const int p_tile = p_t0 * hop;
+    const bool last_tile = (p_t0 + p_nt == T_used);
+    const float* cin = s_carry + cur * carry_len;
+    float* cout = s_carry + (cur ^ 1) * carry_len;
+    if (fast_hop) {
+      // rows of 256 positions; row jj gets frame jj (n = r) and frame jj-1 (n = r + 256)
+      for (int idx = tid; idx < (p_nt + 1) * kM; idx += blockDim.x) {
+        const int jj = idx >> 8, r = idx & (kM - 1);
+        float val = jj >= 1 ? s_frames[(jj - 1) * kNfft + kM + r] : cin[r];
+        if (jj < p_nt) val += s_frames[jj * kNfft + r];
+        if (jj < p_nt || last_tile) {
+          const int p = p_tile + idx;
+          const int q = p - pad;
+          if (p >= own_begin && q >= 0 && q < a.n_out) {
+            const int t = p_t0 + jj;               // frame starting at this row
+            if (t >= 1 && t < T_used) {
+              val *= s_rw[r];
+            } else {
+              const float wss = (t < T_used ? s_wsq[r] : 0.f) + (t >= 1 ? s_wsq[kM + r] : 0.f);
+              if (wss > SETK_TINY32) val /= wss;
+            }
+            yb[q] = val;
+            peak = fmaxf(peak, fabsf(val));
+          }
+        } else {
+          cout[r] = val;
+        }
+      }
+    } else {
+      const int span = (p_nt - 1) * hop + kNfft;         // positions touched by this tile
+      const int final_len = last_tile ? span : p_nt * hop;
+      for (int jj = 0; jj * hop < span; ++jj) {          // hop-sized rows of positions
+        const int rmax = imin(hop, span - jj * hop);
+        for (int r = tid; r < rmax; r += blockDim.x) {
+          const int rel = jj * hop + r;
+          float val = rel < carry_len ? cin[rel] : 0.f;
+          float wss = 0.f;
+          // frames t = (p_t0 + jj) - d overlap position p at sample n = r + d*hop
+          for (int d = 0, n = r; n < kNfft; ++d, n += hop) {
+            const int j = jj - d;                        // index inside this tile
+            const int t = p_t0 + j;                      // absolute frame
+            if (j >= 0 && j < p_nt) val += s_frames[j * kNfft + n];
+            if (t >= 0 && t < T_used) wss += s_wsq[n];
+          }
+          if (rel < final_len) {
+            const int p = p_tile + rel;
+            const int q = p - pad;
+            if (p >= own_begin && q >= 0 && q < a.n_out) {
+              if (wss > SETK_TINY32) val /= wss;
+              yb[q] = val;
+              peak = fmaxf(peak, fabsf(val));
+            }
+          } else {
+            cout[rel - p_nt * hop] = val;
+          }
+        }
+      }
+    }
+    cur ^= 1;
+  };
 
   const int R = (kNfft + hop - 1) / hop - 1;       // frames before t that overlap frame t
-  int cur = 0;                                     // which carry buffer is the input
   // tile sequence: an optional halo tile [t_begin-R, t_begin), then full tiles
   int t0 = imax(0, t_begin - R);
   if (t_begin >= t_end) t0 = t_end;                // nothing to do for this chunk
@@ -116,10 +215,11 @@ __global__ void __maxnreg__(112) apply_istft_kernel(ApplyIstftArgs a) {
   bool async_cur = false;
   if (t0 < t_end) async_cur = stage_tile_begin<C, TT>(sm, 0, xb, a.N, nb, t0, nt, hop, pad, vec_ok);
   int buf = 0;
+  int prev_t0 = 0, prev_nt = 0;                    // tile whose Zi is waiting for its inverse FFT
   while (t0 < t_end) {
     const int t_next = t0 + nt;
     const int nt_next = imin(TT, t_end - t_next);
-    __syncthreads();   // previous tile fully consumed (sm.z, s_frames, audio[buf^1])
+    __syncthreads();   // phase B of the previous tile is complete
     bool async_next = false;
     if (t_next < t_end)
       async_next = stage_tile_begin<C, TT>(sm, buf ^ 1, xb, a.N, nb, t_next, nt_next, hop, pad, vec_ok);
@@ -127,9 +227,14 @@ __global__ void __maxnreg__(112) apply_istft_kernel(ApplyIstftArgs a) {
       mbar_wait(&sm.bar[buf], (par >> buf) & 1u);
       par ^= 1u << buf;
     }
-    if (warp < 8) fft_tile<C, TT>(sm, buf, nt, hop, w1, amax_unused);
+    // ---- phase A: forward FFT of this tile || inverse FFT of the previous one ----
+    if (warp < 8) {
+      fft_tile<C, TT>(sm, buf, nt, hop, w1, amax_unused);
+    } else if (prev_nt > 0) {
+      ifft_tile(prev_nt);
+    }
     __syncthreads();
-    // ---- apply + inverse split ----
+    // ---- phase B: apply + inverse split of this tile ----
     for (int it = tid; it < nt * NPAIR; it += blockDim.x) {
       const int j = it / NPAIR, k = it - j * NPAIR;
       const int km = kM - k;                              // mirrored bin 256-k
@@ -141,7 +246,7 @@ __global__ void __maxnreg__(112) apply_istft_kernel(ApplyIstftArgs a) {
         float2 xk, xm;
         split_pair(z[k & (kM - 1)], z[km & (kM - 1)], tw, xk, xm);
         if (k == 0) { xk.y = 0.f; xm.y = 0.f; }
-        const float2 wk = s_w[k * C + c], wm = s_w[km * C + c];
+        const float2 wk = s_w[c * kWPitch + k], wm = s_w[c * kWPitch + km];
         // conj(w) * x
         yk.x += wk.x * xk.x + wk.y * xk.y;  yk.y += wk.x * xk.y - wk.y * xk.x;
         ym.x += wm.x * xm.x + wm.y * xm.y;  ym.y += wm.x * xm.y - wm.y * xm.x;
@@ -166,68 +271,20 @@ __global__ void __maxnreg__(112) apply_istft_kernel(ApplyIstftArgs a) {
         }
       }
     }
-    __syncthreads();
-    // ---- inverse FFT: one half-warp per frame ----
-    if (warp * 2 < TT) {
-      const int job = warp * 2 + half;
-      float2 v[16];
-      const float2* zi = s_zi + job * SETK_ZSLOT;
-#pragma unroll
-      for (int m1 = 0; m1 < 16; ++m1) {
-        float2 x = make_float2(0.f, 0.f);
-        if (job < nt) { x = zi[16 * m1 + lane16]; x.y = -x.y; }
-        v[m1] = x;
-      }
-      halfwarp_fft256(v, sm.z + job * SETK_ZSLOT, lane16, w1);
-      float* fr = s_frames + job * kNfft;
-#pragma unroll
-      for (int s = 0; s < 16; ++s) {
-        const int m = lane16 + 16 * kof(s);
-        const float2 ws = *reinterpret_cast<const float2*>(s_wsyn + 2 * m);
-        *reinterpret_cast<float2*>(fr + 2 * m) = make_float2(v[s].x * ws.x, -v[s].y * ws.y);
-      }
-    }
-    __syncthreads();
-    // ---- flush: gather overlap-add, normalise, trim, write ----
-    {
-      const int p_tile = t0 * hop;
-      const bool last_tile = (t_next == T_used);
-      const int span = (nt - 1) * hop + kNfft;           // positions touched by this tile
-      const int final_len = last_tile ? span : nt * hop;
-      const float* cin = s_carry + cur * kNfft;
-      float* cout = s_carry + (cur ^ 1) * kNfft;
-      for (int jj = 0; jj * hop < span; ++jj) {          // hop-sized rows of positions
-        const int rmax = imin(hop, span - jj * hop);
-        for (int r = tid; r < rmax; r += blockDim.x) {
-          const int rel = jj * hop + r;
-          float val = rel < carry_len ? cin[rel] : 0.f;
-          float wss = 0.f;
-          // frames t = (t0 + jj) - d overlap position p at sample n = r + d*hop
-          for (int d = 0, n = r; n < kNfft; ++d, n += hop) {
-            const int j = jj - d;                        // index inside this tile
-            const int t = t0 + j;                        // absolute frame
-            if (j >= 0 && j < nt) val += s_frames[j * kNfft + n];
-            if (t >= 0 && t < T_used) wss += s_wsq[n];
-          }
-          if (rel < final_len) {
-            const int p = p_tile + rel;
-            const int q = p - pad;
-            if (p >= t_begin * hop && q >= 0 && q < a.n_out) {
-              if (wss > SETK_TINY32) val /= wss;
-              yb[q] = val;
-              peak = fmaxf(peak, fabsf(val));
-            }
-          } else {
-            cout[rel - nt * hop] = val;
-          }
-        }
-      }
-      cur ^= 1;
-    }
+    // ---- phase B: flush of the previous tile (its frames were made in phase A) ----
+    if (prev_nt > 0) flush_tile(prev_t0, prev_nt);
+    prev_t0 = t0; prev_nt = nt;
     t0 = t_next;
     nt = nt_next;
     async_cur = async_next;
     buf ^= 1;
+  }
+  // ---- drain the pipeline: the last tile's inverse FFT and flush ----
+  if (prev_nt > 0) {
+    __syncthreads();
+    if (warp >= 8) ifft_tile(prev_nt);
+    __syncthreads();
+    flush_tile(prev_t0, prev_nt);
   }
 
   // zero-fill what no frame reaches (fix_length padding / too-short input)
@@ -244,12 +301,13 @@ __global__ void __maxnreg__(112) apply_istft_kernel(ApplyIstftArgs a) {
 template <int C, int TT>
 static size_t apply_istft_smem_bytes(int hop) {
   size_t fl = TileSmem<C, TT>::floats(hop);
-  fl += 2 * (size_t)kBins * C;            // s_w
+  fl += 2 * (size_t)C * kWPitch;          // s_w
   fl += 2 * (size_t)TT * SETK_ZSLOT;      // s_zi
+  fl += 2 * (size_t)(kM / 2 + 2);         // s_tw
   fl += (size_t)TT * kNfft;               // s_frames
   fl += 2 * (size_t)kNfft;                // s_wsyn, s_wsq
-  fl += 2 * (size_t)kNfft;                // carry x2
-  fl += 2 * (size_t)(kM / 2 + 1) + 2;     // split twiddles
+  fl += (size_t)kM;                       // s_rw
+  fl += 2 * (size_t)(kNfft - hop);        // carry x2
   return fl * sizeof(float);
 }
 
@@ -259,7 +317,8 @@ static cudaError_t run_apply_istft_t(const ApplyIstftArgs& a, int B, void* strea
   cudaError_t e = cudaFuncSetAttribute(apply_istft_kernel<C, TT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  return launch(apply_istft_kernel<C, TT>, dim3(a.n_chunks, B), dim3(288), smem, stream, false, a);
+  return launch(apply_istft_kernel<C, TT>, dim3(a.n_chunks, B), dim3(kApplyThreads), smem, stream,
+                false, a);
 }
 
 bool apply_istft_fused_supported(const Geometry& g) {
