@@ -175,6 +175,17 @@ int setk_weights(int32_t kind, double beta, int32_t ref_channel, int32_t rank1,
                  int32_t r_dtype, int32_t B, int32_t F, int32_t C, void* w,
                  int32_t w_dtype, uint32_t* status, int32_t* ref_used, void* stream);
 
+/* do_ban(weight, Rn): beamformer.py:14-28.  w_in / w_out [B][F][C], Rn [B][F][C][C],
+ * all of `dtype` (SETK_C64 / SETK_C128). */
+int setk_ban(const void* w_in, const void* Rn, int32_t dtype, int32_t B, int32_t F, int32_t C,
+             void* w_out, void* stream);
+
+/* rank1_constraint(Rs, Rn=None): beamformer.py:66-84.  Rn == NULL: principal
+ * eigenvector of Rs; else Rn * (principal generalised eigenvector of (Rs, Rn)).
+ * R1_out [B][F][C][C] = v v^H * tr(Rs) / max(tr(v v^H), eps32).  status u32[B] or NULL. */
+int setk_rank1(const void* Rs, const void* Rn, int32_t dtype, int32_t B, int32_t F, int32_t C,
+               void* R1_out, uint32_t* status, void* stream);
+
 /* Beamformer.beamform on an explicit STFT: beamformer.py:220-234, C++ twin
  * Beamform (beamformer.cc:215-230).  enh[b][f][t] = sum_c conj(w[b][f][c]) x[b][c][f][t]
  *   post_mask f32 [B][T][F] or NULL: enh *= mask^T (apply_adaptive_beamformer.py:174-175) */

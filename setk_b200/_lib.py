@@ -64,6 +64,10 @@ _PROTOTYPES = {
                              c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                              c_int32, c_int32, c_void_p, c_int32, c_void_p,
                              c_void_p, c_void_p]),
+    "setk_ban": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                         c_void_p, c_void_p]),
+    "setk_rank1": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                           c_void_p, c_void_p, c_void_p]),
     "setk_apply": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int32,
                            c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "setk_istft": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32,

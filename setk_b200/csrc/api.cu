@@ -38,6 +38,8 @@ cudaError_t weights_run(int kind, double beta, int ref_channel, int rank1, int b
                         int w_dtype, unsigned* status, int* ref_used, void* stream);
 cudaError_t maxabs_generic(const float* audio, const int* n_samples, int B, int C, int N,
                            unsigned* bits, float* out, void* stream);
+cudaError_t post_run(int mode, const void* A, const void* Rn, int dtype, int B, int F, int C, void* out,
+                     unsigned* status, void* stream);
 
 static thread_local char g_err[512] = "";
 
@@ -249,6 +251,24 @@ int setk_weights(int32_t kind, double beta, int32_t ref_channel, int32_t rank1, 
   cudaError_t e = weights_run(kind, beta, ref_channel, rank1, ban, Rs, Rn, Ry, r_dtype, B, F, C, w, w_dtype,
                               status, ref_used, stream);
   return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_weights");
+}
+
+int setk_ban(const void* w_in, const void* Rn, int32_t dtype, int32_t B, int32_t F, int32_t C,
+             void* w_out, void* stream) {
+  if (!w_in || !Rn || !w_out) return fail(SETK_EINVAL, "setk_ban: null buffer");
+  if (B < 1 || F < 1 || C < 1 || C > SETK_MAX_CHANNELS) return fail(SETK_ESHAPE, "setk_ban: bad shape");
+  if (dtype != SETK_C64 && dtype != SETK_C128) return fail(SETK_EINVAL, "setk_ban: bad dtype");
+  cudaError_t e = post_run(0, w_in, Rn, dtype, B, F, C, w_out, nullptr, stream);
+  return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_ban");
+}
+
+int setk_rank1(const void* Rs, const void* Rn, int32_t dtype, int32_t B, int32_t F, int32_t C,
+               void* R1_out, uint32_t* status, void* stream) {
+  if (!Rs || !R1_out) return fail(SETK_EINVAL, "setk_rank1: null buffer");
+  if (B < 1 || F < 1 || C < 1 || C > SETK_MAX_CHANNELS) return fail(SETK_ESHAPE, "setk_rank1: bad shape");
+  if (dtype != SETK_C64 && dtype != SETK_C128) return fail(SETK_EINVAL, "setk_rank1: bad dtype");
+  cudaError_t e = post_run(1, Rs, Rn, dtype, B, F, C, R1_out, status, stream);
+  return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_rank1");
 }
 
 int setk_apply(const void* stft, const void* w, int32_t w_dtype, const float* post_mask, int32_t B,

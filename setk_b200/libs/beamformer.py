@@ -1,0 +1,335 @@
+"""
+setk_b200.libs.beamformer -- drop-in for the mask-based adaptive beamformer part
+of the reference's scripts/sptk/libs/beamformer.py on libsetk_b200 kernels.
+
+Same names, argument names, defaults and array axis orders as the reference
+(for N: num_mics, F: num_bins, T: num_frames):
+    obs (N,F,T), tf_mask (T,F), covariance (F,N,N), weight (F,N), enhanced (F,T)
+
+  do_ban 14-28, solve_pevd 31-63, rank1_constraint 66-84, compute_covar 87-103,
+  Beamformer.beamform 220-234, SupervisedBeamformer 237-283,
+  OnlineSupervisedBeamformer 286-320, MvdrBeamformer 515-539,
+  MpdrBeamformer 542-590, PmwfBeamformer 593-659, GevdBeamformer 662-682,
+  OnlineGevdBeamformer 685-703, OnlineMvdrBeamformer 706-728.
+
+numpy in -> numpy out, torch in -> torch out (same device).  Every function
+accepts an optional leading batch dimension on its array arguments.
+
+Differences from the reference, all deliberate:
+  * eigenvectors follow this library's convention (unit norm, component 0 real
+    and >= 0; GEV normalised to w^H Rn w = 1) -- the reference's are defined
+    up to a LAPACK-chosen sign per bin;
+  * the C x C solves run in float64 whatever the input dtype; results are
+    returned as complex64 for complex64/float32 inputs, complex128 otherwise;
+  * singular / non-positive-definite covariances raise
+    numpy.linalg.LinAlgError (the reference's GEV silently falls back to a
+    non-Hermitian eig, beamformer.py:55-58);
+  * OnlineSupervisedBeamformer.run takes `ban=` (the reference CLI passes
+    `normalize=`, a TypeError, apply_adaptive_beamformer.py:45) and the reset
+    flag is cleared after the first chunk (the reference never clears it);
+  * MpdrBeamformer.run(ban=True) without whiten computes Rn instead of raising
+    UnboundLocalError (beamformer.py:590).
+"""
+import numpy as np
+import torch
+
+from .. import _lib
+from .. import plan as _plan
+from ..engine import status_message
+from .utils import EPSILON, _back, _to_tensor, cmat_abs  # noqa: F401
+
+__all__ = [
+    "do_ban", "solve_pevd", "rank1_constraint", "compute_covar", "Beamformer",
+    "SupervisedBeamformer", "OnlineSupervisedBeamformer", "MvdrBeamformer", "MpdrBeamformer",
+    "PmwfBeamformer", "GevdBeamformer", "OnlineGevdBeamformer", "OnlineMvdrBeamformer"
+]
+
+
+def _complex(x):
+    t, was_np = _to_tensor(x)
+    if not t.is_complex():
+        t = t.to(torch.complex64)
+    return t, was_np
+
+
+def _batched(t, ndim):
+    """Add a leading batch axis if `t` has exactly `ndim` dims."""
+    if t.dim() == ndim:
+        return t.unsqueeze(0), True
+    if t.dim() == ndim + 1:
+        return t, False
+    raise ValueError(f"expected {ndim} or {ndim + 1} dimensions, got {tuple(t.shape)}")
+
+
+def _check_status(status):
+    st = status.cpu().numpy()
+    bad = np.nonzero(st)[0]
+    if bad.size:
+        i = int(bad[0])
+        if int(st[i]) & _lib.ST_BAD_REF:
+            raise RuntimeError("Reference channel ID exceeds total channels")
+        raise np.linalg.LinAlgError(status_message(int(st[i])))
+
+
+def _solve_dtype(*mats):
+    """float64 solve always; complex128 out only if an input is complex128."""
+    return torch.complex128 if any(m is not None and m.dtype == torch.complex128
+                                   for m in mats) else torch.complex64
+
+
+def _weights(kind, Rs, Rn=None, Ry=None, **kw):
+    Rs, was_np = _complex(Rs)
+    Rs, squeeze = _batched(Rs, 3)
+    mats = [Rs]
+    for m in (Rn, Ry):
+        if m is None:
+            mats.append(None)
+        else:
+            t, _ = _complex(m)
+            mats.append(_batched(t.to(Rs.device), 3)[0])
+    dt = _solve_dtype(*mats)
+    mats = [None if m is None else m.to(dt) for m in mats]
+    w, status, ref = _plan.weights(kind, mats[0], mats[1], mats[2], out_dtype=dt, **kw)
+    _check_status(status)
+    return _back(w[0] if squeeze else w, was_np)
+
+
+def do_ban(weight, Rn):
+    """
+    Do Blind Analytical Normalization(BAN)  (beamformer.py:14-28)
+    Arguments: weight F x N, Rn F x N x N.  Return: ban_weight F x N
+    """
+    w, was_np = _complex(weight)
+    w, squeeze = _batched(w, 2)
+    R, _ = _complex(Rn)
+    R = _batched(R.to(w.device), 3)[0]
+    dt = _solve_dtype(w, R)
+    out = _plan.ban(w.to(dt), R.to(dt))
+    return _back(out[0] if squeeze else out, was_np)
+
+
+def solve_pevd(Rs, Rn=None):
+    """
+    Return principle eigenvector of covariance matrix (pair)  (beamformer.py:31-63)
+    Arguments: Rs F x N x N, Rn same or None.  Return: pvector F x N
+    """
+    return _weights(_lib.BF_PEVD, Rs, Rn)
+
+
+def rank1_constraint(Rs, Rn=None):
+    """
+    Return generalized rank1 approximation of covariance matrix  (beamformer.py:66-84)
+    """
+    R, was_np = _complex(Rs)
+    R, squeeze = _batched(R, 3)
+    Rn_t = None
+    if Rn is not None:
+        Rn_t, _ = _complex(Rn)
+        Rn_t = _batched(Rn_t.to(R.device), 3)[0]
+    dt = _solve_dtype(R, Rn_t)
+    out, status = _plan.rank1(R.to(dt), None if Rn_t is None else Rn_t.to(dt))
+    _check_status(status)
+    return _back(out[0] if squeeze else out, was_np)
+
+
+def compute_covar(obs, tf_mask):
+    """
+    (beamformer.py:87-103)
+    Arguments: tf_mask T x F, obs N x F x T.  Return: covar_mat F x N x N
+    """
+    x, was_np = _complex(obs)
+    x, squeeze = _batched(x, 3)
+    m, _ = _to_tensor(tf_mask, torch.float32)
+    m = _batched(m.to(x.device), 2)[0]
+    R = _plan.covariance(x, m)
+    return _back(R[0] if squeeze else R, was_np)
+
+
+class Beamformer(object):
+
+    def __init__(self):
+        pass
+
+    def beamform(self, weight, obs):
+        """
+        (beamformer.py:220-234)
+        Arguments: weight F x N, obs N x F x T.  Return: stft_enhan F x T
+        """
+        x, was_np = _complex(obs)
+        w, _ = _complex(weight)
+        w = w.to(x.device)
+        x, squeeze = _batched(x, 3)
+        w = _batched(w, 2)[0]
+        if w.shape[-2] != x.shape[-2] or w.shape[-1] != x.shape[-3]:
+            raise ValueError("Input obs do not match with weight, " +
+                             f"{tuple(w.shape[-2:])} vs {tuple(x.shape[-3:])}")
+        enh = _plan.apply_weights(x, w)
+        return _back(enh[0] if squeeze else enh, was_np)
+
+
+class SupervisedBeamformer(Beamformer):
+    """
+    BaseClass for TF-mask based beamformer  (beamformer.py:237-283)
+    """
+
+    def __init__(self, num_bins):
+        super(SupervisedBeamformer, self).__init__()
+        self.num_bins = num_bins
+
+    def compute_covar_mat(self, target_mask, obs):
+        """
+        Arguments: target_mask T x F, obs N x F x T.  Return: covar_mat F x N x N
+        """
+        if target_mask.shape[-1] != self.num_bins or target_mask.ndim not in (2, 3):
+            raise ValueError("Input mask matrix should be shape as " +
+                             f"[num_frames x num_bins], now is {tuple(target_mask.shape)}")
+        if obs.shape[-2] != target_mask.shape[-1] or obs.shape[-1] != target_mask.shape[-2]:
+            raise ValueError("Shape of input obs do not match with " +
+                             f"mask matrix, {tuple(obs.shape)} vs {tuple(target_mask.shape)}")
+        return compute_covar(obs, target_mask)
+
+    def weight(self, Rs, Rn):
+        """
+        Need reimplement for different beamformer
+        """
+        raise NotImplementedError
+
+    def run(self, mask_s, obs, mask_n=None, ban=False):
+        """
+        Run beamformer based on TF-mask  (beamformer.py:270-283)
+        Arguments: mask_s T x F, obs N x F x T.  Returns: stft_enhan F x T
+        """
+        Rn = self.compute_covar_mat(1 - mask_s if mask_n is None else mask_n, obs)
+        Rs = self.compute_covar_mat(mask_s, obs)
+        weight = self.weight(Rs, Rn)
+        return self.beamform(do_ban(weight, Rn) if ban else weight, obs)
+
+
+class OnlineSupervisedBeamformer(SupervisedBeamformer):
+    """
+    Online version of SupervisedBeamformer  (beamformer.py:286-320)
+    """
+
+    def __init__(self, num_bins, num_channels, alpha=0.8):
+        super(OnlineSupervisedBeamformer, self).__init__(num_bins)
+        self.covar_mat_shape = (num_bins, num_channels, num_channels)
+        self.reset_stats(alpha=alpha)
+
+    def reset_stats(self, alpha=0.8):
+        self.Rs = None
+        self.Rn = None
+        self.alpha = alpha
+        self.reset = True
+
+    def run(self, mask_s, obs, mask_n=None, ban=False):
+        Rn = self.compute_covar_mat(1 - mask_s if mask_n is None else mask_n, obs)
+        Rs = self.compute_covar_mat(mask_s, obs)
+        if tuple(Rs.shape[-3:]) != self.covar_mat_shape:
+            raise ValueError(f"covariance shape {tuple(Rs.shape)} vs {self.covar_mat_shape}")
+        # update stats
+        phi = 1 if self.reset else (1 - self.alpha)
+        self.Rs = phi * Rs if self.Rs is None else self.Rs * self.alpha + phi * Rs
+        self.Rn = phi * Rn if self.Rn is None else self.Rn * self.alpha + phi * Rn
+        self.reset = False
+        # do beamforming
+        weight = self.weight(self.Rs, self.Rn)
+        return self.beamform(do_ban(weight, Rn) if ban else weight, obs)
+
+
+class MvdrBeamformer(SupervisedBeamformer):
+    """
+    MVDR (Minimum Variance Distortionless Response) Beamformer  (beamformer.py:515-539)
+        h_mvdr(f) = R(f)_{vv}^{-1}*d(f) / [d(f)^H*R(f)_{vv}^{-1}*d(f)],  d(f) = P(R(f)_{xx})
+    """
+
+    def __init__(self, num_bins):
+        super(MvdrBeamformer, self).__init__(num_bins)
+
+    def weight(self, Rs, Rn):
+        return _weights(_lib.BF_MVDR, Rs, Rn)
+
+
+class MpdrBeamformer(SupervisedBeamformer):
+    """
+    MPDR (Minimum Power Distortionless Response) Beamformer  (beamformer.py:542-590)
+        h_mpdr(f) = R(f)_{yy}^{-1}*d(f) / [d(f)^H*R(f)_{yy}^{-1}*d(f)]
+    """
+
+    def __init__(self, num_bins, whiten=False):
+        super(MpdrBeamformer, self).__init__(num_bins)
+        self.whiten = whiten
+
+    def weight(self, Rs, Ry, Rn=None):
+        if Rn is None:
+            return _weights(_lib.BF_MPDR, Rs, None, Ry)
+        return _weights(_lib.BF_MPDR_WHITEN, Rs, Rn, Ry)
+
+    def run(self, mask_s, obs, mask_n=None, ban=False):
+        Rs = self.compute_covar_mat(mask_s, obs)
+        ones = torch.ones_like(mask_s) if isinstance(mask_s, torch.Tensor) else np.ones_like(mask_s)
+        Ry = self.compute_covar_mat(ones, obs)
+        Rn = None
+        if self.whiten or ban:
+            Rn = self.compute_covar_mat(1 - mask_s if mask_n is None else mask_n, obs)
+        weight = self.weight(Rs, Ry, Rn=Rn if self.whiten else None)
+        return self.beamform(do_ban(weight, Rn) if ban else weight, obs)
+
+
+class PmwfBeamformer(SupervisedBeamformer):
+    """
+    PMWF (Parameterized Multichannel Non-Causal Wiener Filter)  (beamformer.py:593-659)
+        h_pmwf(f) = numerator(f)*u(f) / (beta + trace(numerator(f))),
+        numerator(f) = R(f)_vv^{-1}*R(f)_xx;  beta = 0 => mvdr, beta = 1 => mcwf
+    """
+
+    def __init__(self, num_bins, beta=0, ref_channel=-1, rank1_appro=""):
+        super(PmwfBeamformer, self).__init__(num_bins)
+        self.ref_channel = ref_channel
+        self.rank1_appro = rank1_appro
+        self.beta = beta
+
+    def weight(self, Rs, Rn):
+        N = Rs.shape[-1]
+        if self.ref_channel >= N:
+            raise RuntimeError("Reference channel ID exceeds total " +
+                               f"channels: {self.ref_channel} vs {N}")
+        r1 = {"eig": _lib.RANK1_EIG, "gev": _lib.RANK1_GEV}.get(self.rank1_appro, _lib.RANK1_NONE)
+        return _weights(_lib.BF_PMWF, Rs, Rn, beta=float(self.beta),
+                        ref_channel=int(self.ref_channel), rank1=r1)
+
+
+class GevdBeamformer(SupervisedBeamformer):
+    """
+    Max-SNR/GEV (Generalized Eigenvalue Decomposition) Beamformer  (beamformer.py:662-682)
+        h_gevd(f) = P(R(f)_xx, R(f)_vv)   P: max generalized eigenvector
+    """
+
+    def __init__(self, num_bins):
+        super(GevdBeamformer, self).__init__(num_bins)
+
+    def weight(self, Rs, Rn):
+        return _weights(_lib.BF_GEVD, Rs, Rn)
+
+
+class OnlineGevdBeamformer(OnlineSupervisedBeamformer):
+    """
+    Online version of GEVD beamformer  (beamformer.py:685-703)
+    """
+
+    def __init__(self, num_bins, num_channels, alpha=0.8):
+        super(OnlineGevdBeamformer, self).__init__(num_bins, num_channels, alpha=alpha)
+
+    def weight(self, Rs, Rn):
+        return _weights(_lib.BF_GEVD, Rs, Rn)
+
+
+class OnlineMvdrBeamformer(OnlineSupervisedBeamformer):
+    """
+    Online version of MVDR beamformer  (beamformer.py:706-728)
+    """
+
+    def __init__(self, num_bins, num_channels, alpha=0.8):
+        super(OnlineMvdrBeamformer, self).__init__(num_bins, num_channels, alpha=alpha)
+
+    def weight(self, Rs, Rn):
+        return _weights(_lib.BF_MVDR, Rs, Rn)

@@ -269,6 +269,32 @@ def weights(kind, Rs, Rn=None, Ry=None, beta=0.0, ref_channel=-1, rank1=_lib.RAN
     return w, status, ref_used
 
 
+def ban(weight, Rn):
+    """do_ban batched: weight (B,F,C), Rn (B,F,C,C), same complex dtype."""
+    Rn = Rn.contiguous()
+    weight = weight.to(Rn.dtype).contiguous()
+    B, F, C = weight.shape
+    out = torch.empty_like(weight)
+    with _ctx(Rn.device):
+        _lib.check(_lib.library().setk_ban(_lib.ptr(weight), _lib.ptr(Rn), _dtype_code(Rn), B, F, C,
+                                           _lib.ptr(out), _lib.current_stream(Rn.device)))
+    return out
+
+
+def rank1(Rs, Rn=None):
+    """rank1_constraint batched.  Returns (R1 (B,F,C,C), status (B,))."""
+    Rs = Rs.contiguous()
+    B, F, C, _ = Rs.shape
+    Rn = None if Rn is None else Rn.to(Rs.dtype).contiguous()
+    out = torch.empty_like(Rs)
+    status = torch.zeros((B,), dtype=torch.int32, device=Rs.device)
+    with _ctx(Rs.device):
+        _lib.check(_lib.library().setk_rank1(_lib.ptr(Rs), _lib.ptr(Rn), _dtype_code(Rs), B, F, C,
+                                             _lib.ptr(out), _lib.ptr(status),
+                                             _lib.current_stream(Rs.device)))
+    return out, status
+
+
 def apply_weights(stft, weight, post_mask=None):
     """Beamformer.beamform batched: (B,C,F,T) x (B,F,C) -> (B,F,T) complex64."""
     stft = stft.contiguous()

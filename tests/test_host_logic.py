@@ -1,0 +1,180 @@
+"""
+CPU tier: the Python host layer (the mirror of the reference's sptk.libs API,
+the batched engine and the CLI) running on the CPU execution model of the
+kernels, against the oracle.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import beamformer_oracle as bo
+from oracle import stft_oracle as so
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture()
+def libs(emu):
+    from setk_b200.libs import beamformer as BF
+    from setk_b200.libs import utils as U
+    U.set_default_device("cpu")
+    yield U, BF
+    U.set_default_device(None)
+
+
+def test_forward_inverse_stft_api(libs):
+    U, _ = libs
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal(3000) * 0.1).astype(np.float32)
+    for kw in (dict(frame_len=512, frame_hop=256, center=True, transpose=False),
+               dict(frame_len=400, frame_hop=160, center=True, transpose=True),
+               dict(frame_len=256, frame_hop=128, center=False, window="hamming", transpose=True)):
+        S = U.forward_stft(x, **kw)
+        So = so.forward_stft(x, **kw)
+        assert S.shape == So.shape and S.dtype == np.complex64
+        assert bo.rel_inf(S, So) <= 2e-5
+        y = U.inverse_stft(S, norm=0.3, **kw)
+        yo = so.inverse_stft(So, norm=0.3, **kw)
+        assert y.shape == yo.shape
+        assert bo.rel_inf(y, yo) <= 2e-5
+    # defaults are the reference's (utils.py:96-105): 1024 / 256 / center False / transpose True
+    S = U.forward_stft(x)
+    assert S.shape == (1 + (3000 - 1024) // 256, 513)
+    mag = U.forward_stft(x, 512, 256, apply_log=True, transpose=False)
+    assert mag.dtype == np.float32 and np.all(np.isfinite(mag))
+    with pytest.raises(RuntimeError):
+        U.forward_stft(np.zeros((2, 3000), dtype=np.float32))
+    # torch in -> torch out
+    St = U.forward_stft(torch.from_numpy(x), 512, 256, center=True)
+    assert isinstance(St, torch.Tensor) and St.dtype == torch.complex64
+    assert U.nextpow2(400) == 512
+
+
+def test_beamformer_api(libs):
+    _, BF = libs
+    rng = np.random.default_rng(1)
+    C, F, T = 4, 257, 10
+    obs = (rng.standard_normal((C, F, T)) + 1j * rng.standard_normal((C, F, T))).astype(np.complex64)
+    mask = rng.uniform(0, 1, (T, F)).astype(np.float32)
+    obs64, mask64 = obs.astype(np.complex128), mask.astype(np.float64)
+    cases = [(BF.MvdrBeamformer(F), "mvdr", {}), (BF.GevdBeamformer(F), "gevd", {}),
+             (BF.PmwfBeamformer(F, beta=1, ref_channel=0), "pmwf", dict(beta=1, ref_channel=0)),
+             (BF.PmwfBeamformer(F, rank1_appro="eig"), "pmwf", dict(rank1_appro="eig")),
+             (BF.MpdrBeamformer(F), "mpdr", {}), (BF.MpdrBeamformer(F, whiten=True), "mpdr-whiten", {})]
+    for bf, kind, kw in cases:
+        for ban in (False, True):
+            enh = bf.run(mask, obs, ban=ban)
+            ref = bo.run_supervised(kind, mask64, obs64, ban=ban, **kw)
+            assert enh.shape == (F, T) and enh.dtype == np.complex64
+            assert bo.rel_inf(bo.align_phase(enh, ref)[0], ref) <= 2e-5, (kind, ban)
+    Rs, Rn = bo.compute_covar(obs64, mask64), bo.compute_covar(obs64, 1 - mask64)
+    assert bo.rel_inf(BF.compute_covar(obs, mask), Rs) <= 2e-5
+    d = BF.solve_pevd(Rs)
+    assert d.dtype == np.complex128
+    assert bo.rel_inf(bo.align_phase(d, bo.solve_pevd(Rs))[0], bo.solve_pevd(Rs)) <= 1e-9
+    assert bo.rel_inf(BF.rank1_constraint(Rs, Rn), bo.rank1_constraint(Rs, Rn)) <= 1e-9
+    w = bo.mvdr_weight(Rs, Rn)
+    assert bo.rel_inf(BF.do_ban(w, Rn), bo.do_ban(w, Rn)) <= 1e-9
+    # error behaviour of the reference
+    with pytest.raises(ValueError):
+        BF.Beamformer().beamform(w[:, :3], obs)
+    with pytest.raises(ValueError):
+        BF.MvdrBeamformer(F).compute_covar_mat(mask[:, :100], obs)
+    with pytest.raises(RuntimeError):
+        BF.PmwfBeamformer(F, ref_channel=7).weight(Rs, Rn)
+    with pytest.raises(np.linalg.LinAlgError):
+        BF.MvdrBeamformer(F).weight(Rs, np.zeros_like(Rn))
+    with pytest.raises(NotImplementedError):
+        BF.SupervisedBeamformer(F).weight(Rs, Rn)
+
+
+def test_online_beamformer(libs):
+    _, BF = libs
+    rng = np.random.default_rng(2)
+    C, F, T = 3, 129, 64
+    obs = (rng.standard_normal((C, F, T)) + 1j * rng.standard_normal((C, F, T))).astype(np.complex64)
+    mask = rng.uniform(0, 1, (T, F)).astype(np.float32)
+    bf = BF.OnlineMvdrBeamformer(F, C, alpha=0.8)
+    out = [bf.run(mask[c:c + 32], np.ascontiguousarray(obs[:, :, c:c + 32])) for c in (0, 32)]
+    assert out[0].shape == (F, 32) and not bf.reset
+    # first chunk equals the offline beamformer on that chunk
+    ref = bo.run_supervised("mvdr", mask[:32].astype(np.float64),
+                            obs[:, :, :32].astype(np.complex128))
+    assert bo.rel_inf(bo.align_phase(out[0], ref)[0], ref) <= 2e-5
+
+
+def test_pipeline_status_maps_to_linalgerror(emu):
+    from setk_b200.engine import BeamformPipeline
+    pipe = BeamformPipeline(4, "mvdr", max_batch=2, max_samples=2000, device=emu)
+    x = torch.zeros(2, 4, 2000)                       # silence: singular covariances
+    m = torch.full((2, pipe.plan.num_frames(2000), 257), 0.5)
+    wave, status = pipe.run(x, m)
+    assert int(status.abs().sum()) != 0
+    with pytest.raises(np.linalg.LinAlgError):
+        BeamformPipeline.raise_for_status(status, ["a", "b"])
+
+
+def _write_wav(path, x):
+    import scipy.io.wavfile as wavfile
+    wavfile.write(path, 16000, so.pcm16_from_float(x.T))
+
+
+def test_cli_end_to_end(tmp_path, emu_library_path):
+    """scripts/sptk/apply_adaptive_beamformer.py with the reference's flags, vs the oracle."""
+    from setk_b200 import synth
+    x, m = synth.make_batch(1, 4, 4000, device="cpu")
+    x, m = x[0].numpy(), m[0].numpy()
+    x = so.float_from_pcm16(so.pcm16_from_float(x))            # what the wav file will hold
+    _write_wav(str(tmp_path / "utt1.wav"), x)
+    np.save(tmp_path / "utt1.npy", m)
+    (tmp_path / "wav.scp").write_text(f"utt1 {tmp_path / 'utt1.wav'}\n")
+    (tmp_path / "mask.scp").write_text(f"utt1 {tmp_path / 'utt1.npy'}\n")
+    env = dict(os.environ, SETK_B200_TEST_LIBRARY=emu_library_path, PYTHONPATH=ROOT)
+    runner = (
+        "import os, sys, runpy; sys.argv = sys.argv[1:];"
+        "from setk_b200 import _lib; _lib.use_library(os.environ['SETK_B200_TEST_LIBRARY']);"
+        "from setk_b200.libs import utils; utils.set_default_device('cpu');"
+        "runpy.run_path(sys.argv[0], run_name='__main__')")
+    import scipy.io.wavfile as wavfile
+    # PMWF is phase invariant, so the waveform itself is comparable with the oracle;
+    # MVDR's per-bin sign is LAPACK-defined in the reference (checked elsewhere after alignment)
+    cases = (("pmwf-0", [], dict(beta=0)),
+             ("pmwf-1", ["--ban", "true", "--pmwf-ref", "1"], dict(beta=1, ref_channel=1, ban=True)),
+             ("mvdr", ["--post-masking", "true"], None))
+    for bf, extra, okw in cases:
+        dst = tmp_path / bf
+        cmd = [sys.executable, "-c", runner,
+               os.path.join(ROOT, "scripts", "sptk", "apply_adaptive_beamformer.py"),
+               "--frame-len", "512", "--frame-hop", "256", "--mask-format", "numpy",
+               "--beamformer", bf, *extra, str(tmp_path / "wav.scp"), str(tmp_path / "mask.scp"),
+               str(dst)]
+        subprocess.run(cmd, check=True, env=env, capture_output=True)
+        sr, out = wavfile.read(str(dst / "utt1.wav"))
+        assert sr == 16000 and out.dtype == np.int16
+        assert out.shape == (256 * (so.num_frames(4000, 512, 256, True) - 1),)
+        if okw is None:
+            assert np.abs(out).max() > 1000
+            continue
+        y, _, _ = bo.enhance_utterance(x, m, kind="pmwf", **okw)
+        ref = so.pcm16_from_float(y)
+        d = np.abs(out.astype(np.int64) - ref.astype(np.int64))
+        assert d.max() <= 1 and np.mean(d > 0) <= 0.05
+
+
+def test_kaldi_matrix_reader(tmp_path):
+    import struct
+    from setk_b200.libs.data_handler import ScriptReader
+    mat = np.arange(12, dtype=np.float32).reshape(3, 4)
+    path = tmp_path / "m.ark"
+    with open(path, "wb") as f:
+        f.write(b"utt1 ")
+        off = f.tell()
+        f.write(b"\0B" + b"FM " + b"\4" + struct.pack("<i", 3) + b"\4" + struct.pack("<i", 4))
+        f.write(mat.tobytes())
+    (tmp_path / "m.scp").write_text(f"utt1 {path}:{off}\n")
+    rd = ScriptReader(str(tmp_path / "m.scp"))
+    assert "utt1" in rd and np.array_equal(rd["utt1"], mat)

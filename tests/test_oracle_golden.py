@@ -1,0 +1,117 @@
+"""
+CPU tier: the oracle (oracle/*.py, the CPU restatement of the reference) against
+the golden vectors generated from the reference's own code and against the
+reference's shipped doc vectors (tests/golden/, oracle/make_golden.py).
+When /root/reference is present (build container) the restatement is also
+cross-checked live against the shimmed reference modules.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import beamformer_oracle as bo
+from oracle import ref_shim
+from oracle import stft_oracle as so
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_pinning_report_records_reference_agreement():
+    with open(os.path.join(GOLD, "PINNING.json")) as f:
+        rep = json.load(f)
+    # reference replay (its own code, imported under the shim) vs its shipped vectors
+    for name in ("doc/pmwf-0", "doc/pmwf-0-eig", "doc/pmwf-0-gev"):
+        assert rep[name]["ref_replay_vs_shipped_max_lsb"] <= 1
+        assert rep[name]["oracle_vs_ref64_relinf_aligned"] <= 1e-12
+    assert rep["doc/pmwf-0"]["oracle_e2e_vs_shipped_max_lsb"] <= 1
+    assert rep["doc/stft_oracle_vs_refshim_maxabs"] == 0.0
+    for name in ("small/c4_512", "small/c5_400", "small/c2_256nc", "small/c8_1024"):
+        assert rep[name]["covar_relinf"] <= 1e-12
+        assert rep[name]["mvdr_w_relinf_aligned"] <= 1e-12
+        assert rep[name]["gev_w_relinf_aligned"] <= 1e-12
+        assert rep[name]["istft_relinf"] <= 1e-12
+
+
+def test_oracle_reproduces_reference_small_cases():
+    g = np.load(os.path.join(GOLD, "ref_small.npz"))
+    for name in ("c4_512", "c5_400", "c2_256nc", "c8_1024"):
+        C, N, fl, hop, center = [int(v) for v in g[name + "/cfg"]]
+        window = str(g[name + "/window"])
+        kw = dict(frame_len=fl, frame_hop=hop, center=bool(center), window=window, transpose=False)
+        mix, mask = g[name + "/mix"], g[name + "/mask"].astype(np.float64)
+        obs = so.multichannel_stft(mix, round_power_of_two=True, out_dtype=np.complex64,
+                                   **kw).astype(np.complex128)
+        Rs = bo.compute_covar(obs, mask)
+        Rn = bo.compute_covar(obs, 1 - mask)
+        assert bo.rel_inf(Rs, g[name + "/Rs"]) <= 1e-12
+        assert bo.rel_inf(Rn, g[name + "/Rn"]) <= 1e-12
+        w = bo.align_phase(bo.mvdr_weight(Rs, Rn), g[name + "/w_mvdr"])[0]
+        assert bo.rel_inf(w, g[name + "/w_mvdr"]) <= 1e-10
+        w = bo.align_phase(bo.gevd_weight(Rs, Rn), g[name + "/w_gev"])[0]
+        assert bo.rel_inf(w, g[name + "/w_gev"]) <= 1e-10
+        w, _ = bo.pmwf_weight(Rs, Rn, beta=1, ref_channel=0)
+        assert bo.rel_inf(w, g[name + "/w_pmwf1_ref0"]) <= 1e-10
+        enh = bo.beamform(g[name + "/w_mvdr"], obs)
+        assert bo.rel_inf(enh, g[name + "/enh_mvdr"]) <= 1e-12
+        y = so.inverse_stft(enh, norm=float(np.max(np.abs(mix))), **kw)
+        assert y.shape == g[name + "/y_mvdr"].shape
+        assert bo.rel_inf(y, g[name + "/y_mvdr"]) <= 1e-12
+
+
+def test_oracle_end_to_end_matches_shipped_doc_vector():
+    """PMWF is phase invariant: the shipped PCM-16 file pins the whole chain (<= 1 LSB)."""
+    g = np.load(os.path.join(GOLD, "doc_adaptive_beamformer.npz"))
+    samps = so.float_from_pcm16(g["egs_pcm16"])
+    for name, r1 in (("pmwf-0", ""), ("pmwf-0-eig", "eig")):
+        y, _, _ = bo.enhance_utterance(samps, g["mask"], kind="pmwf", beta=0, rank1_appro=r1,
+                                       stft_dtype=np.complex64)
+        d = np.abs(so.pcm16_from_float(y).astype(np.int64) - g["shipped/" + name].astype(np.int64))
+        assert d.max() <= 1
+        assert np.mean(d > 0) <= 0.05
+
+
+def test_bookkeeping_table():
+    """frame counts and iSTFT lengths at N = 160000, hop 256."""
+    rows = [(512, True, 512, 257, 626, 160000), (1024, True, 1024, 513, 626, 160000),
+            (400, True, 512, 257, 626, 160000), (512, False, 512, 257, 624, 160000),
+            (1024, False, 1024, 513, 622, 160000)]
+    for fl, center, n_fft, F, T, n_out in rows:
+        assert so.nextpow2(fl) == n_fft
+        assert so.num_frames(160000, n_fft, 256, center) == T
+        if center:
+            assert so.istft_length(T, n_fft, 256, center) == 256 * (T - 1)
+    assert so.num_frames(94010, 512, 256, True) == 368
+    assert so.istft_length(368, 512, 256, True) == 93952
+
+
+def test_stft_istft_round_trip():
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(16000).astype(np.float32)
+    for fl, hop in ((512, 256), (1024, 256), (400, 160)):
+        S = so.forward_stft(x, fl, hop, center=True, transpose=False)
+        y = so.inverse_stft(S, fl, hop, center=True, transpose=False)
+        n = min(len(x), len(y))
+        assert bo.rel_inf(y[:n], x[:n].astype(np.float64)) <= 1e-6
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="needs /root/reference")
+def test_restatement_against_live_reference():
+    ref = ref_shim.load_reference()
+    rng = np.random.default_rng(3)
+    C, N = 3, 5000
+    x = (rng.standard_normal((C, N)) * 0.1).astype(np.float32)
+    kw = dict(frame_len=512, frame_hop=256, center=True, window="hann", transpose=False)
+    S_ref = np.stack([ref.utils.forward_stft(x[c], round_power_of_two=True, **kw) for c in range(C)])
+    S_or = so.multichannel_stft(x, round_power_of_two=True, out_dtype=np.complex64, **kw)
+    assert np.array_equal(S_ref, S_or)
+    T, F = S_ref.shape[2], S_ref.shape[1]
+    mask = rng.uniform(0, 1, (T, F))
+    obs = S_ref.astype(np.complex128)
+    for kind, bf in (("mvdr", ref.beamformer.MvdrBeamformer(F)),
+                     ("gevd", ref.beamformer.GevdBeamformer(F)),
+                     ("pmwf", ref.beamformer.PmwfBeamformer(F, beta=0))):
+        e_ref = bf.run(mask, obs, ban=(kind == "gevd"))
+        e_or = bo.run_supervised(kind, mask, obs, ban=(kind == "gevd"))
+        assert bo.rel_inf(bo.align_phase(e_or, e_ref)[0], e_ref) <= 1e-10
