@@ -132,12 +132,25 @@ def launch_count():
     return int(library().setk_launch_count())
 
 
+def emulated():
+    """True when the bound library is the CPU test tier's build (tests/emu)."""
+    return hasattr(library(), "setk_emulated")
+
+
 def ptr(t):
-    """Raw data pointer of a torch tensor / numpy array (None -> NULL)."""
+    """
+    Raw data pointer of a torch tensor (None -> NULL).  The product library
+    takes DEVICE pointers only: a host tensor is an error, not a slow path.
+    """
     if t is None:
         return None
     if isinstance(t, np.ndarray):
+        if not emulated():
+            raise RuntimeError("libsetk_b200 needs device memory (no CPU fallback)")
         return c_void_p(t.ctypes.data)
+    if not t.is_cuda and not emulated():
+        raise RuntimeError("libsetk_b200 needs CUDA tensors (no CPU fallback); got a "
+                           f"{t.device} tensor")
     return c_void_p(t.data_ptr())
 
 

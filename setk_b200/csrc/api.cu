@@ -75,6 +75,11 @@ using namespace setk;
 extern "C" {
 
 int setk_version(void) { return SETK_VERSION; }
+#ifdef SETK_EMU
+// present only in the CPU test tier's build (tests/emu): lets the Python layer
+// tell the two apart so that the product library never sees host pointers
+int setk_emulated(void) { return 1; }
+#endif
 const char* setk_last_error_string(void) { return g_err; }
 int64_t setk_launch_count(void) { return (int64_t)g_launch_count.load(); }
 

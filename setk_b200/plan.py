@@ -69,6 +69,8 @@ class StftPlan(object):
                  max_samples=160000, device=None):
         self.device = torch.device(device if device is not None else (
             "cuda" if torch.cuda.is_available() else "cpu"))
+        if self.device.type != "cuda" and not _lib.emulated():
+            raise RuntimeError("StftPlan needs a CUDA device (setk_b200 has no CPU fallback)")
         self.num_channels = int(num_channels)
         self.frame_len = int(frame_len)
         self.frame_hop = int(frame_hop)
