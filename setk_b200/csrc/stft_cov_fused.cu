@@ -85,51 +85,61 @@ __global__ void __maxnreg__(112) stft_cov_kernel(StftCovArgs a) {
                       ((reinterpret_cast<uintptr_t>(a.audio) & 15) == 0);
 
   // software pipeline: tile i+1 streams into the other audio buffer while tile i
-  // is transformed and accumulated
-  unsigned par = 0;                 // mbarrier phase parity per buffer (bit b)
-  bool async_cur = false;
-  if (t_begin < t_end)
-    async_cur = stage_tile_begin<C, TT>(sm, 0, xb, a.N, nb, t_begin, imin(TT, t_end - t_begin), hop,
-                                        pad, vec_ok);
-  // mask rows of this thread's bin: one frame per step of `mstride`.  They are
-  // fetched with 4-byte cp.async straight into shared memory at the top of the
-  // tile and first touched after the FFT phase, so their latency costs neither
-  // registers nor issue slots
+  // is transformed and accumulated.  Warp 8 (which has no FFT job) is the
+  // producer: it issues the TMA bulk copies of the next tile and the 4-byte
+  // cp.async of this tile's mask rows (first touched after the FFT phase), so
+  // the eight FFT warps carry no staging instructions at all.
   const bool has_mn = a.mask_n != nullptr;
   const bool clip = (a.flags & SETK_F_CLIP_MASK) != 0;
-  const long long mstride = (a.flags & SETK_F_MASK_FT) ? 1 : F;
-  const long long mbase = (a.flags & SETK_F_MASK_FT) ? ((long long)b * F + (cov_thread ? bin : 0)) * a.T
-                                                     : (long long)b * a.T * F + (cov_thread ? bin : 0);
-  const float* mps = a.mask_s + mbase + (long long)t_begin * mstride;
-  const float* mpn = has_mn ? a.mask_n + mbase + (long long)t_begin * mstride : nullptr;
+  // element (bin, t) of a mask: base + bin * m_bs + t * m_ts
+  const long long m_bs = (a.flags & SETK_F_MASK_FT) ? a.T : 1;
+  const long long m_ts = (a.flags & SETK_F_MASK_FT) ? 1 : F;
+  const long long m_base = (long long)b * a.T * F;
   float* s_mask = sm.end();                        // [TT][2][MPITCH]
   constexpr int MPITCH = 260;
+  unsigned par = 0;                 // mbarrier phase parity per buffer (bit b)
+  bool async_cur = false;
+  if (t_begin < t_end) {
+    const int nt0 = imin(TT, t_end - t_begin);
+    async_cur = tile_bulk_ok(t_begin, nt0, hop, pad, nb, vec_ok);
+    if (async_cur) {
+      if (tid == 256) stage_tile_bulk<C, TT>(sm, 0, xb, a.N, t_begin, nt0, hop, pad);
+    } else {
+      stage_tile_scalar<C, TT>(sm, 0, xb, a.N, nb, t_begin, nt0, hop, pad);
+    }
+  }
   int buf = 0;
   for (int t0 = t_begin; t0 < t_end; t0 += TT, buf ^= 1) {
     const int nt = imin(TT, t_end - t0);
-    __syncthreads();   // tile i-1 fully consumed: sm.z and audio[buf^1] are free
+    __syncthreads();   // tile i-1 fully consumed: sm.z, s_mask and audio[buf^1] are free
     bool async_next = false;
-    if (t0 + TT < t_end)
-      async_next = stage_tile_begin<C, TT>(sm, buf ^ 1, xb, a.N, nb, t0 + TT,
-                                           imin(TT, t_end - t0 - TT), hop, pad, vec_ok);
-    if (cov_thread) {
+    const bool have_next = t0 + TT < t_end;
+    const int nt_next = imin(TT, t_end - t0 - TT);
+    if (have_next) async_next = tile_bulk_ok(t0 + TT, nt_next, hop, pad, nb, vec_ok);
+    if (have_next && !async_next)
+      stage_tile_scalar<C, TT>(sm, buf ^ 1, xb, a.N, nb, t0 + TT, nt_next, hop, pad);
+    if (warp == 8) {
+      if (have_next && async_next && lane == 0)
+        stage_tile_bulk<C, TT>(sm, buf ^ 1, xb, a.N, t0 + TT, nt_next, hop, pad);
+      const float* ms_t = a.mask_s + m_base + (long long)t0 * m_ts;
+      const float* mn_t = has_mn ? a.mask_n + m_base + (long long)t0 * m_ts : nullptr;
+      for (int j = 0; j < nt; ++j) {
 #pragma unroll
-      for (int j = 0; j < TT; ++j) {
-        if (j < nt) {
-          cp_async_f32(s_mask + (2 * j) * MPITCH + bin, mps + j * mstride);
-          if (has_mn) cp_async_f32(s_mask + (2 * j + 1) * MPITCH + bin, mpn + j * mstride);
+        for (int i = 0; i < 9; ++i) {
+          const int k = lane + 32 * i;
+          if (k < F) {
+            cp_async_f32(s_mask + (2 * j) * MPITCH + k, ms_t + k * m_bs + j * m_ts);
+            if (has_mn) cp_async_f32(s_mask + (2 * j + 1) * MPITCH + k, mn_t + k * m_bs + j * m_ts);
+          }
         }
       }
-      mps += TT * mstride;
-      if (has_mn) mpn += TT * mstride;
+      cp_async_wait_all();
+    } else {
+      if (async_cur) mbar_wait(&sm.bar[buf], (par >> buf) & 1u);
+      fft_tile<C, TT>(sm, buf, nt, hop, w1, amax);
     }
-    if (async_cur) {
-      mbar_wait(&sm.bar[buf], (par >> buf) & 1u);
-      par ^= 1u << buf;
-    }
-    if (warp < 8) fft_tile<C, TT>(sm, buf, nt, hop, w1, amax);
+    if (async_cur) par ^= 1u << buf;
     async_cur = async_next;
-    cp_async_wait_all();
     __syncthreads();
     // ---- covariance: thread per bin ----
     if (cov_thread) {

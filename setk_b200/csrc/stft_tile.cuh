@@ -81,6 +81,43 @@ __device__ __forceinline__ bool stage_tile_begin(const TileSmem<C, TT>& sm, int 
   return false;
 }
 
+// The same decision and the two delivery paths as separate pieces, for kernels
+// that give the bulk-copy issue to one producer warp.
+__device__ __forceinline__ bool tile_bulk_ok(int t0, int nt, int hop, int pad, int nb, bool vec_ok) {
+  const int i0 = t0 * hop - pad;
+  return vec_ok && i0 >= 0 && i0 + (nt - 1) * hop + kNfft <= nb;
+}
+template <int C, int TT>
+__device__ __forceinline__ void stage_tile_bulk(const TileSmem<C, TT>& sm, int buf,
+                                                const float* __restrict__ xb, int N, int t0, int nt,
+                                                int hop, int pad) {   // ONE thread
+  const int need = (nt - 1) * hop + kNfft;
+  const int i0 = t0 * hop - pad;
+  float* dst = sm.abuf(buf);
+  fence_proxy_async();
+  mbar_expect_tx(&sm.bar[buf], (unsigned)(C * need * sizeof(float)));
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    bulk_g2s(dst + c * sm.Lp, xb + (long long)c * N + i0, (unsigned)(need * sizeof(float)),
+             &sm.bar[buf]);
+}
+template <int C, int TT>
+__device__ __forceinline__ void stage_tile_scalar(const TileSmem<C, TT>& sm, int buf,
+                                                  const float* __restrict__ xb, int N, int nb, int t0,
+                                                  int nt, int hop, int pad) {   // ALL threads
+  const int p0 = t0 * hop;
+  const int need = (nt - 1) * hop + kNfft;
+  float* dst = sm.abuf(buf);
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float* src = xb + (long long)c * N;
+    for (int q = threadIdx.x; q < need; q += blockDim.x) {
+      const int i = pad ? reflect_index(p0 + q, pad, nb) : (p0 + q);
+      dst[c * sm.Lp + q] = src[i];
+    }
+  }
+}
+
 // Forward FFT of every (frame, channel) of the tile by warps 0..7, reading
 // audio[buf].  All threads of warps 0..7 must call it; hop must be even.
 // amax accumulates max |sample| of everything the tile reads.

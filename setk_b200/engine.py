@@ -106,6 +106,12 @@ class BeamformPipeline(object):
                                      n_samples=n_samples)
         return wave, status
 
+    def run_pcm16(self, audio_pcm16, mask_s, **kw):
+        """As run(), from PCM-16 samples (what the wav files hold): the int16/32768
+        conversion of read_wav (libs/utils.py:80-92) happens on the device."""
+        from .plan import pcm16_to_float
+        return self.run(pcm16_to_float(audio_pcm16), mask_s, **kw)
+
     @staticmethod
     def raise_for_status(status, keys=None):
         """Map per-utterance status words to numpy.linalg.LinAlgError (first failure)."""
@@ -115,3 +121,66 @@ class BeamformPipeline(object):
             i = int(bad[0])
             key = keys[i] if keys is not None else i
             raise np.linalg.LinAlgError(f"utterance {key}: {status_message(int(st[i]))}")
+
+
+class HostBatchStreamer(object):
+    """
+    Host-resident batches through the pipeline with copies and compute overlapped:
+    `slots` independent (pipeline, device buffers, CUDA stream) lanes; batch i runs
+    on lane i % slots as  H2D(audio, mask) -> run -> D2H(wave)  on that lane's
+    stream, so the upload of batch i+1, the kernels of batch i and the download of
+    batch i-1 proceed concurrently (PCIe is full duplex).  Host buffers must be
+    pinned for the copies to be asynchronous.  This is the B200 answer to the
+    reference's per-utterance soundfile reads.
+    """
+
+    def __init__(self, make_pipeline, batch, num_channels, num_samples, slots=2, pcm16=False,
+                 device=None):
+        self.device = torch.device(device if device is not None else "cuda")
+        self.slots = []
+        self.pcm16 = bool(pcm16)
+        for _ in range(slots):
+            pipe = make_pipeline()
+            T, F = pipe.plan.num_frames(num_samples), pipe.plan.num_bins
+            lane = {
+                "pipe": pipe,
+                "stream": torch.cuda.Stream(device=self.device),
+                "audio": torch.empty((batch, num_channels, num_samples),
+                                     dtype=torch.int16 if pcm16 else torch.float32,
+                                     device=self.device),
+                "mask": torch.empty((batch, T, F), dtype=torch.float32, device=self.device),
+                "status": None,
+            }
+            self.slots.append(lane)
+        self._i = 0
+
+    def submit(self, h_audio, h_mask, h_out, after=None):
+        """Enqueue one host batch; returns the lane used.  `after`: event to wait on first."""
+        lane = self.slots[self._i % len(self.slots)]
+        self._i += 1
+        with torch.cuda.stream(lane["stream"]):
+            if after is not None:
+                lane["stream"].wait_event(after)
+            lane["audio"].copy_(h_audio, non_blocking=True)
+            lane["mask"].copy_(h_mask, non_blocking=True)
+            if self.pcm16:
+                wave, status = lane["pipe"].run_pcm16(lane["audio"], lane["mask"])
+            else:
+                wave, status = lane["pipe"].run(lane["audio"], lane["mask"])
+            h_out.copy_(wave, non_blocking=True)
+            lane["status"] = status
+            lane["wave"] = wave           # keep alive until the D2H copy has run
+        return lane
+
+    def record_all(self):
+        """One end-of-work event per lane."""
+        evs = []
+        for lane in self.slots:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(lane["stream"])
+            evs.append(ev)
+        return evs
+
+    def synchronize(self):
+        for lane in self.slots:
+            lane["stream"].synchronize()
