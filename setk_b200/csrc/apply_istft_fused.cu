@@ -117,6 +117,7 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
   const float* xb = a.audio + (long long)b * C * a.N;
   const bool vec_ok = ((a.N & 3) == 0) && ((hop & 3) == 0) && ((pad & 3) == 0) &&
                       ((reinterpret_cast<uintptr_t>(a.audio) & 15) == 0);
+  __syncthreads();   // tables and mbarriers are initialised before the producer thread arms them
   const bool fast_hop = (hop == kM);               // 50 % overlap: every position has two frames
 
   // ---- inverse FFT of the frames of the pending tile (warps 8, 9) ----

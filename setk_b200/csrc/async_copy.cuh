@@ -19,17 +19,30 @@ struct alignas(8) MBar {
 
 #ifdef SETK_EMU
 
-__device__ inline void mbar_init(MBar* b, int) { __atomic_store_n(&b->v, 0ull, __ATOMIC_SEQ_CST); }
+// layout of the emulated barrier word: [63:48] magic, [47:32] phase, [31:0] pending bytes
+#define SETK_EMU_MBAR_MAGIC 0xBA55ull
+__device__ inline void mbar_check(const MBar* b) {
+  if ((__atomic_load_n(&b->v, __ATOMIC_SEQ_CST) >> 48) != SETK_EMU_MBAR_MAGIC)
+    emu::die("mbarrier used before mbar_init (missing __syncthreads after init?)");
+}
+__device__ inline void mbar_init(MBar* b, int) {
+  __atomic_store_n(&b->v, SETK_EMU_MBAR_MAGIC << 48, __ATOMIC_SEQ_CST);
+}
 __device__ inline void fence_proxy_async() {}
 __device__ inline void mbar_expect_tx(MBar* b, unsigned bytes) {
+  mbar_check(b);
   __atomic_fetch_add(&b->v, (unsigned long long)bytes, __ATOMIC_SEQ_CST);
 }
 __device__ inline void bulk_g2s(void* dst, const void* src, unsigned bytes, MBar* b) {
+  mbar_check(b);
+  if ((bytes & 15u) || (reinterpret_cast<uintptr_t>(dst) & 15u) || (reinterpret_cast<uintptr_t>(src) & 15u))
+    emu::die("cp.async.bulk needs 16-byte aligned addresses and size");
   memcpy(dst, src, bytes);
   unsigned long long after = __atomic_sub_fetch(&b->v, (unsigned long long)bytes, __ATOMIC_SEQ_CST);
   if ((after & 0xffffffffull) == 0) __atomic_fetch_add(&b->v, 1ull << 32, __ATOMIC_SEQ_CST);  // phase++
 }
 __device__ inline void mbar_wait(MBar* b, unsigned parity) {
+  mbar_check(b);
   while ((((__atomic_load_n(&b->v, __ATOMIC_SEQ_CST)) >> 32) & 1ull) == (unsigned long long)parity)
     std::this_thread::yield();
 }

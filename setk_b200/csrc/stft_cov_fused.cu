@@ -64,6 +64,7 @@ __global__ void __maxnreg__(112) stft_cov_kernel(StftCovArgs a) {
 
   for (int n = tid; n < kNfft; n += blockDim.x) sm.win[n] = 0.5f * a.window[n];
   if (tid == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); }
+  __syncthreads();   // barriers are initialised before the producer thread arms them
 
   // thread constants
   float w1s, w1c;

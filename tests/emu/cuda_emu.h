@@ -150,6 +150,7 @@ void launch(dim3 grid, dim3 block, size_t smem, bool serial, F&& body) {
           int n = nthr - 32 * w; ctx.warps[w].init(n > 32 ? 32 : n);
         }
         ctx.slots.assign(nthr, 0);
+        memset(dyn, 0xCD, smem);   // shared memory starts as garbage, like on the device
         auto run = [&](int tid) {
           g_ctx = &ctx; g_tid = tid;
           threadIdx = uint3{tid % block.x, (tid / block.x) % block.y, tid / (block.x * block.y)};
