@@ -49,6 +49,8 @@ __device__ inline void mbar_wait(MBar* b, unsigned parity) {
 // 4-byte cp.async (LDGSTS): global -> shared without a register round trip
 __device__ inline void cp_async_f32(float* dst, const float* src) { *dst = *src; }
 __device__ inline void cp_async_wait_all() {}
+__device__ inline void cp_async_commit() {}
+__device__ inline void cp_async_wait_group1() {}
 
 #else
 
@@ -95,6 +97,9 @@ __device__ __forceinline__ void cp_async_f32(float* dst, const float* src) {
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// all but the most recently committed group have landed
+__device__ __forceinline__ void cp_async_wait_group1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 #endif
 

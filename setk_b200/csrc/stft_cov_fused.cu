@@ -96,12 +96,29 @@ __global__ void __maxnreg__(112) stft_cov_kernel(StftCovArgs a) {
   const long long m_bs = (a.flags & SETK_F_MASK_FT) ? a.T : 1;
   const long long m_ts = (a.flags & SETK_F_MASK_FT) ? 1 : F;
   const long long m_base = (long long)b * a.T * F;
-  float* s_mask = sm.end();                        // [TT][2][MPITCH]
+  float* s_mask = sm.end();                        // [2 buffers][TT][2][MPITCH]
   constexpr int MPITCH = 260;
+  constexpr int MBUF = TT * 2 * MPITCH;
+  auto issue_masks = [&](int mt0, int mnt, int mbuf) {      // warp 8 only
+    const float* ms_t = a.mask_s + m_base + (long long)mt0 * m_ts;
+    const float* mn_t = has_mn ? a.mask_n + m_base + (long long)mt0 * m_ts : nullptr;
+    float* dst = s_mask + mbuf * MBUF;
+    for (int j = 0; j < mnt; ++j) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const int k = lane + 32 * i;
+        if (k < F) {
+          cp_async_f32(dst + (2 * j) * MPITCH + k, ms_t + k * m_bs + j * m_ts);
+          if (has_mn) cp_async_f32(dst + (2 * j + 1) * MPITCH + k, mn_t + k * m_bs + j * m_ts);
+        }
+      }
+    }
+  };
   unsigned par = 0;                 // mbarrier phase parity per buffer (bit b)
   bool async_cur = false;
   if (t_begin < t_end) {
     const int nt0 = imin(TT, t_end - t_begin);
+    if (warp == 8) { issue_masks(t_begin, nt0, 0); cp_async_commit(); }
     async_cur = tile_bulk_ok(t_begin, nt0, hop, pad, nb, vec_ok);
     if (async_cur) {
       if (tid == 256) stage_tile_bulk<C, TT>(sm, 0, xb, a.N, t_begin, nt0, hop, pad);
@@ -122,19 +139,11 @@ __global__ void __maxnreg__(112) stft_cov_kernel(StftCovArgs a) {
     if (warp == 8) {
       if (have_next && async_next && lane == 0)
         stage_tile_bulk<C, TT>(sm, buf ^ 1, xb, a.N, t0 + TT, nt_next, hop, pad);
-      const float* ms_t = a.mask_s + m_base + (long long)t0 * m_ts;
-      const float* mn_t = has_mn ? a.mask_n + m_base + (long long)t0 * m_ts : nullptr;
-      for (int j = 0; j < nt; ++j) {
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-          const int k = lane + 32 * i;
-          if (k < F) {
-            cp_async_f32(s_mask + (2 * j) * MPITCH + k, ms_t + k * m_bs + j * m_ts);
-            if (has_mn) cp_async_f32(s_mask + (2 * j + 1) * MPITCH + k, mn_t + k * m_bs + j * m_ts);
-          }
-        }
-      }
-      cp_async_wait_all();
+      // masks of the NEXT tile (a whole tile of latency hiding); this tile's were
+      // requested one iteration ago
+      if (have_next) issue_masks(t0 + TT, nt_next, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait_group1();
     } else {
       if (async_cur) mbar_wait(&sm.bar[buf], (par >> buf) & 1u);
       fft_tile<C, TT>(sm, buf, nt, hop, w1, amax);
@@ -157,9 +166,10 @@ __global__ void __maxnreg__(112) stft_cov_kernel(StftCovArgs a) {
 #pragma unroll
             for (int c = 0; c < C; ++c) x[c].y = 0.f;               // DC / Nyquist are real
           }
-          const float m_raw = s_mask[(2 * j) * MPITCH + bin];
+          const float* mrow = s_mask + buf * MBUF + (2 * j) * MPITCH + bin;
+          const float m_raw = mrow[0];
           const float m_s = clip ? fminf(m_raw, 1.0f) : m_raw;
-          const float m_n = has_mn ? s_mask[(2 * j + 1) * MPITCH + bin] : 1.0f - m_s;
+          const float m_n = has_mn ? mrow[MPITCH] : 1.0f - m_s;
           sum_s += m_s; sum_n += m_n;
           int o = C;
 #pragma unroll
@@ -245,7 +255,7 @@ cudaError_t run_bits_to_float(const unsigned* bits, int n, float* out, void* str
 
 template <int C, int TT>
 static size_t stft_cov_smem_bytes(int hop) {
-  return sizeof(float) * (TileSmem<C, TT>::floats(hop) + (size_t)TT * 2 * 260);
+  return sizeof(float) * (TileSmem<C, TT>::floats(hop) + 2 * (size_t)TT * 2 * 260);
 }
 
 template <int C, int TT>
