@@ -103,6 +103,27 @@ __global__ void __maxnreg__(112) stft_cov_kernel(StftCovArgs a) {
     const float* ms_t = a.mask_s + m_base + (long long)mt0 * m_ts;
     const float* mn_t = has_mn ? a.mask_n + m_base + (long long)mt0 * m_ts : nullptr;
     float* dst = s_mask + mbuf * MBUF;
+    if (m_bs == 1) {
+      // (T, F) layout, the reference's: rows of F contiguous floats, every offset a constant
+      const float* ps = ms_t + lane;
+      const float* pn = has_mn ? mn_t + lane : nullptr;
+      float* d = dst + lane;
+#pragma unroll
+      for (int j = 0; j < TT; ++j) {
+        if (j < mnt) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cp_async_f32(d + (2 * j) * MPITCH + 32 * i, ps + j * F + 32 * i);
+          if (lane == 0) cp_async_f32(d + (2 * j) * MPITCH + 256, ps + j * F + 256);
+          if (has_mn) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              cp_async_f32(d + (2 * j + 1) * MPITCH + 32 * i, pn + j * F + 32 * i);
+            if (lane == 0) cp_async_f32(d + (2 * j + 1) * MPITCH + 256, pn + j * F + 256);
+          }
+        }
+      }
+      return;
+    }
     for (int j = 0; j < mnt; ++j) {
 #pragma unroll
       for (int i = 0; i < 9; ++i) {
