@@ -117,7 +117,6 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
   const float* xb = a.audio + (long long)b * C * a.N;
   const bool vec_ok = ((a.N & 3) == 0) && ((hop & 3) == 0) && ((pad & 3) == 0) &&
                       ((reinterpret_cast<uintptr_t>(a.audio) & 15) == 0);
-  __syncthreads();   // tables and mbarriers are initialised before the producer thread arms them
   const bool fast_hop = (hop == kM);               // 50 % overlap: every position has two frames
 
   // ---- inverse FFT of the frames of the pending tile (warps 8, 9) ----
@@ -214,14 +213,7 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
   unsigned par = 0;
   float amax_unused = 0.f;
   bool async_cur = false;
-  if (t0 < t_end) {
-    async_cur = tile_bulk_ok(t0, nt, hop, pad, nb, vec_ok);
-    if (async_cur) {
-      if (tid == 256) stage_tile_bulk<C, TT>(sm, 0, xb, a.N, t0, nt, hop, pad);
-    } else {
-      stage_tile_scalar<C, TT>(sm, 0, xb, a.N, nb, t0, nt, hop, pad);
-    }
-  }
+  if (t0 < t_end) async_cur = stage_tile_begin<C, TT>(sm, 0, xb, a.N, nb, t0, nt, hop, pad, vec_ok);
   int buf = 0;
   int prev_t0 = 0, prev_nt = 0;                    // tile whose Zi is waiting for its inverse FFT
   while (t0 < t_end) {
@@ -229,22 +221,18 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
     const int nt_next = imin(TT, t_end - t_next);
     __syncthreads();   // phase B of the previous tile is complete
     bool async_next = false;
-    if (t_next < t_end) {
-      async_next = tile_bulk_ok(t_next, nt_next, hop, pad, nb, vec_ok);
-      if (async_next) {
-        if (tid == 256) stage_tile_bulk<C, TT>(sm, buf ^ 1, xb, a.N, t_next, nt_next, hop, pad);
-      } else {
-        stage_tile_scalar<C, TT>(sm, buf ^ 1, xb, a.N, nb, t_next, nt_next, hop, pad);
-      }
+    if (t_next < t_end)
+      async_next = stage_tile_begin<C, TT>(sm, buf ^ 1, xb, a.N, nb, t_next, nt_next, hop, pad, vec_ok);
+    if (async_cur) {
+      mbar_wait(&sm.bar[buf], (par >> buf) & 1u);
+      par ^= 1u << buf;
     }
     // ---- phase A: forward FFT of this tile || inverse FFT of the previous one ----
     if (warp < 8) {
-      if (async_cur) mbar_wait(&sm.bar[buf], (par >> buf) & 1u);
       fft_tile<C, TT>(sm, buf, nt, hop, w1, amax_unused);
     } else if (prev_nt > 0) {
       ifft_tile(prev_nt);
     }
-    if (async_cur) par ^= 1u << buf;
     __syncthreads();
     // ---- phase B: apply + inverse split of this tile ----
     for (int it = tid; it < nt * NPAIR; it += blockDim.x) {

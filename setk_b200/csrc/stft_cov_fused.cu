@@ -64,7 +64,6 @@ __global__ void __maxnreg__(112) stft_cov_kernel(StftCovArgs a) {
 
   for (int n = tid; n < kNfft; n += blockDim.x) sm.win[n] = 0.5f * a.window[n];
   if (tid == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); }
-  __syncthreads();   // barriers are initialised before the producer thread arms them
 
   // thread constants
   float w1s, w1c;
@@ -86,91 +85,51 @@ __global__ void __maxnreg__(112) stft_cov_kernel(StftCovArgs a) {
                       ((reinterpret_cast<uintptr_t>(a.audio) & 15) == 0);
 
   // software pipeline: tile i+1 streams into the other audio buffer while tile i
-  // is transformed and accumulated.  Warp 8 (which has no FFT job) is the
-  // producer: it issues the TMA bulk copies of the next tile and the 4-byte
-  // cp.async of this tile's mask rows (first touched after the FFT phase), so
-  // the eight FFT warps carry no staging instructions at all.
-  const bool has_mn = a.mask_n != nullptr;
-  const bool clip = (a.flags & SETK_F_CLIP_MASK) != 0;
-  // element (bin, t) of a mask: base + bin * m_bs + t * m_ts
-  const long long m_bs = (a.flags & SETK_F_MASK_FT) ? a.T : 1;
-  const long long m_ts = (a.flags & SETK_F_MASK_FT) ? 1 : F;
-  const long long m_base = (long long)b * a.T * F;
-  float* s_mask = sm.end();                        // [2 buffers][TT][2][MPITCH]
-  constexpr int MPITCH = 260;
-  constexpr int MBUF = TT * 2 * MPITCH;
-  auto issue_masks = [&](int mt0, int mnt, int mbuf) {      // warp 8 only
-    const float* ms_t = a.mask_s + m_base + (long long)mt0 * m_ts;
-    const float* mn_t = has_mn ? a.mask_n + m_base + (long long)mt0 * m_ts : nullptr;
-    float* dst = s_mask + mbuf * MBUF;
-    if (m_bs == 1) {
-      // (T, F) layout, the reference's: rows of F contiguous floats, every offset a constant
-      const float* ps = ms_t + lane;
-      const float* pn = has_mn ? mn_t + lane : nullptr;
-      float* d = dst + lane;
-#pragma unroll
-      for (int j = 0; j < TT; ++j) {
-        if (j < mnt) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) cp_async_f32(d + (2 * j) * MPITCH + 32 * i, ps + j * F + 32 * i);
-          if (lane == 0) cp_async_f32(d + (2 * j) * MPITCH + 256, ps + j * F + 256);
-          if (has_mn) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              cp_async_f32(d + (2 * j + 1) * MPITCH + 32 * i, pn + j * F + 32 * i);
-            if (lane == 0) cp_async_f32(d + (2 * j + 1) * MPITCH + 256, pn + j * F + 256);
-          }
-        }
-      }
-      return;
-    }
-    for (int j = 0; j < mnt; ++j) {
-#pragma unroll
-      for (int i = 0; i < 9; ++i) {
-        const int k = lane + 32 * i;
-        if (k < F) {
-          cp_async_f32(dst + (2 * j) * MPITCH + k, ms_t + k * m_bs + j * m_ts);
-          if (has_mn) cp_async_f32(dst + (2 * j + 1) * MPITCH + k, mn_t + k * m_bs + j * m_ts);
-        }
-      }
-    }
-  };
+  // is transformed and accumulated
   unsigned par = 0;                 // mbarrier phase parity per buffer (bit b)
   bool async_cur = false;
-  if (t_begin < t_end) {
-    const int nt0 = imin(TT, t_end - t_begin);
-    if (warp == 8) { issue_masks(t_begin, nt0, 0); cp_async_commit(); }
-    async_cur = tile_bulk_ok(t_begin, nt0, hop, pad, nb, vec_ok);
-    if (async_cur) {
-      if (tid == 256) stage_tile_bulk<C, TT>(sm, 0, xb, a.N, t_begin, nt0, hop, pad);
-    } else {
-      stage_tile_scalar<C, TT>(sm, 0, xb, a.N, nb, t_begin, nt0, hop, pad);
-    }
-  }
+  if (t_begin < t_end)
+    async_cur = stage_tile_begin<C, TT>(sm, 0, xb, a.N, nb, t_begin, imin(TT, t_end - t_begin), hop,
+                                        pad, vec_ok);
+  // mask rows of this thread's bin: one frame per step of `mstride`.  They are
+  // fetched with 4-byte cp.async straight into shared memory at the top of the
+  // tile and first touched after the FFT phase, so their latency costs neither
+  // registers nor issue slots
+  const bool has_mn = a.mask_n != nullptr;
+  const bool clip = (a.flags & SETK_F_CLIP_MASK) != 0;
+  const long long mstride = (a.flags & SETK_F_MASK_FT) ? 1 : F;
+  const long long mbase = (a.flags & SETK_F_MASK_FT) ? ((long long)b * F + (cov_thread ? bin : 0)) * a.T
+                                                     : (long long)b * a.T * F + (cov_thread ? bin : 0);
+  const float* mps = a.mask_s + mbase + (long long)t_begin * mstride;
+  const float* mpn = has_mn ? a.mask_n + mbase + (long long)t_begin * mstride : nullptr;
+  float* s_mask = sm.end();                        // [TT][2][MPITCH]
+  constexpr int MPITCH = 260;
   int buf = 0;
   for (int t0 = t_begin; t0 < t_end; t0 += TT, buf ^= 1) {
     const int nt = imin(TT, t_end - t0);
-    __syncthreads();   // tile i-1 fully consumed: sm.z, s_mask and audio[buf^1] are free
+    __syncthreads();   // tile i-1 fully consumed: sm.z and audio[buf^1] are free
     bool async_next = false;
-    const bool have_next = t0 + TT < t_end;
-    const int nt_next = imin(TT, t_end - t0 - TT);
-    if (have_next) async_next = tile_bulk_ok(t0 + TT, nt_next, hop, pad, nb, vec_ok);
-    if (have_next && !async_next)
-      stage_tile_scalar<C, TT>(sm, buf ^ 1, xb, a.N, nb, t0 + TT, nt_next, hop, pad);
-    if (warp == 8) {
-      if (have_next && async_next && lane == 0)
-        stage_tile_bulk<C, TT>(sm, buf ^ 1, xb, a.N, t0 + TT, nt_next, hop, pad);
-      // masks of the NEXT tile (a whole tile of latency hiding); this tile's were
-      // requested one iteration ago
-      if (have_next) issue_masks(t0 + TT, nt_next, buf ^ 1);
-      cp_async_commit();
-      cp_async_wait_group1();
-    } else {
-      if (async_cur) mbar_wait(&sm.bar[buf], (par >> buf) & 1u);
-      fft_tile<C, TT>(sm, buf, nt, hop, w1, amax);
+    if (t0 + TT < t_end)
+      async_next = stage_tile_begin<C, TT>(sm, buf ^ 1, xb, a.N, nb, t0 + TT,
+                                           imin(TT, t_end - t0 - TT), hop, pad, vec_ok);
+    if (cov_thread) {
+#pragma unroll
+      for (int j = 0; j < TT; ++j) {
+        if (j < nt) {
+          cp_async_f32(s_mask + (2 * j) * MPITCH + bin, mps + j * mstride);
+          if (has_mn) cp_async_f32(s_mask + (2 * j + 1) * MPITCH + bin, mpn + j * mstride);
+        }
+      }
+      mps += TT * mstride;
+      if (has_mn) mpn += TT * mstride;
     }
-    if (async_cur) par ^= 1u << buf;
+    if (async_cur) {
+      mbar_wait(&sm.bar[buf], (par >> buf) & 1u);
+      par ^= 1u << buf;
+    }
+    if (warp < 8) fft_tile<C, TT>(sm, buf, nt, hop, w1, amax);
     async_cur = async_next;
+    cp_async_wait_all();
     __syncthreads();
     // ---- covariance: thread per bin ----
     if (cov_thread) {
@@ -187,10 +146,9 @@ __global__ void __maxnreg__(112) stft_cov_kernel(StftCovArgs a) {
 #pragma unroll
             for (int c = 0; c < C; ++c) x[c].y = 0.f;               // DC / Nyquist are real
           }
-          const float* mrow = s_mask + buf * MBUF + (2 * j) * MPITCH + bin;
-          const float m_raw = mrow[0];
+          const float m_raw = s_mask[(2 * j) * MPITCH + bin];
           const float m_s = clip ? fminf(m_raw, 1.0f) : m_raw;
-          const float m_n = has_mn ? mrow[MPITCH] : 1.0f - m_s;
+          const float m_n = has_mn ? s_mask[(2 * j + 1) * MPITCH + bin] : 1.0f - m_s;
           sum_s += m_s; sum_n += m_n;
           int o = C;
 #pragma unroll
@@ -276,7 +234,7 @@ cudaError_t run_bits_to_float(const unsigned* bits, int n, float* out, void* str
 
 template <int C, int TT>
 static size_t stft_cov_smem_bytes(int hop) {
-  return sizeof(float) * (TileSmem<C, TT>::floats(hop) + 2 * (size_t)TT * 2 * 260);
+  return sizeof(float) * (TileSmem<C, TT>::floats(hop) + (size_t)TT * 2 * 260);
 }
 
 template <int C, int TT>
