@@ -203,6 +203,15 @@ __global__ void peak_scale_kernel(float* __restrict__ wave, int n_out, const flo
   if (nm == 0.f) return;
   const float den = __uint_as_float(peak[b]) + SETK_EPS32;
   float* y = wave + (long long)b * n_out;
+  if ((n_out & 3) == 0 && (reinterpret_cast<uintptr_t>(wave) & 15) == 0) {
+    float4* y4 = reinterpret_cast<float4*>(y);
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < (n_out >> 2); q += gridDim.x * blockDim.x) {
+      float4 v = y4[q];
+      v.x = (v.x * nm) / den; v.y = (v.y * nm) / den; v.z = (v.z * nm) / den; v.w = (v.w * nm) / den;
+      y4[q] = v;
+    }
+    return;
+  }
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_out; q += gridDim.x * blockDim.x)
     y[q] = (y[q] * nm) / den;
 }
@@ -239,6 +248,22 @@ __global__ void pcm16_to_float_kernel(const int16_t* __restrict__ pcm, long long
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   wave[i] = (float)pcm[i] * (1.0f / 32768.0f);
+}
+
+// 8 samples per thread: one 16-byte load, two 16-byte stores
+__global__ void pcm16_to_float_vec_kernel(const int4* __restrict__ pcm8, long long n8,
+                                          float4* __restrict__ wave4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const int4 p = pcm8[i];
+  const float s = 1.0f / 32768.0f;
+  float4 a, b;
+  a.x = (float)(short)(p.x & 0xffff) * s; a.y = (float)(short)(p.x >> 16) * s;
+  a.z = (float)(short)(p.y & 0xffff) * s; a.w = (float)(short)(p.y >> 16) * s;
+  b.x = (float)(short)(p.z & 0xffff) * s; b.y = (float)(short)(p.z >> 16) * s;
+  b.z = (float)(short)(p.w & 0xffff) * s; b.w = (float)(short)(p.w >> 16) * s;
+  wave4[2 * i] = a;
+  wave4[2 * i + 1] = b;
 }
 
 // ---------------------------------------------------------------------------
@@ -301,6 +326,12 @@ cudaError_t run_float_to_pcm16(const float* wave, long long n, int16_t* pcm, voi
                 wave, n, pcm);
 }
 cudaError_t run_pcm16_to_float(const int16_t* pcm, long long n, float* wave, void* stream) {
+  if ((n & 7) == 0 && (reinterpret_cast<uintptr_t>(pcm) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(wave) & 15) == 0) {
+    const long long n8 = n >> 3;
+    return launch(pcm16_to_float_vec_kernel, dim3((unsigned)((n8 + 255) / 256)), dim3(256), 0, stream,
+                  true, reinterpret_cast<const int4*>(pcm), n8, reinterpret_cast<float4*>(wave));
+  }
   return launch(pcm16_to_float_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, true,
                 pcm, n, wave);
 }

@@ -284,3 +284,15 @@ def mvdr_end_to_end(device, x, mask, kind="mvdr", frame_len=512, hop=256, center
         yo = so.inverse_stft(bo.beamform(w_al, So), norm=float(np.max(np.abs(x[b]))), **kw)
         worst = max(worst, bo.rel_inf(y[b], yo))
     return worst
+
+
+def check_pcm(device, rng):
+    """read_wav / write_wav sample conversions: bit-exact integer work."""
+    for n in (4096, 4099):
+        pcm = rng.integers(-32768, 32768, size=n, dtype=np.int16)
+        w = P.pcm16_to_float(torch.from_numpy(pcm).to(device)).cpu().numpy()
+        assert np.array_equal(w, so.float_from_pcm16(pcm))
+        y = (rng.standard_normal(n) * 0.5).astype(np.float32)
+        y[:4] = [1.5, -1.5, 0.99999, -1.0]
+        q = P.float_to_pcm16(torch.from_numpy(y).to(device)).cpu().numpy()
+        assert np.array_equal(q, so.pcm16_from_float(y))

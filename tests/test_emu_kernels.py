@@ -118,3 +118,7 @@ def test_argument_errors(emu):
         pl.stft_cov(torch.zeros(1, 4, 2000), torch.zeros(1, 3, 257))    # wrong mask shape
     with pytest.raises(ValueError):
         pl.num_frames(100)
+
+
+def test_pcm_conversions(emu):
+    pc.check_pcm(emu, np.random.default_rng(40))

@@ -228,3 +228,7 @@ def test_golden_doc_vectors_gevd_sign_fit(cuda):
     d = np.abs(out - g["shipped/gevd"].astype(np.int64))
     assert d.max() <= 2, d.max()
     assert np.mean(d > 0) <= 0.05
+
+
+def test_pcm_conversions(cuda):
+    pc.check_pcm(cuda, np.random.default_rng(40))
