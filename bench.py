@@ -62,6 +62,23 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(batch):
+    """
+    dram__bytes_read + dram__bytes_write of the dominant kernel per launch, from the
+    committed `ncu --set full` capture (profiles/r1_traffic.json); only valid for the
+    batch it was captured on, else null.
+    """
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        with open(path) as fh:
+            d = json.load(fh)
+        if batch * algorithmic_bytes_stft_cov() == d["algorithmic_bytes_per_launch"]:
+            return d["traffic_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -336,7 +353,7 @@ def gpu_arm(args):
                              f"exceed the 126 MB L2 (no flush needed)",
                        "unique_utterances_per_gpu": uniq},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": measured_traffic(B), "peak_source": peak_src,
                          "kernel": "setk_stft_cov (stft_cov_kernel<4,4> + finalize)",
                          "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms},
             "cpu_baseline": cpu_base,

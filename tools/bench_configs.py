@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""
+tools/bench_configs.py -- device-resident throughput of the other BASELINE.json
+configurations (3: 8-ch GEV / 1024-pt; 4: 6-ch MVDR; 5: {4, 8, 16}-ch sweep).
+Informational (the contract line is bench.py's, config 2); prints one JSON
+object per configuration with the route each stage took.
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from setk_b200 import synth  # noqa: E402
+from setk_b200.engine import BeamformPipeline  # noqa: E402
+
+
+def run(name, C, frame_len, beamformer, B, N=160000, steps=5):
+    dev = torch.device("cuda:0")
+    pipe = BeamformPipeline(C, beamformer, frame_len=frame_len, frame_hop=256, max_batch=B,
+                            max_samples=N, device=dev)
+    a, m = synth.make_batch(min(B, 4), C, N, device=dev, frame_len=frame_len, n_fft=pipe.plan.n_fft)
+    reps = (B + a.shape[0] - 1) // a.shape[0]
+    audio = a.repeat(reps, 1, 1)[:B].contiguous()
+    mask = m.repeat(reps, 1, 1)[:B].contiguous()
+    wave, status = pipe.run(audio, mask)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        wave, status = pipe.run(audio, mask)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    fused = C <= 4 and pipe.plan.n_fft == 512
+    print(json.dumps({"config": name, "channels": C, "n_fft": pipe.plan.n_fft, "beamformer": beamformer,
+                      "batch": B, "ms_per_batch": ms, "utts_per_s": B / ms * 1e3,
+                      "route": "fused" if fused else "generic (explicit STFT in HBM)",
+                      "status_failures": int((status != 0).sum())}), flush=True)
+    del pipe, audio, mask, wave
+    torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    run("cfg2 4ch MVDR 512", 4, 512, "mvdr", 256)
+    run("cfg4 6ch MVDR 512", 6, 512, "mvdr", 64)
+    run("cfg5 8ch MVDR 512", 8, 512, "mvdr", 64)
+    run("cfg5 16ch MVDR 512", 16, 512, "mvdr", 32)
+    run("cfg3 8ch GEV 1024", 8, 1024, "gevd", 64)
