@@ -32,6 +32,15 @@ bool apply_istft_fused_supported(const Geometry&);
 cudaError_t run_apply_istft_fused(setk_plan*, const float*, const int*, int, int, int, const void*, int,
                                   const float*, int, int, float*, unsigned*, void*);
 
+bool stft_spill_supported(const Geometry&);
+size_t stft_spill_bytes(const Geometry&, int, int);
+size_t cov_spill_partial_bytes(const Geometry&, int, int);
+cudaError_t run_stft_spill(setk_plan*, const float*, const int*, int, int, int, int, float2*, unsigned*,
+                           void*);
+cudaError_t run_cov_spill(setk_plan*, const float2*, const float*, const float*, unsigned, const int*,
+                          int, int, int, int, float*, float2*, float2*, void*);
+cudaError_t run_bits_to_float(const unsigned*, int, float*, void*);
+
 struct WeightsArgs;
 cudaError_t weights_run(int kind, double beta, int ref_channel, int rank1, int ban, const void* Rs,
                         const void* Rn, const void* Ry, int r_dtype, int B, int F, int C, void* w,
@@ -216,6 +225,23 @@ int setk_stft_cov(setk_plan_t* pl, const float* audio, const int32_t* n_samples,
                            pl->d_partials, maxabs_bits, static_cast<float2*>(Rs),
                            static_cast<float2*>(Rn), maxabs, stream);
     return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_stft_cov");
+  }
+  if (stft_spill_supported(g)) {
+    // many-channel route (C > 4 at n_fft = 512): fast STFT into a bin-major
+    // workspace, then a streaming covariance kernel (stft_spill.cu)
+    const int groups = (g.C + 3) / 4;
+    const int chunks_a = stft_cov_pick_chunks(pl, B * groups, T);
+    const int chunks_b = stft_cov_pick_chunks(pl, B * g.C, T);
+    e = ensure(&pl->d_stft_ws, &pl->stft_ws_bytes, stft_spill_bytes(g, B, T));
+    if (e == cudaSuccess)
+      e = ensure(&pl->d_partials, &pl->partials_bytes, cov_spill_partial_bytes(g, B, chunks_b));
+    if (e != cudaSuccess) return cuda_fail(e, "setk_stft_cov(workspace)");
+    e = run_stft_spill(pl, audio, n_samples, B, N, T, chunks_a, pl->d_stft_ws, maxabs_bits, stream);
+    if (e == cudaSuccess)
+      e = run_cov_spill(pl, pl->d_stft_ws, mask_s, mask_n, flags, n_samples, B, N, T, chunks_b,
+                        pl->d_partials, static_cast<float2*>(Rs), static_cast<float2*>(Rn), stream);
+    if (e == cudaSuccess && maxabs) e = run_bits_to_float(maxabs_bits, B, maxabs, stream);
+    return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_stft_cov(spill)");
   }
   // shape-generic route: explicit STFT in workspace, then two covariance passes
   const size_t want = sizeof(float2) * (size_t)B * g.C * g.F * T;

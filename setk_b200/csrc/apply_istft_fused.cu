@@ -44,6 +44,8 @@ struct ApplyIstftArgs {
   int n_out;
   float* wave;          // [B][n_out]
   unsigned* peak;       // [B] or null
+  int c0, c_total;      // this launch handles channels [c0, c0 + C) of c_total
+  int accumulate;       // != 0: wave += this block's contribution (iSTFT is linear)
 };
 
 constexpr int kApplyThreads = 320;
@@ -99,7 +101,7 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
   for (int k = tid; k < NPAIR; k += blockDim.x) s_tw[k] = split_twiddle(k);
   for (int e = tid; e < F * C; e += blockDim.x) {
     const int k = e / C, c = e - k * C;
-    const long long wi = (long long)b * F * C + e;
+    const long long wi = ((long long)b * F + k) * a.c_total + a.c0 + c;
     float2 v;
     if (a.w_dtype == SETK_C128) {
       const double* p = reinterpret_cast<const double*>(a.w) + 2 * wi;
@@ -114,7 +116,7 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
   float w1s, w1c;
   sincospif((float)lane16 / 128.0f, &w1s, &w1c);
   const float2 w1 = make_float2(w1c, -w1s);
-  const float* xb = a.audio + (long long)b * C * a.N;
+  const float* xb = a.audio + ((long long)b * a.c_total + a.c0) * a.N;
   const bool vec_ok = ((a.N & 3) == 0) && ((hop & 3) == 0) && ((pad & 3) == 0) &&
                       ((reinterpret_cast<uintptr_t>(a.audio) & 15) == 0);
   const bool fast_hop = (hop == kM);               // 50 % overlap: every position has two frames
@@ -165,6 +167,7 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
               const float wss = (t < T_used ? s_wsq[r] : 0.f) + (t >= 1 ? s_wsq[kM + r] : 0.f);
               if (wss > SETK_TINY32) val /= wss;
             }
+            if (a.accumulate) val += yb[q];
             yb[q] = val;
             peak = fmaxf(peak, fabsf(val));
           }
@@ -193,6 +196,7 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
             const int q = p - pad;
             if (p >= own_begin && q >= 0 && q < a.n_out) {
               if (wss > SETK_TINY32) val /= wss;
+              if (a.accumulate) val += yb[q];
               yb[q] = val;
               peak = fmaxf(peak, fabsf(val));
             }
@@ -288,7 +292,7 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
   }
 
   // zero-fill what no frame reaches (fix_length padding / too-short input)
-  if (chunk == a.n_chunks - 1) {
+  if (chunk == a.n_chunks - 1 && !a.accumulate) {
     const int q0 = imax(expected - pad, 0);
     for (int q = q0 + tid; q < a.n_out; q += blockDim.x) yb[q] = 0.f;
   }
@@ -323,7 +327,7 @@ static cudaError_t run_apply_istft_t(const ApplyIstftArgs& a, int B, void* strea
 
 bool apply_istft_fused_supported(const Geometry& g) {
   if (g.n_fft != 512) return false;
-  if (g.C < 1 || g.C > 4) return false;
+  if (g.C < 1 || g.C > SETK_MAX_CHANNELS) return false;   // C > 4: channel blocks of <= 4, accumulated
   if (g.hop < 128 || g.hop > 512 || (g.hop & 1)) return false;   // halo <= TT frames
   return true;
 }
@@ -344,14 +348,24 @@ cudaError_t run_apply_istft_fused(setk_plan* pl, const float* audio, const int* 
   a.wsq = pl->d_wsq;
   a.n_out = n_out;
   a.wave = wave;
-  a.peak = peak;
-  switch (pl->geo.C) {
-    case 1: return run_apply_istft_t<1, TT>(a, B, stream);
-    case 2: return run_apply_istft_t<2, TT>(a, B, stream);
-    case 3: return run_apply_istft_t<3, TT>(a, B, stream);
-    case 4: return run_apply_istft_t<4, TT>(a, B, stream);
-    default: return cudaErrorInvalidValue;
+  // channel blocks of <= 4: the first block writes, the others accumulate; the
+  // peak is taken by the last block (it sees the complete sums)
+  const int Ctot = pl->geo.C;
+  a.c_total = Ctot;
+  cudaError_t e = cudaSuccess;
+  for (int c0 = 0; c0 < Ctot && e == cudaSuccess; c0 += 4) {
+    const int cb = Ctot - c0 < 4 ? Ctot - c0 : 4;
+    a.c0 = c0;
+    a.accumulate = c0 > 0;
+    a.peak = (c0 + cb >= Ctot) ? peak : nullptr;
+    switch (cb) {
+      case 1: e = run_apply_istft_t<1, TT>(a, B, stream); break;
+      case 2: e = run_apply_istft_t<2, TT>(a, B, stream); break;
+      case 3: e = run_apply_istft_t<3, TT>(a, B, stream); break;
+      default: e = run_apply_istft_t<4, TT>(a, B, stream); break;
+    }
   }
+  return e;
 }
 
 }  // namespace setk

@@ -57,6 +57,25 @@ def test_stft_cov_generic_route(emu):
                       with_mask_n=True)
 
 
+@pytest.mark.parametrize("C", [5, 6, 8, 11])
+def test_many_channel_routes(emu, C):
+    # C > 4 at n_fft = 512: STFT spill + streaming covariance; apply+iSTFT in
+    # accumulated channel blocks of <= 4
+    rng = np.random.default_rng(50 + C)
+    pc.check_stft_cov(emu, rng, 2, C, 2300, 512, 256, True, "hann", with_mask_n=(C == 6),
+                      clip=(C == 8))
+    pc.check_apply_istft(emu, rng, 2, C, 2300, 512, 256, True, "hann", post_mask=(C == 6))
+
+
+def test_many_channel_ragged_and_nocenter(emu):
+    rng = np.random.default_rng(60)
+    ns = torch.tensor([3000, 1701], dtype=torch.int32)
+    pc.check_stft_cov(emu, rng, 2, 6, 3000, n_samples=ns)
+    pc.check_apply_istft(emu, rng, 2, 6, 3000, n_samples=ns)
+    pc.check_stft_cov(emu, rng, 1, 7, 2500, 512, 256, False, "hamming")
+    pc.check_apply_istft(emu, rng, 1, 7, 2500, 512, 128, False, "hamming")
+
+
 def test_cov_generic(emu):
     pc.check_cov_generic(emu, np.random.default_rng(7), 2, 6, 9, 70)
 

@@ -70,6 +70,25 @@ def test_stft_cov_generic_route(cuda):
     pc.check_stft_cov(cuda, np.random.default_rng(7), 1, 16, 8000, 512, 256, True, "hann")
 
 
+@pytest.mark.parametrize("C", [5, 6, 8, 16])
+def test_many_channel_routes(cuda, C):
+    """C > 4 at n_fft = 512 (configs 4 and 5): STFT spill + streaming covariance,
+    apply+iSTFT in accumulated channel blocks."""
+    rng = np.random.default_rng(50 + C)
+    pc.check_stft_cov(cuda, rng, 3, C, 24000, 512, 256, True, "hann", with_mask_n=(C == 6),
+                      clip=(C == 8))
+    pc.check_apply_istft(cuda, rng, 3, C, 24000, 512, 256, True, "hann", post_mask=(C == 6))
+
+
+def test_many_channel_ragged_and_nocenter(cuda):
+    rng = np.random.default_rng(60)
+    ns = torch.tensor([30000, 17001, 900], dtype=torch.int32)
+    pc.check_stft_cov(cuda, rng, 3, 6, 30000, n_samples=ns)
+    pc.check_apply_istft(cuda, rng, 3, 6, 30000, n_samples=ns)
+    pc.check_stft_cov(cuda, rng, 1, 7, 25000, 512, 256, False, "hamming")
+    pc.check_apply_istft(cuda, rng, 1, 7, 25000, 512, 128, False, "hamming")
+
+
 def test_cov_generic(cuda):
     pc.check_cov_generic(cuda, np.random.default_rng(7), 2, 6, 33, 300)
 

@@ -18,7 +18,7 @@ from setk_b200 import synth  # noqa: E402
 from setk_b200.engine import BeamformPipeline  # noqa: E402
 
 
-def run(name, C, frame_len, beamformer, B, N=160000, steps=5):
+def run(name, C, frame_len, beamformer, B, N=160000, steps=10):
     dev = torch.device("cuda:0")
     pipe = BeamformPipeline(C, beamformer, frame_len=frame_len, frame_hop=256, max_batch=B,
                             max_samples=N, device=dev)
@@ -26,7 +26,8 @@ def run(name, C, frame_len, beamformer, B, N=160000, steps=5):
     reps = (B + a.shape[0] - 1) // a.shape[0]
     audio = a.repeat(reps, 1, 1)[:B].contiguous()
     mask = m.repeat(reps, 1, 1)[:B].contiguous()
-    wave, status = pipe.run(audio, mask)
+    for _ in range(3):
+        wave, status = pipe.run(audio, mask)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -36,9 +37,23 @@ def run(name, C, frame_len, beamformer, B, N=160000, steps=5):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     fused = C <= 4 and pipe.plan.n_fft == 512
+
+    def timed(fn, n=3):
+        fn(); torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(n):
+            r = fn()
+        a1.record(); torch.cuda.synchronize()
+        return a0.elapsed_time(a1) / n, r
+
+    t_cov, (Rs, Rn, mx) = timed(lambda: pipe.covariances(audio, mask))
+    t_w, (w, _, _) = timed(lambda: pipe.solve(Rs, Rn))
+    t_ai, _ = timed(lambda: pipe.plan.apply_istft(audio, w, norm=mx))
+    stages = {"stft_cov_ms": t_cov, "weights_ms": t_w, "apply_istft_ms": t_ai}
     print(json.dumps({"config": name, "channels": C, "n_fft": pipe.plan.n_fft, "beamformer": beamformer,
                       "batch": B, "ms_per_batch": ms, "utts_per_s": B / ms * 1e3,
-                      "route": "fused" if fused else "generic (explicit STFT in HBM)",
+                      "route": "fused" if fused else "generic (explicit STFT in HBM)", "stages": stages,
                       "status_failures": int((status != 0).sum())}), flush=True)
     del pipe, audio, mask, wave
     torch.cuda.empty_cache()
