@@ -231,7 +231,10 @@ int setk_stft_cov(setk_plan_t* pl, const float* audio, const int32_t* n_samples,
     // workspace, then a streaming covariance kernel (stft_spill.cu)
     const int groups = (g.C + 3) / 4;
     const int chunks_a = stft_cov_pick_chunks(pl, B * groups, T);
-    const int chunks_b = stft_cov_pick_chunks(pl, B * g.C, T);
+    // >= 16 short fp32 runs per utterance, combined in double by the finalize kernel
+    int chunks_b = stft_cov_pick_chunks(pl, B * g.C, T);
+    if (chunks_b < 16) chunks_b = 16;
+    if (chunks_b > T) chunks_b = T;
     e = ensure(&pl->d_stft_ws, &pl->stft_ws_bytes, stft_spill_bytes(g, B, T));
     if (e == cudaSuccess)
       e = ensure(&pl->d_partials, &pl->partials_bytes, cov_spill_partial_bytes(g, B, chunks_b));

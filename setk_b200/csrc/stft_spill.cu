@@ -192,22 +192,22 @@ __global__ void cov_spill_finalize_kernel(const float* __restrict__ partials, in
   const int W = 2 * C + 1;
 #pragma unroll
   for (int which = 0; which < 2; ++which) {
-    float acc[2 * C + 1];
+    double acc[2 * C + 1];   // short fp32 runs are combined in double
 #pragma unroll
-    for (int i = 0; i < W; ++i) acc[i] = 0.f;
+    for (int i = 0; i < W; ++i) acc[i] = 0.0;
     for (int ch = 0; ch < n_chunks; ++ch) {
       const float* pp = partials + (((((long long)b * n_chunks + ch) * C + row) * 2 + which) * W) * F + f;
 #pragma unroll
       for (int i = 0; i < W; ++i) acc[i] += pp[(long long)i * F];
     }
-    const float inv = 1.0f / fmaxf(acc[2 * C], 1e-6f);
+    const double inv = 1.0 / fmax(acc[2 * C], 1e-6);
     float2* R = (which == 0 ? Rs : Rn) + ((long long)b * F + f) * (C * C);
 #pragma unroll
     for (int j = 0; j < C; ++j) {
       if (j == row) {
-        R[row * C + row] = make_float2(acc[2 * j] * inv, 0.f);
+        R[row * C + row] = make_float2((float)(acc[2 * j] * inv), 0.f);
       } else if (j > row) {
-        const float re = acc[2 * j] * inv, im = acc[2 * j + 1] * inv;
+        const float re = (float)(acc[2 * j] * inv), im = (float)(acc[2 * j + 1] * inv);
         R[row * C + j] = make_float2(re, im);
         R[j * C + row] = make_float2(re, -im);
       }
