@@ -40,7 +40,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "utts/sec 4-ch MVDR 10s@16kHz"
+METRIC = "utts/sec 4-ch MVDR 10s@16kHz at 1/2/4/8 B200; STFT+cov HBM GB/s vs peak"   # BASELINE.json
 UNIT = "utts/s"
 C, N, FRAME_LEN, HOP, NFFT = 4, 160000, 512, 256, 512
 BATCH = 256
@@ -140,16 +140,14 @@ def reference_arm(args):
         return
     from oracle.cpu_bench import usable_cores
     cores = usable_cores()
-    per_step = max(cores, 8)                       # utterances per "step" sample
+    # a "step" of this arm = one utterance per worker process (a bounded sample of
+    # the 256-utterance GPU step); each worker warms up on one utterance first
+    # (oracle/cpu_bench.py), then times `per_worker` utterances back to back
+    per_worker = max(4, min(args.steps, 24))
     t0 = time.time()
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        run_cpu_arm(1, cores)
-    vals = []
-    for _ in range(max(1, min(args.steps, 3))):
-        vals.append(run_cpu_arm(max(1, per_step // cores), cores))
-    val = sum(vals) / len(vals)
-    sample = (f"{len(vals)} steps x {max(1, per_step // cores) * cores} utterances of the "
-              f"workload, {cores} worker processes, compute only")
+    val = run_cpu_arm(per_worker, cores)
+    sample = (f"{per_worker} steps x {cores} utterances of the workload "
+              f"({cores} single-threaded worker processes like run.pl nj={cores}), compute only")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -377,8 +375,8 @@ def gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--unique", type=int, default=32,
