@@ -60,6 +60,9 @@ extern "C" {
 #define SETK_ST_NO_CONVERGE 4u  /* Jacobi eigen-iteration hit its sweep limit  */
 #define SETK_ST_NONFINITE 8u    /* NaN/Inf in the result                       */
 #define SETK_ST_BAD_REF 16u     /* PMWF reference channel >= C (RuntimeError, beamformer.py:656-658) */
+#define SETK_ST_REGULARIZED 32u /* WARNING only: Rn was numerically not PD in a GEV reduction and its
+                                   diagonal was loaded (the reference falls back to a non-Hermitian eig
+                                   there, beamformer.py:55-58) */
 
 /* ---- beamformer kinds: apply_adaptive_beamformer.py:22,92-110 ---- */
 #define SETK_BF_MVDR 0          /* beamformer.py:527-539 */

@@ -18,6 +18,9 @@ TEST INFRASTRUCTURE.  Writes:
       seeded small synthetic cases pushed through the reference's
       forward_stft / compute_covar / solve_pevd / *Beamformer.weight /
       beamform / inverse_stft with float64 masks (complex128 path).
+  tests/golden/ref_configs.npz
+      BASELINE.json configs 3 (reference CGMM mask -> GEV, 8 ch, 1024-pt) and 4
+      (reference WPE -> MVDR, 6 ch) on short seeded utterances.
   tests/golden/PINNING.json
       what matched what, to how many LSB / what rel-inf.
 """
@@ -225,6 +228,58 @@ def small_cases(ref, report):
     np.savez_compressed(os.path.join(GOLD, "ref_small.npz"), **out)
 
 
+def config_cases(ref, report):
+    """
+    BASELINE.json configs 3 and 4 as parity cases, with the mask producer /
+    pre-processor run by the REFERENCE's own code (they are outside the hot path):
+      cfg3: 8-ch, 1024-pt, mask = reference CGMM (CgmmTrainer, 20 iterations) -> GEV
+      cfg4: 6-ch, 512-pt, STFT dereverberated by the reference WPE
+            (taps 10, delay 3, context 1, 3 iterations) -> MVDR with an IRM mask
+    """
+    rng = np.random.default_rng(20240924)
+    out = {}
+    B = ref.beamformer
+    # ---- config 3 ----
+    C, N, fl, hop = 8, 24000, 1024, 256
+    mix, tgt, noise = synth_case(rng, C, N)
+    kw = dict(frame_len=fl, frame_hop=hop, window="hann", center=True, transpose=False)
+    obs = ref_multichannel_stft(ref, mix, round_power_of_two=True, **kw)        # c64 N x F x T
+    np.random.seed(777)
+    gamma = ref.cluster.CgmmTrainer(obs, 2, gamma=None, update_alpha=False).train(20)
+    mask = np.transpose(gamma, (0, 2, 1))[0].astype(np.float32)                  # T x F
+    F = obs.shape[1]
+    obs64 = obs.astype(np.complex128)
+    m64 = np.minimum(mask, 1).astype(np.float64)
+    enh = B.GevdBeamformer(F).run(m64, obs64)
+    y = ref.utils.inverse_stft(enh, norm=float(np.max(np.abs(mix))), **kw)
+    out["cfg3/mix"] = mix
+    out["cfg3/mask_cgmm"] = mask
+    out["cfg3/enh_gevd"] = enh.astype(np.complex64)
+    out["cfg3/y_gevd"] = y.astype(np.float32)
+    enh_o = bo.run_supervised("gevd", m64, obs64)
+    report["cfg3/oracle_vs_ref_relinf_aligned"] = bo.rel_inf(bo.align_phase(enh_o, enh)[0], enh)
+    report["cfg3/mask_mean"] = float(mask.mean())
+    # ---- config 4 ----
+    C, N, fl, hop = 6, 32000, 512, 256     # T = 126 frames >> 60 prediction taps
+    mix, tgt, noise = synth_case(rng, C, N)
+    kw = dict(frame_len=fl, frame_hop=hop, window="hann", center=True, transpose=False)
+    obs = ref_multichannel_stft(ref, mix, round_power_of_two=True, **kw)
+    # apply_wpe.py:45-60: wpe works on F x N x T
+    derev = ref.wpe.wpe(np.einsum("nft->fnt", obs), taps=10, delay=3, context=1, num_iters=3)
+    derev = np.einsum("fnt->nft", derev).astype(np.complex64)
+    S = so.forward_stft(tgt[0].astype(np.float32), round_power_of_two=True, **kw)
+    V = so.forward_stft(noise[0].astype(np.float32), round_power_of_two=True, **kw)
+    mask = (np.abs(S) / np.sqrt(np.abs(S)**2 + np.abs(V)**2 + so.EPSILON)).T.astype(np.float32)
+    F = obs.shape[1]
+    enh = B.MvdrBeamformer(F).run(mask.astype(np.float64), derev.astype(np.complex128))
+    out["cfg4/stft_wpe"] = derev
+    out["cfg4/mask"] = mask
+    out["cfg4/enh_mvdr"] = enh.astype(np.complex64)
+    enh_o = bo.run_supervised("mvdr", mask.astype(np.float64), derev.astype(np.complex128))
+    report["cfg4/oracle_vs_ref_relinf_aligned"] = bo.rel_inf(bo.align_phase(enh_o, enh)[0], enh)
+    np.savez_compressed(os.path.join(GOLD, "ref_configs.npz"), **out)
+
+
 def main():
     if not ref_shim.reference_available():
         print("reference tree absent; nothing generated", file=sys.stderr)
@@ -238,6 +293,7 @@ def main():
     }
     doc_example(ref, report)
     small_cases(ref, report)
+    config_cases(ref, report)
     with open(os.path.join(GOLD, "PINNING.json"), "w") as f:
         json.dump(report, f, indent=1, sort_keys=True)
     print(json.dumps(report, indent=1, sort_keys=True))

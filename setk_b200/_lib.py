@@ -22,6 +22,8 @@ DEFAULT_LIBRARY = os.path.join(_HERE, "libsetk_b200.so")
 SETK_MAX_CHANNELS = 16
 SETK_EINVAL, SETK_ENOMEM, SETK_ESHAPE, SETK_EUNSUPPORTED = -1, -2, -3, -4
 ST_SINGULAR, ST_NOT_PD, ST_NO_CONVERGE, ST_NONFINITE, ST_BAD_REF = 1, 2, 4, 8, 16
+ST_REGULARIZED = 32          # warning only
+ST_ERROR_MASK = 31
 BF_MVDR, BF_MPDR, BF_MPDR_WHITEN, BF_GEVD, BF_PMWF, BF_PEVD = 0, 1, 2, 3, 4, 5
 RANK1_NONE, RANK1_EIG, RANK1_GEV = 0, 1, 2
 F_CLIP_MASK, F_MASK_FT = 1, 2

@@ -230,8 +230,31 @@ __device__ inline void forward_subst(const CMat<C>& L, CMat<C>& B) {
 template <int C>
 __device__ inline unsigned gev_principal(CMat<C>& Rs, CMat<C>& Rn, CVec<C>& w) {
   unsigned st = 0;
-  // read only the lower triangle of Rn (scipy.linalg.eigh default lower=True)
-  if (!cholesky_lower<C>(Rn)) st |= SETK_ST_NOT_PD;
+  // read only the lower triangle of Rn (scipy.linalg.eigh default lower=True).
+  // When Rn is numerically not positive definite (e.g. a near-binary mask leaves
+  // fewer noise frames than channels) the reference falls back to a non-Hermitian
+  // scipy.linalg.eig (beamformer.py:55-58) whose answer on a singular pencil is
+  // arbitrary; here the diagonal is loaded by tr(Rn)/C * 1e-10, 1e-8, ... and the
+  // SETK_ST_REGULARIZED warning bit is set.  Only a matrix that stays non-PD
+  // (zero / negative trace) reports SETK_ST_NOT_PD.
+  {
+    double tr = 0.0;
+    SETK_UNROLL_C
+    for (int i = 0; i < C; ++i) tr += Rn.a[i][i].x;
+    CMat<C> L = Rn;
+    bool ok = cholesky_lower<C>(L);
+    double load = 1e-10;
+    SETK_NOUNROLL
+    for (int attempt = 0; attempt < 5 && !ok && tr > 0.0; ++attempt, load *= 100.0) {
+      L = Rn;
+      SETK_UNROLL_C
+      for (int i = 0; i < C; ++i) L.a[i][i].x += load * tr / C;
+      ok = cholesky_lower<C>(L);
+      st |= SETK_ST_REGULARIZED;
+    }
+    if (!ok) st |= SETK_ST_NOT_PD;
+    Rn = L;
+  }
   // Rs from its lower triangle as well
   SETK_UNROLL_C
   for (int i = 0; i < C; ++i) {

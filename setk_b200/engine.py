@@ -115,7 +115,7 @@ class BeamformPipeline(object):
     @staticmethod
     def raise_for_status(status, keys=None):
         """Map per-utterance status words to numpy.linalg.LinAlgError (first failure)."""
-        st = status.detach().cpu().numpy()
+        st = status.detach().cpu().numpy() & _lib.ST_ERROR_MASK   # bit 32 is a warning
         bad = np.nonzero(st)[0]
         if bad.size:
             i = int(bad[0])

@@ -62,7 +62,7 @@ def _batched(t, ndim):
 
 
 def _check_status(status):
-    st = status.cpu().numpy()
+    st = status.cpu().numpy() & _lib.ST_ERROR_MASK        # SETK_ST_REGULARIZED is a warning
     bad = np.nonzero(st)[0]
     if bad.size:
         i = int(bad[0])

@@ -254,3 +254,9 @@ def test_golden_doc_vectors_gevd_sign_fit(cuda):
 
 def test_pcm_conversions(cuda):
     pc.check_pcm(cuda, np.random.default_rng(40))
+
+
+@pytest.mark.parametrize("name", ["cfg3", "cfg4"])
+def test_config_fixtures_from_reference(cuda, name):
+    """configs 3 (reference CGMM mask -> GEV) and 4 (reference WPE -> MVDR)."""
+    pc.check_config_fixture(cuda, name)

@@ -178,3 +178,9 @@ def test_kaldi_matrix_reader(tmp_path):
     (tmp_path / "m.scp").write_text(f"utt1 {path}:{off}\n")
     rd = ScriptReader(str(tmp_path / "m.scp"))
     assert "utt1" in rd and np.array_equal(rd["utt1"], mat)
+
+
+def test_config3_fixture_cgmm_mask_gev(emu):
+    """config 3 (8 ch, 1024-pt, reference CGMM mask -> GEV) on the CPU execution model."""
+    import parity_cases as pc
+    pc.check_config_fixture(emu, "cfg3", stft_from_oracle=True)

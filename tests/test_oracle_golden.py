@@ -72,6 +72,22 @@ def test_oracle_end_to_end_matches_shipped_doc_vector():
         assert np.mean(d > 0) <= 0.05
 
 
+def test_oracle_reproduces_reference_config_cases():
+    """configs 3 / 4: reference CGMM mask -> GEV, reference WPE -> MVDR (ref_configs.npz)."""
+    g = np.load(os.path.join(GOLD, "ref_configs.npz"))
+    kw = dict(frame_len=1024, frame_hop=256, center=True, window="hann", transpose=False)
+    obs = so.multichannel_stft(g["cfg3/mix"], round_power_of_two=True, out_dtype=np.complex64,
+                               **kw).astype(np.complex128)
+    m = np.minimum(g["cfg3/mask_cgmm"], 1).astype(np.float64)
+    enh = bo.run_supervised("gevd", m, obs)
+    ref = g["cfg3/enh_gevd"].astype(np.complex128)
+    assert bo.rel_inf(bo.align_phase(enh, ref)[0], ref) <= 1e-6      # fixture stored as complex64
+    enh4 = bo.run_supervised("mvdr", g["cfg4/mask"].astype(np.float64),
+                             g["cfg4/stft_wpe"].astype(np.complex128))
+    ref4 = g["cfg4/enh_mvdr"].astype(np.complex128)
+    assert bo.rel_inf(bo.align_phase(enh4, ref4)[0], ref4) <= 1e-6
+
+
 def test_bookkeeping_table():
     """frame counts and iSTFT lengths at N = 160000, hop 256."""
     rows = [(512, True, 512, 257, 626, 160000), (1024, True, 1024, 513, 626, 160000),
