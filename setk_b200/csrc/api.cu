@@ -17,7 +17,8 @@ std::atomic<long long> g_launch_count{0};
 cudaError_t run_stft_generic(const setk_plan*, const float*, const int*, int, int, int, float2*, void*);
 cudaError_t run_cov_generic(const float2*, const float*, unsigned, int, int, int, int, float2*, void*);
 cudaError_t run_apply_generic(const float2*, const void*, int, const float*, int, int, int, int, float2*, void*);
-cudaError_t run_istft_generic(const setk_plan*, const float2*, int, int, int, int, float*, float*, unsigned*, void*);
+cudaError_t run_istft_generic(const setk_plan*, const float2*, int, int, int, int, const int*, float*, float*,
+                              unsigned*, void*);
 cudaError_t run_peak_scale(float*, int, int, const float*, const unsigned*, void*);
 cudaError_t run_float_to_pcm16(const float*, long long, int16_t*, void*);
 cudaError_t run_pcm16_to_float(const int16_t*, long long, float*, void*);
@@ -34,6 +35,10 @@ cudaError_t run_apply_istft_fused(setk_plan*, const float*, const int*, int, int
 
 bool stft_spill_supported(const Geometry&);
 size_t stft_spill_bytes(const Geometry&, int, int);
+size_t apply_spill_bytes(const Geometry&, int, int);
+cudaError_t run_apply_spill(setk_plan*, const float2*, const void*, int, const float*, int, int, float2*, void*);
+cudaError_t run_istft_strided(const setk_plan*, const float2*, long long, long long, long long, int, int, int,
+                              const int*, float*, float*, unsigned*, void*);
 size_t cov_spill_partial_bytes(const Geometry&, int, int);
 cudaError_t run_stft_spill(setk_plan*, const float*, const int*, int, int, int, int, float2*, unsigned*,
                            void*);
@@ -227,12 +232,12 @@ int setk_stft_cov(setk_plan_t* pl, const float* audio, const int32_t* n_samples,
     return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_stft_cov");
   }
   if (stft_spill_supported(g)) {
-    // many-channel route (C > 4 at n_fft = 512): fast STFT into a bin-major
-    // workspace, then a streaming covariance kernel (stft_spill.cu)
+    // many-channel route (C > 4 at n_fft = 512, any C at n_fft = 1024): fast STFT
+    // into a bin-major workspace, then a streaming covariance kernel (stft_spill.cu)
     const int groups = (g.C + 3) / 4;
     const int chunks_a = stft_cov_pick_chunks(pl, B * groups, T);
     // >= 16 short fp32 runs per utterance, combined in double by the finalize kernel
-    int chunks_b = stft_cov_pick_chunks(pl, B * g.C, T);
+    int chunks_b = stft_cov_pick_chunks(pl, B * g.C * ((g.F + 287) / 288), T);
     if (chunks_b < 16) chunks_b = 16;
     if (chunks_b > T) chunks_b = T;
     e = ensure(&pl->d_stft_ws, &pl->stft_ws_bytes, stft_spill_bytes(g, B, T));
@@ -335,8 +340,8 @@ int setk_istft(setk_plan_t* pl, const void* enh, int32_t B, int32_t T, int32_t n
     e = cudaMemsetAsync(peak, 0, sizeof(unsigned) * B, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "setk_istft(memset)");
   }
-  e = run_istft_generic(pl, static_cast<const float2*>(enh), B, T, T_used, n_out, pl->d_frames_ws, wave,
-                        peak, stream);
+  e = run_istft_generic(pl, static_cast<const float2*>(enh), B, T, T_used, n_out, nullptr, pl->d_frames_ws,
+                        wave, peak, stream);
   if (e == cudaSuccess && norm) e = run_peak_scale(wave, B, n_out, norm, peak, stream);
   return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_istft");
 }
@@ -361,6 +366,24 @@ int setk_apply_istft(setk_plan_t* pl, const float* audio, const int32_t* n_sampl
     const int n_chunks = stft_cov_pick_chunks(pl, B, T);
     e = run_apply_istft_fused(pl, audio, n_samples, B, N, T, w, w_dtype, post_mask, n_out, n_chunks,
                               wave, peak, stream);
+  } else if (stft_spill_supported(g)) {
+    // tile STFT into the bin-major workspace, y = w^H x over it, then the
+    // frame-wise inverse FFT + overlap-add reading Y[b][t][f] in place
+    const int T_used = T_used_for(g, T, n_out);
+    const int groups = (g.C + 3) / 4;
+    const int chunks = stft_cov_pick_chunks(pl, B * groups, T);
+    const long long pitch = (long long)(apply_spill_bytes(g, 1, 1) / sizeof(float2));
+    e = ensure(&pl->d_stft_ws, &pl->stft_ws_bytes, stft_spill_bytes(g, B, T));
+    if (e == cudaSuccess) e = ensure(&pl->d_enh_ws, &pl->enh_ws_bytes, apply_spill_bytes(g, B, T));
+    if (e == cudaSuccess)
+      e = ensure(&pl->d_frames_ws, &pl->frames_ws_bytes, sizeof(float) * (size_t)B * T_used * g.n_fft);
+    if (e == cudaSuccess)
+      e = run_stft_spill(pl, audio, n_samples, B, N, T, chunks, pl->d_stft_ws, nullptr, stream);
+    if (e == cudaSuccess)
+      e = run_apply_spill(pl, pl->d_stft_ws, w, w_dtype, post_mask, B, T, pl->d_enh_ws, stream);
+    if (e == cudaSuccess)
+      e = run_istft_strided(pl, pl->d_enh_ws, (long long)T * pitch, 1, pitch, B, T_used, n_out, n_samples,
+                            pl->d_frames_ws, wave, peak, stream);
   } else {
     const int T_used = T_used_for(g, T, n_out);
     e = ensure(&pl->d_stft_ws, &pl->stft_ws_bytes, sizeof(float2) * (size_t)B * g.C * g.F * T);
@@ -371,7 +394,8 @@ int setk_apply_istft(setk_plan_t* pl, const float* audio, const int32_t* n_sampl
     if (e == cudaSuccess)
       e = run_apply_generic(pl->d_stft_ws, w, w_dtype, post_mask, B, g.C, g.F, T, pl->d_enh_ws, stream);
     if (e == cudaSuccess)
-      e = run_istft_generic(pl, pl->d_enh_ws, B, T, T_used, n_out, pl->d_frames_ws, wave, peak, stream);
+      e = run_istft_generic(pl, pl->d_enh_ws, B, T, T_used, n_out, n_samples, pl->d_frames_ws, wave, peak,
+                            stream);
   }
   if (e == cudaSuccess && norm) e = run_peak_scale(wave, B, n_out, norm, peak, stream);
   return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_apply_istft");

@@ -143,15 +143,18 @@ __global__ void apply_generic_kernel(const float2* __restrict__ stft, const void
 
 // irfft of one enhanced frame x synthesis window -> frames[b][t][n]
 // (librosa.istft: ytmp = ifft_window * irfft(stft_matrix)).  grid (T_used, B).
-__global__ void istft_frames_kernel(Geometry g, const float2* __restrict__ enh, int T,
+// enh element (b, f, t) lives at  b*sb + f*sf + t*st  (the API layout [B][F][T]
+// or the bin-major workspace of stft_spill.cu).
+__global__ void istft_frames_kernel(Geometry g, const float2* __restrict__ enh, long long sb,
+                                    long long sf, long long st,
                                     const float* __restrict__ window, float* __restrict__ frames,
                                     int T_used) {
   SETK_DYN_SMEM(float2, s);
   const int t = blockIdx.x, b = blockIdx.y;
-  const float2* e = enh + ((long long)b * g.F) * T + t;
+  const float2* e = enh + (long long)b * sb + (long long)t * st;
   const int n = g.n_fft;
   for (int k = threadIdx.x; k < g.F; k += blockDim.x) {
-    float2 v = e[(long long)k * T];
+    float2 v = e[(long long)k * sf];
     if (k == 0 || k == n / 2) v.y = 0.f;      // c2r ignores these imaginary parts
     s[bitrev(k, g.log2n)] = v;
     if (k > 0 && k < n / 2) s[bitrev(n - k, g.log2n)] = make_float2(v.x, -v.y);
@@ -167,16 +170,19 @@ __global__ void istft_frames_kernel(Geometry g, const float2* __restrict__ enh, 
 // later `norm` rescale (utils.py:166-168).  One thread per output sample.
 __global__ void istft_ola_kernel(Geometry g, const float* __restrict__ frames,
                                  const float* __restrict__ wsq, int T_used, int n_out,
-                                 float* __restrict__ wave, unsigned* __restrict__ peak) {
+                                 const int* __restrict__ n_samples, float* __restrict__ wave,
+                                 unsigned* __restrict__ peak) {
   const int b = blockIdx.y;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  // a ragged batch: each utterance overlap-adds its own frames only
+  const int Tu = n_samples ? imin(T_used, frames_of(n_samples[b], g.n_fft, g.hop, g.pad)) : T_used;
   float val = 0.f;
   if (q < n_out) {
     const int p = q + g.pad;
-    const int expected = g.n_fft + g.hop * (T_used - 1);
+    const int expected = Tu > 0 ? g.n_fft + g.hop * (Tu - 1) : 0;
     if (p < expected) {
       const int t_lo = (p >= g.n_fft) ? (p - g.n_fft) / g.hop + 1 : 0;
-      const int t_hi = imin(T_used - 1, p / g.hop);
+      const int t_hi = imin(Tu - 1, p / g.hop);
       float wss = 0.f;
       for (int t = t_lo; t <= t_hi; ++t) {
         const int n = p - t * g.hop;
@@ -292,15 +298,23 @@ cudaError_t run_apply_generic(const float2* stft, const void* w, int w_dtype, co
                 stft, w, w_dtype, post_mask, B, C, F, T, enh);
 }
 
-cudaError_t run_istft_generic(const setk_plan* pl, const float2* enh, int B, int T, int T_used,
-                              int n_out, float* frames_ws, float* wave, unsigned* peak, void* stream) {
+cudaError_t run_istft_strided(const setk_plan* pl, const float2* enh, long long sb, long long sf,
+                              long long st, int B, int T_used, int n_out, const int* n_samples,
+                              float* frames_ws, float* wave, unsigned* peak, void* stream) {
   const Geometry& g = pl->geo;
   cudaError_t e = launch(istft_frames_kernel, dim3(T_used, B), dim3(imin(256, g.n_fft / 2)),
-                         (size_t)g.n_fft * sizeof(float2), stream, false, g, enh, T,
+                         (size_t)g.n_fft * sizeof(float2), stream, false, g, enh, sb, sf, st,
                          (const float*)pl->d_window, frames_ws, T_used);
   if (e != cudaSuccess) return e;
   return launch(istft_ola_kernel, dim3((n_out + 255) / 256, B), dim3(256), 0, stream, false, g,
-                (const float*)frames_ws, (const float*)pl->d_wsq, T_used, n_out, wave, peak);
+                (const float*)frames_ws, (const float*)pl->d_wsq, T_used, n_out, n_samples, wave, peak);
+}
+
+cudaError_t run_istft_generic(const setk_plan* pl, const float2* enh, int B, int T, int T_used,
+                              int n_out, const int* n_samples, float* frames_ws, float* wave,
+                              unsigned* peak, void* stream) {
+  return run_istft_strided(pl, enh, (long long)pl->geo.F * T, T, 1, B, T_used, n_out, n_samples,
+                           frames_ws, wave, peak, stream);
 }
 
 cudaError_t run_peak_scale(float* wave, int B, int n_out, const float* norm, const unsigned* peak,

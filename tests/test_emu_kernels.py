@@ -76,6 +76,25 @@ def test_many_channel_ragged_and_nocenter(emu):
     pc.check_apply_istft(emu, rng, 1, 7, 2500, 512, 128, False, "hamming")
 
 
+@pytest.mark.parametrize("C,hop,center", [(8, 256, True), (3, 512, False), (1, 128, True), (6, 340, True)])
+def test_nfft1024_routes(emu, C, hop, center):
+    # config-3 geometry: 1024-point tile STFT (even/odd half-warp jobs) into the
+    # workspace, streaming covariance, w^H x + inverse FFT over the workspace
+    rng = np.random.default_rng(70 + C)
+    pc.check_stft_cov(emu, rng, 2, C, 4200, 1024, hop, center, "hann", with_mask_n=(C == 3),
+                      clip=(C == 1))
+    pc.check_apply_istft(emu, rng, 2, C, 4200, 1024, hop, center, "hann", post_mask=(C == 3))
+
+
+def test_nfft1024_ragged(emu):
+    rng = np.random.default_rng(75)
+    ns = torch.tensor([5000, 2703], dtype=torch.int32)
+    pc.check_stft_cov(emu, rng, 2, 5, 5000, 1024, 256, True, "hann", n_samples=ns)
+    pc.check_apply_istft(emu, rng, 2, 5, 5000, 1024, 256, True, "hann", n_samples=ns)
+    pc.check_apply_istft(emu, rng, 2, 2, 3000, 256, 64, True, "hann",
+                         n_samples=torch.tensor([3000, 1501], dtype=torch.int32))   # generic route
+
+
 def test_cov_generic(emu):
     pc.check_cov_generic(emu, np.random.default_rng(7), 2, 6, 9, 70)
 
