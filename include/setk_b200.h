@@ -216,6 +216,26 @@ int setk_apply_istft(setk_plan_t* plan, const float* audio, const int32_t* n_sam
                      const float* post_mask, int32_t n_out, const float* norm,
                      float* wave, void* stream);
 
+/*
+ * CGMM time-frequency mask estimation from audio: the tile STFT, then
+ * CgmmTrainer(stft, num_classes, gamma=init, update_alpha=...).train(num_iters)
+ * (scripts/sptk/libs/cluster.py:396-465 with 94-130, 187-287) for every utterance
+ * of the batch, and the CLI's transpose (scripts/sptk/estimate_cgmm_masks.py:36-60).
+ * fp64 arithmetic after the complex64 STFT, like the reference.
+ *
+ *   num_classes  2..4.  init_gamma == NULL needs num_classes == 2 (the reference's
+ *                deterministic start R_0 = sum_t y y^H / T, R_1 = I; for more classes
+ *                it draws numpy random posteriors -- pass them in).
+ *   init_gamma   f32 [B][K][T][F] starting posteriors or NULL
+ *   update_alpha nonzero: the priors follow mean_t gamma (cluster.py:251-252)
+ *   masks        f32 [B][K][T][F]  (the reference writes masks[0] when K == 2)
+ *   status       u32 [B] or NULL, OR-ed SETK_ST_NO_CONVERGE (caller zeroes it)
+ * Needs n_fft 512 or 1024 (the tile STFT); SETK_EUNSUPPORTED otherwise.
+ */
+int setk_cgmm_masks(setk_plan_t* plan, const float* audio, const int32_t* n_samples, int32_t B, int32_t N,
+                    int32_t num_classes, int32_t num_iters, const float* init_gamma, int32_t update_alpha,
+                    float* masks, uint32_t* status, void* stream);
+
 /* floor(y * 32768) clipped to int16: the PCM_16 conversion of
  * WaveWriter.write -> write_wav -> soundfile (data_handler.py:600-605,
  * utils.py:45-62; SURVEY.md finding 3).  wave f32 [n], pcm i16 [n]. */

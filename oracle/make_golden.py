@@ -280,7 +280,53 @@ def config_cases(ref, report):
     np.savez_compressed(os.path.join(GOLD, "ref_configs.npz"), **out)
 
 
+def cgmm_cases(ref, report):
+    """
+    The CGMM paths the documented command does not take (it is pinned by
+    doc_example / config_cases): a start from given posteriors, more than two
+    classes, and the prior update -- CgmmTrainer(obs, K, gamma=..., update_alpha=...)
+    (cluster.py:396-465) run by the REFERENCE on small mixtures.
+    """
+    from oracle import cgmm_oracle as co
+    rng = np.random.default_rng(20240925)
+    out = {}
+    kw = dict(frame_len=512, frame_hop=256, window="hann", center=True, transpose=False)
+    for name, C, N, K, iters, upd in (("k3_alpha", 3, 6000, 3, 6, True), ("k2_init", 4, 5000, 2, 5, False)):
+        mix, _, _ = synth_case(rng, C, N)
+        obs = ref_multichannel_stft(ref, mix, round_power_of_two=True, **kw)      # c64 C x F x T
+        _, F, T = obs.shape
+        if K == 2:
+            init = rng.uniform(0.05, 0.95, size=(F, T)).astype(np.float32)
+        else:
+            init = rng.uniform(size=(K, F, T))
+            init = (init / init.sum(0, keepdims=True)).astype(np.float32)
+        gamma = ref.cluster.CgmmTrainer(obs, K, gamma=init.astype(np.float64),
+                                        update_alpha=upd).train(iters)
+        masks = np.transpose(gamma, (0, 2, 1)).astype(np.float32)                  # K x T x F
+        out[name + "/mix"] = mix
+        out[name + "/init_gamma"] = init
+        out[name + "/masks"] = masks
+        out[name + "/cfg"] = np.array([K, iters, int(upd)], dtype=np.int64)
+        mo = co.cgmm_masks(obs, K, iters, init_gamma=init.astype(np.float64), update_alpha=upd)
+        mo = mo[None] if K == 2 else mo
+        report["cgmm/" + name + "/oracle_vs_ref_maxabs"] = float(
+            np.max(np.abs(mo - np.transpose(gamma, (0, 2, 1))[:mo.shape[0]])))
+    np.savez_compressed(os.path.join(GOLD, "ref_cgmm.npz"), **out)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "cgmm":      # add the CGMM fixture only
+        ref = ref_shim.load_reference()
+        report = {}
+        cgmm_cases(ref, report)
+        path = os.path.join(GOLD, "PINNING.json")
+        with open(path) as f:
+            full = json.load(f)
+        full.update(report)
+        with open(path, "w") as f:
+            json.dump(full, f, indent=1, sort_keys=True)
+        print(json.dumps(report, indent=1, sort_keys=True))
+        return 0
     if not ref_shim.reference_available():
         print("reference tree absent; nothing generated", file=sys.stderr)
         return 1
@@ -294,6 +340,7 @@ def main():
     doc_example(ref, report)
     small_cases(ref, report)
     config_cases(ref, report)
+    cgmm_cases(ref, report)
     with open(os.path.join(GOLD, "PINNING.json"), "w") as f:
         json.dump(report, f, indent=1, sort_keys=True)
     print(json.dumps(report, indent=1, sort_keys=True))

@@ -36,6 +36,10 @@ cudaError_t run_apply_istft_fused(setk_plan*, const float*, const int*, int, int
 bool stft_spill_supported(const Geometry&);
 size_t stft_spill_bytes(const Geometry&, int, int);
 size_t apply_spill_bytes(const Geometry&, int, int);
+cudaError_t run_spill_to_bcft(const setk_plan*, const float2*, int, int, float2*, void*);
+size_t cgmm_workspace_bytes(const setk_plan*, int, int, int, int);
+cudaError_t run_cgmm(setk_plan*, const float2*, int, double*, const int*, int, int, int, int, int, const float*,
+                     int, float*, unsigned*, void*);
 cudaError_t run_apply_spill(setk_plan*, const float2*, const void*, int, const float*, int, int, float2*, void*);
 cudaError_t run_istft_strided(const setk_plan*, const float2*, long long, long long, long long, int, int, int,
                               const int*, float*, float*, unsigned*, void*);
@@ -156,6 +160,7 @@ int setk_plan_destroy(setk_plan_t* pl) {
   if (pl->d_stft_ws) cudaFree(pl->d_stft_ws);
   if (pl->d_enh_ws) cudaFree(pl->d_enh_ws);
   if (pl->d_frames_ws) cudaFree(pl->d_frames_ws);
+  if (pl->d_cgmm_ws) cudaFree(pl->d_cgmm_ws);
   if (pl->d_peak) cudaFree(pl->d_peak);
   free(pl);
   return SETK_OK;
@@ -189,8 +194,21 @@ int setk_stft(setk_plan_t* pl, const float* audio, const int32_t* n_samples, int
   int rc = check_batch(pl, B, N, "setk_stft");
   if (rc) return rc;
   if (!audio || !stft_out) return fail(SETK_EINVAL, "setk_stft: null buffer");
-  const int T = frames_of(N, pl->geo.n_fft, pl->geo.hop, pl->geo.pad);
-  cudaError_t e = run_stft_generic(pl, audio, n_samples, B, N, T, static_cast<float2*>(stft_out), stream);
+  const Geometry& g = pl->geo;
+  const int T = frames_of(N, g.n_fft, g.hop, g.pad);
+  cudaError_t e;
+  if (stft_spill_supported(g) && (long long)B * g.C <= 65535) {
+    // tile STFT into the bin-major workspace, then one transposing copy
+    e = ensure(&pl->d_stft_ws, &pl->stft_ws_bytes, stft_spill_bytes(g, B, T));
+    if (e != cudaSuccess) return cuda_fail(e, "setk_stft(workspace)");
+    const int groups = (g.C + 3) / 4;
+    e = run_stft_spill(pl, audio, n_samples, B, N, T, stft_cov_pick_chunks(pl, B * groups, T), pl->d_stft_ws,
+                       nullptr, stream);
+    if (e == cudaSuccess)
+      e = run_spill_to_bcft(pl, pl->d_stft_ws, B, T, static_cast<float2*>(stft_out), stream);
+  } else {
+    e = run_stft_generic(pl, audio, n_samples, B, N, T, static_cast<float2*>(stft_out), stream);
+  }
   return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_stft");
 }
 
@@ -399,6 +417,37 @@ int setk_apply_istft(setk_plan_t* pl, const float* audio, const int32_t* n_sampl
   }
   if (e == cudaSuccess && norm) e = run_peak_scale(wave, B, n_out, norm, peak, stream);
   return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_apply_istft");
+}
+
+int setk_cgmm_masks(setk_plan_t* pl, const float* audio, const int32_t* n_samples, int32_t B, int32_t N,
+                    int32_t num_classes, int32_t num_iters, const float* init_gamma, int32_t update_alpha,
+                    float* masks, uint32_t* status, void* stream) {
+  int rc = check_batch(pl, B, N, "setk_cgmm_masks");
+  if (rc) return rc;
+  if (!audio || !masks) return fail(SETK_EINVAL, "setk_cgmm_masks: null buffer");
+  if (num_classes < 2 || num_classes > 4)
+    return fail(SETK_EINVAL, "setk_cgmm_masks: num_classes %d outside 2..4", num_classes);
+  if (!init_gamma && num_classes != 2)
+    return fail(SETK_EINVAL, "setk_cgmm_masks: %d classes need init_gamma (the reference's start is random)",
+                num_classes);
+  if (num_iters < 0) return fail(SETK_EINVAL, "setk_cgmm_masks: num_iters %d", num_iters);
+  const Geometry& g = pl->geo;
+  if (!stft_spill_supported(g))
+    return fail(SETK_EUNSUPPORTED, "setk_cgmm_masks: needs n_fft 512 or 1024 (got %d, hop %d)", g.n_fft, g.hop);
+  const int T = frames_of(N, g.n_fft, g.hop, g.pad);
+  if (T < 1) return fail(SETK_ESHAPE, "setk_cgmm_masks: no frame in %d samples", N);
+  const int P = (int)(apply_spill_bytes(g, 1, 1) / sizeof(float2));
+  cudaError_t e = ensure(&pl->d_stft_ws, &pl->stft_ws_bytes, stft_spill_bytes(g, B, T));
+  if (e == cudaSuccess)
+    e = ensure(&pl->d_cgmm_ws, &pl->cgmm_ws_bytes, cgmm_workspace_bytes(pl, B, T, num_classes, P));
+  if (e != cudaSuccess) return cuda_fail(e, "setk_cgmm_masks(workspace)");
+  const int groups = (g.C + 3) / 4;
+  e = run_stft_spill(pl, audio, n_samples, B, N, T, stft_cov_pick_chunks(pl, B * groups, T), pl->d_stft_ws,
+                     nullptr, stream);
+  if (e == cudaSuccess)
+    e = run_cgmm(pl, pl->d_stft_ws, P, pl->d_cgmm_ws, n_samples, B, N, T, num_classes, num_iters, init_gamma,
+                 update_alpha, masks, status, stream);
+  return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_cgmm_masks");
 }
 
 int setk_float_to_pcm16(const float* wave, int64_t n, int16_t* pcm, void* stream) {

@@ -1,0 +1,550 @@
+// cgmm.cu -- CGMM time-frequency mask estimation (the mask producer of BASELINE
+// config 3).  Replaces, per utterance and frequency bin,
+//   scripts/sptk/libs/cluster.py:94-130   Covariance (eigh, scaled + floored
+//                                          eigenvalues, R^-1, log det)
+//   scripts/sptk/libs/cluster.py:187-231  CgDistribution.update_parameters / log_pdf
+//   scripts/sptk/libs/cluster.py:234-287  Cgmm.update / predict
+//   scripts/sptk/libs/cluster.py:396-465  CgmmTrainer (K = 2 start or given posteriors)
+//   scripts/sptk/estimate_cgmm_masks.py:36-60  K x F x T -> K x T x F float32
+//
+// Every bin is an independent EM problem, so the data stay bin-major:
+//   X     c64  [B][T][C][P]   the tile STFT's workspace (stft_spill.cu), read-only
+//   G, W  f64  [B][K][T][P]   posteriors gamma and M-step weights gamma M / phi
+// and one EM iteration is three launches that each touch X at most once:
+//   cgmm_cov_kernel     R_k <- sum_t W_k y y^H, sum_t G_k.  A CTA owns 64 bins and
+//                       a run of frames; tiles of X go through shared memory once
+//                       and the C(C+1)/2 Hermitian entries are dealt to thread
+//                       groups, <= 10 per thread, both classes sharing a product.
+//   cgmm_factor_kernel  thread per (b, k, f): fixed-order sum of the chunk partials,
+//                       / max(sum gamma, eps), Jacobi eigh, eigenvalue scaling and
+//                       floor, packed Hermitian R^-1 and log det  (fp64).
+//   cgmm_estep_kernel   thread per (bin, frame lane), R^-1 of the CTA's bins in
+//                       shared memory: phi_k = max(|y^H R_k^-1 y|, eps)/M, the
+//                       posterior (log-sum-exp shifted), G and W for the next pass.
+// All arithmetic after the complex64 STFT is fp64, as in the reference.
+#include "common.cuh"
+#include "hermitian_solve.cuh"
+
+namespace setk {
+
+// covariance pass: BINS bins per CTA, <= NE Hermitian entries per thread
+//   C <= 8 : 64 bins x <= 4 entry groups of <= 10 entries   (<= 256 threads)
+//   C  > 8 : 32 bins x <= 28 groups of <= 5 entries         (<= 896 threads)
+SETK_HD inline int cgmm_groups(int C, int NE) {
+  const int E = C * (C + 1) / 2;
+  int g = (E + NE - 1) / NE;
+  return g < 2 ? 2 : g;
+}
+// packed Hermitian slots of a C x C matrix: [0, C) the real diagonal, then
+// (re, im) of the entries above it in row-major order; C*C doubles in all
+SETK_HD inline int cgmm_slot(int C, int i, int j) {   // i < j
+  return C + 2 * (i * C - i * (i + 1) / 2 + (j - i - 1));
+}
+
+struct CgmmCovArgs {
+  const float2* X; int P;
+  const double* W;          // [B][K][T][P] or null: weight 1 (the K = 2 start)
+  const double* G;          // [B][K][T][P] or null: sum gamma = number of frames
+  const int* n_samples; int N; Geometry g;
+  int T, K, k0;             // this launch accumulates classes k0 and k0 + 1
+  int frames_per_chunk, n_chunks, tile_frames;
+  double* part;             // [B][n_chunks][K][C*C + 1][F]
+};
+
+template <int kCgBins, int kCgNE, int MAXT>
+__global__ void __launch_bounds__(MAXT) cgmm_cov_kernel(CgmmCovArgs a) {
+  SETK_DYN_SMEM(float2, ys);                 // [tile_frames][C][BINS]
+  const int C = a.g.C, F = a.g.F;
+  const int E = C * (C + 1) / 2;
+  const int G = blockDim.x / kCgBins;
+  double* ws = reinterpret_cast<double*>(ys + a.tile_frames * C * kCgBins);   // [tile][2][64]
+  unsigned char* pi = reinterpret_cast<unsigned char*>(ws + a.tile_frames * 2 * kCgBins);
+  unsigned char* pj = pi + 256;
+  const int tid = threadIdx.x;
+  const int bl = tid & (kCgBins - 1), grp = tid / kCgBins;
+  const int nbb = (F + kCgBins - 1) / kCgBins;
+  const int chunk = blockIdx.x / nbb, bin0 = (blockIdx.x - chunk * nbb) * kCgBins;
+  const int b = blockIdx.y;
+  const int bin = bin0 + bl;
+  const bool live = bin < F;
+  const int nb = a.n_samples ? a.n_samples[b] : a.N;
+  const int Tb = imin(frames_of(nb, a.g.n_fft, a.g.hop, a.g.pad), a.T);
+  const int t_begin = chunk * a.frames_per_chunk;
+  const int t_end = imin(t_begin + a.frames_per_chunk, Tb);
+  const int k1 = a.k0 + 1 < a.K ? a.k0 + 1 : a.k0;     // a lone last class is computed twice
+  if (tid < E) {                                       // entry -> (i, j), row-major upper triangle
+    int e = tid, i = 0;
+    while (e >= C - i) { e -= C - i; ++i; }
+    pi[tid] = (unsigned char)i; pj[tid] = (unsigned char)(i + e);
+  }
+  double ar[kCgNE][2], ai[kCgNE][2];
+#pragma unroll
+  for (int n = 0; n < kCgNE; ++n) { ar[n][0] = ar[n][1] = ai[n][0] = ai[n][1] = 0.0; }
+  double gs0 = 0.0, gs1 = 0.0;
+  const long long P = a.P;
+  for (int t0 = t_begin; t0 < t_end; t0 += a.tile_frames) {
+    const int nt = imin(a.tile_frames, t_end - t0);
+    __syncthreads();
+    for (int q = tid; q < nt * C * kCgBins; q += blockDim.x) {
+      const int l = q & (kCgBins - 1), tc = q / kCgBins;      // tc = t * C + c
+      const int f = bin0 + l;
+      ys[q] = f < F ? a.X[(((long long)b * a.T + t0) * C + tc) * P + f] : make_float2(0.f, 0.f);
+    }
+    for (int q = tid; q < nt * 2 * kCgBins; q += blockDim.x) {
+      const int l = q & (kCgBins - 1), tk = q / kCgBins;
+      const int t = tk >> 1, k = (tk & 1) ? k1 : a.k0;
+      const int f = bin0 + l;
+      ws[q] = (a.W && f < F) ? a.W[(((long long)b * a.K + k) * a.T + t0 + t) * P + f] : 1.0;
+    }
+    __syncthreads();
+    for (int t = 0; t < nt; ++t) {
+      const float2* yt = ys + t * C * kCgBins + bl;
+      const double w0 = ws[(2 * t) * kCgBins + bl], w1 = ws[(2 * t + 1) * kCgBins + bl];
+#pragma unroll
+      for (int n = 0; n < kCgNE; ++n) {
+        const int e = grp + n * G;
+        if (e < E) {
+          const float2 yi = yt[pi[e] * kCgBins], yj = yt[pj[e] * kCgBins];
+          const double xr = yi.x, xi = yi.y, zr = yj.x, zi = yj.y;
+          const double pr = xr * zr + xi * zi;             // y_i conj(y_j)
+          const double pm = xi * zr - xr * zi;
+          ar[n][0] += w0 * pr; ai[n][0] += w0 * pm;
+          ar[n][1] += w1 * pr; ai[n][1] += w1 * pm;
+        }
+      }
+      if (grp == 0 && live) {
+        if (a.G) {
+          gs0 += a.G[(((long long)b * a.K + a.k0) * a.T + t0 + t) * P + bin];
+          gs1 += a.G[(((long long)b * a.K + k1) * a.T + t0 + t) * P + bin];
+        } else {
+          gs0 += 1.0; gs1 += 1.0;
+        }
+      }
+    }
+  }
+  if (!live) return;
+  const int S = C * C + 1;
+  double* p0 = a.part + ((((long long)b * a.n_chunks + chunk) * a.K + a.k0) * S) * F + bin;
+  double* p1 = a.part + ((((long long)b * a.n_chunks + chunk) * a.K + k1) * S) * F + bin;
+#pragma unroll
+  for (int n = 0; n < kCgNE; ++n) {
+    const int e = grp + n * G;
+    if (e < E) {
+      const int i = pi[e], j = pj[e];
+      if (i == j) {
+        p0[(long long)i * F] = ar[n][0];
+        p1[(long long)i * F] = ar[n][1];
+      } else {
+        const int s = cgmm_slot(C, i, j);
+        p0[(long long)s * F] = ar[n][0]; p0[(long long)(s + 1) * F] = ai[n][0];
+        p1[(long long)s * F] = ar[n][1]; p1[(long long)(s + 1) * F] = ai[n][1];
+      }
+    }
+  }
+  if (grp == 0) {
+    p0[(long long)(C * C) * F] = gs0;
+    p1[(long long)(C * C) * F] = gs1;
+  }
+}
+
+struct CgmmFactorArgs {
+  const double* part; int n_chunks;
+  const int* n_samples; int N; Geometry g;
+  int B, T, K;
+  int identity_class;        // >= 0: that class gets R = I (cluster.py:421-425)
+  int update_alpha;
+  double* Rinv;              // [B][K][C*C][F]
+  double* logdet;            // [B][K][F]
+  double* alpha;             // [B][K][F]
+  unsigned* status;          // [B] or null
+};
+
+template <int C>
+__global__ void __launch_bounds__(64) cgmm_factor_kernel(CgmmFactorArgs a) {
+  const int F = a.g.F;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)a.B * a.K * F) return;
+  const int f = (int)(idx % F);
+  const int k = (int)((idx / F) % a.K);
+  const int b = (int)(idx / ((long long)F * a.K));
+  constexpr int S = C * C + 1;
+  CMat<C> A, V;
+  double gsum = 0.0;
+  if (k == a.identity_class) {
+    SETK_UNROLL_C
+    for (int i = 0; i < C; ++i)
+      SETK_UNROLL_C
+      for (int j = 0; j < C; ++j) A.a[i][j] = cd_make(i == j ? 1.0 : 0.0, 0.0);
+  } else {
+    SETK_UNROLL_C
+    for (int i = 0; i < C; ++i)
+      SETK_UNROLL_C
+      for (int j = 0; j < C; ++j) A.a[i][j] = cd_make(0.0, 0.0);
+    SETK_NOUNROLL
+    for (int ch = 0; ch < a.n_chunks; ++ch) {
+      const double* p = a.part + ((((long long)b * a.n_chunks + ch) * a.K + k) * S) * F + f;
+      SETK_UNROLL_C
+      for (int i = 0; i < C; ++i) {
+        A.a[i][i].x += p[(long long)i * F];
+        SETK_UNROLL_C
+        for (int j = i + 1; j < C; ++j) {
+          const int s = cgmm_slot(C, i, j);
+          A.a[i][j].x += p[(long long)s * F];
+          A.a[i][j].y += p[(long long)(s + 1) * F];
+        }
+      }
+      gsum += p[(long long)(C * C) * F];
+    }
+    const double inv = 1.0 / fmax(gsum, SETK_EPS32_D);
+    SETK_UNROLL_C
+    for (int i = 0; i < C; ++i) {
+      A.a[i][i].x *= inv;
+      SETK_UNROLL_C
+      for (int j = i + 1; j < C; ++j) {
+        A.a[i][j] = cd_scale(A.a[i][j], inv);
+        A.a[j][i] = cd_conj(A.a[i][j]);
+      }
+    }
+  }
+  if (a.update_alpha && k != a.identity_class) {
+    const int nb = a.n_samples ? a.n_samples[b] : a.N;
+    const int Tb = imin(frames_of(nb, a.g.n_fft, a.g.hop, a.g.pad), a.T);
+    a.alpha[((long long)b * a.K + k) * F + f] = gsum / (double)imax(Tb, 1);   // cluster.py:252
+  }
+  if (jacobi_eigh<C>(A, V) < 0 && a.status) atomicOr(a.status + b, (unsigned)SETK_ST_NO_CONVERGE);
+  double w[C];
+  double wmax = A.a[0][0].x;
+  SETK_UNROLL_C
+  for (int m = 1; m < C; ++m) wmax = fmax(wmax, A.a[m][m].x);
+  wmax = fmax(wmax, SETK_EPS32_D);
+  double ld = 0.0;
+  SETK_UNROLL_C
+  for (int m = 0; m < C; ++m) {
+    const double v = fmax(A.a[m][m].x / wmax, SETK_EPS32_D);
+    ld += log(v);
+    w[m] = 1.0 / v;
+  }
+  double* o = a.Rinv + (((long long)b * a.K + k) * (C * C)) * F + f;
+  SETK_UNROLL_C
+  for (int i = 0; i < C; ++i) {
+    SETK_UNROLL_C
+    for (int j = i; j < C; ++j) {
+      cd s = cd_make(0.0, 0.0);
+      SETK_UNROLL_C
+      for (int m = 0; m < C; ++m) s = cd_add(s, cd_scale(cd_mulc(V.a[i][m], V.a[j][m]), w[m]));
+      if (i == j) {
+        o[(long long)i * F] = s.x;
+      } else {
+        const int sl = cgmm_slot(C, i, j);
+        o[(long long)sl * F] = s.x;
+        o[(long long)(sl + 1) * F] = s.y;
+      }
+    }
+  }
+  a.logdet[((long long)b * a.K + k) * F + f] = ld;
+}
+
+struct CgmmEstepArgs {
+  const float2* X; int P;
+  const double* Rinv; const double* logdet; const double* alpha;
+  const int* n_samples; int N; Geometry g;
+  int T, frames_per_chunk;
+  double* G; double* W;      // [B][K][T][P]
+};
+
+// BL bins x (256 / BL) frame lanes per CTA; R^-1 of the BL bins in shared memory
+template <int C, int K, int BL>
+__global__ void __launch_bounds__(256) cgmm_estep_kernel(CgmmEstepArgs a) {
+  SETK_DYN_SMEM(double, rs);                 // [K][C*C][BL]
+  constexpr int L = 256 / BL, CC = C * C;
+  const int F = a.g.F;
+  const int tid = threadIdx.x;
+  const int bl = tid % BL, lane = tid / BL;
+  const int nbb = (F + BL - 1) / BL;
+  const int chunk = blockIdx.x / nbb, bin0 = (blockIdx.x - chunk * nbb) * BL;
+  const int b = blockIdx.y;
+  const int bin = bin0 + bl;
+  for (int q = tid; q < K * CC * BL; q += 256) {
+    const int l = q % BL, ks = q / BL;       // ks = k * CC + slot
+    const int f = bin0 + l;
+    rs[q] = f < F ? a.Rinv[((long long)b * K * CC + ks) * F + f] : 0.0;
+  }
+  __syncthreads();
+  if (bin >= F) return;
+  const int nb = a.n_samples ? a.n_samples[b] : a.N;
+  const int Tb = imin(frames_of(nb, a.g.n_fft, a.g.hop, a.g.pad), a.T);
+  const int t_begin = chunk * a.frames_per_chunk;
+  const int t_end = imin(t_begin + a.frames_per_chunk, Tb);
+  double ld[K], al[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    ld[k] = a.logdet[((long long)b * K + k) * F + bin];
+    al[k] = a.alpha[((long long)b * K + k) * F + bin];
+  }
+  const long long P = a.P;
+  const double* r = rs + bl;
+  for (int t = t_begin + lane; t < t_end; t += L) {
+    const float2* xt = a.X + (((long long)b * a.T + t) * C) * P + bin;
+    double yr[C], yi[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float2 v = xt[(long long)c * P];
+      yr[c] = v.x; yi[c] = v.y;
+    }
+    double q[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) q[k] = 0.0;
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+      const double n2 = yr[i] * yr[i] + yi[i] * yi[i];
+#pragma unroll
+      for (int k = 0; k < K; ++k) q[k] += r[(k * CC + i) * BL] * n2;
+#pragma unroll
+      for (int j = i + 1; j < C; ++j) {
+        // conj(y_i) y_j ;  y^H R^-1 y = sum_i R_ii |y_i|^2 + 2 Re sum_{i<j} conj(y_i) R_ij y_j
+        const double cr = yr[i] * yr[j] + yi[i] * yi[j];
+        const double ci = yr[i] * yi[j] - yi[i] * yr[j];
+        const int s = C + 2 * (i * C - i * (i + 1) / 2 + (j - i - 1));
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          q[k] += 2.0 * (r[(k * CC + s) * BL] * cr - r[(k * CC + s + 1) * BL] * ci);
+      }
+    }
+    double phi[K], lp[K], mx = -1.0e300;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      phi[k] = fmax(fabs(q[k]), SETK_EPS32_D) / (double)C;      // cluster.py:203-206
+      lp[k] = -(double)C * log(phi[k]) - ld[k];                 // cluster.py:228-229
+      mx = fmax(mx, lp[k]);
+    }
+    double den = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) { lp[k] = exp(lp[k] - mx) * al[k]; den += lp[k]; }   // cluster.py:276-281
+    den = fmax(den, SETK_EPS32_D);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const double gm = lp[k] / den;
+      const long long o = (((long long)b * K + k) * a.T + t) * P + bin;
+      a.G[o] = gm;
+      a.W[o] = gm * (double)C / phi[k];
+    }
+  }
+}
+
+// init_gamma f32 [B][K][T][F] -> G = W = gamma  (cluster.py:436-440: R = sum gamma y y^H / sum gamma)
+__global__ void cgmm_import_kernel(const float* __restrict__ gin, int B, int K, int T, int F, int P,
+                                   double* __restrict__ G, double* __restrict__ W) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * K * T * F) return;
+  const int f = (int)(idx % F);
+  const long long row = idx / F;             // (b * K + k) * T + t
+  const double v = gin[idx];
+  G[row * P + f] = v;
+  W[row * P + f] = v;
+}
+
+// G -> masks f32 [B][K][T][F]; frames past the utterance's own count are zero
+__global__ void cgmm_export_kernel(const double* __restrict__ G, const int* __restrict__ n_samples, int N,
+                                   Geometry g, int B, int K, int T, int P, float* __restrict__ masks) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * K * T * g.F) return;
+  const int f = (int)(idx % g.F);
+  const long long row = idx / g.F;
+  const int t = (int)(row % T);
+  const int b = (int)(row / ((long long)T * K));
+  const int nb = n_samples ? n_samples[b] : N;
+  const int Tb = frames_of(nb, g.n_fft, g.hop, g.pad);
+  masks[idx] = t < Tb ? (float)G[row * P + f] : 0.f;
+}
+
+__global__ void cgmm_fill_kernel(double* __restrict__ p, long long n, double v) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct CgmmWorkspace {
+  double *G, *W, *part, *Rinv, *logdet, *alpha;
+  int n_chunks;
+};
+
+static int cgmm_cov_chunks(const setk_plan* pl, int B, int T) {
+  const int bins = pl->geo.C <= 8 ? 64 : 32;
+  const int nbb = (pl->geo.F + bins - 1) / bins;
+  int chunks = (2 * pl->sm_count + B * nbb - 1) / (B * nbb);
+  if (chunks < 1) chunks = 1;
+  if (chunks > 8) chunks = 8;
+  if (chunks > T) chunks = T;
+  return chunks;
+}
+
+size_t cgmm_workspace_bytes(const setk_plan* pl, int B, int T, int K, int P) {
+  const Geometry& g = pl->geo;
+  const int chunks = cgmm_cov_chunks(pl, B, T);
+  size_t n = 2 * (size_t)B * K * T * P;                          // G, W
+  n += (size_t)B * chunks * K * (g.C * g.C + 1) * g.F;           // part
+  n += (size_t)B * K * g.C * g.C * g.F;                          // Rinv
+  n += 2 * (size_t)B * K * g.F;                                  // logdet, alpha
+  return n * sizeof(double);
+}
+
+static CgmmWorkspace cgmm_carve(const setk_plan* pl, double* base, int B, int T, int K, int P) {
+  const Geometry& g = pl->geo;
+  CgmmWorkspace w;
+  w.n_chunks = cgmm_cov_chunks(pl, B, T);
+  w.G = base;
+  w.W = w.G + (size_t)B * K * T * P;
+  w.part = w.W + (size_t)B * K * T * P;
+  w.Rinv = w.part + (size_t)B * w.n_chunks * K * (g.C * g.C + 1) * g.F;
+  w.logdet = w.Rinv + (size_t)B * K * g.C * g.C * g.F;
+  w.alpha = w.logdet + (size_t)B * K * g.F;
+  return w;
+}
+
+template <int BINS, int NE, int MAXT>
+static cudaError_t cgmm_cov_t(const setk_plan* pl, CgmmCovArgs a, bool uniform, int B, void* stream) {
+  const Geometry& g = pl->geo;
+  int tile = 6144 / (g.C * BINS);                        // <= 48 KB of c64 per tile
+  if (tile < 2) tile = 2;
+  if (tile > 32) tile = 32;
+  a.tile_frames = tile;
+  const int G = cgmm_groups(g.C, NE);
+  const size_t smem = (size_t)tile * g.C * BINS * sizeof(float2) + (size_t)tile * 2 * BINS * sizeof(double) + 512;
+#ifndef SETK_EMU
+  cudaError_t ea = cudaFuncSetAttribute(cgmm_cov_kernel<BINS, NE, MAXT>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  if (ea != cudaSuccess) return ea;
+#endif
+  const int nbb = (g.F + BINS - 1) / BINS;
+  const int k_last = uniform ? 1 : a.K;                  // the start needs class 0 only
+  for (int k0 = 0; k0 < k_last; k0 += 2) {
+    a.k0 = k0;
+    cudaError_t e = launch(cgmm_cov_kernel<BINS, NE, MAXT>, dim3(a.n_chunks * nbb, B), dim3(G * BINS), smem,
+                           stream, false, a);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+static cudaError_t cgmm_cov(const setk_plan* pl, const float2* X, int P, const CgmmWorkspace& w,
+                            bool uniform, const int* n_samples, int B, int N, int T, int K, void* stream) {
+  CgmmCovArgs a;
+  a.X = X; a.P = P;
+  a.W = uniform ? nullptr : w.W;
+  a.G = uniform ? nullptr : w.G;
+  a.n_samples = n_samples; a.N = N; a.g = pl->geo;
+  a.T = T; a.K = K; a.k0 = 0;
+  a.n_chunks = w.n_chunks;
+  a.frames_per_chunk = (T + w.n_chunks - 1) / w.n_chunks;
+  a.tile_frames = 2;
+  a.part = w.part;
+  if (pl->geo.C <= 8) return cgmm_cov_t<64, 10, 256>(pl, a, uniform, B, stream);
+  return cgmm_cov_t<32, 5, 1024>(pl, a, uniform, B, stream);
+}
+
+template <int C>
+static cudaError_t cgmm_factor_t(const CgmmFactorArgs& a, void* stream) {
+  const long long n = (long long)a.B * a.K * a.g.F;
+  return launch(cgmm_factor_kernel<C>, dim3((unsigned)((n + 63) / 64)), dim3(64), 0, stream, true, a);
+}
+
+static cudaError_t cgmm_factor(const setk_plan* pl, const CgmmWorkspace& w, int identity_class,
+                               int update_alpha, const int* n_samples, int B, int N, int T, int K,
+                               unsigned* status, void* stream) {
+  CgmmFactorArgs a;
+  a.part = w.part; a.n_chunks = w.n_chunks;
+  a.n_samples = n_samples; a.N = N; a.g = pl->geo;
+  a.B = B; a.T = T; a.K = K;
+  a.identity_class = identity_class; a.update_alpha = update_alpha;
+  a.Rinv = w.Rinv; a.logdet = w.logdet; a.alpha = w.alpha; a.status = status;
+  switch (pl->geo.C) {
+#define SETK_CASE(k) case k: return cgmm_factor_t<k>(a, stream);
+    SETK_CASE(1) SETK_CASE(2) SETK_CASE(3) SETK_CASE(4) SETK_CASE(5) SETK_CASE(6) SETK_CASE(7) SETK_CASE(8)
+    SETK_CASE(9) SETK_CASE(10) SETK_CASE(11) SETK_CASE(12) SETK_CASE(13) SETK_CASE(14) SETK_CASE(15) SETK_CASE(16)
+#undef SETK_CASE
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+template <int C, int K>
+static cudaError_t cgmm_estep_t(const setk_plan* pl, CgmmEstepArgs a, int B, void* stream) {
+  constexpr int BL = C <= 8 ? 64 : 16;
+  const size_t smem = sizeof(double) * K * C * C * BL;
+#ifndef SETK_EMU
+  cudaError_t e = cudaFuncSetAttribute(cgmm_estep_kernel<C, K, BL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
+  if (e != cudaSuccess) return e;
+#endif
+  const int nbb = (a.g.F + BL - 1) / BL;
+  int chunks = (4 * pl->sm_count + B * nbb - 1) / (B * nbb);
+  if (chunks < 1) chunks = 1;
+  if (chunks > a.T) chunks = a.T;
+  a.frames_per_chunk = (a.T + chunks - 1) / chunks;
+  chunks = (a.T + a.frames_per_chunk - 1) / a.frames_per_chunk;
+  return launch(cgmm_estep_kernel<C, K, BL>, dim3(chunks * nbb, B), dim3(256), smem, stream, false, a);
+}
+
+template <int C>
+static cudaError_t cgmm_estep_c(const setk_plan* pl, const CgmmEstepArgs& a, int B, int K, void* stream) {
+  switch (K) {
+    case 2: return cgmm_estep_t<C, 2>(pl, a, B, stream);
+    case 3: return cgmm_estep_t<C, 3>(pl, a, B, stream);
+    case 4: return cgmm_estep_t<C, 4>(pl, a, B, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+static cudaError_t cgmm_estep(const setk_plan* pl, const float2* X, int P, const CgmmWorkspace& w,
+                              const int* n_samples, int B, int N, int T, int K, void* stream) {
+  CgmmEstepArgs a;
+  a.X = X; a.P = P;
+  a.Rinv = w.Rinv; a.logdet = w.logdet; a.alpha = w.alpha;
+  a.n_samples = n_samples; a.N = N; a.g = pl->geo;
+  a.T = T; a.frames_per_chunk = T;
+  a.G = w.G; a.W = w.W;
+  switch (pl->geo.C) {
+#define SETK_CASE(k) case k: return cgmm_estep_c<k>(pl, a, B, K, stream);
+    SETK_CASE(1) SETK_CASE(2) SETK_CASE(3) SETK_CASE(4) SETK_CASE(5) SETK_CASE(6) SETK_CASE(7) SETK_CASE(8)
+    SETK_CASE(9) SETK_CASE(10) SETK_CASE(11) SETK_CASE(12) SETK_CASE(13) SETK_CASE(14) SETK_CASE(15) SETK_CASE(16)
+#undef SETK_CASE
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// CgmmTrainer(...).train(num_iters) over the workspace X of B utterances.
+cudaError_t run_cgmm(setk_plan* pl, const float2* X, int P, double* ws, const int* n_samples, int B, int N,
+                     int T, int K, int num_iters, const float* init_gamma, int update_alpha, float* masks,
+                     unsigned* status, void* stream) {
+  const Geometry& g = pl->geo;
+  const CgmmWorkspace w = cgmm_carve(pl, ws, B, T, K, P);
+  cudaError_t e;
+  {  // alpha = 1 / K  (cluster.py:447)
+    const long long n = (long long)B * K * g.F;
+    e = launch(cgmm_fill_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, true, w.alpha, n,
+               1.0 / (double)K);
+    if (e != cudaSuccess) return e;
+  }
+  const bool uniform = init_gamma == nullptr;           // K = 2: R_0 = sum y y^H / T, R_1 = I
+  if (!uniform) {
+    const long long n = (long long)B * K * T * g.F;
+    e = launch(cgmm_import_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, true, init_gamma,
+               B, K, T, g.F, P, w.G, w.W);
+    if (e != cudaSuccess) return e;
+  }
+  e = cgmm_cov(pl, X, P, w, uniform, n_samples, B, N, T, K, stream);
+  if (e == cudaSuccess) e = cgmm_factor(pl, w, uniform ? 1 : -1, 0, n_samples, B, N, T, K, status, stream);
+  if (e == cudaSuccess) e = cgmm_estep(pl, X, P, w, n_samples, B, N, T, K, stream);
+  for (int it = 0; it < num_iters && e == cudaSuccess; ++it) {
+    e = cgmm_cov(pl, X, P, w, false, n_samples, B, N, T, K, stream);
+    if (e == cudaSuccess) e = cgmm_factor(pl, w, -1, update_alpha, n_samples, B, N, T, K, status, stream);
+    if (e == cudaSuccess) e = cgmm_estep(pl, X, P, w, n_samples, B, N, T, K, stream);
+  }
+  if (e != cudaSuccess) return e;
+  const long long n = (long long)B * K * T * g.F;
+  return launch(cgmm_export_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, true,
+                (const double*)w.G, n_samples, N, g, B, K, T, P, masks);
+}
+
+}  // namespace setk

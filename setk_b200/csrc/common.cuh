@@ -63,5 +63,6 @@ struct setk_plan {
   float2* d_enh_ws;      size_t enh_ws_bytes;     // generic path enhanced STFT [B][F][T]
   float* d_frames_ws;    size_t frames_ws_bytes;  // generic iSTFT frames [B][T][n_fft]
   unsigned* d_peak;      size_t peak_bytes;       // [B] max|y| as uint bits
+  double* d_cgmm_ws;     size_t cgmm_ws_bytes;    // CGMM posteriors, partials, R^-1 (cgmm.cu)
   int sm_count;
 };

@@ -355,6 +355,25 @@ __global__ void __launch_bounds__(288) apply_spill_kernel(ApplySpillArgs a) {
   }
 }
 
+// workspace [B][T][C][P] -> the API's STFT layout [B][C][F][T] (forward_stft with
+// transpose=False, utils.py:96-138): 32 x 32 (t, f) tiles through shared memory
+__global__ void __launch_bounds__(256) spill_to_bcft_kernel(const float2* __restrict__ xws, int P, int C,
+                                                            int F, int T, float2* __restrict__ out) {
+  __shared__ float2 tile[32][33];
+  const int bc = blockIdx.z, b = bc / C, c = bc - b * C;
+  const int t0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int t = t0 + r, f = f0 + tx;
+    if (t < T && f < F) tile[r][tx] = xws[(((long long)b * T + t) * C + c) * P + f];
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int f = f0 + r, t = t0 + tx;
+    if (t < T && f < F) out[(((long long)b * C + c) * F + f) * T + t] = tile[tx][r];
+  }
+}
+
 struct CovSpillArgs {
   const float2* xws;     // [B][T][C][pitch]
   int pitch;
@@ -548,6 +567,12 @@ cudaError_t run_cov_spill(setk_plan* pl, const float2* xws, const float* mask_s,
 #undef SETK_CASE
     default: return cudaErrorInvalidValue;
   }
+}
+
+cudaError_t run_spill_to_bcft(const setk_plan* pl, const float2* xws, int B, int T, float2* out, void* stream) {
+  const Geometry& g = pl->geo;
+  return launch(spill_to_bcft_kernel, dim3((T + 31) / 32, (g.F + 31) / 32, B * g.C), dim3(256), 0, stream,
+                false, xws, spill_pitch(g.n_fft), g.C, g.F, T, out);
 }
 
 // y = w^H x over the workspace -> yws [B][T][pitch]

@@ -8,6 +8,7 @@
 //   solve_pevd 31-63, do_ban 14-28, rank1_constraint 66-84,
 //   MvdrBeamformer.weight 527-539, MpdrBeamformer.weight 555-573,
 //   PmwfBeamformer.weight/_snr 620-659, GevdBeamformer.weight 674-682.
+#include <cstdlib>
 #include "common.cuh"
 #include "hermitian_solve.cuh"
 
@@ -252,7 +253,12 @@ __global__ void __launch_bounds__(128) pmwf_select_kernel(WeightsArgs a) {
 template <int C>
 static cudaError_t launch_weights(const WeightsArgs& a, void* stream) {
   long long n = (long long)a.B * a.F;
-  dim3 block(128), grid((unsigned)((n + 127) / 128));
+  // one bin per thread and data-dependent run times: small CTAs spread a batch
+  // of only B*F threads over all SMs and keep the tail short
+  static int forced = -1;
+  if (forced < 0) { const char* s = getenv("SETK_WEIGHTS_BLOCK"); forced = s ? atoi(s) : 0; }
+  const int bs = forced > 0 ? forced : 128;
+  dim3 block(bs), grid((unsigned)((n + bs - 1) / bs));
   cudaError_t e = launch(weights_kernel<C>, grid, block, 0, stream, /*barrier_free=*/true, a);
   if (e != cudaSuccess) return e;
   if (a.kind == SETK_BF_PMWF && a.ref_channel < 0)

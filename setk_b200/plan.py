@@ -180,6 +180,31 @@ class StftPlan(object):
                 flags, _lib.ptr(Rs), _lib.ptr(Rn), _lib.ptr(maxabs), self._stream()))
         return Rs, Rn, maxabs
 
+    def cgmm_masks(self, audio, num_classes=2, num_iters=20, init_gamma=None, update_alpha=False,
+                   n_samples=None):
+        """
+        CGMM mask estimation from audio (STFT + CgmmTrainer(...).train(num_iters),
+        cluster.py:396-465).  init_gamma (B,K,T,F) or None (2 classes only).
+        Returns (masks (B,K,T,F) float32, status (B,) int32).
+        """
+        audio = self._check_audio(audio)
+        B, C, N = audio.shape
+        T = self.num_frames(N)
+        F = self.num_bins
+        K = int(num_classes)
+        if init_gamma is not None:
+            init_gamma = _f32(init_gamma, self.device)
+            if tuple(init_gamma.shape) != (B, K, T, F):
+                raise ValueError(f"init_gamma must be {(B, K, T, F)}, got {tuple(init_gamma.shape)}")
+        ns = self._nsamp(n_samples, B)
+        masks = torch.empty((B, K, T, F), dtype=torch.float32, device=self.device)
+        status = torch.zeros((B,), dtype=torch.int32, device=self.device)
+        with self._device_ctx():
+            _lib.check(_lib.library().setk_cgmm_masks(
+                self._h, _lib.ptr(audio), _lib.ptr(ns), B, N, K, int(num_iters), _lib.ptr(init_gamma),
+                1 if update_alpha else 0, _lib.ptr(masks), _lib.ptr(status), self._stream()))
+        return masks, status
+
     def istft(self, enh, n_out=None, norm=None):
         """enh (B,F,T) complex64 -> wave (B,n_out) float32 (inverse_stft)."""
         enh = torch.as_tensor(enh, device=self.device)

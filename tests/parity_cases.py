@@ -344,3 +344,105 @@ def check_config_fixture(device, name, tol=TOL_E2E, stft_from_oracle=False):
 
 def rel_inf_aligned(test, ref):
     return bo.rel_inf(bo.align_phase(np.asarray(test, dtype=np.complex128), ref)[0], ref)
+
+
+# ---------------------------------------------------------------- CGMM masks ---
+TOL_CGMM = 1e-6          # fp64 kernels vs the float64 oracle on the same STFT (observed 3e-8:
+                         # the float32 rounding of the stored mask)
+
+
+def structured_audio(rng, B, C, N):
+    """A gated common source through short random filters plus sensor noise."""
+    x = (rng.standard_normal((B, C, N)) * 0.05).astype(np.float32)
+    for b in range(B):
+        s = rng.standard_normal(N) * 0.3 * (np.sin(np.arange(N) / (200.0 + 50 * b)) > 0)
+        for c in range(C):
+            h = rng.standard_normal(8) * np.exp(-np.arange(8) / 3.0)
+            x[b, c] += np.convolve(s, h)[:N].astype(np.float32)
+    return x
+
+
+def check_cgmm(device, rng, B, C, N, frame_len=512, hop=256, K=2, iters=4, with_init=False,
+               update_alpha=False, n_samples=None):
+    """setk_cgmm_masks vs oracle.cgmm_oracle fed the library's own STFT."""
+    from oracle import cgmm_oracle as co
+    x = structured_audio(rng, B, C, N)
+    pl = P.StftPlan(C, frame_len, hop, True, True, "hann", B, N, device)
+    xt = torch.from_numpy(x).to(device)
+    X = pl.stft(xt, n_samples=n_samples).cpu().numpy()          # (B, C, F, T)
+    T, F = X.shape[-1], X.shape[2]
+    init = None
+    if with_init:
+        g = rng.uniform(0.05, 1.0, size=(B, K, T, F))
+        init = (g / g.sum(1, keepdims=True)).astype(np.float32)
+    masks, status = pl.cgmm_masks(xt, K, iters, init_gamma=None if init is None else torch.from_numpy(init).to(device),
+                                  update_alpha=update_alpha, n_samples=n_samples)
+    masks = masks.cpu().numpy()
+    assert masks.shape == (B, K, T, F) and masks.dtype == np.float32
+    assert int(status.cpu().abs().sum()) == 0
+    worst = 0.0
+    for b in range(B):
+        Tb = T if n_samples is None else pl.num_frames(int(n_samples[b]))
+        ig = None if init is None else np.transpose(init[b, :, :Tb].astype(np.float64), (0, 2, 1))
+        ref = co.cgmm_masks(X[b][:, :, :Tb], K, iters, init_gamma=ig, update_alpha=update_alpha,
+                            return_all=True)[1][-1]              # K x F x T
+        ref = np.transpose(ref, (0, 2, 1))
+        err = float(np.max(np.abs(masks[b, :, :Tb] - ref)))
+        assert err <= TOL_CGMM, f"cgmm masks differ by {err}"
+        assert np.all(masks[b, :, Tb:] == 0)
+        worst = max(worst, err)
+    pl.close()
+    return worst
+
+
+def check_cgmm_fixture(device, name, mean_tol=2e-5, max_tol=5e-3):
+    """
+    From the fixture's audio to the REFERENCE's masks (tests/golden/ref_cgmm.npz,
+    CgmmTrainer run by the reference on its float64 STFT).  The library's STFT is
+    float32 arithmetic, and EM amplifies that rounding exactly as it amplifies the
+    float32 rounding of the reference's own start (oracle/cgmm_oracle.py header:
+    1.9e-3 worst cell, 8e-7 mean on the config-3 fixture) -- hence a mean and a
+    worst-cell bound rather than one tight rel-inf.
+    """
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_cgmm.npz"))
+    mix = g[name + "/mix"]
+    K, iters, upd = (int(v) for v in g[name + "/cfg"])
+    init = g[name + "/init_gamma"]                               # F x T or K x F x T
+    if init.ndim == 2:
+        init = np.stack([init, 1 - init])                        # cluster.py:428-429
+    init = np.ascontiguousarray(np.transpose(init, (0, 2, 1)))[None]   # 1 x K x T x F
+    C, N = mix.shape
+    pl = P.StftPlan(C, 512, 256, True, True, "hann", 1, N, device)
+    masks, _ = pl.cgmm_masks(torch.from_numpy(mix[None]).to(device), K, iters,
+                             init_gamma=torch.from_numpy(init).to(device), update_alpha=bool(upd))
+    d = np.abs(masks[0].cpu().numpy() - g[name + "/masks"])
+    pl.close()
+    assert d.mean() <= mean_tol and d.max() <= max_tol, (name, float(d.mean()), float(d.max()))
+    return float(d.mean()), float(d.max())
+
+
+def check_cgmm_documented(device, which):
+    """
+    The documented mask command (estimate_cgmm_masks.py --num-iters 20) from audio:
+    "doc"  egs.wav, 5 ch, 512/256  vs the reference's mask (doc_adaptive_beamformer.npz)
+    "cfg3" config-3 mixture, 8 ch, 1024/256 vs ref_configs.npz "cfg3/mask_cgmm".
+    Returns (mean, max, fraction of cells off by more than 1e-3).
+    """
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    if which == "doc":
+        g = np.load(os.path.join(gold, "doc_adaptive_beamformer.npz"))
+        x, ref, fl = so.float_from_pcm16(g["egs_pcm16"]), g["mask"], 512
+    else:
+        g = np.load(os.path.join(gold, "ref_configs.npz"))
+        x, ref, fl = g["cfg3/mix"], g["cfg3/mask_cgmm"], 1024
+    C, N = x.shape
+    pl = P.StftPlan(C, fl, 256, True, True, "hann", 1, N, device)
+    masks, status = pl.cgmm_masks(torch.from_numpy(np.ascontiguousarray(x[None])).to(device), 2, 20)
+    m = masks[0, 0].cpu().numpy()
+    pl.close()
+    assert int(status.cpu().abs().sum()) == 0
+    assert m.shape == ref.shape
+    d = np.abs(m - ref)
+    return float(d.mean()), float(d.max()), float(np.mean(d > 1e-3))

@@ -95,6 +95,37 @@ def test_nfft1024_ragged(emu):
                          n_samples=torch.tensor([3000, 1501], dtype=torch.int32))   # generic route
 
 
+@pytest.mark.parametrize("C,fl,K,init,alpha", [
+    (4, 512, 2, False, False),        # the documented command: 2 classes, deterministic start
+    (3, 1024, 3, True, True),         # given posteriors, 3 classes, prior update
+    (9, 512, 2, False, False),        # C > 8: 32-bin CTAs, 5 entries per thread
+])
+def test_cgmm_masks(emu, C, fl, K, init, alpha):
+    rng = np.random.default_rng(80 + C)
+    pc.check_cgmm(emu, rng, 2, C, 4600, fl, 256, K, 3, with_init=init, update_alpha=alpha,
+                  n_samples=torch.tensor([4600, 3300], dtype=torch.int32) if C == 3 else None)
+
+
+def test_cgmm_reference_fixtures(emu):
+    for name in ("k3_alpha", "k2_init"):
+        pc.check_cgmm_fixture(emu, name)
+
+
+def test_cgmm_argument_errors(emu):
+    from setk_b200 import plan as P
+    pl = P.StftPlan(2, 512, 256, True, True, "hann", 1, 3000, emu)
+    x = torch.zeros((1, 2, 3000))
+    with pytest.raises(Exception):
+        pl.cgmm_masks(x, 3, 2)                   # 3 classes need a start
+    with pytest.raises(Exception):
+        pl.cgmm_masks(x, 5, 2, init_gamma=torch.zeros((1, 5, pl.num_frames(3000), 257)))
+    pl.close()
+    pl = P.StftPlan(2, 256, 64, True, True, "hann", 1, 3000, emu)
+    with pytest.raises(Exception):
+        pl.cgmm_masks(x, 2, 2)                   # n_fft 256: no tile STFT
+    pl.close()
+
+
 def test_cov_generic(emu):
     pc.check_cov_generic(emu, np.random.default_rng(7), 2, 6, 9, 70)
 

@@ -260,3 +260,37 @@ def test_pcm_conversions(cuda):
 def test_config_fixtures_from_reference(cuda, name):
     """configs 3 (reference CGMM mask -> GEV) and 4 (reference WPE -> MVDR)."""
     pc.check_config_fixture(cuda, name)
+
+
+@pytest.mark.parametrize("C,fl,K,init,alpha,ragged", [
+    (4, 512, 2, False, False, False),
+    (5, 512, 2, True, False, True),
+    (8, 1024, 2, False, False, False),     # config-3 geometry
+    (3, 1024, 3, True, True, True),
+    (6, 512, 4, True, True, False),
+    (12, 512, 2, False, False, False),     # C > 8 kernels
+    (16, 512, 3, True, False, False),
+])
+def test_cgmm_masks(cuda, C, fl, K, init, alpha, ragged):
+    rng = np.random.default_rng(300 + C)
+    ns = torch.tensor([16000, 9100, 12345], dtype=torch.int32) if ragged else None
+    pc.check_cgmm(cuda, rng, 3, C, 16000, fl, 256, K, 8, with_init=init, update_alpha=alpha,
+                  n_samples=ns)
+
+
+def test_cgmm_reference_fixtures(cuda):
+    """given posteriors / 3 classes / prior update, run by the reference (ref_cgmm.npz)"""
+    for name in ("k3_alpha", "k2_init"):
+        pc.check_cgmm_fixture(cuda, name)
+
+
+@pytest.mark.parametrize("which", ["doc", "cfg3"])
+def test_cgmm_documented_command_from_audio(cuda, which):
+    """
+    estimate_cgmm_masks.py --num-iters 20 from audio vs the reference's masks.
+    The bounds are the reference's own sensitivity to float32 rounding of its
+    start (oracle/cgmm_oracle.py header), since this path's STFT is float32.
+    """
+    mean, worst, frac = pc.check_cgmm_documented(cuda, which)
+    print(f"cgmm {which}: mean {mean:.3g} max {worst:.3g} frac>1e-3 {frac:.3g}")
+    assert mean <= 2e-5 and frac <= 1e-3 and worst <= 5e-2

@@ -88,6 +88,39 @@ def test_oracle_reproduces_reference_config_cases():
     assert bo.rel_inf(bo.align_phase(enh4, ref4)[0], ref4) <= 1e-6
 
 
+def test_cgmm_oracle_pinned_to_reference_masks():
+    """
+    cluster.py CgmmTrainer run by the reference (make_golden.py): the documented
+    command on egs.wav, the config-3 mixture, and the given-posteriors / 3-class /
+    prior-update paths.  With the reference's complex64 start the restatement agrees
+    to the float32 rounding of the stored masks.
+    """
+    from oracle import cgmm_oracle as co
+    g = np.load(os.path.join(GOLD, "doc_adaptive_beamformer.npz"))
+    kw = dict(frame_len=512, frame_hop=256, center=True, window="hann", transpose=False)
+    obs = so.multichannel_stft(so.float_from_pcm16(g["egs_pcm16"]), round_power_of_two=True,
+                               out_dtype=np.complex64, **kw)
+    m = co.cgmm_masks(obs, 2, 20, start_dtype=np.complex64)
+    assert np.max(np.abs(m - g["mask"])) <= 1e-7
+    g3 = np.load(os.path.join(GOLD, "ref_configs.npz"))
+    kw["frame_len"] = 1024
+    obs = so.multichannel_stft(g3["cfg3/mix"], round_power_of_two=True, out_dtype=np.complex64, **kw)
+    m = co.cgmm_masks(obs, 2, 20, start_dtype=np.complex64)
+    assert np.max(np.abs(m - g3["cfg3/mask_cgmm"])) <= 1e-7
+    # the float64 start moves a few cells: the reference's own sensitivity (see the oracle header)
+    d = np.abs(co.cgmm_masks(obs, 2, 20) - g3["cfg3/mask_cgmm"])
+    assert d.mean() <= 5e-6 and d.max() <= 1e-2
+    gc = np.load(os.path.join(GOLD, "ref_cgmm.npz"))
+    kw["frame_len"] = 512
+    for name in ("k3_alpha", "k2_init"):
+        K, iters, upd = (int(v) for v in gc[name + "/cfg"])
+        obs = so.multichannel_stft(gc[name + "/mix"], round_power_of_two=True, out_dtype=np.complex64, **kw)
+        m = co.cgmm_masks(obs, K, iters, init_gamma=gc[name + "/init_gamma"].astype(np.float64),
+                          update_alpha=bool(upd))
+        m = m[None] if K == 2 else m
+        assert np.max(np.abs(m - gc[name + "/masks"][:m.shape[0]])) <= 1e-7
+
+
 def test_bookkeeping_table():
     """frame counts and iSTFT lengths at N = 160000, hop 256."""
     rows = [(512, True, 512, 257, 626, 160000), (1024, True, 1024, 513, 626, 160000),

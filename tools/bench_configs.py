@@ -18,7 +18,7 @@ from setk_b200 import synth  # noqa: E402
 from setk_b200.engine import BeamformPipeline  # noqa: E402
 
 
-def run(name, C, frame_len, beamformer, B, N=160000, steps=10):
+def run(name, C, frame_len, beamformer, B, N=160000, steps=10, cgmm=False):
     dev = torch.device("cuda:0")
     pipe = BeamformPipeline(C, beamformer, frame_len=frame_len, frame_hop=256, max_batch=B,
                             max_samples=N, device=dev)
@@ -36,7 +36,9 @@ def run(name, C, frame_len, beamformer, B, N=160000, steps=10):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    fused = C <= 4 and pipe.plan.n_fft == 512
+    nf = pipe.plan.n_fft
+    route = ("fused" if (C <= 4 and nf == 512) else
+             "tile STFT -> bin-major workspace" if nf in (512, 1024) else "generic (explicit STFT in HBM)")
 
     def timed(fn, n=3):
         fn(); torch.cuda.synchronize()
@@ -51,17 +53,32 @@ def run(name, C, frame_len, beamformer, B, N=160000, steps=10):
     t_w, (w, _, _) = timed(lambda: pipe.solve(Rs, Rn))
     t_ai, _ = timed(lambda: pipe.plan.apply_istft(audio, w, norm=mx))
     stages = {"stft_cov_ms": t_cov, "weights_ms": t_w, "apply_istft_ms": t_ai}
+    cg = None
+    if cgmm:
+        torch.cuda.synchronize()
+        t_cg, (masks, st) = timed(lambda: pipe.plan.cgmm_masks(audio, 2, 20), n=2)
+        cg = {"cgmm_20it_ms": t_cg, "cgmm_utts_per_s": B / t_cg * 1e3,
+              "mask_mean": float(masks[:, 0].mean()), "status_failures": int((st != 0).sum())}
+        stages["cgmm"] = cg
     print(json.dumps({"config": name, "channels": C, "n_fft": pipe.plan.n_fft, "beamformer": beamformer,
                       "batch": B, "ms_per_batch": ms, "utts_per_s": B / ms * 1e3,
-                      "route": "fused" if fused else "generic (explicit STFT in HBM)", "stages": stages,
+                      "route": route, "stages": stages,
                       "status_failures": int((status != 0).sum())}), flush=True)
     del pipe, audio, mask, wave
     torch.cuda.empty_cache()
 
 
+CONFIGS = [
+    ("cfg2 4ch MVDR 512", 4, 512, "mvdr", 256),
+    ("cfg4 6ch MVDR 512", 6, 512, "mvdr", 64),
+    ("cfg5 8ch MVDR 512", 8, 512, "mvdr", 64),
+    ("cfg5 16ch MVDR 512", 16, 512, "mvdr", 32),
+    ("cfg3 8ch GEV 1024", 8, 1024, "gevd", 64),
+]
+
 if __name__ == "__main__":
-    run("cfg2 4ch MVDR 512", 4, 512, "mvdr", 256)
-    run("cfg4 6ch MVDR 512", 6, 512, "mvdr", 64)
-    run("cfg5 8ch MVDR 512", 8, 512, "mvdr", 64)
-    run("cfg5 16ch MVDR 512", 16, 512, "mvdr", 32)
-    run("cfg3 8ch GEV 1024", 8, 1024, "gevd", 64)
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
+    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+    for cfg in CONFIGS:
+        if only in cfg[0]:
+            run(*cfg, steps=steps, cgmm=(len(sys.argv) > 3 and sys.argv[3] == "cgmm"))
