@@ -18,7 +18,7 @@ DEPS[weights_post]="common.cuh compat.cuh hermitian_solve.cuh"
 DEPS[stft_cov_fused]="common.cuh compat.cuh stft_tile.cuh fft16.cuh async_copy.cuh"
 DEPS[apply_istft_fused]="common.cuh compat.cuh stft_tile.cuh fft16.cuh async_copy.cuh"
 DEPS[stft_spill]="common.cuh compat.cuh stft_tile.cuh fft16.cuh async_copy.cuh"
-DEPS[cgmm]="common.cuh compat.cuh hermitian_solve.cuh"
+DEPS[cgmm]="common.cuh compat.cuh hermitian_solve.cuh jacobi_coop.cuh"
 pids=()
 for f in api generic weights weights_post stft_cov_fused apply_istft_fused stft_spill cgmm; do
   stale=0

@@ -23,18 +23,17 @@
 //                       posterior (log-sum-exp shifted), G and W for the next pass.
 // All arithmetic after the complex64 STFT is fp64, as in the reference.
 #include "common.cuh"
-#include "hermitian_solve.cuh"
+#include "jacobi_coop.cuh"
 
 namespace setk {
 
-// covariance pass: BINS bins per CTA, <= NE Hermitian entries per thread
-//   C <= 8 : 64 bins x <= 4 entry groups of <= 10 entries   (<= 256 threads)
-//   C  > 8 : 32 bins x <= 28 groups of <= 5 entries         (<= 896 threads)
-SETK_HD inline int cgmm_groups(int C, int NE) {
-  const int E = C * (C + 1) / 2;
-  int g = (E + NE - 1) / NE;
-  return g < 2 ? 2 : g;
-}
+// covariance pass: BINS bins per CTA; the upper triangle of R is cut into 2 x 2
+// blocks over (row pair I, column pair J >= I) and every thread owns <= NBT of
+// them, so four entries share four shared-memory loads:
+//   C <= 8 : 64 bins x <= 5 groups   (<= 320 threads)
+//   C  > 8 : 32 bins x <= 18 groups  (<= 576 threads)
+SETK_HD inline int cgmm_blocks(int C) { const int nb = (C + 1) / 2; return nb * (nb + 1) / 2; }
+SETK_HD inline int cgmm_groups(int C, int NBT) { return (cgmm_blocks(C) + NBT - 1) / NBT; }
 // packed Hermitian slots of a C x C matrix: [0, C) the real diagonal, then
 // (re, im) of the entries above it in row-major order; C*C doubles in all
 SETK_HD inline int cgmm_slot(int C, int i, int j) {   // i < j
@@ -51,19 +50,20 @@ struct CgmmCovArgs {
   double* part;             // [B][n_chunks][K][C*C + 1][F]
 };
 
-template <int kCgBins, int kCgNE, int MAXT>
+template <int BINS, int NBT, int MAXT>
 __global__ void __launch_bounds__(MAXT) cgmm_cov_kernel(CgmmCovArgs a) {
-  SETK_DYN_SMEM(float2, ys);                 // [tile_frames][C][BINS]
+  SETK_DYN_SMEM(double2, ys);                // [tile_frames][Cp][BINS], converted once
   const int C = a.g.C, F = a.g.F;
-  const int E = C * (C + 1) / 2;
-  const int G = blockDim.x / kCgBins;
-  double* ws = reinterpret_cast<double*>(ys + a.tile_frames * C * kCgBins);   // [tile][2][64]
-  unsigned char* pi = reinterpret_cast<unsigned char*>(ws + a.tile_frames * 2 * kCgBins);
-  unsigned char* pj = pi + 256;
+  const int NB = (C + 1) / 2, Cp = 2 * NB;   // an odd C gets a zero row
+  const int NBK = NB * (NB + 1) / 2;
+  const int G = blockDim.x / BINS;
+  double* ws = reinterpret_cast<double*>(ys + a.tile_frames * Cp * BINS);    // [tile][2][BINS]
+  unsigned char* bi = reinterpret_cast<unsigned char*>(ws + a.tile_frames * 2 * BINS);
+  unsigned char* bj = bi + 64;
   const int tid = threadIdx.x;
-  const int bl = tid & (kCgBins - 1), grp = tid / kCgBins;
-  const int nbb = (F + kCgBins - 1) / kCgBins;
-  const int chunk = blockIdx.x / nbb, bin0 = (blockIdx.x - chunk * nbb) * kCgBins;
+  const int bl = tid & (BINS - 1), grp = tid / BINS;
+  const int nbb = (F + BINS - 1) / BINS;
+  const int chunk = blockIdx.x / nbb, bin0 = (blockIdx.x - chunk * nbb) * BINS;
   const int b = blockIdx.y;
   const int bin = bin0 + bl;
   const bool live = bin < F;
@@ -72,44 +72,56 @@ __global__ void __launch_bounds__(MAXT) cgmm_cov_kernel(CgmmCovArgs a) {
   const int t_begin = chunk * a.frames_per_chunk;
   const int t_end = imin(t_begin + a.frames_per_chunk, Tb);
   const int k1 = a.k0 + 1 < a.K ? a.k0 + 1 : a.k0;     // a lone last class is computed twice
-  if (tid < E) {                                       // entry -> (i, j), row-major upper triangle
+  if (tid < NBK) {                                     // block -> (I, J), row-major upper triangle
     int e = tid, i = 0;
-    while (e >= C - i) { e -= C - i; ++i; }
-    pi[tid] = (unsigned char)i; pj[tid] = (unsigned char)(i + e);
+    while (e >= NB - i) { e -= NB - i; ++i; }
+    bi[tid] = (unsigned char)i; bj[tid] = (unsigned char)(i + e);
   }
-  double ar[kCgNE][2], ai[kCgNE][2];
+  // acc[n][e][k]: block n, entry e = (row 2I + e/2, column 2J + e%2), class k
+  double ar[NBT][4][2], ai[NBT][4][2];
 #pragma unroll
-  for (int n = 0; n < kCgNE; ++n) { ar[n][0] = ar[n][1] = ai[n][0] = ai[n][1] = 0.0; }
+  for (int n = 0; n < NBT; ++n)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { ar[n][e][0] = ar[n][e][1] = ai[n][e][0] = ai[n][e][1] = 0.0; }
   double gs0 = 0.0, gs1 = 0.0;
   const long long P = a.P;
   for (int t0 = t_begin; t0 < t_end; t0 += a.tile_frames) {
     const int nt = imin(a.tile_frames, t_end - t0);
     __syncthreads();
-    for (int q = tid; q < nt * C * kCgBins; q += blockDim.x) {
-      const int l = q & (kCgBins - 1), tc = q / kCgBins;      // tc = t * C + c
+    for (int q = tid; q < nt * Cp * BINS; q += blockDim.x) {
+      const int l = q & (BINS - 1), tc = q / BINS;
+      const int t = tc / Cp, c = tc - t * Cp;
       const int f = bin0 + l;
-      ys[q] = f < F ? a.X[(((long long)b * a.T + t0) * C + tc) * P + f] : make_float2(0.f, 0.f);
+      float2 v = make_float2(0.f, 0.f);
+      if (c < C && f < F) v = a.X[(((long long)b * a.T + t0 + t) * C + c) * P + f];
+      ys[q] = make_double2((double)v.x, (double)v.y);
     }
-    for (int q = tid; q < nt * 2 * kCgBins; q += blockDim.x) {
-      const int l = q & (kCgBins - 1), tk = q / kCgBins;
+    for (int q = tid; q < nt * 2 * BINS; q += blockDim.x) {
+      const int l = q & (BINS - 1), tk = q / BINS;
       const int t = tk >> 1, k = (tk & 1) ? k1 : a.k0;
       const int f = bin0 + l;
       ws[q] = (a.W && f < F) ? a.W[(((long long)b * a.K + k) * a.T + t0 + t) * P + f] : 1.0;
     }
     __syncthreads();
     for (int t = 0; t < nt; ++t) {
-      const float2* yt = ys + t * C * kCgBins + bl;
-      const double w0 = ws[(2 * t) * kCgBins + bl], w1 = ws[(2 * t + 1) * kCgBins + bl];
+      const double2* yt = ys + t * Cp * BINS + bl;
+      const double w0 = ws[(2 * t) * BINS + bl], w1 = ws[(2 * t + 1) * BINS + bl];
 #pragma unroll
-      for (int n = 0; n < kCgNE; ++n) {
-        const int e = grp + n * G;
-        if (e < E) {
-          const float2 yi = yt[pi[e] * kCgBins], yj = yt[pj[e] * kCgBins];
-          const double xr = yi.x, xi = yi.y, zr = yj.x, zi = yj.y;
-          const double pr = xr * zr + xi * zi;             // y_i conj(y_j)
-          const double pm = xi * zr - xr * zi;
-          ar[n][0] += w0 * pr; ai[n][0] += w0 * pm;
-          ar[n][1] += w1 * pr; ai[n][1] += w1 * pm;
+      for (int n = 0; n < NBT; ++n) {
+        const int blk = grp + n * G;
+        if (blk < NBK) {
+          const int I = bi[blk], J = bj[blk];
+          double2 ya[2], yb[2];
+          ya[0] = yt[(2 * I) * BINS]; ya[1] = yt[(2 * I + 1) * BINS];
+          yb[0] = yt[(2 * J) * BINS]; yb[1] = yt[(2 * J + 1) * BINS];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const double2 u = ya[e >> 1], v = yb[e & 1];
+            const double pr = u.x * v.x + u.y * v.y;       // y_i conj(y_j)
+            const double pm = u.y * v.x - u.x * v.y;
+            ar[n][e][0] += w0 * pr; ai[n][e][0] += w0 * pm;
+            ar[n][e][1] += w1 * pr; ai[n][e][1] += w1 * pm;
+          }
         }
       }
       if (grp == 0 && live) {
@@ -127,17 +139,21 @@ __global__ void __launch_bounds__(MAXT) cgmm_cov_kernel(CgmmCovArgs a) {
   double* p0 = a.part + ((((long long)b * a.n_chunks + chunk) * a.K + a.k0) * S) * F + bin;
   double* p1 = a.part + ((((long long)b * a.n_chunks + chunk) * a.K + k1) * S) * F + bin;
 #pragma unroll
-  for (int n = 0; n < kCgNE; ++n) {
-    const int e = grp + n * G;
-    if (e < E) {
-      const int i = pi[e], j = pj[e];
-      if (i == j) {
-        p0[(long long)i * F] = ar[n][0];
-        p1[(long long)i * F] = ar[n][1];
-      } else {
-        const int s = cgmm_slot(C, i, j);
-        p0[(long long)s * F] = ar[n][0]; p0[(long long)(s + 1) * F] = ai[n][0];
-        p1[(long long)s * F] = ar[n][1]; p1[(long long)(s + 1) * F] = ai[n][1];
+  for (int n = 0; n < NBT; ++n) {
+    const int blk = grp + n * G;
+    if (blk < NBK) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = 2 * bi[blk] + (e >> 1), j = 2 * bj[blk] + (e & 1);
+        if (i > j || j >= C) continue;                     // mirrored entry / the zero row
+        if (i == j) {
+          p0[(long long)i * F] = ar[n][e][0];
+          p1[(long long)i * F] = ar[n][e][1];
+        } else {
+          const int s = cgmm_slot(C, i, j);
+          p0[(long long)s * F] = ar[n][e][0]; p0[(long long)(s + 1) * F] = ai[n][e][0];
+          p1[(long long)s * F] = ar[n][e][1]; p1[(long long)(s + 1) * F] = ai[n][e][1];
+        }
       }
     }
   }
@@ -159,89 +175,114 @@ struct CgmmFactorArgs {
   unsigned* status;          // [B] or null
 };
 
+// One group of Coop<C>::GS threads per (b, k, f); 128 threads per CTA (one
+// group per CTA under the CPU execution model, whose barriers are OS-level).
 template <int C>
-__global__ void __launch_bounds__(64) cgmm_factor_kernel(CgmmFactorArgs a) {
-  const int F = a.g.F;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)a.B * a.K * F) return;
-  const int f = (int)(idx % F);
-  const int k = (int)((idx / F) % a.K);
-  const int b = (int)(idx / ((long long)F * a.K));
+struct FactorCfg {
+#ifdef SETK_EMU
+  static constexpr int THREADS = Coop<C>::GS;
+#else
+  static constexpr int THREADS = 128;
+#endif
+  static constexpr int MPB = THREADS / Coop<C>::GS;      // matrices per CTA
+};
+template <int C>
+__global__ void __launch_bounds__(FactorCfg<C>::THREADS) cgmm_factor_kernel(CgmmFactorArgs a) {
+  using K = Coop<C>;
+  constexpr int GS = K::GS, LD = K::LD, MPB = FactorCfg<C>::MPB;
   constexpr int S = C * C + 1;
-  CMat<C> A, V;
+  SETK_DYN_SMEM(double, sm);
+  const int F = a.g.F;
+  const int tid = threadIdx.x;
+  const int grp = tid / GS, r = tid - grp * GS;
+  cd* A = reinterpret_cast<cd*>(sm) + (size_t)grp * 2 * K::MAT;
+  cd* V = A + K::MAT;
+  double* rot = sm + (size_t)MPB * 4 * K::MAT + grp * K::ROT;
+  const long long idx = (long long)blockIdx.x * MPB + grp;   // (b, k, f), f fastest
+  const bool active = idx < (long long)a.B * a.K * F;
+  const int f = active ? (int)(idx % F) : 0;
+  const int k = active ? (int)((idx / F) % a.K) : 0;
+  const int b = active ? (int)(idx / ((long long)F * a.K)) : 0;
+  const bool row = active && r < C;
   double gsum = 0.0;
-  if (k == a.identity_class) {
-    SETK_UNROLL_C
-    for (int i = 0; i < C; ++i)
-      SETK_UNROLL_C
-      for (int j = 0; j < C; ++j) A.a[i][j] = cd_make(i == j ? 1.0 : 0.0, 0.0);
-  } else {
-    SETK_UNROLL_C
-    for (int i = 0; i < C; ++i)
-      SETK_UNROLL_C
-      for (int j = 0; j < C; ++j) A.a[i][j] = cd_make(0.0, 0.0);
-    SETK_NOUNROLL
-    for (int ch = 0; ch < a.n_chunks; ++ch) {
-      const double* p = a.part + ((((long long)b * a.n_chunks + ch) * a.K + k) * S) * F + f;
-      SETK_UNROLL_C
-      for (int i = 0; i < C; ++i) {
-        A.a[i][i].x += p[(long long)i * F];
-        SETK_UNROLL_C
-        for (int j = i + 1; j < C; ++j) {
-          const int s = cgmm_slot(C, i, j);
-          A.a[i][j].x += p[(long long)s * F];
-          A.a[i][j].y += p[(long long)(s + 1) * F];
+  if (row) {
+    if (k == a.identity_class) {
+      for (int j = 0; j < C; ++j) A[r * LD + j] = cd_make(r == j ? 1.0 : 0.0, 0.0);
+    } else {
+      cd acc[C];                                  // row r, columns >= r
+#pragma unroll
+      for (int j = 0; j < C; ++j) acc[j] = cd_make(0.0, 0.0);
+      for (int ch = 0; ch < a.n_chunks; ++ch) {
+        const double* p = a.part + ((((long long)b * a.n_chunks + ch) * a.K + k) * S) * F + f;
+        gsum += p[(long long)(C * C) * F];
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+          if (j == r) {
+            acc[j].x += p[(long long)r * F];
+          } else if (j > r) {
+            const int sl = cgmm_slot(C, r, j);
+            acc[j].x += p[(long long)sl * F];
+            acc[j].y += p[(long long)(sl + 1) * F];
+          }
         }
       }
-      gsum += p[(long long)(C * C) * F];
-    }
-    const double inv = 1.0 / fmax(gsum, SETK_EPS32_D);
-    SETK_UNROLL_C
-    for (int i = 0; i < C; ++i) {
-      A.a[i][i].x *= inv;
-      SETK_UNROLL_C
-      for (int j = i + 1; j < C; ++j) {
-        A.a[i][j] = cd_scale(A.a[i][j], inv);
-        A.a[j][i] = cd_conj(A.a[i][j]);
+      const double inv = 1.0 / fmax(gsum, SETK_EPS32_D);     // cluster.py:200-201
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        if (j == r) {
+          A[r * LD + r] = cd_make(acc[j].x * inv, 0.0);
+        } else if (j > r) {
+          const cd v = cd_scale(acc[j], inv);
+          A[r * LD + j] = v;
+          A[j * LD + r] = cd_conj(v);                         // (R + R^H) / 2 of cluster.py:100-102
+        }
       }
     }
   }
-  if (a.update_alpha && k != a.identity_class) {
-    const int nb = a.n_samples ? a.n_samples[b] : a.N;
-    const int Tb = imin(frames_of(nb, a.g.n_fft, a.g.hop, a.g.pad), a.T);
-    a.alpha[((long long)b * a.K + k) * F + f] = gsum / (double)imax(Tb, 1);   // cluster.py:252
-  }
-  if (jacobi_eigh<C>(A, V) < 0 && a.status) atomicOr(a.status + b, (unsigned)SETK_ST_NO_CONVERGE);
-  double w[C];
-  double wmax = A.a[0][0].x;
-  SETK_UNROLL_C
-  for (int m = 1; m < C; ++m) wmax = fmax(wmax, A.a[m][m].x);
+  __syncwarp();
+  const bool ok = jacobi_coop<C>(A, V, rot, r, active);
+  if (!row) return;
+  if (!ok && r == 0 && a.status) atomicOr(a.status + b, (unsigned)SETK_ST_NO_CONVERGE);
+  // eigenvalues scaled by the largest and floored (cluster.py:108-113)
+  double wmax = A[0].x;
+#pragma unroll
+  for (int m = 1; m < C; ++m) wmax = fmax(wmax, A[m * LD + m].x);
   wmax = fmax(wmax, SETK_EPS32_D);
+  double winv[C];
   double ld = 0.0;
-  SETK_UNROLL_C
+#pragma unroll
   for (int m = 0; m < C; ++m) {
-    const double v = fmax(A.a[m][m].x / wmax, SETK_EPS32_D);
+    const double v = fmax(A[m * LD + m].x / wmax, SETK_EPS32_D);
     ld += log(v);
-    w[m] = 1.0 / v;
+    winv[m] = 1.0 / v;
   }
+  // row r of R^-1 = V diag(1/w) V^H, columns >= r, in packed slots
   double* o = a.Rinv + (((long long)b * a.K + k) * (C * C)) * F + f;
-  SETK_UNROLL_C
-  for (int i = 0; i < C; ++i) {
-    SETK_UNROLL_C
-    for (int j = i; j < C; ++j) {
-      cd s = cd_make(0.0, 0.0);
-      SETK_UNROLL_C
-      for (int m = 0; m < C; ++m) s = cd_add(s, cd_scale(cd_mulc(V.a[i][m], V.a[j][m]), w[m]));
-      if (i == j) {
-        o[(long long)i * F] = s.x;
-      } else {
-        const int sl = cgmm_slot(C, i, j);
-        o[(long long)sl * F] = s.x;
-        o[(long long)(sl + 1) * F] = s.y;
-      }
+  cd vr[C];
+#pragma unroll
+  for (int m = 0; m < C; ++m) vr[m] = cd_scale(V[r * LD + m], winv[m]);
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    if (j < r) continue;
+    cd sacc = cd_make(0.0, 0.0);
+#pragma unroll
+    for (int m = 0; m < C; ++m) sacc = cd_add(sacc, cd_mulc(vr[m], V[j * LD + m]));
+    if (j == r) {
+      o[(long long)r * F] = sacc.x;
+    } else {
+      const int sl = cgmm_slot(C, r, j);
+      o[(long long)sl * F] = sacc.x;
+      o[(long long)(sl + 1) * F] = sacc.y;
     }
   }
-  a.logdet[((long long)b * a.K + k) * F + f] = ld;
+  if (r == 0) {
+    a.logdet[((long long)b * a.K + k) * F + f] = ld;
+    if (a.update_alpha && k != a.identity_class) {
+      const int nb = a.n_samples ? a.n_samples[b] : a.N;
+      const int Tb = imin(frames_of(nb, a.g.n_fft, a.g.hop, a.g.pad), a.T);
+      a.alpha[((long long)b * a.K + k) * F + f] = gsum / (double)imax(Tb, 1);   // cluster.py:252
+    }
+  }
 }
 
 struct CgmmEstepArgs {
@@ -283,50 +324,73 @@ __global__ void __launch_bounds__(256) cgmm_estep_kernel(CgmmEstepArgs a) {
   }
   const long long P = a.P;
   const double* r = rs + bl;
-  for (int t = t_begin + lane; t < t_end; t += L) {
-    const float2* xt = a.X + (((long long)b * a.T + t) * C) * P + bin;
-    double yr[C], yi[C];
+  constexpr int FR = 2;                      // frames in flight per thread: R^-1 is read once for both
+#pragma unroll 1
+  for (int t = t_begin + lane; t < t_end; t += FR * L) {
+    double yr[FR][C], yi[FR][C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const float2 v = xt[(long long)c * P];
-      yr[c] = v.x; yi[c] = v.y;
+    for (int u = 0; u < FR; ++u) {
+      const int tt = t + u * L;
+      const float2* xt = a.X + (((long long)b * a.T + imin(tt, t_end - 1)) * C) * P + bin;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float2 v = xt[(long long)c * P];
+        yr[u][c] = v.x; yi[u][c] = v.y;
+      }
     }
-    double q[K];
+    double q[FR][K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) q[k] = 0.0;
+    for (int u = 0; u < FR; ++u)
+#pragma unroll
+      for (int k = 0; k < K; ++k) q[u][k] = 0.0;
 #pragma unroll
     for (int i = 0; i < C; ++i) {
-      const double n2 = yr[i] * yr[i] + yi[i] * yi[i];
 #pragma unroll
-      for (int k = 0; k < K; ++k) q[k] += r[(k * CC + i) * BL] * n2;
+      for (int k = 0; k < K; ++k) {
+        const double rii = r[(k * CC + i) * BL];
+#pragma unroll
+        for (int u = 0; u < FR; ++u) q[u][k] += rii * (yr[u][i] * yr[u][i] + yi[u][i] * yi[u][i]);
+      }
 #pragma unroll
       for (int j = i + 1; j < C; ++j) {
         // conj(y_i) y_j ;  y^H R^-1 y = sum_i R_ii |y_i|^2 + 2 Re sum_{i<j} conj(y_i) R_ij y_j
-        const double cr = yr[i] * yr[j] + yi[i] * yi[j];
-        const double ci = yr[i] * yi[j] - yi[i] * yr[j];
+        double cr[FR], ci[FR];
+#pragma unroll
+        for (int u = 0; u < FR; ++u) {
+          cr[u] = yr[u][i] * yr[u][j] + yi[u][i] * yi[u][j];
+          ci[u] = yr[u][i] * yi[u][j] - yi[u][i] * yr[u][j];
+        }
         const int s = C + 2 * (i * C - i * (i + 1) / 2 + (j - i - 1));
 #pragma unroll
-        for (int k = 0; k < K; ++k)
-          q[k] += 2.0 * (r[(k * CC + s) * BL] * cr - r[(k * CC + s + 1) * BL] * ci);
+        for (int k = 0; k < K; ++k) {
+          const double rr = 2.0 * r[(k * CC + s) * BL], ri = 2.0 * r[(k * CC + s + 1) * BL];
+#pragma unroll
+          for (int u = 0; u < FR; ++u) q[u][k] += rr * cr[u] - ri * ci[u];
+        }
       }
     }
-    double phi[K], lp[K], mx = -1.0e300;
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      phi[k] = fmax(fabs(q[k]), SETK_EPS32_D) / (double)C;      // cluster.py:203-206
-      lp[k] = -(double)C * log(phi[k]) - ld[k];                 // cluster.py:228-229
-      mx = fmax(mx, lp[k]);
-    }
-    double den = 0.0;
+    for (int u = 0; u < FR; ++u) {
+      const int tt = t + u * L;
+      if (tt >= t_end) break;
+      double phi[K], lp[K], mx = -1.0e300;
 #pragma unroll
-    for (int k = 0; k < K; ++k) { lp[k] = exp(lp[k] - mx) * al[k]; den += lp[k]; }   // cluster.py:276-281
-    den = fmax(den, SETK_EPS32_D);
+      for (int k = 0; k < K; ++k) {
+        phi[k] = fmax(fabs(q[u][k]), SETK_EPS32_D) / (double)C;      // cluster.py:203-206
+        lp[k] = -(double)C * log(phi[k]) - ld[k];                    // cluster.py:228-229
+        mx = fmax(mx, lp[k]);
+      }
+      double den = 0.0;
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const double gm = lp[k] / den;
-      const long long o = (((long long)b * K + k) * a.T + t) * P + bin;
-      a.G[o] = gm;
-      a.W[o] = gm * (double)C / phi[k];
+      for (int k = 0; k < K; ++k) { lp[k] = exp(lp[k] - mx) * al[k]; den += lp[k]; }   // cluster.py:276-281
+      den = fmax(den, SETK_EPS32_D);
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const double gm = lp[k] / den;
+        const long long o = (((long long)b * K + k) * a.T + tt) * P + bin;
+        a.G[o] = gm;
+        a.W[o] = gm * (double)C / phi[k];
+      }
     }
   }
 }
@@ -403,17 +467,18 @@ static CgmmWorkspace cgmm_carve(const setk_plan* pl, double* base, int B, int T,
   return w;
 }
 
-template <int BINS, int NE, int MAXT>
+template <int BINS, int NBT, int MAXT>
 static cudaError_t cgmm_cov_t(const setk_plan* pl, CgmmCovArgs a, bool uniform, int B, void* stream) {
   const Geometry& g = pl->geo;
-  int tile = 6144 / (g.C * BINS);                        // <= 48 KB of c64 per tile
+  const int Cp = 2 * ((g.C + 1) / 2);
+  int tile = 65536 / (Cp * BINS * (int)sizeof(double2));      // <= 64 KB of converted samples
   if (tile < 2) tile = 2;
-  if (tile > 32) tile = 32;
+  if (tile > 16) tile = 16;
   a.tile_frames = tile;
-  const int G = cgmm_groups(g.C, NE);
-  const size_t smem = (size_t)tile * g.C * BINS * sizeof(float2) + (size_t)tile * 2 * BINS * sizeof(double) + 512;
+  const int G = cgmm_groups(g.C, NBT);
+  const size_t smem = (size_t)tile * Cp * BINS * sizeof(double2) + (size_t)tile * 2 * BINS * sizeof(double) + 128;
 #ifndef SETK_EMU
-  cudaError_t ea = cudaFuncSetAttribute(cgmm_cov_kernel<BINS, NE, MAXT>,
+  cudaError_t ea = cudaFuncSetAttribute(cgmm_cov_kernel<BINS, NBT, MAXT>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   if (ea != cudaSuccess) return ea;
 #endif
@@ -421,7 +486,7 @@ static cudaError_t cgmm_cov_t(const setk_plan* pl, CgmmCovArgs a, bool uniform, 
   const int k_last = uniform ? 1 : a.K;                  // the start needs class 0 only
   for (int k0 = 0; k0 < k_last; k0 += 2) {
     a.k0 = k0;
-    cudaError_t e = launch(cgmm_cov_kernel<BINS, NE, MAXT>, dim3(a.n_chunks * nbb, B), dim3(G * BINS), smem,
+    cudaError_t e = launch(cgmm_cov_kernel<BINS, NBT, MAXT>, dim3(a.n_chunks * nbb, B), dim3(G * BINS), smem,
                            stream, false, a);
     if (e != cudaSuccess) return e;
   }
@@ -440,14 +505,22 @@ static cudaError_t cgmm_cov(const setk_plan* pl, const float2* X, int P, const C
   a.frames_per_chunk = (T + w.n_chunks - 1) / w.n_chunks;
   a.tile_frames = 2;
   a.part = w.part;
-  if (pl->geo.C <= 8) return cgmm_cov_t<64, 10, 256>(pl, a, uniform, B, stream);
-  return cgmm_cov_t<32, 5, 1024>(pl, a, uniform, B, stream);
+  if (pl->geo.C <= 8) return cgmm_cov_t<64, 2, 320>(pl, a, uniform, B, stream);
+  return cgmm_cov_t<32, 2, 576>(pl, a, uniform, B, stream);
 }
 
 template <int C>
 static cudaError_t cgmm_factor_t(const CgmmFactorArgs& a, void* stream) {
+  using K = Coop<C>;
+  constexpr int MPB = FactorCfg<C>::MPB;
+  const size_t smem = sizeof(double) * ((size_t)MPB * 4 * K::MAT + (size_t)MPB * K::ROT);
+#ifndef SETK_EMU
+  cudaError_t ea = cudaFuncSetAttribute(cgmm_factor_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem);
+  if (ea != cudaSuccess) return ea;
+#endif
   const long long n = (long long)a.B * a.K * a.g.F;
-  return launch(cgmm_factor_kernel<C>, dim3((unsigned)((n + 63) / 64)), dim3(64), 0, stream, true, a);
+  return launch(cgmm_factor_kernel<C>, dim3((unsigned)((n + MPB - 1) / MPB)), dim3(FactorCfg<C>::THREADS), smem, stream, false, a);
 }
 
 static cudaError_t cgmm_factor(const setk_plan* pl, const CgmmWorkspace& w, int identity_class,

@@ -93,18 +93,36 @@ struct Barrier {
   std::mutex m;
   std::condition_variable cv;
   int expected = 0, waiting = 0;
-  unsigned gen = 0;
-  void init(int n) { expected = n; waiting = 0; gen = 0; }
+  std::atomic<unsigned> gen{0};
+  void init(int n) { expected = n; waiting = 0; gen.store(0); }
   void wait() {
+    unsigned g;
+    {
+      std::unique_lock<std::mutex> lk(m);
+      g = gen.load(std::memory_order_relaxed);
+      if (++waiting >= expected) {
+        waiting = 0;
+        gen.store(g + 1, std::memory_order_release);
+        cv.notify_all();
+        return;
+      }
+    }
+    // spin first (kernels with many short barrier episodes), then block
+    for (int i = 0; i < 4000; ++i) {
+      if (gen.load(std::memory_order_acquire) != g) return;
+      if ((i & 15) == 15) std::this_thread::yield();
+    }
     std::unique_lock<std::mutex> lk(m);
-    unsigned g = gen;
-    if (++waiting >= expected) { waiting = 0; ++gen; cv.notify_all(); return; }
-    cv.wait(lk, [&] { return gen != g; });
+    cv.wait(lk, [&] { return gen.load(std::memory_order_acquire) != g; });
   }
   void drop() {  // a thread that exited no longer participates
     std::unique_lock<std::mutex> lk(m);
     --expected;
-    if (expected > 0 && waiting >= expected) { waiting = 0; ++gen; cv.notify_all(); }
+    if (expected > 0 && waiting >= expected) {
+      waiting = 0;
+      gen.fetch_add(1, std::memory_order_release);
+      cv.notify_all();
+    }
   }
 };
 
