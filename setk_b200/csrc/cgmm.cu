@@ -30,8 +30,9 @@ namespace setk {
 // covariance pass: BINS bins per CTA; the upper triangle of R is cut into 2 x 2
 // blocks over (row pair I, column pair J >= I) and every thread owns <= NBT of
 // them, so four entries share four shared-memory loads:
-//   C <= 8 : 64 bins x <= 5 groups   (<= 320 threads)
-//   C  > 8 : 32 bins x <= 18 groups  (<= 576 threads)
+//   C <= 4 : 64 bins x <= 3 groups of 1 block   (<= 192 threads)
+//   C <= 8 : 32 bins x <= 5 groups of 2 blocks  (<= 160 threads)
+//   C  > 8 : 32 bins x <= 18 groups of 2 blocks (<= 576 threads)
 SETK_HD inline int cgmm_blocks(int C) { const int nb = (C + 1) / 2; return nb * (nb + 1) / 2; }
 SETK_HD inline int cgmm_groups(int C, int NBT) { return (cgmm_blocks(C) + NBT - 1) / NBT; }
 // packed Hermitian slots of a C x C matrix: [0, C) the real diagonal, then
@@ -77,6 +78,17 @@ __global__ void __launch_bounds__(MAXT) cgmm_cov_kernel(CgmmCovArgs a) {
     while (e >= NB - i) { e -= NB - i; ++i; }
     bi[tid] = (unsigned char)i; bj[tid] = (unsigned char)(i + e);
   }
+  __syncthreads();
+  // this thread's blocks: shared-memory row offsets of (2I, 2I+1) and (2J, 2J+1)
+  int oa[NBT], ob[NBT];
+  bool has[NBT];
+#pragma unroll
+  for (int n = 0; n < NBT; ++n) {
+    const int blk = grp + n * G;
+    has[n] = blk < NBK;
+    oa[n] = has[n] ? 2 * bi[blk] * BINS : 0;
+    ob[n] = has[n] ? 2 * bj[blk] * BINS : 0;
+  }
   // acc[n][e][k]: block n, entry e = (row 2I + e/2, column 2J + e%2), class k
   double ar[NBT][4][2], ai[NBT][4][2];
 #pragma unroll
@@ -85,22 +97,22 @@ __global__ void __launch_bounds__(MAXT) cgmm_cov_kernel(CgmmCovArgs a) {
     for (int e = 0; e < 4; ++e) { ar[n][e][0] = ar[n][e][1] = ai[n][e][0] = ai[n][e][1] = 0.0; }
   double gs0 = 0.0, gs1 = 0.0;
   const long long P = a.P;
+  const int f_ld = bin0 + bl;
+  const bool f_ok = f_ld < F;
   for (int t0 = t_begin; t0 < t_end; t0 += a.tile_frames) {
     const int nt = imin(a.tile_frames, t_end - t0);
     __syncthreads();
-    for (int q = tid; q < nt * Cp * BINS; q += blockDim.x) {
-      const int l = q & (BINS - 1), tc = q / BINS;
-      const int t = tc / Cp, c = tc - t * Cp;
-      const int f = bin0 + l;
-      float2 v = make_float2(0.f, 0.f);
-      if (c < C && f < F) v = a.X[(((long long)b * a.T + t0 + t) * C + c) * P + f];
-      ys[q] = make_double2((double)v.x, (double)v.y);
+    for (int t = 0; t < nt; ++t) {           // thread (bl, grp) stages bin bl of rows grp, grp + G, ...
+      const float2* xr = a.X + (((long long)b * a.T + t0 + t) * C) * P + f_ld;
+      for (int c = grp; c < Cp; c += G) {
+        float2 v = make_float2(0.f, 0.f);
+        if (c < C && f_ok) v = xr[(long long)c * P];
+        ys[(t * Cp + c) * BINS + bl] = make_double2((double)v.x, (double)v.y);
+      }
     }
-    for (int q = tid; q < nt * 2 * BINS; q += blockDim.x) {
-      const int l = q & (BINS - 1), tk = q / BINS;
+    for (int tk = grp; tk < 2 * nt; tk += G) {
       const int t = tk >> 1, k = (tk & 1) ? k1 : a.k0;
-      const int f = bin0 + l;
-      ws[q] = (a.W && f < F) ? a.W[(((long long)b * a.K + k) * a.T + t0 + t) * P + f] : 1.0;
+      ws[tk * BINS + bl] = (a.W && f_ok) ? a.W[(((long long)b * a.K + k) * a.T + t0 + t) * P + f_ld] : 1.0;
     }
     __syncthreads();
     for (int t = 0; t < nt; ++t) {
@@ -108,12 +120,10 @@ __global__ void __launch_bounds__(MAXT) cgmm_cov_kernel(CgmmCovArgs a) {
       const double w0 = ws[(2 * t) * BINS + bl], w1 = ws[(2 * t + 1) * BINS + bl];
 #pragma unroll
       for (int n = 0; n < NBT; ++n) {
-        const int blk = grp + n * G;
-        if (blk < NBK) {
-          const int I = bi[blk], J = bj[blk];
+        if (has[n]) {
           double2 ya[2], yb[2];
-          ya[0] = yt[(2 * I) * BINS]; ya[1] = yt[(2 * I + 1) * BINS];
-          yb[0] = yt[(2 * J) * BINS]; yb[1] = yt[(2 * J + 1) * BINS];
+          ya[0] = yt[oa[n]]; ya[1] = yt[oa[n] + BINS];
+          yb[0] = yt[ob[n]]; yb[1] = yt[ob[n] + BINS];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const double2 u = ya[e >> 1], v = yb[e & 1];
@@ -124,13 +134,14 @@ __global__ void __launch_bounds__(MAXT) cgmm_cov_kernel(CgmmCovArgs a) {
           }
         }
       }
-      if (grp == 0 && live) {
-        if (a.G) {
-          gs0 += a.G[(((long long)b * a.K + a.k0) * a.T + t0 + t) * P + bin];
-          gs1 += a.G[(((long long)b * a.K + k1) * a.T + t0 + t) * P + bin];
-        } else {
-          gs0 += 1.0; gs1 += 1.0;
-        }
+    }
+    if (grp == G - 1 && live) {               // the last group has the fewest blocks
+      if (a.G) {
+        const double* g0 = a.G + (((long long)b * a.K + a.k0) * a.T + t0) * P + bin;
+        const double* g1 = a.G + (((long long)b * a.K + k1) * a.T + t0) * P + bin;
+        for (int t = 0; t < nt; ++t) { gs0 += g0[(long long)t * P]; gs1 += g1[(long long)t * P]; }
+      } else {
+        gs0 += (double)nt; gs1 += (double)nt;
       }
     }
   }
@@ -157,7 +168,7 @@ __global__ void __launch_bounds__(MAXT) cgmm_cov_kernel(CgmmCovArgs a) {
       }
     }
   }
-  if (grp == 0) {
+  if (grp == G - 1) {
     p0[(long long)(C * C) * F] = gs0;
     p1[(long long)(C * C) * F] = gs1;
   }
@@ -435,7 +446,7 @@ struct CgmmWorkspace {
 };
 
 static int cgmm_cov_chunks(const setk_plan* pl, int B, int T) {
-  const int bins = pl->geo.C <= 8 ? 64 : 32;
+  const int bins = pl->geo.C <= 4 ? 64 : 32;
   const int nbb = (pl->geo.F + bins - 1) / bins;
   int chunks = (2 * pl->sm_count + B * nbb - 1) / (B * nbb);
   if (chunks < 1) chunks = 1;
@@ -505,7 +516,8 @@ static cudaError_t cgmm_cov(const setk_plan* pl, const float2* X, int P, const C
   a.frames_per_chunk = (T + w.n_chunks - 1) / w.n_chunks;
   a.tile_frames = 2;
   a.part = w.part;
-  if (pl->geo.C <= 8) return cgmm_cov_t<64, 2, 320>(pl, a, uniform, B, stream);
+  if (pl->geo.C <= 4) return cgmm_cov_t<64, 1, 192>(pl, a, uniform, B, stream);   // <= 3 blocks, one each
+  if (pl->geo.C <= 8) return cgmm_cov_t<32, 2, 160>(pl, a, uniform, B, stream);   // <= 10 blocks, 5 groups
   return cgmm_cov_t<32, 2, 576>(pl, a, uniform, B, stream);
 }
 
