@@ -48,6 +48,7 @@ __device__ inline void mbar_wait(MBar* b, unsigned parity) {
 }
 // 4-byte cp.async (LDGSTS): global -> shared without a register round trip
 __device__ inline void cp_async_f32(float* dst, const float* src) { *dst = *src; }
+__device__ inline void cp_async_8(void* dst, const void* src) { memcpy(dst, src, 8); }
 __device__ inline void cp_async_wait_all() {}
 __device__ inline void cp_async_commit() {}
 __device__ inline void cp_async_wait_group1() {}
@@ -93,6 +94,10 @@ __device__ __forceinline__ void mbar_wait(MBar* b, unsigned parity) {
 // 4-byte cp.async (LDGSTS): global -> shared without a register round trip
 __device__ __forceinline__ void cp_async_f32(float* dst, const float* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// 8-byte cp.async (one complex64 or one double)
+__device__ __forceinline__ void cp_async_8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");

@@ -22,6 +22,7 @@
 //                       shared memory: phi_k = max(|y^H R_k^-1 y|, eps)/M, the
 //                       posterior (log-sum-exp shifted), G and W for the next pass.
 // All arithmetic after the complex64 STFT is fp64, as in the reference.
+#include "async_copy.cuh"
 #include "common.cuh"
 #include "jacobi_coop.cuh"
 
@@ -53,13 +54,15 @@ struct CgmmCovArgs {
 
 template <int BINS, int NBT, int MAXT>
 __global__ void __launch_bounds__(MAXT) cgmm_cov_kernel(CgmmCovArgs a) {
-  SETK_DYN_SMEM(double2, ys);                // [tile_frames][Cp][BINS], converted once
+  SETK_DYN_SMEM(double2, ys);                // [tile_frames][Cp][BINS], converted once per tile
   const int C = a.g.C, F = a.g.F;
   const int NB = (C + 1) / 2, Cp = 2 * NB;   // an odd C gets a zero row
   const int NBK = NB * (NB + 1) / 2;
   const int G = blockDim.x / BINS;
-  double* ws = reinterpret_cast<double*>(ys + a.tile_frames * Cp * BINS);    // [tile][2][BINS]
-  unsigned char* bi = reinterpret_cast<unsigned char*>(ws + a.tile_frames * 2 * BINS);
+  double* ws = reinterpret_cast<double*>(ys + a.tile_frames * Cp * BINS);    // [2][tile][2][BINS]
+  double* gsm = ws + 2 * a.tile_frames * 2 * BINS;                           // [2][tile][2][BINS] gamma
+  float2* raw = reinterpret_cast<float2*>(gsm + 2 * a.tile_frames * 2 * BINS);  // [tile][Cp][BINS] in flight
+  unsigned char* bi = reinterpret_cast<unsigned char*>(raw + a.tile_frames * Cp * BINS);
   unsigned char* bj = bi + 64;
   const int tid = threadIdx.x;
   const int bl = tid & (BINS - 1), grp = tid / BINS;
@@ -99,25 +102,54 @@ __global__ void __launch_bounds__(MAXT) cgmm_cov_kernel(CgmmCovArgs a) {
   const long long P = a.P;
   const int f_ld = bin0 + bl;
   const bool f_ok = f_ld < F;
-  for (int t0 = t_begin; t0 < t_end; t0 += a.tile_frames) {
+  // Tiles are pipelined: cp.async (LDGSTS) brings tile i+1 of X (raw complex64)
+  // and of W into shared memory while tile i is being accumulated; every
+  // thread converts the samples it copied itself to fp64 once per tile.
+  // thread (bl, grp) owns bin bl of rows grp, grp + G, ... of each tile.
+  auto issue = [&](int t0, int wb) {
     const int nt = imin(a.tile_frames, t_end - t0);
-    __syncthreads();
-    for (int t = 0; t < nt; ++t) {           // thread (bl, grp) stages bin bl of rows grp, grp + G, ...
-      const float2* xr = a.X + (((long long)b * a.T + t0 + t) * C) * P + f_ld;
-      for (int c = grp; c < Cp; c += G) {
-        float2 v = make_float2(0.f, 0.f);
-        if (c < C && f_ok) v = xr[(long long)c * P];
-        ys[(t * Cp + c) * BINS + bl] = make_double2((double)v.x, (double)v.y);
+    if (f_ok) {
+      for (int t = 0; t < nt; ++t) {
+        const float2* xr = a.X + (((long long)b * a.T + t0 + t) * C) * P + f_ld;
+        for (int c = grp; c < C; c += G) cp_async_8(raw + (t * Cp + c) * BINS + bl, xr + (long long)c * P);
       }
+      if (a.W)
+        for (int tk = grp; tk < 2 * nt; tk += G) {
+          const int t = tk >> 1, k = (tk & 1) ? k1 : a.k0;
+          cp_async_8(ws + (wb * a.tile_frames * 2 + tk) * BINS + bl,
+                     a.W + (((long long)b * a.K + k) * a.T + t0 + t) * P + f_ld);
+          cp_async_8(gsm + (wb * a.tile_frames * 2 + tk) * BINS + bl,
+                     a.G + (((long long)b * a.K + k) * a.T + t0 + t) * P + f_ld);
+        }
     }
-    for (int tk = grp; tk < 2 * nt; tk += G) {
-      const int t = tk >> 1, k = (tk & 1) ? k1 : a.k0;
-      ws[tk * BINS + bl] = (a.W && f_ok) ? a.W[(((long long)b * a.K + k) * a.T + t0 + t) * P + f_ld] : 1.0;
-    }
+    cp_async_commit();
+  };
+  if (!f_ok || !a.W) {                        // lanes past F and the weight-1 start: constants
+    for (int q = grp; q < 2 * a.tile_frames * 2; q += G) { ws[q * BINS + bl] = 1.0; gsm[q * BINS + bl] = 1.0; }
+  }
+  if (!f_ok || Cp != C) {                     // zero samples for lanes past F and for the pad row
+    for (int q = grp; q < a.tile_frames * Cp; q += G)
+      if (!f_ok || (q % Cp) >= C) ys[q * BINS + bl] = make_double2(0.0, 0.0);
+  }
+  int wb = 0;
+  if (t_begin < t_end) issue(t_begin, 0);
+  for (int t0 = t_begin; t0 < t_end; t0 += a.tile_frames, wb ^= 1) {
+    const int nt = imin(a.tile_frames, t_end - t0);
+    cp_async_wait_all();                      // my own copies of this tile have landed
+    __syncthreads();                          // everyone is done reading ys of the previous tile
+    if (f_ok)
+      for (int t = 0; t < nt; ++t)
+        for (int c = grp; c < C; c += G) {
+          const float2 v = raw[(t * Cp + c) * BINS + bl];
+          ys[(t * Cp + c) * BINS + bl] = make_double2((double)v.x, (double)v.y);
+        }
+    if (t0 + a.tile_frames < t_end) issue(t0 + a.tile_frames, wb ^ 1);
     __syncthreads();
+    const double* wt = ws + (wb * a.tile_frames * 2) * BINS + bl;
+    const double* gt = gsm + (wb * a.tile_frames * 2) * BINS + bl;
     for (int t = 0; t < nt; ++t) {
       const double2* yt = ys + t * Cp * BINS + bl;
-      const double w0 = ws[(2 * t) * BINS + bl], w1 = ws[(2 * t + 1) * BINS + bl];
+      const double w0 = wt[(2 * t) * BINS], w1 = wt[(2 * t + 1) * BINS];
 #pragma unroll
       for (int n = 0; n < NBT; ++n) {
         if (has[n]) {
@@ -135,15 +167,8 @@ __global__ void __launch_bounds__(MAXT) cgmm_cov_kernel(CgmmCovArgs a) {
         }
       }
     }
-    if (grp == G - 1 && live) {               // the last group has the fewest blocks
-      if (a.G) {
-        const double* g0 = a.G + (((long long)b * a.K + a.k0) * a.T + t0) * P + bin;
-        const double* g1 = a.G + (((long long)b * a.K + k1) * a.T + t0) * P + bin;
-        for (int t = 0; t < nt; ++t) { gs0 += g0[(long long)t * P]; gs1 += g1[(long long)t * P]; }
-      } else {
-        gs0 += (double)nt; gs1 += (double)nt;
-      }
-    }
+    if (grp == G - 1)                          // the last group has the fewest blocks
+      for (int t = 0; t < nt; ++t) { gs0 += gt[(2 * t) * BINS]; gs1 += gt[(2 * t + 1) * BINS]; }
   }
   if (!live) return;
   const int S = C * C + 1;
@@ -482,12 +507,13 @@ template <int BINS, int NBT, int MAXT>
 static cudaError_t cgmm_cov_t(const setk_plan* pl, CgmmCovArgs a, bool uniform, int B, void* stream) {
   const Geometry& g = pl->geo;
   const int Cp = 2 * ((g.C + 1) / 2);
-  int tile = 65536 / (Cp * BINS * (int)sizeof(double2));      // <= 64 KB of converted samples
+  int tile = 32768 / (Cp * BINS * (int)sizeof(double2));      // <= 32 KB of converted samples
   if (tile < 2) tile = 2;
-  if (tile > 16) tile = 16;
+  if (tile > 8) tile = 8;
   a.tile_frames = tile;
   const int G = cgmm_groups(g.C, NBT);
-  const size_t smem = (size_t)tile * Cp * BINS * sizeof(double2) + (size_t)tile * 2 * BINS * sizeof(double) + 128;
+  const size_t smem = (size_t)tile * Cp * BINS * (sizeof(double2) + sizeof(float2)) +
+                      4 * (size_t)tile * 2 * BINS * sizeof(double) + 128;
 #ifndef SETK_EMU
   cudaError_t ea = cudaFuncSetAttribute(cgmm_cov_kernel<BINS, NBT, MAXT>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
