@@ -236,6 +236,17 @@ int setk_cgmm_masks(setk_plan_t* plan, const float* audio, const int32_t* n_samp
                     int32_t num_classes, int32_t num_iters, const float* init_gamma, int32_t update_alpha,
                     float* masks, uint32_t* status, void* stream);
 
+/*
+ * The same estimator for a caller that brings its own STFT -- the reference's
+ * CgmmTrainer(obs, num_classes, gamma, update_alpha).train(num_iters) signature
+ * (cluster.py:401-466).  Plan-free; scratch is stream-ordered (cudaMallocAsync).
+ *   stft   c64 [B][C][F][T]  (forward_stft with transpose=False, stacked over channels)
+ *   other arguments as for setk_cgmm_masks; any F, T >= 1.
+ */
+int setk_cgmm_stft(const void* stft, int32_t B, int32_t C, int32_t F, int32_t T, int32_t num_classes,
+                   int32_t num_iters, const float* init_gamma, int32_t update_alpha, float* masks,
+                   uint32_t* status, void* stream);
+
 /* floor(y * 32768) clipped to int16: the PCM_16 conversion of
  * WaveWriter.write -> write_wav -> soundfile (data_handler.py:600-605,
  * utils.py:45-62; SURVEY.md finding 3).  wave f32 [n], pcm i16 [n]. */

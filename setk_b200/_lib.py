@@ -80,6 +80,8 @@ _PROTOTYPES = {
     "setk_cgmm_masks": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                 c_int32, c_int32, c_void_p, c_int32, c_void_p,
                                 c_void_p, c_void_p]),
+    "setk_cgmm_stft": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                               c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "setk_float_to_pcm16": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "setk_pcm16_to_float": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
 }

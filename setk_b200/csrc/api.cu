@@ -37,9 +37,11 @@ bool stft_spill_supported(const Geometry&);
 size_t stft_spill_bytes(const Geometry&, int, int);
 size_t apply_spill_bytes(const Geometry&, int, int);
 cudaError_t run_spill_to_bcft(const setk_plan*, const float2*, int, int, float2*, void*);
-size_t cgmm_workspace_bytes(const setk_plan*, int, int, int, int);
-cudaError_t run_cgmm(setk_plan*, const float2*, int, double*, const int*, int, int, int, int, int, const float*,
+struct CgCtx { Geometry geo; int sm_count; };
+size_t cgmm_workspace_bytes(const CgCtx*, int, int, int, int);
+cudaError_t run_cgmm(const CgCtx*, const float2*, int, double*, const int*, int, int, int, int, int, const float*,
                      int, float*, unsigned*, void*);
+cudaError_t run_bcft_to_spill(const float2*, int, int, int, int, int, float2*, void*);
 cudaError_t run_apply_spill(setk_plan*, const float2*, const void*, int, const float*, int, int, float2*, void*);
 cudaError_t run_istft_strided(const setk_plan*, const float2*, long long, long long, long long, int, int, int,
                               const int*, float*, float*, unsigned*, void*);
@@ -437,17 +439,56 @@ int setk_cgmm_masks(setk_plan_t* pl, const float* audio, const int32_t* n_sample
   const int T = frames_of(N, g.n_fft, g.hop, g.pad);
   if (T < 1) return fail(SETK_ESHAPE, "setk_cgmm_masks: no frame in %d samples", N);
   const int P = (int)(apply_spill_bytes(g, 1, 1) / sizeof(float2));
+  CgCtx ctx;
+  ctx.geo = g; ctx.sm_count = pl->sm_count;
   cudaError_t e = ensure(&pl->d_stft_ws, &pl->stft_ws_bytes, stft_spill_bytes(g, B, T));
   if (e == cudaSuccess)
-    e = ensure(&pl->d_cgmm_ws, &pl->cgmm_ws_bytes, cgmm_workspace_bytes(pl, B, T, num_classes, P));
+    e = ensure(&pl->d_cgmm_ws, &pl->cgmm_ws_bytes, cgmm_workspace_bytes(&ctx, B, T, num_classes, P));
   if (e != cudaSuccess) return cuda_fail(e, "setk_cgmm_masks(workspace)");
   const int groups = (g.C + 3) / 4;
   e = run_stft_spill(pl, audio, n_samples, B, N, T, stft_cov_pick_chunks(pl, B * groups, T), pl->d_stft_ws,
                      nullptr, stream);
   if (e == cudaSuccess)
-    e = run_cgmm(pl, pl->d_stft_ws, P, pl->d_cgmm_ws, n_samples, B, N, T, num_classes, num_iters, init_gamma,
+    e = run_cgmm(&ctx, pl->d_stft_ws, P, pl->d_cgmm_ws, n_samples, B, N, T, num_classes, num_iters, init_gamma,
                  update_alpha, masks, status, stream);
   return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_cgmm_masks");
+}
+
+int setk_cgmm_stft(const void* stft, int32_t B, int32_t C, int32_t F, int32_t T, int32_t num_classes,
+                   int32_t num_iters, const float* init_gamma, int32_t update_alpha, float* masks,
+                   uint32_t* status, void* stream) {
+  if (!stft || !masks) return fail(SETK_EINVAL, "setk_cgmm_stft: null buffer");
+  if (B < 1 || B > 65535 || F < 1 || T < 1 || C < 1 || C > SETK_MAX_CHANNELS)
+    return fail(SETK_ESHAPE, "setk_cgmm_stft: bad shape B=%d C=%d F=%d T=%d", B, C, F, T);
+  if (num_classes < 2 || num_classes > 4)
+    return fail(SETK_EINVAL, "setk_cgmm_stft: num_classes %d outside 2..4", num_classes);
+  if (!init_gamma && num_classes != 2)
+    return fail(SETK_EINVAL, "setk_cgmm_stft: %d classes need init_gamma (the reference's start is random)",
+                num_classes);
+  if (num_iters < 0) return fail(SETK_EINVAL, "setk_cgmm_stft: num_iters %d", num_iters);
+  CgCtx ctx;
+  // frames are given, not derived from samples: a geometry whose frame count never limits
+  ctx.geo.C = C; ctx.geo.F = F; ctx.geo.n_fft = 2; ctx.geo.log2n = 1; ctx.geo.hop = 1; ctx.geo.pad = 0;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx.sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return cuda_fail(e, "setk_cgmm_stft(device)");
+  const int P = (F + 7) & ~7;
+  const size_t x_bytes = sizeof(float2) * (size_t)B * T * C * P;
+  const size_t w_bytes = cgmm_workspace_bytes(&ctx, B, T, num_classes, P);
+  char* ws = nullptr;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  e = cudaMallocAsync(reinterpret_cast<void**>(&ws), x_bytes + w_bytes + 256, st);   // stream-ordered scratch
+  if (e != cudaSuccess) return cuda_fail(e, "setk_cgmm_stft(workspace)");
+  float2* X = reinterpret_cast<float2*>(ws);
+  double* cw = reinterpret_cast<double*>(ws + ((x_bytes + 255) / 256) * 256);
+  e = run_bcft_to_spill(static_cast<const float2*>(stft), B, C, F, T, P, X, stream);
+  if (e == cudaSuccess)
+    e = run_cgmm(&ctx, X, P, cw, nullptr, B, /*N=*/T + 1, T, num_classes, num_iters, init_gamma, update_alpha,
+                 masks, status, stream);
+  cudaError_t ef = cudaFreeAsync(ws, st);
+  if (e == cudaSuccess) e = ef;
+  return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_cgmm_stft");
 }
 
 int setk_float_to_pcm16(const float* wave, int64_t n, int16_t* pcm, void* stream) {

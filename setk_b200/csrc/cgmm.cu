@@ -361,17 +361,35 @@ __global__ void __launch_bounds__(256) cgmm_estep_kernel(CgmmEstepArgs a) {
   const long long P = a.P;
   const double* r = rs + bl;
   constexpr int FR = 2;                      // frames in flight per thread: R^-1 is read once for both
+  constexpr bool PF = C <= 8;                // prefetch the next pair of frames (registers allow it)
+  float2 nx[FR][PF ? C : 1];
+  auto fetch = [&](int t) {
+#pragma unroll
+    for (int u = 0; u < FR; ++u) {
+      const float2* xt = a.X + (((long long)b * a.T + imin(t + u * L, t_end - 1)) * C) * P + bin;
+#pragma unroll
+      for (int c = 0; c < C; ++c) nx[u][PF ? c : 0] = xt[(long long)c * P];
+    }
+  };
+  if (PF && t_begin + lane < t_end) fetch(t_begin + lane);
 #pragma unroll 1
   for (int t = t_begin + lane; t < t_end; t += FR * L) {
     double yr[FR][C], yi[FR][C];
+    if (PF) {
 #pragma unroll
-    for (int u = 0; u < FR; ++u) {
-      const int tt = t + u * L;
-      const float2* xt = a.X + (((long long)b * a.T + imin(tt, t_end - 1)) * C) * P + bin;
+      for (int u = 0; u < FR; ++u)
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const float2 v = xt[(long long)c * P];
-        yr[u][c] = v.x; yi[u][c] = v.y;
+        for (int c = 0; c < C; ++c) { yr[u][c] = nx[u][PF ? c : 0].x; yi[u][c] = nx[u][PF ? c : 0].y; }
+      if (t + FR * L < t_end) fetch(t + FR * L);
+    } else {
+#pragma unroll
+      for (int u = 0; u < FR; ++u) {
+        const float2* xt = a.X + (((long long)b * a.T + imin(t + u * L, t_end - 1)) * C) * P + bin;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float2 v = xt[(long long)c * P];
+          yr[u][c] = v.x; yi[u][c] = v.y;
+        }
       }
     }
     double q[FR][K];
@@ -462,15 +480,41 @@ __global__ void cgmm_fill_kernel(double* __restrict__ p, long long n, double v) 
   if (i < n) p[i] = v;
 }
 
+// API layout [B][C][F][T] (forward_stft, transpose=False) -> bin-major workspace
+// [B][T][C][P] for callers that bring their own STFT (CgmmTrainer(obs, ...))
+__global__ void __launch_bounds__(256) bcft_to_spill_kernel(const float2* __restrict__ in, int P, int C, int F,
+                                                            int T, float2* __restrict__ xws) {
+  __shared__ float2 tile[32][33];
+  const int bc = blockIdx.z, b = bc / C, c = bc - b * C;
+  const int t0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int f = f0 + r, t = t0 + tx;
+    if (t < T && f < F) tile[r][tx] = in[(((long long)b * C + c) * F + f) * T + t];
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int t = t0 + r, f = f0 + tx;
+    if (t < T && f < F) xws[(((long long)b * T + t) * C + c) * P + f] = tile[tx][r];
+  }
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+struct CgCtx { Geometry geo; int sm_count; };
+
+cudaError_t run_bcft_to_spill(const float2* in, int B, int C, int F, int T, int P, float2* xws, void* stream) {
+  return launch(bcft_to_spill_kernel, dim3((T + 31) / 32, (F + 31) / 32, B * C), dim3(256), 0, stream, false,
+                in, P, C, F, T, xws);
+}
+
 struct CgmmWorkspace {
   double *G, *W, *part, *Rinv, *logdet, *alpha;
   int n_chunks;
 };
 
-static int cgmm_cov_chunks(const setk_plan* pl, int B, int T) {
+static int cgmm_cov_chunks(const CgCtx* pl, int B, int T) {
   const int bins = pl->geo.C <= 4 ? 64 : 32;
   const int nbb = (pl->geo.F + bins - 1) / bins;
   int chunks = (2 * pl->sm_count + B * nbb - 1) / (B * nbb);
@@ -480,7 +524,7 @@ static int cgmm_cov_chunks(const setk_plan* pl, int B, int T) {
   return chunks;
 }
 
-size_t cgmm_workspace_bytes(const setk_plan* pl, int B, int T, int K, int P) {
+size_t cgmm_workspace_bytes(const CgCtx* pl, int B, int T, int K, int P) {
   const Geometry& g = pl->geo;
   const int chunks = cgmm_cov_chunks(pl, B, T);
   size_t n = 2 * (size_t)B * K * T * P;                          // G, W
@@ -490,7 +534,7 @@ size_t cgmm_workspace_bytes(const setk_plan* pl, int B, int T, int K, int P) {
   return n * sizeof(double);
 }
 
-static CgmmWorkspace cgmm_carve(const setk_plan* pl, double* base, int B, int T, int K, int P) {
+static CgmmWorkspace cgmm_carve(const CgCtx* pl, double* base, int B, int T, int K, int P) {
   const Geometry& g = pl->geo;
   CgmmWorkspace w;
   w.n_chunks = cgmm_cov_chunks(pl, B, T);
@@ -504,7 +548,7 @@ static CgmmWorkspace cgmm_carve(const setk_plan* pl, double* base, int B, int T,
 }
 
 template <int BINS, int NBT, int MAXT>
-static cudaError_t cgmm_cov_t(const setk_plan* pl, CgmmCovArgs a, bool uniform, int B, void* stream) {
+static cudaError_t cgmm_cov_t(const CgCtx* pl, CgmmCovArgs a, bool uniform, int B, void* stream) {
   const Geometry& g = pl->geo;
   const int Cp = 2 * ((g.C + 1) / 2);
   int tile = 32768 / (Cp * BINS * (int)sizeof(double2));      // <= 32 KB of converted samples
@@ -530,7 +574,7 @@ static cudaError_t cgmm_cov_t(const setk_plan* pl, CgmmCovArgs a, bool uniform, 
   return cudaSuccess;
 }
 
-static cudaError_t cgmm_cov(const setk_plan* pl, const float2* X, int P, const CgmmWorkspace& w,
+static cudaError_t cgmm_cov(const CgCtx* pl, const float2* X, int P, const CgmmWorkspace& w,
                             bool uniform, const int* n_samples, int B, int N, int T, int K, void* stream) {
   CgmmCovArgs a;
   a.X = X; a.P = P;
@@ -561,7 +605,7 @@ static cudaError_t cgmm_factor_t(const CgmmFactorArgs& a, void* stream) {
   return launch(cgmm_factor_kernel<C>, dim3((unsigned)((n + MPB - 1) / MPB)), dim3(FactorCfg<C>::THREADS), smem, stream, false, a);
 }
 
-static cudaError_t cgmm_factor(const setk_plan* pl, const CgmmWorkspace& w, int identity_class,
+static cudaError_t cgmm_factor(const CgCtx* pl, const CgmmWorkspace& w, int identity_class,
                                int update_alpha, const int* n_samples, int B, int N, int T, int K,
                                unsigned* status, void* stream) {
   CgmmFactorArgs a;
@@ -580,7 +624,7 @@ static cudaError_t cgmm_factor(const setk_plan* pl, const CgmmWorkspace& w, int 
 }
 
 template <int C, int K>
-static cudaError_t cgmm_estep_t(const setk_plan* pl, CgmmEstepArgs a, int B, void* stream) {
+static cudaError_t cgmm_estep_t(const CgCtx* pl, CgmmEstepArgs a, int B, void* stream) {
   constexpr int BL = C <= 8 ? 64 : 16;
   const size_t smem = sizeof(double) * K * C * C * BL;
 #ifndef SETK_EMU
@@ -598,7 +642,7 @@ static cudaError_t cgmm_estep_t(const setk_plan* pl, CgmmEstepArgs a, int B, voi
 }
 
 template <int C>
-static cudaError_t cgmm_estep_c(const setk_plan* pl, const CgmmEstepArgs& a, int B, int K, void* stream) {
+static cudaError_t cgmm_estep_c(const CgCtx* pl, const CgmmEstepArgs& a, int B, int K, void* stream) {
   switch (K) {
     case 2: return cgmm_estep_t<C, 2>(pl, a, B, stream);
     case 3: return cgmm_estep_t<C, 3>(pl, a, B, stream);
@@ -607,7 +651,7 @@ static cudaError_t cgmm_estep_c(const setk_plan* pl, const CgmmEstepArgs& a, int
   }
 }
 
-static cudaError_t cgmm_estep(const setk_plan* pl, const float2* X, int P, const CgmmWorkspace& w,
+static cudaError_t cgmm_estep(const CgCtx* pl, const float2* X, int P, const CgmmWorkspace& w,
                               const int* n_samples, int B, int N, int T, int K, void* stream) {
   CgmmEstepArgs a;
   a.X = X; a.P = P;
@@ -625,7 +669,7 @@ static cudaError_t cgmm_estep(const setk_plan* pl, const float2* X, int P, const
 }
 
 // CgmmTrainer(...).train(num_iters) over the workspace X of B utterances.
-cudaError_t run_cgmm(setk_plan* pl, const float2* X, int P, double* ws, const int* n_samples, int B, int N,
+cudaError_t run_cgmm(const CgCtx* pl, const float2* X, int P, double* ws, const int* n_samples, int B, int N,
                      int T, int K, int num_iters, const float* init_gamma, int update_alpha, float* masks,
                      unsigned* status, void* stream) {
   const Geometry& g = pl->geo;

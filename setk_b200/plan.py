@@ -255,6 +255,32 @@ def _ctx(device):
     return contextlib.nullcontext()
 
 
+def cgmm_from_stft(stft, num_classes=2, num_iters=20, init_gamma=None, update_alpha=False):
+    """
+    CgmmTrainer(obs, K, gamma, update_alpha).train(num_iters) batched (cluster.py:396-465).
+    stft (B,C,F,T) complex64; init_gamma (B,K,T,F) or None (2 classes only).
+    Returns (masks (B,K,T,F) float32, status (B,) int32).
+    """
+    stft = stft.contiguous()
+    if stft.dtype != torch.complex64:
+        stft = stft.to(torch.complex64)
+    if stft.dim() != 4:
+        raise ValueError(f"stft must be (B, C, F, T), got {tuple(stft.shape)}")
+    B, C, F, T = stft.shape
+    K = int(num_classes)
+    if init_gamma is not None:
+        init_gamma = _f32(init_gamma, stft.device)
+        if tuple(init_gamma.shape) != (B, K, T, F):
+            raise ValueError(f"init_gamma must be {(B, K, T, F)}, got {tuple(init_gamma.shape)}")
+    masks = torch.empty((B, K, T, F), dtype=torch.float32, device=stft.device)
+    status = torch.zeros((B,), dtype=torch.int32, device=stft.device)
+    with _ctx(stft.device):
+        _lib.check(_lib.library().setk_cgmm_stft(
+            _lib.ptr(stft), B, C, F, T, K, int(num_iters), _lib.ptr(init_gamma), 1 if update_alpha else 0,
+            _lib.ptr(masks), _lib.ptr(status), _lib.current_stream(stft.device)))
+    return masks, status
+
+
 def covariance(stft, mask, clip_mask=False, mask_ft=False):
     """compute_covar batched: stft (B,C,F,T) c64, mask (B,T,F) -> (B,F,C,C) c64."""
     stft = stft.contiguous()

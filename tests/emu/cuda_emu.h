@@ -68,6 +68,8 @@ static inline cudaError_t cudaMalloc(void** p, size_t n) {
   return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }
 static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaMallocAsync(void** p, size_t n, cudaStream_t) { return cudaMalloc(p, n); }
+static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) {
   memcpy(d, s, n); return cudaSuccess;
 }

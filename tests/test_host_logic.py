@@ -165,6 +165,73 @@ def test_cli_end_to_end(tmp_path, emu_library_path):
         assert d.max() <= 1 and np.mean(d > 0) <= 0.05
 
 
+def test_cgmm_trainer_mirror_and_cli(tmp_path, emu, emu_library_path):
+    """libs.cluster.CgmmTrainer (reference signature) and scripts/sptk/estimate_cgmm_masks.py."""
+    from oracle import cgmm_oracle as co
+    from setk_b200.libs import utils
+    from setk_b200.libs.cluster import CgmmTrainer
+    import parity_cases as pc
+    utils.set_default_device("cpu")
+    rng = np.random.default_rng(11)
+    x = pc.structured_audio(rng, 1, 3, 3000)[0]
+    x = so.float_from_pcm16(so.pcm16_from_float(x))
+    # (a) the trainer on a caller-provided STFT (n_fft = 256: plan-free setk_cgmm_stft)
+    obs = so.multichannel_stft(x, frame_len=256, frame_hop=128, center=True, window="hann",
+                               round_power_of_two=True, transpose=False, out_dtype=np.complex64)
+    gamma = CgmmTrainer(obs, 2).train(3)
+    assert isinstance(gamma, np.ndarray) and gamma.shape == (2,) + obs.shape[1:]
+    ref = co.cgmm_masks(obs, 2, 3, return_all=True)[1][-1]
+    assert np.max(np.abs(gamma - ref)) <= 1e-6
+    tr = CgmmTrainer(torch.from_numpy(obs), 2, gamma=ref[0].astype(np.float32), update_alpha=True)
+    tr.train(1)
+    g2 = tr.train(1)                                     # continues: 2 iterations in all
+    ref2 = co.cgmm_masks(obs, 2, 2, init_gamma=ref[0].astype(np.float32).astype(np.float64),
+                         update_alpha=True, return_all=True)[1][-1]
+    assert torch.is_tensor(g2) and np.max(np.abs(g2.numpy() - ref2)) <= 1e-6
+    with pytest.raises(RuntimeError):
+        CgmmTrainer(obs, 3)
+    # (b) the CLI, documented flags, from a wav file
+    _write_wav(str(tmp_path / "utt1.wav"), x)
+    (tmp_path / "wav.scp").write_text(f"utt1 {tmp_path / 'utt1.wav'}\n")
+    env = dict(os.environ, SETK_B200_TEST_LIBRARY=emu_library_path, PYTHONPATH=ROOT)
+    runner = (
+        "import os, sys, runpy; sys.argv = sys.argv[1:];"
+        "from setk_b200 import _lib; _lib.use_library(os.environ['SETK_B200_TEST_LIBRARY']);"
+        "from setk_b200.libs import utils; utils.set_default_device('cpu');"
+        "runpy.run_path(sys.argv[0], run_name='__main__')")
+    cmd = [sys.executable, "-c", runner, os.path.join(ROOT, "scripts", "sptk", "estimate_cgmm_masks.py"),
+           "--frame-len", "512", "--frame-hop", "256", "--num-iters", "3", "--center", "true",
+           str(tmp_path / "wav.scp"), str(tmp_path / "masks")]
+    subprocess.run(cmd, check=True, env=env, capture_output=True)
+    mask = np.load(tmp_path / "masks" / "utt1.npy")
+    T = so.num_frames(3000, 512, 256, True)
+    assert mask.shape == (T, 257) and mask.dtype == np.float32
+    obs512 = so.multichannel_stft(x, frame_len=512, frame_hop=256, center=True, window="hann",
+                                  round_power_of_two=True, transpose=False, out_dtype=np.complex64)
+    d = np.abs(mask - co.cgmm_masks(obs512, 2, 3))
+    assert d.mean() <= 1e-4                              # float32 tile STFT vs float64 oracle STFT
+
+
+def test_permu_aligner_restores_a_scrambled_mask():
+    from setk_b200.libs.cluster import permu_aligner
+    rng = np.random.default_rng(12)
+    K, T, F = 3, 40, 257
+    act = (rng.uniform(size=(K, T)) > 0.5).astype(np.float64) + 0.05          # class activity over time
+    masks = np.repeat(act[:, :, None], F, axis=2) + 0.02 * rng.uniform(size=(K, T, F))
+    masks /= masks.sum(0, keepdims=True)
+    scrambled = masks.copy()
+    for f in range(F):
+        scrambled[..., f] = masks[rng.permutation(K), :, f]
+    out = permu_aligner(scrambled)
+    # all bins carry one common class order
+    ref_order = [int(np.argmax([np.sum(out[k, :, 0] * masks[j, :, 0]) for j in range(K)])) for k in range(K)]
+    assert sorted(ref_order) == list(range(K))
+    for f in range(F):
+        assert np.allclose(out[..., f], masks[ref_order, :, f])
+    with pytest.raises(ValueError):
+        permu_aligner(np.zeros((2, 5, 100)))
+
+
 def test_kaldi_matrix_reader(tmp_path):
     import struct
     from setk_b200.libs.data_handler import ScriptReader
