@@ -251,14 +251,13 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
         split_pair(z[k & (kM - 1)], z[km & (kM - 1)], tw, xk, xm);
         if (k == 0) { xk.y = 0.f; xm.y = 0.f; }
         const float2 wk = s_w[c * kWPitch + k], wm = s_w[c * kWPitch + km];
-        // conj(w) * x
-        yk.x += wk.x * xk.x + wk.y * xk.y;  yk.y += wk.x * xk.y - wk.y * xk.x;
-        ym.x += wm.x * xm.x + wm.y * xm.y;  ym.y += wm.x * xm.y - wm.y * xm.x;
+        yk = cmad_conjw(wk, xk, yk);                       // += conj(w) x: two packed instructions
+        ym = cmad_conjw(wm, xm, ym);
       }
       if (a.post_mask) {
         const float* pm = a.post_mask + ((long long)b * a.T + (t0 + j)) * F;
         const float mk = pm[k], mm = pm[km];
-        yk.x *= mk; yk.y *= mk; ym.x *= mm; ym.y *= mm;
+        yk = f2mul(yk, make_float2(mk, mk)); ym = f2mul(ym, make_float2(mm, mm));
       }
       float2* zi = s_zi + j * SETK_ZSLOT;
       if (k == 0) {
@@ -266,12 +265,14 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
         zi[0] = make_float2(yk.x + ym.x, yk.x - ym.x);
       } else {
         // Zi[k]   = (Yk + conj(Ym)) + conj(tw) (Yk - conj(Ym))
-        const float er = yk.x + ym.x, ei = yk.y - ym.y;
-        const float dr = yk.x - ym.x, di = yk.y + ym.y;
-        zi[k] = make_float2(er + tw.x * dr + tw.y * di, ei + tw.x * di - tw.y * dr);
+        const float2 cm = make_float2(ym.x, -ym.y);
+        const float2 e = f2add(yk, cm), d = f2sub(yk, cm);
+        const float2 p = cmul_conj(d, tw);                 // conj(tw) D
+        zi[k] = f2add(e, p);
         if (k != kM / 2) {
-          // Zi[256-k] = (Ym + conj(Yk)) + tw (Ym - conj(Yk)) = conj(E) - tw conj(D)
-          zi[km] = make_float2(er - tw.x * dr - tw.y * di, -ei + tw.x * di - tw.y * dr);
+          // Zi[256-k] = (Ym + conj(Yk)) + tw (Ym - conj(Yk)) = conj(E) - tw conj(D) = conj(E - conj(tw) D)
+          const float2 q = f2sub(e, p);
+          zi[km] = make_float2(q.x, -q.y);
         }
       }
     }

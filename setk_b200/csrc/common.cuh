@@ -43,11 +43,73 @@ SETK_HD inline int reflect_index(int p, int pad, int n) {
 
 struct cf { float x, y; };  // not used for storage; float2 is
 
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+// ---------------------------------------------------------------------------
+// Packed fp32 pairs.  sm_100a executes add/sub/mul/fma.f32x2 (SASS FADD2 /
+// FMUL2 / FFMA2) on 64-bit register pairs with per-operand half swizzles,
+// per-half negation and scalar broadcast, so ptxas folds the (re, im) shuffles
+// written below into the instruction: a complex add is ONE instruction, a
+// complex multiply TWO.  The fp32 pipe does the same flops per clock either way
+// (measured: tools/micro/ffma2_rate.cu, 72 vs 64 TFLOP/s); what halves is the
+// number of issue slots, which is what bounds the STFT kernels.
+// ---------------------------------------------------------------------------
+#ifdef SETK_EMU
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) {
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
 }
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#else
+__device__ __forceinline__ unsigned long long f2pack(float2 a) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+  return r;
+}
+__device__ __forceinline__ float2 f2unpack(unsigned long long r) {
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(r));
+  return d;
+}
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2pack(a)), "l"(f2pack(b)));
+  return f2unpack(d);
+}
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) {
+  unsigned long long d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2pack(a)), "l"(f2pack(b)));
+  return f2unpack(d);
+}
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2pack(a)), "l"(f2pack(b)));
+  return f2unpack(d);
+}
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2pack(a)), "l"(f2pack(b)), "l"(f2pack(c)));
+  return f2unpack(d);
+}
+#endif
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return f2add(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return f2sub(a, b); }
+// a * b = (ax bx, ay bx) + (-ay by, ax by)
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return f2fma(make_float2(a.y, a.x), make_float2(-b.y, b.y), f2mul(a, make_float2(b.x, b.x)));
+}
+// a * b + c
+__device__ __forceinline__ float2 cmad(float2 a, float2 b, float2 c) {
+  return f2fma(make_float2(a.y, a.x), make_float2(-b.y, b.y), f2fma(a, make_float2(b.x, b.x), c));
+}
+// a * conj(b) = (ax bx, ay bx) + (ay by, -ax by)
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {
+  return f2fma(make_float2(a.y, a.x), make_float2(b.y, -b.y), f2mul(a, make_float2(b.x, b.x)));
+}
+// conj(w) * x + c = (wx xx, wx xy) + (wy xy, -wy xx) + c
+__device__ __forceinline__ float2 cmad_conjw(float2 w, float2 x, float2 c) {
+  return f2fma(make_float2(x.y, x.x), make_float2(w.y, -w.y), f2fma(x, make_float2(w.x, w.x), c));
+}
 
 }  // namespace setk
 

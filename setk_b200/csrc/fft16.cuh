@@ -25,22 +25,24 @@ __device__ __forceinline__ constexpr int slot_of(int k) { return ((k & 3) << 2) 
 // forward 4-point DFT in place (W4 = -i)
 __device__ __forceinline__ void dft4(float2& a, float2& b, float2& c, float2& d) {
   const float2 e = cadd(a, c), f = csub(a, c), g = cadd(b, d), h = csub(b, d);
+  const float2 r = make_float2(h.y, -h.x);           // -i h: a swizzle on the consumer's operand
   a = cadd(e, g);
   c = csub(e, g);
-  b = make_float2(f.x + h.y, f.y - h.x);
-  d = make_float2(f.x - h.y, f.y + h.x);
+  b = cadd(f, r);
+  d = csub(f, r);
 }
 
 // v <- v * W16^m  (forward twiddle, compile-time m)
 template <int M>
 __device__ __forceinline__ float2 mul_w16(float2 v) {
   if (M == 0) return v;
-  if (M == 1) return make_float2(v.x * SETK_C16_1R + v.y * SETK_C16_1I, v.y * SETK_C16_1R - v.x * SETK_C16_1I);
-  if (M == 2) return make_float2((v.x + v.y) * SETK_SQRT1_2, (v.y - v.x) * SETK_SQRT1_2);
-  if (M == 3) return make_float2(v.x * SETK_C16_1I + v.y * SETK_C16_1R, v.y * SETK_C16_1I - v.x * SETK_C16_1R);
+  // W16^m = (cos, -sin)(2 pi m / 16) as a compile-time constant: two packed instructions each
+  if (M == 1) return cmul(v, make_float2(SETK_C16_1R, -SETK_C16_1I));
+  if (M == 2) return cmul(v, make_float2(SETK_SQRT1_2, -SETK_SQRT1_2));
+  if (M == 3) return cmul(v, make_float2(SETK_C16_1I, -SETK_C16_1R));
   if (M == 4) return make_float2(v.y, -v.x);
-  if (M == 6) return make_float2((v.y - v.x) * SETK_SQRT1_2, -(v.x + v.y) * SETK_SQRT1_2);
-  if (M == 9) return make_float2(-(v.x * SETK_C16_1R + v.y * SETK_C16_1I), v.x * SETK_C16_1I - v.y * SETK_C16_1R);
+  if (M == 6) return cmul(v, make_float2(-SETK_SQRT1_2, -SETK_SQRT1_2));
+  if (M == 9) return cmul(v, make_float2(-SETK_C16_1R, SETK_C16_1I));
   return v;
 }
 

@@ -74,10 +74,15 @@ __global__ void __maxnreg__(112) stft_cov_kernel(StftCovArgs a) {
   const float2 tw = split_twiddle(bin);
   const int zk = bin & (kM - 1), zn = (kM - bin) & (kM - 1);
 
-  float acc_s[NACC], acc_n[NACC];
+  // accumulators as packed pairs (FFMA2): dg[i] = (sum m_s |x_i|^2, sum m_n |x_i|^2),
+  // os[p] / on[p] = sum m x_i conj(x_k) for the p-th (i < k), sm = (sum m_s, sum m_n)
+  constexpr int NOFF = C * (C - 1) / 2;
+  float2 dg[C], os[NOFF > 0 ? NOFF : 1], on[NOFF > 0 ? NOFF : 1];
 #pragma unroll
-  for (int i = 0; i < NACC; ++i) { acc_s[i] = 0.f; acc_n[i] = 0.f; }
-  float sum_s = 0.f, sum_n = 0.f;
+  for (int i = 0; i < C; ++i) dg[i] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < NOFF; ++i) { os[i] = make_float2(0.f, 0.f); on[i] = make_float2(0.f, 0.f); }
+  float2 sm2 = make_float2(0.f, 0.f);
   float amax = 0.f;
 
   const float* xb = a.audio + (long long)b * C * a.N;
@@ -149,21 +154,20 @@ __global__ void __maxnreg__(112) stft_cov_kernel(StftCovArgs a) {
           const float m_raw = s_mask[(2 * j) * MPITCH + bin];
           const float m_s = clip ? fminf(m_raw, 1.0f) : m_raw;
           const float m_n = has_mn ? s_mask[(2 * j + 1) * MPITCH + bin] : 1.0f - m_s;
-          sum_s += m_s; sum_n += m_n;
-          int o = C;
+          const float2 msn = make_float2(m_s, m_n);
+          const float2 mss = make_float2(m_s, m_s), mnn = make_float2(m_n, m_n);
+          sm2 = f2add(sm2, msn);
+          int o = 0;
 #pragma unroll
           for (int i = 0; i < C; ++i) {
             const float pii = x[i].x * x[i].x + x[i].y * x[i].y;
-            acc_s[i] += m_s * pii;
-            acc_n[i] += m_n * pii;
+            dg[i] = f2fma(msn, make_float2(pii, pii), dg[i]);
 #pragma unroll
             for (int k = i + 1; k < C; ++k) {
-              // x_i conj(x_k)
-              const float pr = x[i].x * x[k].x + x[i].y * x[k].y;
-              const float pi = x[i].y * x[k].x - x[i].x * x[k].y;
-              acc_s[o] += m_s * pr; acc_s[o + 1] += m_s * pi;
-              acc_n[o] += m_n * pr; acc_n[o + 1] += m_n * pi;
-              o += 2;
+              const float2 pr = cmul_conj(x[i], x[k]);        // x_i conj(x_k): two packed instructions
+              os[o] = f2fma(pr, mss, os[o]);
+              on[o] = f2fma(pr, mnn, on[o]);
+              ++o;
             }
           }
         }
@@ -183,9 +187,14 @@ __global__ void __maxnreg__(112) stft_cov_kernel(StftCovArgs a) {
   if (cov_thread) {
     float* pp = a.partials + (((long long)b * a.n_chunks + chunk) * (2 * NACC + 2)) * F + bin;
 #pragma unroll
-    for (int i = 0; i < NACC; ++i) { pp[(long long)i * F] = acc_s[i]; pp[(long long)(NACC + i) * F] = acc_n[i]; }
-    pp[(long long)(2 * NACC) * F] = sum_s;
-    pp[(long long)(2 * NACC + 1) * F] = sum_n;
+    for (int i = 0; i < C; ++i) { pp[(long long)i * F] = dg[i].x; pp[(long long)(NACC + i) * F] = dg[i].y; }
+#pragma unroll
+    for (int i = 0; i < NOFF; ++i) {
+      pp[(long long)(C + 2 * i) * F] = os[i].x;        pp[(long long)(C + 2 * i + 1) * F] = os[i].y;
+      pp[(long long)(NACC + C + 2 * i) * F] = on[i].x; pp[(long long)(NACC + C + 2 * i + 1) * F] = on[i].y;
+    }
+    pp[(long long)(2 * NACC) * F] = sm2.x;
+    pp[(long long)(2 * NACC + 1) * F] = sm2.y;
   }
   if (a.maxabs_bits) {
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));

@@ -145,7 +145,7 @@ __device__ __forceinline__ void fft_tile(const TileSmem<C, TT>& sm, int buf, int
           const float2 s = *reinterpret_cast<const float2*>(src + 32 * m1);
           const float2 w = *reinterpret_cast<const float2*>(wsrc + 32 * m1);
           amax = fmaxf(amax, fmaxf(fabsf(s.x), fabsf(s.y)));
-          x = make_float2(s.x * w.x, s.y * w.y);
+          x = f2mul(s, w);
         }
         v[m1] = x;
       }
@@ -167,17 +167,17 @@ __device__ __forceinline__ float2 split_twiddle(int k) {
 // X[k] from the half-size spectrum (Z was computed from samples x 0.5):
 //   X[k] = (Zk + conj(Zn)) + (-i W^k)(Zk - conj(Zn)),  Zn = Z[(256-k) & 255]
 __device__ __forceinline__ float2 split_bin(float2 zk, float2 zn, float2 tw) {
-  const float er = zk.x + zn.x, ei = zk.y - zn.y;
-  const float dr = zk.x - zn.x, di = zk.y + zn.y;
-  return make_float2(er + tw.x * dr - tw.y * di, ei + tw.x * di + tw.y * dr);
+  const float2 cn = make_float2(zn.x, -zn.y);               // conj(Zn): an operand modifier
+  return cmad(f2sub(zk, cn), tw, f2add(zk, cn));            // E + tw D
 }
 // the mirrored bin from the same pair: X[256-k] = conj(E - P), P = (-iW^k) D
 __device__ __forceinline__ void split_pair(float2 zk, float2 zn, float2 tw, float2& xk, float2& xm) {
-  const float er = zk.x + zn.x, ei = zk.y - zn.y;
-  const float dr = zk.x - zn.x, di = zk.y + zn.y;
-  const float pr = tw.x * dr - tw.y * di, pi = tw.x * di + tw.y * dr;
-  xk = make_float2(er + pr, ei + pi);
-  xm = make_float2(er - pr, -(ei - pi));
+  const float2 cn = make_float2(zn.x, -zn.y);
+  const float2 e = f2add(zk, cn);
+  const float2 p = cmul(f2sub(zk, cn), tw);
+  xk = f2add(e, p);
+  const float2 m = f2sub(e, p);
+  xm = make_float2(m.x, -m.y);
 }
 
 }  // namespace setk
