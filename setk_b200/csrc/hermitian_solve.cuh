@@ -12,6 +12,7 @@
 // Plain C++ on purpose (no CUDA intrinsics): the same source is compiled for
 // the device by nvcc and for the CPU test tier by g++ (tests/emu).
 #pragma once
+#include "common.cuh"
 #include "compat.cuh"
 #include <math.h>
 

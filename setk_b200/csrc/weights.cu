@@ -8,25 +8,13 @@
 //   solve_pevd 31-63, do_ban 14-28, rank1_constraint 66-84,
 //   MvdrBeamformer.weight 527-539, MpdrBeamformer.weight 555-573,
 //   PmwfBeamformer.weight/_snr 620-659, GevdBeamformer.weight 674-682.
-#include <cstdlib>
 #include "common.cuh"
 #include "hermitian_solve.cuh"
+#include "weights_args.cuh"
 
 namespace setk {
 
-struct WeightsArgs {
-  int kind, rank1, ban, ref_channel;
-  double beta;
-  const void* Rs; const void* Rn; const void* Ry;
-  int r_dtype;  // SETK_C64 / SETK_C128
-  int B, F;
-  void* w; int w_dtype;
-  unsigned* status;
-  int* ref_used;
-  // PMWF automatic reference selection
-  double* Wfull;   // [B][F][C][C] complex128 (interleaved)
-  double* pows;    // [B][F][C][2]  (Re w^H Rs w, Re w^H Rn w)
-};
+
 
 template <int C>
 __device__ inline void load_mat(const void* base, int dtype, long long idx, CMat<C>& M) {
@@ -250,14 +238,14 @@ __global__ void __launch_bounds__(128) pmwf_select_kernel(WeightsArgs a) {
   if (st) atomicOr(a.status + b, st);
 }
 
+bool weights_coop_supported(const WeightsArgs& a, int C);
+cudaError_t weights_coop_launch(const WeightsArgs& a, int C, void* stream);
+
 template <int C>
 static cudaError_t launch_weights(const WeightsArgs& a, void* stream) {
+  if (weights_coop_supported(a, C)) return weights_coop_launch(a, C, stream);
   long long n = (long long)a.B * a.F;
-  // one bin per thread and data-dependent run times: small CTAs spread a batch
-  // of only B*F threads over all SMs and keep the tail short
-  static int forced = -1;
-  if (forced < 0) { const char* s = getenv("SETK_WEIGHTS_BLOCK"); forced = s ? atoi(s) : 0; }
-  const int bs = forced > 0 ? forced : 128;
+  const int bs = 128;
   dim3 block(bs), grid((unsigned)((n + bs - 1) / bs));
   cudaError_t e = launch(weights_kernel<C>, grid, block, 0, stream, /*barrier_free=*/true, a);
   if (e != cudaSuccess) return e;

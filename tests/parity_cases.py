@@ -181,15 +181,15 @@ def check_weights(device, rng, B, F, C, dtype=np.complex128):
     assert np.allclose(np.abs(wd), 1, atol=1e-6 if dtype == np.complex128 else 1e-3)
 
 
-def check_weights_status(device):
+def check_weights_status(device, C=3):
     """Singular / non-PD inputs set status bits instead of failing the call."""
-    F, C = 3, 3
+    F = 3
     Rs = np.tile(np.eye(C, dtype=np.complex128), (1, F, 1, 1))
     Rn = np.zeros((1, F, C, C), dtype=np.complex128)          # exactly singular
     w, st, _ = P.weights(_lib.BF_MVDR, torch.from_numpy(Rs).to(device),
                          torch.from_numpy(Rn).to(device))
     assert int(st[0]) & _lib.ST_SINGULAR
-    Rn2 = np.tile(np.diag([1.0, -1.0, 1.0]).astype(np.complex128), (1, F, 1, 1))
+    Rn2 = np.tile(np.diag([1.0, -1.0] + [1.0] * (C - 2)).astype(np.complex128), (1, F, 1, 1))
     w, st, _ = P.weights(_lib.BF_GEVD, torch.from_numpy(Rs).to(device),
                          torch.from_numpy(Rn2).to(device))
     assert int(st[0]) & _lib.ST_NOT_PD

@@ -138,6 +138,7 @@ def test_weights_all_kinds(emu, C):
 def test_weights_c64_and_status(emu):
     pc.check_weights(emu, np.random.default_rng(20), 1, 5, 4, dtype=np.complex64)
     pc.check_weights_status(emu)
+    pc.check_weights_status(emu, C=6)          # the thread-group kernels of weights_coop.cu
 
 
 @pytest.mark.parametrize("C,N,hop,center,pm,norm", [

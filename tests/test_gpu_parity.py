@@ -101,6 +101,8 @@ def test_weights_all_kinds(cuda, C):
 def test_weights_c64_and_status(cuda):
     pc.check_weights(cuda, np.random.default_rng(20), 2, 64, 4, dtype=np.complex64)
     pc.check_weights_status(cuda)
+    pc.check_weights_status(cuda, C=6)         # the thread-group kernels of weights_coop.cu
+    pc.check_weights_status(cuda, C=16)
 
 
 @pytest.mark.parametrize("C,N,hop,center,pm,norm", [
