@@ -16,7 +16,7 @@
 namespace setk {
 
 #ifdef SETK_EMU
-template <int C> struct WCfg { static constexpr int THREADS = Coop<C>::GS; };      // one group per CTA
+template <int C> struct WCfg { static constexpr int THREADS = 32; };   // one warp: groups still share barriers
 #else
 template <int C> struct WCfg { static constexpr int THREADS = C <= 8 ? 128 : 64; };
 #endif
@@ -90,8 +90,8 @@ __device__ __forceinline__ cd lu_solve_coop(cd* M, int r, bool row, bool* singul
       if (r == 0) { t = M[k * LD + C]; M[k * LD + C] = M[piv * LD + C]; M[piv * LD + C] = t; }
     }
     __syncwarp();
-    if (m == 0.0) { *singular = true; continue; }
-    if (row && r > k) {
+    if (m == 0.0) *singular = true;                 // (no early exit: the barriers below are warp-wide)
+    if (row && r > k && m != 0.0) {
       const cd inv = cd_div(cd_make(1.0, 0.0), M[k * LD + k]);
       const cd l = cd_mul(M[r * LD + k], inv);
       M[r * LD + k] = l;
@@ -196,20 +196,29 @@ __global__ void __launch_bounds__(WCfg<C>::THREADS) weights_coop_kernel(WeightsA
     double tr = 0.0;
     if (row) tr = load_c(a.Rn, a.r_dtype, idx * (C * C) + r * C + r).x;
     tr = group_sum<GS>(tr);
-    bool ok = false;
+    // diagonal loading retries as in gev_principal(); the groups of a warp take the
+    // same number of trips (the factorisation synchronises the whole warp)
+    bool ok = !active;
     double load = 0.0;
-    for (int attempt = 0; attempt < 6 && !ok; ++attempt) {
-      if (attempt > 0 && !(tr > 0.0)) break;
-      if (row) {
+    for (int attempt = 0; attempt < 6; ++attempt) {
+      const bool need = active && !ok && (attempt == 0 || tr > 0.0);
+      int any = need ? 1 : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) any |= __shfl_xor_sync(0xffffffffu, any, o);
+      if (!any) break;
+      if (row && need) {
         for (int j = 0; j <= r; ++j) M[r * LD + j] = load_c(a.Rn, a.r_dtype, idx * (C * C) + r * C + j);
         M[r * LD + r].x += load * tr / C;
       }
       __syncwarp();
-      ok = cholesky_coop<C>(M, r, row, lane_base);
-      if (attempt > 0) st |= SETK_ST_REGULARIZED;
+      const bool fact = cholesky_coop<C>(M, r, row && need, lane_base);
+      if (need) {
+        ok = fact;
+        if (attempt > 0) st |= SETK_ST_REGULARIZED;
+      }
       load = attempt == 0 ? 1e-10 : load * 100.0;
     }
-    if (!ok) st |= SETK_ST_NOT_PD;
+    if (active && !ok) st |= SETK_ST_NOT_PD;
     if (row) load_lower_hermitian<C>(a.Rs, a.r_dtype, idx, A, r);
     __syncwarp();
     forward_subst_coop<C>(M, A, r, row);              // X = L^-1 Rs
