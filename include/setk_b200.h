@@ -247,6 +247,22 @@ int setk_cgmm_stft(const void* stft, int32_t B, int32_t C, int32_t F, int32_t T,
                    int32_t num_iters, const float* init_gamma, int32_t update_alpha, float* masks,
                    uint32_t* status, void* stream);
 
+/*
+ * WPE dereverberation of a multichannel STFT: libs/wpe.py wpe(reverb, taps, delay,
+ * context, num_iters) (scripts/sptk/libs/wpe.py:82-110 with 14-79; driven by
+ * apply_wpe.py:36-52) for every utterance of the batch.  Plan-free; scratch is
+ * stream-ordered.  fp64 arithmetic (the reference computes in complex64 for
+ * complex64 input).
+ *   stft   c64 [B][C][F][T]   (the reference's F x N x T per utterance, channel-major here)
+ *   out    c64 [B][C][F][T]   dereverberated
+ *   status u32 [B] or NULL, SETK_ST_SINGULAR when solve(R, r) hits an exactly singular
+ *          matrix (numpy.linalg.LinAlgError in the reference, caught per utterance by its CLI)
+ * channels x taps <= 128 and the bin's time series must fit shared memory
+ * (SETK_EUNSUPPORTED otherwise; 8 ch x 10 taps x 10 s at hop 256 does).
+ */
+int setk_wpe_stft(const void* stft, int32_t B, int32_t C, int32_t F, int32_t T, int32_t taps, int32_t delay,
+                  int32_t context, int32_t num_iters, void* out, uint32_t* status, void* stream);
+
 /* floor(y * 32768) clipped to int16: the PCM_16 conversion of
  * WaveWriter.write -> write_wav -> soundfile (data_handler.py:600-605,
  * utils.py:45-62; SURVEY.md finding 3).  wave f32 [n], pcm i16 [n]. */

@@ -314,11 +314,38 @@ def cgmm_cases(ref, report):
     np.savez_compressed(os.path.join(GOLD, "ref_cgmm.npz"), **out)
 
 
+def wpe_cases(ref, report):
+    """
+    libs/wpe.py wpe() run by the REFERENCE (complex64 in, as apply_wpe.py feeds it)
+    on small mixtures; configs chosen so that T > channels * taps.
+    """
+    from oracle import wpe_oracle as wo
+    rng = np.random.default_rng(20240926)
+    out = {}
+    for name, C, N, fl, hop, taps, delay, ctx, iters in (
+            ("c3_t4", 3, 6000, 512, 128, 4, 2, 1, 2),
+            ("c4_t10", 4, 20000, 512, 256, 10, 3, 1, 3),
+            ("c2_t6_ctx0", 2, 5000, 256, 64, 6, 1, 0, 1)):
+        mix, _, _ = synth_case(rng, C, N)
+        kw = dict(frame_len=fl, frame_hop=hop, window="hann", center=True, transpose=False)
+        obs = ref_multichannel_stft(ref, mix, round_power_of_two=True, **kw)        # c64 C x F x T
+        derev = ref.wpe.wpe(np.einsum("nft->fnt", obs), taps=taps, delay=delay, context=ctx,
+                            num_iters=iters)                                        # F x N x T
+        out[name + "/mix"] = mix
+        out[name + "/cfg"] = np.array([fl, hop, taps, delay, ctx, iters], dtype=np.int64)
+        out[name + "/derev"] = np.einsum("fnt->nft", derev).astype(np.complex64)
+        o32 = wo.wpe(np.einsum("nft->fnt", obs), taps, delay, ctx, iters, dtype=np.complex64)
+        o64 = wo.wpe(np.einsum("nft->fnt", obs), taps, delay, ctx, iters, dtype=np.complex128)
+        report["wpe/" + name + "/oracle_c64_vs_ref_relinf"] = bo.rel_inf(o32, derev)
+        report["wpe/" + name + "/oracle_c128_vs_ref_relinf"] = bo.rel_inf(o64, derev)
+    np.savez_compressed(os.path.join(GOLD, "ref_wpe.npz"), **out)
+
+
 def main():
-    if len(sys.argv) > 1 and sys.argv[1] == "cgmm":      # add the CGMM fixture only
+    if len(sys.argv) > 1 and sys.argv[1] in ("cgmm", "wpe"):   # add one fixture only
         ref = ref_shim.load_reference()
         report = {}
-        cgmm_cases(ref, report)
+        (cgmm_cases if sys.argv[1] == "cgmm" else wpe_cases)(ref, report)
         path = os.path.join(GOLD, "PINNING.json")
         with open(path) as f:
             full = json.load(f)
@@ -341,6 +368,7 @@ def main():
     small_cases(ref, report)
     config_cases(ref, report)
     cgmm_cases(ref, report)
+    wpe_cases(ref, report)
     with open(os.path.join(GOLD, "PINNING.json"), "w") as f:
         json.dump(report, f, indent=1, sort_keys=True)
     print(json.dumps(report, indent=1, sort_keys=True))

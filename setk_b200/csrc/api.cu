@@ -42,6 +42,9 @@ size_t cgmm_workspace_bytes(const CgCtx*, int, int, int, int);
 cudaError_t run_cgmm(const CgCtx*, const float2*, int, double*, const int*, int, int, int, int, int, const float*,
                      int, float*, unsigned*, void*);
 cudaError_t run_bcft_to_spill(const float2*, int, int, int, int, int, float2*, void*);
+bool wpe_supported(int, int, int, int);
+size_t wpe_workspace_bytes(int, int, int, int);
+cudaError_t run_wpe(const float2*, int, int, int, int, int, int, int, int, int, double*, float2*, unsigned*, void*);
 cudaError_t run_apply_spill(setk_plan*, const float2*, const void*, int, const float*, int, int, float2*, void*);
 cudaError_t run_istft_strided(const setk_plan*, const float2*, long long, long long, long long, int, int, int,
                               const int*, float*, float*, unsigned*, void*);
@@ -489,6 +492,34 @@ int setk_cgmm_stft(const void* stft, int32_t B, int32_t C, int32_t F, int32_t T,
   cudaError_t ef = cudaFreeAsync(ws, st);
   if (e == cudaSuccess) e = ef;
   return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_cgmm_stft");
+}
+
+int setk_wpe_stft(const void* stft, int32_t B, int32_t C, int32_t F, int32_t T, int32_t taps, int32_t delay,
+                  int32_t context, int32_t num_iters, void* out, uint32_t* status, void* stream) {
+  if (!stft || !out) return fail(SETK_EINVAL, "setk_wpe_stft: null buffer");
+  if (B < 1 || F < 1 || T < 1 || C < 1 || C > SETK_MAX_CHANNELS || (long long)B * F > 2000000000LL)
+    return fail(SETK_ESHAPE, "setk_wpe_stft: bad shape B=%d C=%d F=%d T=%d", B, C, F, T);
+  if (taps < 1 || delay < 0 || context < 0 || num_iters < 1)
+    return fail(SETK_EINVAL, "setk_wpe_stft: taps=%d delay=%d context=%d num_iters=%d", taps, delay, context,
+                num_iters);
+  if (!wpe_supported(C, T, taps, delay))
+    return fail(SETK_EUNSUPPORTED, "setk_wpe_stft: %d channels x %d taps over %d frames exceeds the kernels' "
+                "shared-memory budget", C, taps, T);
+  const int P = (F + 7) & ~7;
+  const size_t x_bytes = sizeof(float2) * (size_t)B * T * C * P;
+  const size_t w_bytes = wpe_workspace_bytes(B, C, F, taps);
+  char* ws = nullptr;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&ws), x_bytes + w_bytes + 256, st);
+  if (e != cudaSuccess) return cuda_fail(e, "setk_wpe_stft(workspace)");
+  float2* X = reinterpret_cast<float2*>(ws);
+  double* dw = reinterpret_cast<double*>(ws + ((x_bytes + 255) / 256) * 256);
+  e = run_bcft_to_spill(static_cast<const float2*>(stft), B, C, F, T, P, X, stream);
+  if (e == cudaSuccess)
+    e = run_wpe(X, P, B, C, F, T, taps, delay, context, num_iters, dw, static_cast<float2*>(out), status, stream);
+  cudaError_t ef = cudaFreeAsync(ws, st);
+  if (e == cudaSuccess) e = ef;
+  return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_wpe_stft");
 }
 
 int setk_float_to_pcm16(const float* wave, int64_t n, int16_t* pcm, void* stream) {

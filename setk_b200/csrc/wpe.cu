@@ -1,0 +1,288 @@
+// wpe.cu -- WPE dereverberation of a multichannel STFT (the pre-processor of
+// BASELINE config 4).  Replaces, per utterance and bin,
+//   scripts/sptk/libs/wpe.py:14-30   compute_tap_mat (the delayed stack, never built here)
+//   scripts/sptk/libs/wpe.py:33-56   compute_lambda  (channel-mean power, +-context box, floor)
+//   scripts/sptk/libs/wpe.py:59-79   wpe_step        (R, r, G = solve(R, r), z = x - G^H yt)
+//   scripts/sptk/libs/wpe.py:82-110  wpe             (num_iters steps)
+//
+// Every bin is an independent problem of size NK = channels x taps, so a CTA
+// owns ONE (utterance, bin) and keeps that bin's whole time series in shared
+// memory as fp64 (converted once; rows padded by taps + delay zero frames, so
+// the delayed stack yt[k N + n, t] = x[n, t - k - delay] is just an offset):
+//   wpe_corr_kernel    prologue: previous filter G -> z -> lambda (or lambda of x);
+//                      then [R | r] = sum_t a_i conj(a_j) / lambda, 4 x 4 register tiles
+//                      over the upper block triangle of the augmented matrix
+//   wpe_solve_kernel   LU with partial pivoting of [R | r], rows owned by threads
+//                      (numpy.linalg.solve), column-oriented back substitution -> G
+//   wpe_filter_kernel  z = x - G^H yt, written in the API layout [B][C][F][T]
+// All arithmetic is fp64 (the reference computes in the dtype of its input,
+// complex64; see oracle/wpe_oracle.py).
+#include "common.cuh"
+#include "hermitian_solve.cuh"
+
+namespace setk {
+
+struct WpeArgs {
+  const float2* X; int P;        // bin-major workspace [B][T][C][P]
+  int B, C, F, T;
+  int taps, delay, ctx;
+  int NK;                        // C * taps
+  int Tp;                        // padded row length in shared memory: T + taps + delay
+  int use_filter;                // corr: lambda from z = x - G^H yt (iterations > 0)
+  const double* G;               // [B*F][NK][C] complex (interleaved)
+  double* Raug;                  // [B*F][NK][NK + C] complex
+  float2* out;                   // filter: [B][C][F][T]
+  unsigned* status;              // [B]
+};
+
+// shared memory: xs [C][Tp] cd | linv [T] | L [T] | Gs [NK][C] cd
+__device__ __forceinline__ void wpe_carve(double* sm, const WpeArgs& a, cd*& xs, double*& linv, double*& L, cd*& Gs) {
+  xs = reinterpret_cast<cd*>(sm);
+  linv = sm + 2 * (size_t)a.C * a.Tp;
+  L = linv + a.T;
+  Gs = reinterpret_cast<cd*>(L + a.T + (a.T & 1));
+}
+SETK_HD inline size_t wpe_smem_bytes(int C, int T, int Tp, int NK) {
+  return sizeof(double) * (2 * (size_t)C * Tp + 2 * (size_t)T + (T & 1) + 2 * (size_t)NK * C);
+}
+
+// bin (b, f) of the workspace -> xs (fp64, zero history in front of every row)
+__device__ __forceinline__ void wpe_load_bin(const WpeArgs& a, int b, int f, cd* xs) {
+  const int pad = a.Tp - a.T;
+  for (int q = threadIdx.x; q < a.C * a.Tp; q += blockDim.x) {
+    const int n = q / a.Tp, tt = q - n * a.Tp;
+    cd v = cd_make(0.0, 0.0);
+    if (tt >= pad) {
+      const float2 x = a.X[(((long long)b * a.T + (tt - pad)) * a.C + n) * a.P + f];
+      v = cd_make((double)x.x, (double)x.y);
+    }
+    xs[q] = v;
+  }
+}
+
+// z_n[t] = x_n[t] - sum_m conj(G[m][n]) yt[m][t]   (wpe.py:78)
+__device__ __forceinline__ cd wpe_filtered(const WpeArgs& a, const cd* xs, const cd* Gs, int n, int t) {
+  const int pad = a.Tp - a.T;
+  cd z = xs[n * a.Tp + pad + t];
+  for (int k = 0; k < a.taps; ++k) {
+    const int tt = pad + t - k - a.delay;          // >= 0 thanks to the padding
+    for (int c = 0; c < a.C; ++c)
+      z = cd_sub(z, cd_mul(cd_conj(Gs[(k * a.C + c) * a.C + n]), xs[c * a.Tp + tt]));
+  }
+  return z;
+}
+
+__global__ void __launch_bounds__(512) wpe_corr_kernel(WpeArgs a) {
+  SETK_DYN_SMEM(double, sm);
+  cd* xs; double* linv; double* L; cd* Gs;
+  wpe_carve(sm, a, xs, linv, L, Gs);
+  const int bin = blockIdx.x, b = bin / a.F, f = bin - b * a.F;
+  const int tid = threadIdx.x;
+  const int pad = a.Tp - a.T, C = a.C, NK = a.NK, NA = NK + C;
+  wpe_load_bin(a, b, f, xs);
+  if (a.use_filter)
+    for (int q = tid; q < NK * C; q += blockDim.x) {
+      const double* g = a.G + ((long long)bin * NK * C + q) * 2;
+      Gs[q] = cd_make(g[0], g[1]);
+    }
+  __syncthreads();
+  // ---- lambda (wpe.py:33-56) ----
+  for (int t = tid; t < a.T; t += blockDim.x) {
+    double p = 0.0;
+    for (int n = 0; n < C; ++n) {
+      const cd z = a.use_filter ? wpe_filtered(a, xs, Gs, n, t) : xs[n * a.Tp + pad + t];
+      p += z.x * z.x + z.y * z.y;
+    }
+    L[t] = p / (double)C;
+  }
+  __syncthreads();
+  for (int t = tid; t < a.T; t += blockDim.x) {
+    double s = 0.0;
+    int cnt = 0;
+    for (int c = -a.ctx; c <= a.ctx; ++c)
+      if (t + c >= 0 && t + c < a.T) { s += L[t + c]; ++cnt; }
+    linv[t] = 1.0 / fmax(s / (double)cnt, SETK_EPS32_D);
+  }
+  __syncthreads();
+  // ---- [R | r]: 4 x 4 tiles (I, J >= I) of the NK x (NK + C) augmented matrix ----
+  const int RT = (NK + 3) / 4, CT = (NA + 3) / 4;
+  int I = 0, e = tid;
+  while (I < RT && e >= CT - I) { e -= CT - I; ++I; }
+  if (I >= RT) return;                                    // (no barrier below)
+  const int J = I + e;
+  // row m of the augmented operand: m < NK -> x_{m % C} delayed by m / C + delay; else x_{m - NK}
+  int oi[4], oj[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int mi = 4 * I + u, mj = 4 * J + u;
+    oi[u] = mi < NK ? (mi % C) * a.Tp + pad - (mi / C) - a.delay : -1;
+    oj[u] = mj < NK ? (mj % C) * a.Tp + pad - (mj / C) - a.delay : (mj < NA ? (mj - NK) * a.Tp + pad : -1);
+  }
+  double ar[4][4], ai[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) { ar[u][v] = 0.0; ai[u][v] = 0.0; }
+  for (int t = 0; t < a.T; ++t) {
+    const double w = linv[t];
+    cd p[4], q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      p[u] = oi[u] >= 0 ? xs[oi[u] + t] : cd_make(0.0, 0.0);
+      q[u] = oj[u] >= 0 ? xs[oj[u] + t] : cd_make(0.0, 0.0);
+      p[u].x *= w; p[u].y *= w;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {                       // p conj(q)
+        ar[u][v] += p[u].x * q[v].x + p[u].y * q[v].y;
+        ai[u][v] += p[u].y * q[v].x - p[u].x * q[v].y;
+      }
+  }
+  double* R = a.Raug + (long long)bin * NK * NA * 2;
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int i = 4 * I + u, j = 4 * J + v;
+      if (i >= NK || j >= NA) continue;
+      if (j >= i) { R[((long long)i * NA + j) * 2] = ar[u][v]; R[((long long)i * NA + j) * 2 + 1] = ai[u][v]; }
+      if (j > i && j < NK) {                              // Hermitian mirror (the solve reads the full matrix)
+        R[((long long)j * NA + i) * 2] = ar[u][v];
+        R[((long long)j * NA + i) * 2 + 1] = -ai[u][v];
+      }
+    }
+}
+
+// CTA per bin, thread r owns row r of the augmented [R | r]  (NK <= blockDim)
+__global__ void __launch_bounds__(128) wpe_solve_kernel(WpeArgs a, double* Gout) {
+  SETK_DYN_SMEM(double, sm);
+  const int NK = a.NK, C = a.C, NA = NK + C, LD = NA + 1;   // odd-ish pitch in cd
+  cd* M = reinterpret_cast<cd*>(sm);                         // [NK][LD]
+  double* red_v = sm + 2 * (size_t)NK * LD;                  // [warps]
+  int* red_i = reinterpret_cast<int*>(red_v + 8);
+  const int bin = blockIdx.x, b = bin / a.F;
+  const int r = threadIdx.x, lane = r & 31, wid = r >> 5, nw = (blockDim.x + 31) >> 5;
+  const bool row = r < NK;
+  const double* R = a.Raug + (long long)bin * NK * NA * 2;
+  for (int q = r; q < NK * NA; q += blockDim.x) {
+    const int i = q / NA, j = q - i * NA;
+    M[i * LD + j] = cd_make(R[2 * (long long)q], R[2 * (long long)q + 1]);
+  }
+  __syncthreads();
+  bool singular = false;
+  for (int k = 0; k < NK; ++k) {
+    double m = (row && r >= k) ? fabs(M[r * LD + k].x) + fabs(M[r * LD + k].y) : -1.0;
+    int piv = r;
+    for (int o = 16; o > 0; o >>= 1) {                        // izamax: first index on ties
+      const double m2 = __shfl_xor_sync(0xffffffffu, m, o);
+      const int p2 = __shfl_xor_sync(0xffffffffu, piv, o);
+      if (m2 > m || (m2 == m && p2 < piv)) { m = m2; piv = p2; }
+    }
+    if (lane == 0) { red_v[wid] = m; red_i[wid] = piv; }
+    __syncthreads();
+    m = red_v[0]; piv = red_i[0];
+    for (int w = 1; w < nw; ++w)
+      if (red_v[w] > m || (red_v[w] == m && red_i[w] < piv)) { m = red_v[w]; piv = red_i[w]; }
+    if (piv != k)                                             // swap rows k, piv: thread j owns columns j, j + blockDim, ...
+      for (int j = r; j < NA; j += blockDim.x) { const cd t = M[k * LD + j]; M[k * LD + j] = M[piv * LD + j]; M[piv * LD + j] = t; }
+    __syncthreads();
+    if (m == 0.0) singular = true;
+    if (row && r > k && m != 0.0) {
+      const cd l = cd_mul(M[r * LD + k], cd_div(cd_make(1.0, 0.0), M[k * LD + k]));
+      M[r * LD + k] = l;
+      for (int j = k + 1; j < NA; ++j) M[r * LD + j] = cd_sub(M[r * LD + j], cd_mul(l, M[k * LD + j]));
+    }
+    __syncthreads();
+  }
+  for (int i = NK - 1; i >= 0; --i) {                         // back substitution, all C right-hand sides
+    if (r < C) M[i * LD + NK + r] = cd_div(M[i * LD + NK + r], M[i * LD + i]);
+    __syncthreads();
+    if (row && r < i)
+      for (int n = 0; n < C; ++n)
+        M[r * LD + NK + n] = cd_sub(M[r * LD + NK + n], cd_mul(M[r * LD + i], M[i * LD + NK + n]));
+    __syncthreads();
+  }
+  double* G = Gout + (long long)bin * NK * C * 2;
+  if (row)
+    for (int n = 0; n < C; ++n) {
+      const cd g = M[r * LD + NK + n];
+      G[((long long)r * C + n) * 2] = g.x;
+      G[((long long)r * C + n) * 2 + 1] = g.y;
+      if (!(isfinite(g.x) && isfinite(g.y))) singular = true;
+    }
+  if (singular && a.status) atomicOr(a.status + b, (unsigned)SETK_ST_SINGULAR);
+}
+
+__global__ void __launch_bounds__(256) wpe_filter_kernel(WpeArgs a) {
+  SETK_DYN_SMEM(double, sm);
+  cd* xs; double* linv; double* L; cd* Gs;
+  wpe_carve(sm, a, xs, linv, L, Gs);
+  const int bin = blockIdx.x, b = bin / a.F, f = bin - b * a.F;
+  wpe_load_bin(a, b, f, xs);
+  for (int q = threadIdx.x; q < a.NK * a.C; q += blockDim.x) {
+    const double* g = a.G + ((long long)bin * a.NK * a.C + q) * 2;
+    Gs[q] = cd_make(g[0], g[1]);
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < a.C * a.T; q += blockDim.x) {
+    const int n = q / a.T, t = q - n * a.T;
+    const cd z = wpe_filtered(a, xs, Gs, n, t);
+    a.out[(((long long)b * a.C + n) * a.F + f) * a.T + t] = make_float2((float)z.x, (float)z.y);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// what the kernels can hold: tiles <= 512 threads, matrices within shared memory
+bool wpe_supported(int C, int T, int taps, int delay) {
+  const int NK = C * taps, NA = NK + C, RT = (NK + 3) / 4, CT = (NA + 3) / 4;
+  if (NK > 128 || RT * CT - RT * (RT - 1) / 2 > 512) return false;
+  if (wpe_smem_bytes(C, T, T + taps + delay, NK) > 200 * 1024) return false;
+  return sizeof(double) * (2 * (size_t)NK * (NA + 1) + 8) + 32 <= 200 * 1024;
+}
+
+size_t wpe_workspace_bytes(int B, int C, int F, int taps) {
+  const size_t NK = (size_t)C * taps;
+  return sizeof(double) * 2 * (size_t)B * F * (NK * (NK + C) + NK * C);
+}
+
+// reverb -> dereverberated STFT, both [B][C][F][T] c64; X is the bin-major copy of reverb
+cudaError_t run_wpe(const float2* X, int P, int B, int C, int F, int T, int taps, int delay, int ctx,
+                    int num_iters, double* ws, float2* out, unsigned* status, void* stream) {
+  WpeArgs a;
+  a.X = X; a.P = P; a.B = B; a.C = C; a.F = F; a.T = T;
+  a.taps = taps; a.delay = delay; a.ctx = ctx;
+  a.NK = C * taps;
+  a.Tp = T + taps + delay;
+  a.Raug = ws;
+  double* G = ws + 2 * (size_t)B * F * a.NK * (a.NK + C);
+  a.G = G;
+  a.out = out; a.status = status;
+  const size_t smem = wpe_smem_bytes(C, T, a.Tp, a.NK);
+  const int NA = a.NK + C, RT = (a.NK + 3) / 4, CT = (NA + 3) / 4;
+  const int ntiles = RT * CT - RT * (RT - 1) / 2;
+  const int corr_threads = ((ntiles + 31) / 32) * 32;
+  const int solve_threads = ((a.NK + 31) / 32) * 32;
+  const size_t solve_smem = sizeof(double) * (2 * (size_t)a.NK * (NA + 1) + 8) + sizeof(int) * 8;
+#ifndef SETK_EMU
+  cudaError_t ea = cudaFuncSetAttribute(wpe_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (ea == cudaSuccess)
+    ea = cudaFuncSetAttribute(wpe_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (ea == cudaSuccess)
+    ea = cudaFuncSetAttribute(wpe_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem);
+  if (ea != cudaSuccess) return ea;
+#endif
+  cudaError_t e = cudaSuccess;
+  for (int it = 0; it < num_iters && e == cudaSuccess; ++it) {
+    a.use_filter = it > 0;
+    e = launch(wpe_corr_kernel, dim3(B * F), dim3(corr_threads), smem, stream, false, a);
+    if (e == cudaSuccess)
+      e = launch(wpe_solve_kernel, dim3(B * F), dim3(solve_threads), solve_smem, stream, false, a, G);
+  }
+  if (e != cudaSuccess) return e;
+  a.use_filter = num_iters > 0;
+  return launch(wpe_filter_kernel, dim3(B * F), dim3(256), smem, stream, false, a);
+}
+
+}  // namespace setk

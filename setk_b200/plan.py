@@ -281,6 +281,26 @@ def cgmm_from_stft(stft, num_classes=2, num_iters=20, init_gamma=None, update_al
     return masks, status
 
 
+def wpe_from_stft(stft, taps=10, delay=3, context=1, num_iters=3):
+    """
+    wpe(reverb, taps, delay, context, num_iters) batched (libs/wpe.py:82-110).
+    stft (B,C,F,T) complex64 -> (dereverberated (B,C,F,T) complex64, status (B,) int32).
+    """
+    stft = stft.contiguous()
+    if stft.dtype != torch.complex64:
+        stft = stft.to(torch.complex64)
+    if stft.dim() != 4:
+        raise ValueError(f"stft must be (B, C, F, T), got {tuple(stft.shape)}")
+    B, C, F, T = stft.shape
+    out = torch.empty_like(stft)
+    status = torch.zeros((B,), dtype=torch.int32, device=stft.device)
+    with _ctx(stft.device):
+        _lib.check(_lib.library().setk_wpe_stft(
+            _lib.ptr(stft), B, C, F, T, int(taps), int(delay), int(context), int(num_iters),
+            _lib.ptr(out), _lib.ptr(status), _lib.current_stream(stft.device)))
+    return out, status
+
+
 def covariance(stft, mask, clip_mask=False, mask_ft=False):
     """compute_covar batched: stft (B,C,F,T) c64, mask (B,T,F) -> (B,F,C,C) c64."""
     stft = stft.contiguous()

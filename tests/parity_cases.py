@@ -446,3 +446,39 @@ def check_cgmm_documented(device, which):
     assert m.shape == ref.shape
     d = np.abs(m - ref)
     return float(d.mean()), float(d.max()), float(np.mean(d > 1e-3))
+
+
+# ------------------------------------------------------------------- WPE ---
+TOL_WPE = 2e-6           # fp64 kernels, complex64 output, vs the float64 oracle on the same STFT
+
+
+def check_wpe(device, rng, B, C, N, frame_len=512, hop=128, taps=4, delay=2, ctx=1, iters=2):
+    """setk_wpe_stft vs oracle.wpe_oracle on the oracle's complex64 STFT."""
+    from oracle import wpe_oracle as wo
+    x = structured_audio(rng, B, C, N)
+    S = np.stack([oracle_stft(x[b], frame_len, hop, True, "hann", dtype=np.complex64) for b in range(B)])
+    out, status = P.wpe_from_stft(torch.from_numpy(S).to(device), taps, delay, ctx, iters)
+    out = out.cpu().numpy()
+    assert out.shape == S.shape and out.dtype == np.complex64
+    assert int(status.cpu().abs().sum()) == 0
+    worst = 0.0
+    for b in range(B):
+        ref = wo.wpe(np.einsum("nft->fnt", S[b]), taps, delay, ctx, iters)       # F x N x T, complex128
+        err = bo.rel_inf(out[b], np.einsum("fnt->nft", ref))
+        assert err <= TOL_WPE, f"wpe rel-inf {err}"
+        worst = max(worst, err)
+    return worst
+
+
+def check_wpe_fixture(device, name):
+    """From the fixture's audio to the REFERENCE's wpe() output (tests/golden/ref_wpe.npz)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_wpe.npz"))
+    fl, hop, taps, delay, ctx, iters = (int(v) for v in g[name + "/cfg"])
+    mix = g[name + "/mix"]
+    S = oracle_stft(mix, fl, hop, True, "hann", dtype=np.complex64)[None]
+    out, status = P.wpe_from_stft(torch.from_numpy(S).to(device), taps, delay, ctx, iters)
+    assert int(status.cpu().abs().sum()) == 0
+    err = bo.rel_inf(out[0].cpu().numpy(), g[name + "/derev"])
+    assert err <= 1e-5, (name, err)      # the reference ran in complex64; both sit ~1e-8 from float64
+    return err

@@ -126,6 +126,28 @@ def test_cgmm_argument_errors(emu):
     pl.close()
 
 
+def test_wpe(emu):
+    rng = np.random.default_rng(90)
+    pc.check_wpe(emu, rng, 2, 3, 3000, 256, 64, taps=4, delay=2, ctx=1, iters=2)
+    pc.check_wpe(emu, rng, 1, 2, 2500, 256, 64, taps=6, delay=1, ctx=0, iters=1)
+    pc.check_wpe(emu, rng, 1, 5, 4000, 256, 128, taps=3, delay=3, ctx=2, iters=3)   # NK = 15: ragged tiles
+
+
+def test_wpe_reference_fixture(emu):
+    pc.check_wpe_fixture(emu, "c2_t6_ctx0")
+
+
+def test_wpe_argument_errors(emu):
+    from setk_b200 import plan as P
+    x = torch.zeros((1, 2, 33, 20), dtype=torch.complex64)
+    with pytest.raises(Exception):
+        P.wpe_from_stft(x, num_iters=0)
+    with pytest.raises(Exception):
+        P.wpe_from_stft(torch.zeros((1, 16, 33, 20), dtype=torch.complex64), taps=10)   # NK = 160
+    out, st = P.wpe_from_stft(x, taps=2, delay=1, num_iters=1)       # silence: singular normal matrix
+    assert int(st[0]) != 0
+
+
 def test_cov_generic(emu):
     pc.check_cov_generic(emu, np.random.default_rng(7), 2, 6, 9, 70)
 

@@ -300,3 +300,20 @@ def test_cgmm_documented_command_from_audio(cuda, which):
     mean, worst, frac = pc.check_cgmm_documented(cuda, which)
     print(f"cgmm {which}: mean {mean:.3g} max {worst:.3g} frac>1e-3 {frac:.3g}")
     assert mean <= 1e-4 and frac <= 1e-2 and worst <= 0.1
+
+
+@pytest.mark.parametrize("C,fl,hop,taps,delay,ctx,iters,N", [
+    (6, 512, 256, 10, 3, 1, 3, 48000),      # config-4 geometry: NK = 60
+    (8, 512, 128, 10, 3, 1, 2, 24000),      # NK = 80
+    (2, 1024, 256, 12, 2, 0, 1, 30000),
+    (5, 512, 128, 3, 3, 2, 3, 16000),       # NK = 15: ragged tiles
+    (1, 512, 128, 10, 3, 1, 3, 16000),
+])
+def test_wpe(cuda, C, fl, hop, taps, delay, ctx, iters, N):
+    pc.check_wpe(cuda, np.random.default_rng(400 + C), 2, C, N, fl, hop, taps, delay, ctx, iters)
+
+
+def test_wpe_reference_fixtures(cuda):
+    """libs/wpe.py wpe() run by the reference (tests/golden/ref_wpe.npz)"""
+    for name in ("c3_t4", "c4_t10", "c2_t6_ctx0"):
+        pc.check_wpe_fixture(cuda, name)

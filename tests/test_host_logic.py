@@ -212,6 +212,49 @@ def test_cgmm_trainer_mirror_and_cli(tmp_path, emu, emu_library_path):
     assert d.mean() <= 1e-4                              # float32 tile STFT vs float64 oracle STFT
 
 
+def test_wpe_mirror_and_cli(tmp_path, emu, emu_library_path):
+    """libs.wpe.wpe (reference signature) and scripts/sptk/apply_wpe.py."""
+    from oracle import wpe_oracle as wo
+    from setk_b200.libs import utils
+    from setk_b200.libs.wpe import wpe
+    import parity_cases as pc
+    utils.set_default_device("cpu")
+    rng = np.random.default_rng(13)
+    x = pc.structured_audio(rng, 1, 2, 2600)[0]
+    x = so.float_from_pcm16(so.pcm16_from_float(x))
+    kw = dict(frame_len=256, frame_hop=64, center=True, window="hann", round_power_of_two=True,
+              transpose=False)
+    obs = np.einsum("nft->fnt", so.multichannel_stft(x, out_dtype=np.complex64, **kw))      # F x N x T
+    ref = wo.wpe(obs, taps=4, delay=2, context=1, num_iters=2)
+    out = wpe(obs, taps=4, delay=2, context=1, num_iters=2)
+    assert isinstance(out, np.ndarray) and out.shape == obs.shape
+    assert bo.rel_inf(out, ref) <= 2e-6
+    out_t = wpe(torch.from_numpy(obs)[None], taps=4, delay=2, context=1, num_iters=2)       # batched tensor
+    assert torch.is_tensor(out_t) and bo.rel_inf(out_t[0].numpy(), ref) <= 2e-6
+    with pytest.raises(np.linalg.LinAlgError):
+        wpe(np.zeros((9, 2, 30), dtype=np.complex64), taps=3, delay=1)
+    # the CLI: all channels of the dereverberated signal as one PCM-16 file
+    _write_wav(str(tmp_path / "utt1.wav"), x)
+    (tmp_path / "wav.scp").write_text(f"utt1 {tmp_path / 'utt1.wav'}\n")
+    env = dict(os.environ, SETK_B200_TEST_LIBRARY=emu_library_path, PYTHONPATH=ROOT)
+    runner = (
+        "import os, sys, runpy; sys.argv = sys.argv[1:];"
+        "from setk_b200 import _lib; _lib.use_library(os.environ['SETK_B200_TEST_LIBRARY']);"
+        "from setk_b200.libs import utils; utils.set_default_device('cpu');"
+        "runpy.run_path(sys.argv[0], run_name='__main__')")
+    cmd = [sys.executable, "-c", runner, os.path.join(ROOT, "scripts", "sptk", "apply_wpe.py"),
+           "--frame-len", "256", "--frame-hop", "64", "--center", "true", "--taps", "4", "--delay", "2",
+           "--num-iters", "2", str(tmp_path / "wav.scp"), str(tmp_path / "out")]
+    subprocess.run(cmd, check=True, env=env, capture_output=True)
+    import scipy.io.wavfile as wavfile
+    sr, y = wavfile.read(str(tmp_path / "out" / "utt1.wav"))
+    assert sr == 16000 and y.dtype == np.int16 and y.shape[1] == 2
+    yo = np.stack([so.inverse_stft(ref[:, n], frame_len=256, frame_hop=64, center=True, window="hann",
+                                   transpose=False) for n in range(2)])
+    d = np.abs(y.T.astype(np.int64) - so.pcm16_from_float(yo).astype(np.int64))
+    assert d.max() <= 1
+
+
 def test_permu_aligner_restores_a_scrambled_mask():
     from setk_b200.libs.cluster import permu_aligner
     rng = np.random.default_rng(12)

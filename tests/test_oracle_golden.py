@@ -123,6 +123,21 @@ def test_cgmm_oracle_pinned_to_reference_masks():
         assert np.max(np.abs(m - gc[name + "/masks"][:m.shape[0]])) <= 1e-7
 
 
+def test_wpe_oracle_pinned_to_reference():
+    """libs/wpe.py wpe() run by the reference on complex64 STFTs (ref_wpe.npz)."""
+    from oracle import wpe_oracle as wo
+    g = np.load(os.path.join(GOLD, "ref_wpe.npz"))
+    for name in ("c3_t4", "c4_t10", "c2_t6_ctx0"):
+        fl, hop, taps, delay, ctx, iters = (int(v) for v in g[name + "/cfg"])
+        obs = so.multichannel_stft(g[name + "/mix"], frame_len=fl, frame_hop=hop, center=True,
+                                   window="hann", round_power_of_two=True, transpose=False,
+                                   out_dtype=np.complex64)
+        x = np.einsum("nft->fnt", obs)
+        ref = np.einsum("nft->fnt", g[name + "/derev"])
+        assert bo.rel_inf(wo.wpe(x, taps, delay, ctx, iters, dtype=np.complex64), ref) <= 1e-6
+        assert bo.rel_inf(wo.wpe(x, taps, delay, ctx, iters), ref) <= 1e-6      # float64 arithmetic
+
+
 def test_bookkeeping_table():
     """frame counts and iSTFT lengths at N = 160000, hop 256."""
     rows = [(512, True, 512, 257, 626, 160000), (1024, True, 1024, 513, 626, 160000),

@@ -15,10 +15,11 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 from setk_b200 import synth  # noqa: E402
+from setk_b200 import plan as P_  # noqa: E402
 from setk_b200.engine import BeamformPipeline  # noqa: E402
 
 
-def run(name, C, frame_len, beamformer, B, N=160000, steps=10, cgmm=False):
+def run(name, C, frame_len, beamformer, B, N=160000, steps=10, cgmm=False, wpe=False):
     dev = torch.device("cuda:0")
     pipe = BeamformPipeline(C, beamformer, frame_len=frame_len, frame_hop=256, max_batch=B,
                             max_samples=N, device=dev)
@@ -60,6 +61,12 @@ def run(name, C, frame_len, beamformer, B, N=160000, steps=10, cgmm=False):
         cg = {"cgmm_20it_ms": t_cg, "cgmm_utts_per_s": B / t_cg * 1e3,
               "mask_mean": float(masks[:, 0].mean()), "status_failures": int((st != 0).sum())}
         stages["cgmm"] = cg
+    if wpe:
+        S = pipe.plan.stft(audio)
+        torch.cuda.synchronize()
+        t_w, (out, st) = timed(lambda: P_.wpe_from_stft(S, 10, 3, 1, 3), n=2)
+        stages["wpe"] = {"wpe_3it_ms": t_w, "wpe_utts_per_s": B / t_w * 1e3,
+                         "status_failures": int((st != 0).sum())}
     print(json.dumps({"config": name, "channels": C, "n_fft": pipe.plan.n_fft, "beamformer": beamformer,
                       "batch": B, "ms_per_batch": ms, "utts_per_s": B / ms * 1e3,
                       "route": route, "stages": stages,
@@ -81,4 +88,5 @@ if __name__ == "__main__":
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
     for cfg in CONFIGS:
         if only in cfg[0]:
-            run(*cfg, steps=steps, cgmm=(len(sys.argv) > 3 and sys.argv[3] == "cgmm"))
+            run(*cfg, steps=steps, cgmm=(len(sys.argv) > 3 and sys.argv[3] == "cgmm"),
+                wpe=(len(sys.argv) > 3 and sys.argv[3] == "wpe"))
