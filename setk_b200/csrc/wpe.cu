@@ -12,7 +12,7 @@
 //   wpe_corr_kernel    prologue: previous filter G -> z -> lambda (or lambda of x);
 //                      then [R | r] = sum_t a_i conj(a_j) / lambda, 4 x 4 register tiles
 //                      over the upper block triangle of the augmented matrix
-//   wpe_solve_kernel   LU with partial pivoting of [R | r], rows owned by threads
+//   wpe_solve_kernel   LU with partial pivoting of [R | r], four threads per row
 //                      (numpy.linalg.solve), column-oriented back substitution -> G
 //   wpe_filter_kernel  z = x - G^H yt, written in the API layout [B][C][F][T]
 // All arithmetic is fp64 (the reference computes in the dtype of its input,
@@ -155,25 +155,28 @@ __global__ void __launch_bounds__(512) wpe_corr_kernel(WpeArgs a) {
     }
 }
 
-// CTA per bin, thread r owns row r of the augmented [R | r]  (NK <= blockDim)
-__global__ void __launch_bounds__(128) wpe_solve_kernel(WpeArgs a, double* Gout) {
+// CTA per bin; thread (r, cg) = (tid / 4, tid % 4) owns columns j = cg (mod 4) of row r of
+// the augmented [R | r].  The multipliers are used and dropped (the right-hand sides
+// ride along), so a step costs three barriers: pivot vote, row swap, elimination.
+__global__ void __launch_bounds__(512) wpe_solve_kernel(WpeArgs a, double* Gout) {
   SETK_DYN_SMEM(double, sm);
-  const int NK = a.NK, C = a.C, NA = NK + C, LD = NA + 1;   // odd-ish pitch in cd
+  const int NK = a.NK, C = a.C, NA = NK + C, LD = NA + 1;
   cd* M = reinterpret_cast<cd*>(sm);                         // [NK][LD]
-  double* red_v = sm + 2 * (size_t)NK * LD;                  // [warps]
-  int* red_i = reinterpret_cast<int*>(red_v + 8);
+  double* red_v = sm + 2 * (size_t)NK * LD;                  // [16 warps]
+  int* red_i = reinterpret_cast<int*>(red_v + 16);
   const int bin = blockIdx.x, b = bin / a.F;
-  const int r = threadIdx.x, lane = r & 31, wid = r >> 5, nw = (blockDim.x + 31) >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = (blockDim.x + 31) >> 5;
+  const int r = tid >> 2, cg = tid & 3;
   const bool row = r < NK;
   const double* R = a.Raug + (long long)bin * NK * NA * 2;
-  for (int q = r; q < NK * NA; q += blockDim.x) {
+  for (int q = tid; q < NK * NA; q += blockDim.x) {
     const int i = q / NA, j = q - i * NA;
     M[i * LD + j] = cd_make(R[2 * (long long)q], R[2 * (long long)q + 1]);
   }
   __syncthreads();
   bool singular = false;
   for (int k = 0; k < NK; ++k) {
-    double m = (row && r >= k) ? fabs(M[r * LD + k].x) + fabs(M[r * LD + k].y) : -1.0;
+    double m = (cg == 0 && row && r >= k) ? fabs(M[r * LD + k].x) + fabs(M[r * LD + k].y) : -1.0;
     int piv = r;
     for (int o = 16; o > 0; o >>= 1) {                        // izamax: first index on ties
       const double m2 = __shfl_xor_sync(0xffffffffu, m, o);
@@ -185,28 +188,27 @@ __global__ void __launch_bounds__(128) wpe_solve_kernel(WpeArgs a, double* Gout)
     m = red_v[0]; piv = red_i[0];
     for (int w = 1; w < nw; ++w)
       if (red_v[w] > m || (red_v[w] == m && red_i[w] < piv)) { m = red_v[w]; piv = red_i[w]; }
-    if (piv != k)                                             // swap rows k, piv: thread j owns columns j, j + blockDim, ...
-      for (int j = r; j < NA; j += blockDim.x) { const cd t = M[k * LD + j]; M[k * LD + j] = M[piv * LD + j]; M[piv * LD + j] = t; }
+    if (piv != k)
+      for (int j = tid; j < NA; j += blockDim.x) { const cd t = M[k * LD + j]; M[k * LD + j] = M[piv * LD + j]; M[piv * LD + j] = t; }
     __syncthreads();
     if (m == 0.0) singular = true;
     if (row && r > k && m != 0.0) {
-      const cd l = cd_mul(M[r * LD + k], cd_div(cd_make(1.0, 0.0), M[k * LD + k]));
-      M[r * LD + k] = l;
-      for (int j = k + 1; j < NA; ++j) M[r * LD + j] = cd_sub(M[r * LD + j], cd_mul(l, M[k * LD + j]));
+      const cd l = cd_mul(M[r * LD + k], cd_div(cd_make(1.0, 0.0), M[k * LD + k]));   // column k is read-only here
+      for (int j = k + 1 + cg; j < NA; j += 4) M[r * LD + j] = cd_sub(M[r * LD + j], cd_mul(l, M[k * LD + j]));
     }
     __syncthreads();
   }
   for (int i = NK - 1; i >= 0; --i) {                         // back substitution, all C right-hand sides
-    if (r < C) M[i * LD + NK + r] = cd_div(M[i * LD + NK + r], M[i * LD + i]);
+    if (tid < C) M[i * LD + NK + tid] = cd_div(M[i * LD + NK + tid], M[i * LD + i]);
     __syncthreads();
     if (row && r < i)
-      for (int n = 0; n < C; ++n)
+      for (int n = cg; n < C; n += 4)
         M[r * LD + NK + n] = cd_sub(M[r * LD + NK + n], cd_mul(M[r * LD + i], M[i * LD + NK + n]));
     __syncthreads();
   }
   double* G = Gout + (long long)bin * NK * C * 2;
   if (row)
-    for (int n = 0; n < C; ++n) {
+    for (int n = cg; n < C; n += 4) {
       const cd g = M[r * LD + NK + n];
       G[((long long)r * C + n) * 2] = g.x;
       G[((long long)r * C + n) * 2 + 1] = g.y;
@@ -239,7 +241,7 @@ bool wpe_supported(int C, int T, int taps, int delay) {
   const int NK = C * taps, NA = NK + C, RT = (NK + 3) / 4, CT = (NA + 3) / 4;
   if (NK > 128 || RT * CT - RT * (RT - 1) / 2 > 512) return false;
   if (wpe_smem_bytes(C, T, T + taps + delay, NK) > 200 * 1024) return false;
-  return sizeof(double) * (2 * (size_t)NK * (NA + 1) + 8) + 32 <= 200 * 1024;
+  return sizeof(double) * (2 * (size_t)NK * (NA + 1) + 16) + 64 <= 200 * 1024;
 }
 
 size_t wpe_workspace_bytes(int B, int C, int F, int taps) {
@@ -263,8 +265,8 @@ cudaError_t run_wpe(const float2* X, int P, int B, int C, int F, int T, int taps
   const int NA = a.NK + C, RT = (a.NK + 3) / 4, CT = (NA + 3) / 4;
   const int ntiles = RT * CT - RT * (RT - 1) / 2;
   const int corr_threads = ((ntiles + 31) / 32) * 32;
-  const int solve_threads = ((a.NK + 31) / 32) * 32;
-  const size_t solve_smem = sizeof(double) * (2 * (size_t)a.NK * (NA + 1) + 8) + sizeof(int) * 8;
+  const int solve_threads = 4 * (((a.NK + 7) / 8) * 8);             // 4 column groups per row, whole warps
+  const size_t solve_smem = sizeof(double) * (2 * (size_t)a.NK * (NA + 1) + 16) + sizeof(int) * 16;
 #ifndef SETK_EMU
   cudaError_t ea = cudaFuncSetAttribute(wpe_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (ea == cudaSuccess)
