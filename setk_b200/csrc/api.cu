@@ -25,13 +25,14 @@ cudaError_t run_pcm16_to_float(const int16_t*, long long, float*, void*);
 
 bool stft_cov_fused_supported(const Geometry&);
 size_t stft_cov_partial_floats(const Geometry&);
+size_t stft_cov_partial_bytes(const setk_plan*, int, int);
 int stft_cov_pick_chunks(const setk_plan*, int, int);
 cudaError_t run_stft_cov_fused(setk_plan*, const float*, const int*, int, int, int, const float*,
-                               const float*, unsigned, int, float*, unsigned*, float2*, float2*, float*,
+                               const float*, unsigned, int*, float*, unsigned*, float2*, float2*, float*,
                                void*);
 bool apply_istft_fused_supported(const Geometry&);
 cudaError_t run_apply_istft_fused(setk_plan*, const float*, const int*, int, int, int, const void*, int,
-                                  const float*, int, int, float*, unsigned*, void*);
+                                  const float*, int, int*, float*, unsigned*, const float*, unsigned*, void*);
 
 bool stft_spill_supported(const Geometry&);
 size_t stft_spill_bytes(const Geometry&, int, int);
@@ -167,6 +168,7 @@ int setk_plan_destroy(setk_plan_t* pl) {
   if (pl->d_frames_ws) cudaFree(pl->d_frames_ws);
   if (pl->d_cgmm_ws) cudaFree(pl->d_cgmm_ws);
   if (pl->d_peak) cudaFree(pl->d_peak);
+  if (pl->d_tile_prefix) cudaFree(pl->d_tile_prefix);
   free(pl);
   return SETK_OK;
 }
@@ -236,7 +238,7 @@ int setk_stft_cov(setk_plan_t* pl, const float* audio, const int32_t* n_samples,
   if (!audio || !mask_s || !Rs || !Rn) return fail(SETK_EINVAL, "setk_stft_cov: null buffer");
   const Geometry& g = pl->geo;
   const int T = frames_of(N, g.n_fft, g.hop, g.pad);
-  cudaError_t e = ensure(&pl->d_peak, &pl->peak_bytes, sizeof(unsigned) * 2 * (size_t)pl->cfg.max_batch);
+  cudaError_t e = ensure(&pl->d_peak, &pl->peak_bytes, sizeof(unsigned) * 3 * (size_t)pl->cfg.max_batch);
   if (e != cudaSuccess) return cuda_fail(e, "setk_stft_cov(workspace)");
   unsigned* maxabs_bits = nullptr;
   if (maxabs) {
@@ -245,11 +247,11 @@ int setk_stft_cov(setk_plan_t* pl, const float* audio, const int32_t* n_samples,
     if (e != cudaSuccess) return cuda_fail(e, "setk_stft_cov(memset)");
   }
   if (stft_cov_fused_supported(g)) {
-    const int n_chunks = stft_cov_pick_chunks(pl, B, T);
-    const size_t want = sizeof(float) * stft_cov_partial_floats(g) * (size_t)n_chunks * B;
-    e = ensure(&pl->d_partials, &pl->partials_bytes, want);
+    e = ensure(&pl->d_partials, &pl->partials_bytes, stft_cov_partial_bytes(pl, B, T));
+    if (e == cudaSuccess && n_samples)
+      e = ensure(&pl->d_tile_prefix, &pl->tile_prefix_bytes, sizeof(int) * ((size_t)pl->cfg.max_batch + 1));
     if (e != cudaSuccess) return cuda_fail(e, "setk_stft_cov(workspace)");
-    e = run_stft_cov_fused(pl, audio, n_samples, B, N, T, mask_s, mask_n, flags, n_chunks,
+    e = run_stft_cov_fused(pl, audio, n_samples, B, N, T, mask_s, mask_n, flags, pl->d_tile_prefix,
                            pl->d_partials, maxabs_bits, static_cast<float2*>(Rs),
                            static_cast<float2*>(Rn), maxabs, stream);
     return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_stft_cov");
@@ -356,7 +358,7 @@ int setk_istft(setk_plan_t* pl, const void* enh, int32_t B, int32_t T, int32_t n
   const Geometry& g = pl->geo;
   const int T_used = T_used_for(g, T, n_out);
   cudaError_t e = ensure(&pl->d_frames_ws, &pl->frames_ws_bytes, sizeof(float) * (size_t)B * T_used * g.n_fft);
-  if (e == cudaSuccess) e = ensure(&pl->d_peak, &pl->peak_bytes, sizeof(unsigned) * 2 * (size_t)pl->cfg.max_batch);
+  if (e == cudaSuccess) e = ensure(&pl->d_peak, &pl->peak_bytes, sizeof(unsigned) * 3 * (size_t)pl->cfg.max_batch);
   if (e != cudaSuccess) return cuda_fail(e, "setk_istft(workspace)");
   unsigned* peak = norm ? pl->d_peak : nullptr;
   if (peak) {
@@ -378,7 +380,7 @@ int setk_apply_istft(setk_plan_t* pl, const float* audio, const int32_t* n_sampl
   if (n_out < 1) return fail(SETK_ESHAPE, "setk_apply_istft: n_out=%d", n_out);
   const Geometry& g = pl->geo;
   const int T = frames_of(N, g.n_fft, g.hop, g.pad);
-  cudaError_t e = ensure(&pl->d_peak, &pl->peak_bytes, sizeof(unsigned) * 2 * (size_t)pl->cfg.max_batch);
+  cudaError_t e = ensure(&pl->d_peak, &pl->peak_bytes, sizeof(unsigned) * 3 * (size_t)pl->cfg.max_batch);
   if (e != cudaSuccess) return cuda_fail(e, "setk_apply_istft(workspace)");
   unsigned* peak = norm ? pl->d_peak : nullptr;
   if (peak) {
@@ -386,9 +388,19 @@ int setk_apply_istft(setk_plan_t* pl, const float* audio, const int32_t* n_sampl
     if (e != cudaSuccess) return cuda_fail(e, "setk_apply_istft(memset)");
   }
   if (apply_istft_fused_supported(g)) {
-    const int n_chunks = stft_cov_pick_chunks(pl, B, T);
-    e = run_apply_istft_fused(pl, audio, n_samples, B, N, T, w, w_dtype, post_mask, n_out, n_chunks,
-                              wave, peak, stream);
+    if (n_samples)
+      e = ensure(&pl->d_tile_prefix, &pl->tile_prefix_bytes, sizeof(int) * ((size_t)pl->cfg.max_batch + 1));
+    if (e != cudaSuccess) return cuda_fail(e, "setk_apply_istft(workspace)");
+    // the fused kernel also applies the `norm` rescale (the CTA that completes an utterance)
+    unsigned* done = nullptr;
+    if (norm) {
+      done = pl->d_peak + 2 * (size_t)pl->cfg.max_batch;
+      e = cudaMemsetAsync(done, 0, sizeof(unsigned) * B, static_cast<cudaStream_t>(stream));
+      if (e != cudaSuccess) return cuda_fail(e, "setk_apply_istft(memset)");
+    }
+    e = run_apply_istft_fused(pl, audio, n_samples, B, N, T, w, w_dtype, post_mask, n_out,
+                              pl->d_tile_prefix, wave, peak, norm, done, stream);
+    return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_apply_istft");
   } else if (stft_spill_supported(g)) {
     // tile STFT into the bin-major workspace, y = w^H x over it, then the
     // frame-wise inverse FFT + overlap-add reading Y[b][t][f] in place

@@ -23,9 +23,12 @@
 //                           carry; positions no later frame can touch are
 //                           divided by the window-sum-square, trimmed and
 //                           written (coalesced rows); the rest is the next carry
+// Persistent CTAs (2 per SM) over equal runs of the batch's (utterance, tile)
+// sequence (TileSched, stft_tile.cuh): no partial last wave; the weights of an
+// utterance are reloaded where a run crosses into the next utterance.
 // Deterministic: no atomics on data.  A CTA owns the output positions of its
-// own frames; the <= ceil(n_fft/hop)-1 frames before its first frame are
-// recomputed as a halo tile.
+// own frames; the <= ceil(n_fft/hop)-1 frames before the first frame of a run
+// are recomputed as a halo tile.
 // Algorithmic bytes per utterance: 4*C*N (audio) + 8*F*C (w) + 4*n_out (wave)
 // (+ 4*T*F with a post-mask).
 #include "common.cuh"
@@ -38,12 +41,14 @@ struct ApplyIstftArgs {
   const float* audio; const int* n_samples; int N;
   const void* w; int w_dtype;
   const float* post_mask; int T;   // mask leading dimension (frames of N samples)
-  int frames_per_chunk, n_chunks;
+  TileSched sched;      // which (utterance, tile) pairs this CTA owns
   const float* window;  // [n_fft] analysis == synthesis window
   const float* wsq;     // [n_fft]
   int n_out;
   float* wave;          // [B][n_out]
   unsigned* peak;       // [B] or null
+  const float* norm;    // [B] or null: rescale y * norm / (max|y| + eps) in this launch (needs peak, done)
+  unsigned* done;       // [B] tiles of each utterance finished so far (zeroed by the caller)
   int c0, c_total;      // this launch handles channels [c0, c0 + C) of c_total
   int accumulate;       // != 0: wave += this block's contribution (iSTFT is linear)
 };
@@ -63,7 +68,8 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
   const int carry_len = kNfft - hop;
   float2* s_w = reinterpret_cast<float2*>(sm.end());          // [C][kWPitch]
   float2* s_zi = s_w + C * kWPitch;                           // [TT][SETK_ZSLOT]
-  float2* s_tw = s_zi + TT * SETK_ZSLOT;                      // [130] split twiddles
+  float2* s_tw = s_zi + TT * SETK_ZSLOT;                      // [130] split twiddles (129 used)
+  int& s_last = *reinterpret_cast<int*>(s_tw + NPAIR);        // spare slot: "this CTA completed the utterance"
   float* s_frames = reinterpret_cast<float*>(s_tw + NPAIR + 1);   // [TT][512]
   float* s_wsyn = s_frames + TT * kNfft;                      // [512] window / 512
   float* s_wsq = s_wsyn + kNfft;                              // [512]
@@ -73,17 +79,19 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int lane16 = lane & 15, half = lane >> 4;
-  const int b = blockIdx.y, chunk = blockIdx.x;
-  const int nb = a.n_samples ? a.n_samples[b] : a.N;
-  const int Tb = frames_of(nb, kNfft, hop, pad);
+
+  // this CTA's run of the (utterance, tile) sequence (TileSched, stft_tile.cuh)
+  const int q = sched_quota(a.sched, gridDim.x);
+  const int total = sched_prefix(a.sched, a.sched.B);
+  int cur_tile = blockIdx.x * q;
+  const int hi_tile = imin(cur_tile + q, total);
+  if (cur_tile >= hi_tile) return;
+
   // frames librosa.istft would use for this output length
   const int T_cap = (a.n_out + 2 * pad + hop - 1) / hop;
-  const int T_used = imin(Tb, T_cap);
-  const int t_begin = chunk * a.frames_per_chunk;
-  const int t_end = imin(t_begin + a.frames_per_chunk, T_used);
-  const int expected = T_used > 0 ? kNfft + hop * (T_used - 1) : 0;   // padded signal length
-  const int own_begin = t_begin * hop;
-  float* yb = a.wave + (long long)b * a.n_out;
+  // per-segment state (set at the top of the segment loop)
+  int b = 0, nb = 0, T_used = 0, own_begin = 0;
+  float* yb = nullptr;
   float peak = 0.f;
 
   for (int n = tid; n < kNfft; n += blockDim.x) {
@@ -96,30 +104,16 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
     const float s = a.wsq[n] + a.wsq[n + kM];
     s_rw[n] = s > SETK_TINY32 ? 1.0f / s : 1.0f;
   }
-  for (int n = tid; n < 2 * carry_len; n += blockDim.x) s_carry[n] = 0.f;
   if (tid == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); }
   for (int k = tid; k < NPAIR; k += blockDim.x) s_tw[k] = split_twiddle(k);
-  for (int e = tid; e < F * C; e += blockDim.x) {
-    const int k = e / C, c = e - k * C;
-    const long long wi = ((long long)b * F + k) * a.c_total + a.c0 + c;
-    float2 v;
-    if (a.w_dtype == SETK_C128) {
-      const double* p = reinterpret_cast<const double*>(a.w) + 2 * wi;
-      v = make_float2((float)p[0], (float)p[1]);
-    } else {
-      const float* p = reinterpret_cast<const float*>(a.w) + 2 * wi;
-      v = make_float2(p[0], p[1]);
-    }
-    s_w[c * kWPitch + k] = v;
-  }
 
   float w1s, w1c;
   sincospif((float)lane16 / 128.0f, &w1s, &w1c);
   const float2 w1 = make_float2(w1c, -w1s);
-  const float* xb = a.audio + ((long long)b * a.c_total + a.c0) * a.N;
   const bool vec_ok = ((a.N & 3) == 0) && ((hop & 3) == 0) && ((pad & 3) == 0) &&
                       ((reinterpret_cast<uintptr_t>(a.audio) & 15) == 0);
   const bool fast_hop = (hop == kM);               // 50 % overlap: every position has two frames
+  const bool out_vec = ((a.n_out & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.wave) & 15) == 0);
 
   // ---- inverse FFT of the frames of the pending tile (warps 8, 9) ----
   auto ifft_tile = [&](int p_nt) {
@@ -151,28 +145,56 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
     const float* cin = s_carry + cur * carry_len;
     float* cout = s_carry + (cur ^ 1) * carry_len;
     if (fast_hop) {
-      // rows of 256 positions; row jj gets frame jj (n = r) and frame jj-1 (n = r + 256)
-      for (int idx = tid; idx < (p_nt + 1) * kM; idx += blockDim.x) {
-        const int jj = idx >> 8, r = idx & (kM - 1);
-        float val = jj >= 1 ? s_frames[(jj - 1) * kNfft + kM + r] : cin[r];
-        if (jj < p_nt) val += s_frames[jj * kNfft + r];
+      // rows of 256 positions; row jj gets frame jj (n = r) and frame jj-1 (n = r + 256).
+      // Four consecutive positions per thread: 16-byte shared loads and (when the
+      // output rows allow it) 16-byte global stores; pad and own_begin are multiples
+      // of 256 here, so the four share every row condition
+      for (int item = tid; item < (p_nt + 1) * (kM / 4); item += blockDim.x) {
+        const int jj = item >> 6, r = (item & 63) * 4;
+        float4 val = jj >= 1 ? *reinterpret_cast<const float4*>(s_frames + (jj - 1) * kNfft + kM + r)
+                             : *reinterpret_cast<const float4*>(cin + r);
+        if (jj < p_nt) {
+          const float4 f = *reinterpret_cast<const float4*>(s_frames + jj * kNfft + r);
+          val.x += f.x; val.y += f.y; val.z += f.z; val.w += f.w;
+        }
         if (jj < p_nt || last_tile) {
-          const int p = p_tile + idx;
+          const int p = p_tile + jj * kM + r;
           const int q = p - pad;
           if (p >= own_begin && q >= 0 && q < a.n_out) {
             const int t = p_t0 + jj;               // frame starting at this row
+            float vv[4] = {val.x, val.y, val.z, val.w};
             if (t >= 1 && t < T_used) {
-              val *= s_rw[r];
+              const float4 rw = *reinterpret_cast<const float4*>(s_rw + r);
+              vv[0] *= rw.x; vv[1] *= rw.y; vv[2] *= rw.z; vv[3] *= rw.w;
             } else {
-              const float wss = (t < T_used ? s_wsq[r] : 0.f) + (t >= 1 ? s_wsq[kM + r] : 0.f);
-              if (wss > SETK_TINY32) val /= wss;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float wss = (t < T_used ? s_wsq[r + i] : 0.f) + (t >= 1 ? s_wsq[kM + r + i] : 0.f);
+                if (wss > SETK_TINY32) vv[i] /= wss;
+              }
             }
-            if (a.accumulate) val += yb[q];
-            yb[q] = val;
-            peak = fmaxf(peak, fabsf(val));
+            if (out_vec && q + 4 <= a.n_out) {
+              float4* dst = reinterpret_cast<float4*>(yb + q);
+              if (a.accumulate) {
+                const float4 o = *dst;
+                vv[0] += o.x; vv[1] += o.y; vv[2] += o.z; vv[3] += o.w;
+              }
+              *dst = make_float4(vv[0], vv[1], vv[2], vv[3]);
+              peak = fmaxf(peak, fmaxf(fmaxf(fabsf(vv[0]), fabsf(vv[1])), fmaxf(fabsf(vv[2]), fabsf(vv[3]))));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (q + i < a.n_out) {
+                  float v1 = vv[i];
+                  if (a.accumulate) v1 += yb[q + i];
+                  yb[q + i] = v1;
+                  peak = fmaxf(peak, fabsf(v1));
+                }
+              }
+            }
           }
         } else {
-          cout[r] = val;
+          *reinterpret_cast<float4*>(cout + r) = val;
         }
       }
     } else {
@@ -210,96 +232,167 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
   };
 
   const int R = (kNfft + hop - 1) / hop - 1;       // frames before t that overlap frame t
-  // tile sequence: an optional halo tile [t_begin-R, t_begin), then full tiles
-  int t0 = imax(0, t_begin - R);
-  if (t_begin >= t_end) t0 = t_end;                // nothing to do for this chunk
-  int nt = (t0 < t_begin) ? (t_begin - t0) : imin(TT, t_end - t0);
   unsigned par = 0;
   float amax_unused = 0.f;
-  bool async_cur = false;
-  if (t0 < t_end) async_cur = stage_tile_begin<C, TT>(sm, 0, xb, a.N, nb, t0, nt, hop, pad, vec_ok);
   int buf = 0;
-  int prev_t0 = 0, prev_nt = 0;                    // tile whose Zi is waiting for its inverse FFT
-  while (t0 < t_end) {
-    const int t_next = t0 + nt;
-    const int nt_next = imin(TT, t_end - t_next);
-    __syncthreads();   // phase B of the previous tile is complete
-    bool async_next = false;
-    if (t_next < t_end)
-      async_next = stage_tile_begin<C, TT>(sm, buf ^ 1, xb, a.N, nb, t_next, nt_next, hop, pad, vec_ok);
-    if (async_cur) {
-      mbar_wait(&sm.bar[buf], (par >> buf) & 1u);
-      par ^= 1u << buf;
-    }
-    // ---- phase A: forward FFT of this tile || inverse FFT of the previous one ----
-    if (warp < 8) {
-      fft_tile<C, TT>(sm, buf, nt, hop, w1, amax_unused);
-    } else if (prev_nt > 0) {
-      ifft_tile(prev_nt);
-    }
-    __syncthreads();
-    // ---- phase B: apply + inverse split of this tile ----
-    for (int it = tid; it < nt * NPAIR; it += blockDim.x) {
-      const int j = it / NPAIR, k = it - j * NPAIR;
-      const int km = kM - k;                              // mirrored bin 256-k
-      const float2 tw = s_tw[k];
-      float2 yk = make_float2(0.f, 0.f), ym = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const float2* z = sm.z + (j * C + c) * SETK_ZSLOT;
-        float2 xk, xm;
-        split_pair(z[k & (kM - 1)], z[km & (kM - 1)], tw, xk, xm);
-        if (k == 0) { xk.y = 0.f; xm.y = 0.f; }
-        const float2 wk = s_w[c * kWPitch + k], wm = s_w[c * kWPitch + km];
-        yk = cmad_conjw(wk, xk, yk);                       // += conj(w) x: two packed instructions
-        ym = cmad_conjw(wm, xm, ym);
-      }
-      if (a.post_mask) {
-        const float* pm = a.post_mask + ((long long)b * a.T + (t0 + j)) * F;
-        const float mk = pm[k], mm = pm[km];
-        yk = f2mul(yk, make_float2(mk, mk)); ym = f2mul(ym, make_float2(mm, mm));
-      }
-      float2* zi = s_zi + j * SETK_ZSLOT;
-      if (k == 0) {
-        // irfft ignores Im Y[0], Im Y[256]
-        zi[0] = make_float2(yk.x + ym.x, yk.x - ym.x);
+  b = sched_find(a.sched, cur_tile);
+  while (cur_tile < hi_tile) {
+    // ---- next segment: the part of utterance b inside [cur_tile, hi_tile) ----
+    int pb = sched_prefix(a.sched, b), pe = sched_prefix(a.sched, b + 1);
+    while (pe <= cur_tile) { ++b; pb = pe; pe = sched_prefix(a.sched, b + 1); }
+    const int seg_end = imin(hi_tile, pe);
+    nb = a.n_samples ? a.n_samples[b] : a.N;
+    const int Tb = frames_of(nb, kNfft, hop, pad);
+    T_used = imin(Tb, T_cap);
+    const int t_begin = (cur_tile - pb) * TT;
+    const int t_end = imin((seg_end - pb) * TT, T_used);
+    const int expected = T_used > 0 ? kNfft + hop * (T_used - 1) : 0;   // padded signal length
+    own_begin = t_begin * hop;
+    yb = a.wave + (long long)b * a.n_out;
+    const float* xb = a.audio + ((long long)b * a.c_total + a.c0) * a.N;
+
+    __syncthreads();   // the previous segment's last flush has read carry / frames / weights
+    for (int n = tid; n < 2 * carry_len; n += blockDim.x) s_carry[n] = 0.f;
+    cur = 0;
+    for (int e = tid; e < F * C; e += blockDim.x) {
+      const int k = e / C, c = e - k * C;
+      const long long wi = ((long long)b * F + k) * a.c_total + a.c0 + c;
+      float2 v;
+      if (a.w_dtype == SETK_C128) {
+        const double* p = reinterpret_cast<const double*>(a.w) + 2 * wi;
+        v = make_float2((float)p[0], (float)p[1]);
       } else {
-        // Zi[k]   = (Yk + conj(Ym)) + conj(tw) (Yk - conj(Ym))
-        const float2 cm = make_float2(ym.x, -ym.y);
-        const float2 e = f2add(yk, cm), d = f2sub(yk, cm);
-        const float2 p = cmul_conj(d, tw);                 // conj(tw) D
-        zi[k] = f2add(e, p);
-        if (k != kM / 2) {
-          // Zi[256-k] = (Ym + conj(Yk)) + tw (Ym - conj(Yk)) = conj(E) - tw conj(D) = conj(E - conj(tw) D)
-          const float2 q = f2sub(e, p);
-          zi[km] = make_float2(q.x, -q.y);
+        const float* p = reinterpret_cast<const float*>(a.w) + 2 * wi;
+        v = make_float2(p[0], p[1]);
+      }
+      s_w[c * kWPitch + k] = v;
+    }
+
+    // tile sequence: an optional halo tile [t_begin-R, t_begin), then full tiles
+    int t0 = imax(0, t_begin - R);
+    if (t_begin >= t_end) t0 = t_end;                // nothing to do for this segment
+    int nt = (t0 < t_begin) ? (t_begin - t0) : imin(TT, t_end - t0);
+    bool async_cur = false;
+    if (t0 < t_end) async_cur = stage_tile_begin<C, TT>(sm, buf, xb, a.N, nb, t0, nt, hop, pad, vec_ok);
+    int prev_t0 = 0, prev_nt = 0;                    // tile whose Zi is waiting for its inverse FFT
+    while (t0 < t_end) {
+      const int t_next = t0 + nt;
+      const int nt_next = imin(TT, t_end - t_next);
+      __syncthreads();   // phase B of the previous tile is complete
+      bool async_next = false;
+      if (t_next < t_end)
+        async_next = stage_tile_begin<C, TT>(sm, buf ^ 1, xb, a.N, nb, t_next, nt_next, hop, pad, vec_ok);
+      if (async_cur) {
+        mbar_wait(&sm.bar[buf], (par >> buf) & 1u);
+        par ^= 1u << buf;
+      }
+      // ---- phase A: forward FFT of this tile || inverse FFT of the previous one ----
+      if (warp < 8) {
+        fft_tile<C, TT>(sm, buf, nt, hop, w1, amax_unused);
+      } else if (prev_nt > 0) {
+        ifft_tile(prev_nt);
+      }
+      __syncthreads();
+      // ---- phase B: apply + inverse split of this tile ----
+      // thread = (bin pair k, frame parity g): the pair's weights and twiddle are
+      // loaded once and serve frames g, g + 2
+      if (tid < 2 * NPAIR) {
+        const int g = tid >= NPAIR ? 1 : 0;
+        const int k = tid - g * NPAIR;
+        const int km = kM - k;                              // mirrored bin 256-k
+        const float2 tw = s_tw[k];
+        float2 wk[C], wm[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) { wk[c] = s_w[c * kWPitch + k]; wm[c] = s_w[c * kWPitch + km]; }
+        for (int j = g; j < nt; j += 2) {
+          float2 yk = make_float2(0.f, 0.f), ym = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float2* z = sm.z + (j * C + c) * SETK_ZSLOT;
+            float2 xk, xm;
+            split_pair(z[k & (kM - 1)], z[km & (kM - 1)], tw, xk, xm);
+            if (k == 0) { xk.y = 0.f; xm.y = 0.f; }
+            yk = cmad_conjw(wk[c], xk, yk);                    // += conj(w) x: two packed instructions
+            ym = cmad_conjw(wm[c], xm, ym);
+          }
+          if (a.post_mask) {
+            const float* pm = a.post_mask + ((long long)b * a.T + (t0 + j)) * F;
+            const float mk = pm[k], mm = pm[km];
+            yk = f2mul(yk, make_float2(mk, mk)); ym = f2mul(ym, make_float2(mm, mm));
+          }
+          float2* zi = s_zi + j * SETK_ZSLOT;
+          if (k == 0) {
+            // irfft ignores Im Y[0], Im Y[256]
+            zi[0] = make_float2(yk.x + ym.x, yk.x - ym.x);
+          } else {
+            // Zi[k]   = (Yk + conj(Ym)) + conj(tw) (Yk - conj(Ym))
+            const float2 cm = make_float2(ym.x, -ym.y);
+            const float2 e = f2add(yk, cm), d = f2sub(yk, cm);
+            const float2 p = cmul_conj(d, tw);                 // conj(tw) D
+            zi[k] = f2add(e, p);
+            if (k != kM / 2) {
+              // Zi[256-k] = (Ym + conj(Yk)) + tw (Ym - conj(Yk)) = conj(E) - tw conj(D) = conj(E - conj(tw) D)
+              const float2 qq = f2sub(e, p);
+              zi[km] = make_float2(qq.x, -qq.y);
+            }
+          }
+        }
+      }
+      // ---- phase B: flush of the previous tile (its frames were made in phase A) ----
+      if (prev_nt > 0) flush_tile(prev_t0, prev_nt);
+      prev_t0 = t0; prev_nt = nt;
+      t0 = t_next;
+      nt = nt_next;
+      async_cur = async_next;
+      buf ^= 1;
+    }
+    // ---- drain the pipeline: the last tile's inverse FFT and flush ----
+    if (prev_nt > 0) {
+      __syncthreads();
+      if (warp >= 8) ifft_tile(prev_nt);
+      __syncthreads();
+      flush_tile(prev_t0, prev_nt);
+    }
+
+    // zero-fill what no frame reaches (fix_length padding / too-short input)
+    if (t_end >= T_used && !a.accumulate) {
+      const int q0 = imax(expected - pad, 0);
+      for (int qq = q0 + tid; qq < a.n_out; qq += blockDim.x) yb[qq] = 0.f;
+    }
+    if (a.peak) {
+      for (int o = 16; o > 0; o >>= 1) peak = fmaxf(peak, __shfl_xor_sync(0xffffffffu, peak, o));
+      if (lane == 0 && peak > 0.f) atomicMax(a.peak + b, __float_as_uint(peak));
+      peak = 0.f;
+    }
+    // ---- `norm` rescale (utils.py:166-168) by whichever CTA completes the utterance:
+    // its 4 n_out bytes are still in L2, so the separate pass over HBM disappears ----
+    if (a.norm) {
+      __threadfence();                 // this thread's samples and peak are visible device-wide
+      __syncthreads();
+      if (tid == 0) {
+        const unsigned mine = (unsigned)(seg_end - cur_tile);
+        s_last = (atomicAdd(a.done + b, mine) + mine == (unsigned)(pe - pb)) ? 1 : 0;
+      }
+      __syncthreads();
+      if (s_last) {
+        __threadfence();
+        const float nm = a.norm[b];
+        if (nm != 0.f) {                // "if norm:"
+          const float den = __uint_as_float(*reinterpret_cast<volatile unsigned*>(a.peak + b)) + SETK_EPS32;
+          if (out_vec) {
+            float4* y4 = reinterpret_cast<float4*>(yb);
+            for (int qq = tid; qq < (a.n_out >> 2); qq += blockDim.x) {
+              float4 v = y4[qq];
+              v.x = (v.x * nm) / den; v.y = (v.y * nm) / den; v.z = (v.z * nm) / den; v.w = (v.w * nm) / den;
+              y4[qq] = v;
+            }
+          } else {
+            for (int qq = tid; qq < a.n_out; qq += blockDim.x) yb[qq] = (yb[qq] * nm) / den;
+          }
         }
       }
     }
-    // ---- phase B: flush of the previous tile (its frames were made in phase A) ----
-    if (prev_nt > 0) flush_tile(prev_t0, prev_nt);
-    prev_t0 = t0; prev_nt = nt;
-    t0 = t_next;
-    nt = nt_next;
-    async_cur = async_next;
-    buf ^= 1;
-  }
-  // ---- drain the pipeline: the last tile's inverse FFT and flush ----
-  if (prev_nt > 0) {
-    __syncthreads();
-    if (warp >= 8) ifft_tile(prev_nt);
-    __syncthreads();
-    flush_tile(prev_t0, prev_nt);
-  }
-
-  // zero-fill what no frame reaches (fix_length padding / too-short input)
-  if (chunk == a.n_chunks - 1 && !a.accumulate) {
-    const int q0 = imax(expected - pad, 0);
-    for (int q = q0 + tid; q < a.n_out; q += blockDim.x) yb[q] = 0.f;
-  }
-  if (a.peak) {
-    for (int o = 16; o > 0; o >>= 1) peak = fmaxf(peak, __shfl_xor_sync(0xffffffffu, peak, o));
-    if (lane == 0 && peak > 0.f) atomicMax(a.peak + b, __float_as_uint(peak));
+    cur_tile = seg_end;
   }
 }
 
@@ -317,13 +410,12 @@ static size_t apply_istft_smem_bytes(int hop) {
 }
 
 template <int C, int TT>
-static cudaError_t run_apply_istft_t(const ApplyIstftArgs& a, int B, void* stream) {
+static cudaError_t run_apply_istft_t(const ApplyIstftArgs& a, int n_ctas, void* stream) {
   const size_t smem = apply_istft_smem_bytes<C, TT>(a.g.hop);
   cudaError_t e = cudaFuncSetAttribute(apply_istft_kernel<C, TT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  return launch(apply_istft_kernel<C, TT>, dim3(a.n_chunks, B), dim3(kApplyThreads), smem, stream,
-                false, a);
+  return launch(apply_istft_kernel<C, TT>, dim3(n_ctas), dim3(kApplyThreads), smem, stream, false, a);
 }
 
 bool apply_istft_fused_supported(const Geometry& g) {
@@ -333,18 +425,34 @@ bool apply_istft_fused_supported(const Geometry& g) {
   return true;
 }
 
+void fused_schedule(const setk_plan* pl, int B, int T, int TT, int* n_ctas, int* slots, int* min_quota);
+cudaError_t run_tile_prefix(const int* n_samples, int B, const Geometry& g, int TT, int T_cap,
+                            int* prefix, void* stream);
+
 cudaError_t run_apply_istft_fused(setk_plan* pl, const float* audio, const int* n_samples, int B, int N,
                                   int T, const void* w, int w_dtype, const float* post_mask, int n_out,
-                                  int n_chunks, float* wave, unsigned* peak, void* stream) {
+                                  int* tile_prefix, float* wave, unsigned* peak, const float* norm,
+                                  unsigned* done, void* stream) {
   constexpr int TT = 4;
   ApplyIstftArgs a;
   a.g = pl->geo;
   a.audio = audio; a.n_samples = n_samples; a.N = N;
   a.w = w; a.w_dtype = w_dtype;
   a.post_mask = post_mask; a.T = T;
-  a.n_chunks = n_chunks;
-  int fpc = (T + n_chunks - 1) / n_chunks;
-  a.frames_per_chunk = ((fpc + TT - 1) / TT) * TT;
+  // persistent schedule over the frames librosa.istft uses for this output length
+  const int T_cap = (n_out + 2 * a.g.pad + a.g.hop - 1) / a.g.hop;
+  const int T_used = T < T_cap ? T : T_cap;
+  int n_ctas, slots_unused;
+  fused_schedule(pl, B, T_used, TT, &n_ctas, &slots_unused, &a.sched.min_quota);
+  a.sched.B = B;
+  a.sched.tiles_u = sched_tiles_of(T_used, TT);
+  a.sched.prefix = nullptr;
+  cudaError_t e = cudaSuccess;
+  if (n_samples) {     // ragged batch: the lengths live on the device
+    e = run_tile_prefix(n_samples, B, pl->geo, TT, T_cap, tile_prefix, stream);
+    if (e != cudaSuccess) return e;
+    a.sched.prefix = tile_prefix;
+  }
   a.window = pl->d_window;
   a.wsq = pl->d_wsq;
   a.n_out = n_out;
@@ -353,17 +461,18 @@ cudaError_t run_apply_istft_fused(setk_plan* pl, const float* audio, const int* 
   // peak is taken by the last block (it sees the complete sums)
   const int Ctot = pl->geo.C;
   a.c_total = Ctot;
-  cudaError_t e = cudaSuccess;
   for (int c0 = 0; c0 < Ctot && e == cudaSuccess; c0 += 4) {
     const int cb = Ctot - c0 < 4 ? Ctot - c0 : 4;
     a.c0 = c0;
     a.accumulate = c0 > 0;
     a.peak = (c0 + cb >= Ctot) ? peak : nullptr;
+    a.norm = (a.peak && done) ? norm : nullptr;      // the block that sees the complete sums rescales
+    a.done = done;
     switch (cb) {
-      case 1: e = run_apply_istft_t<1, TT>(a, B, stream); break;
-      case 2: e = run_apply_istft_t<2, TT>(a, B, stream); break;
-      case 3: e = run_apply_istft_t<3, TT>(a, B, stream); break;
-      default: e = run_apply_istft_t<4, TT>(a, B, stream); break;
+      case 1: e = run_apply_istft_t<1, TT>(a, n_ctas, stream); break;
+      case 2: e = run_apply_istft_t<2, TT>(a, n_ctas, stream); break;
+      case 3: e = run_apply_istft_t<3, TT>(a, n_ctas, stream); break;
+      default: e = run_apply_istft_t<4, TT>(a, n_ctas, stream); break;
     }
   }
   return e;

@@ -126,5 +126,6 @@ struct setk_plan {
   float* d_frames_ws;    size_t frames_ws_bytes;  // generic iSTFT frames [B][T][n_fft]
   unsigned* d_peak;      size_t peak_bytes;       // [B] max|y| as uint bits
   double* d_cgmm_ws;     size_t cgmm_ws_bytes;    // CGMM posteriors, partials, R^-1 (cgmm.cu)
+  int* d_tile_prefix;   size_t tile_prefix_bytes;   // ragged batches: tiles before each utterance
   int sm_count;
 };

@@ -88,15 +88,42 @@ __device__ __forceinline__ void twiddle_pass1(float2 (&v)[16], float2 w1) {
   }
 }
 
+// The same multiplication with the powers read from a shared-memory table
+// tab[k * 16 + lane16] = W256^{lane16 * k}, k = 1..15 (tab[0..15] unused): 15
+// broadcast-friendly 8-byte loads instead of 15 complex multiplies for the power
+// tree, and no registers held for it (the fused covariance kernel needs them for
+// its accumulators to keep two CTAs per SM).
+__device__ __forceinline__ void twiddle_pass1_tab(float2 (&v)[16], const float2* tab, int lane16) {
+  const float2* t = tab + lane16;              // one base register, immediate offsets
+#pragma unroll
+  for (int s = 1; s < 16; ++s) {
+    const int k = kof(s);
+    if (k != 0) v[s] = cmul(v[s], t[k * 16]);
+  }
+}
+// fill the table (any number of threads; sincospif is exact to an ulp)
+__device__ __forceinline__ void twiddle_table_fill(float2* tab, int tid, int nthreads) {
+  for (int e = tid; e < 256; e += nthreads) {
+    const int k = e >> 4, l = e & 15;
+    float sn, cs;
+    sincospif((float)((k * l) & 255) / 128.0f, &sn, &cs);
+    tab[e] = make_float2(cs, -sn);
+  }
+}
+
 // 256-point forward complex FFT by one half-warp.
 //   v     in : v[m1] = z[16*m1 + lane16]
 //         out: slot s = Z[lane16 + 16*kof(s)]
 //   xch   : this half-warp's SETK_ZSLOT float2 exchange tile in shared memory
 //   w1    : W256^{lane16} = (cos(2 pi lane16/256), -sin(2 pi lane16/256))
 // All 32 lanes of the warp must call this together (it uses __syncwarp).
-__device__ __forceinline__ void halfwarp_fft256(float2 (&v)[16], float2* xch, int lane16, float2 w1) {
+// tab != nullptr: inter-pass twiddles from the shared-memory table instead of w1's power tree
+template <bool TAB = false>
+__device__ __forceinline__ void halfwarp_fft256(float2 (&v)[16], float2* xch, int lane16, float2 w1,
+                                                const float2* tab = nullptr) {
   dft16(v);
-  twiddle_pass1(v, w1);
+  if (TAB) twiddle_pass1_tab(v, tab, lane16);
+  else twiddle_pass1(v, w1);
 #pragma unroll
   for (int s = 0; s < 16; ++s) xch[kof(s) * SETK_XPITCH + lane16] = v[s];
   __syncwarp();

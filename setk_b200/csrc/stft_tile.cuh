@@ -23,6 +23,53 @@ constexpr int kNfft = 512;      // frame size of the fused kernels
 constexpr int kM = 256;         // half-size complex transform
 constexpr int kBins = 257;
 
+// ---------------------------------------------------------------------------
+// Balanced persistent schedule.  The work of a launch is the sequence of
+// (utterance, tile) pairs, utterance-major; every utterance has >= 1 tile (a
+// too-short one gets an empty tile so that its outputs are still initialised).
+// CTA g of G owns the tiles [g*q, (g+1)*q) of that sequence, q = the quota
+// below: all CTAs carry the same load (no last partial wave, which cost 14 % at
+// 256 utterances on 296 CTA slots) and an utterance is cut only where a CTA
+// range ends.  q >= min_quota bounds how many CTAs can share one utterance.
+// ---------------------------------------------------------------------------
+struct TileSched {
+  const int* prefix;   // [B+1] tiles before utterance b (ragged batch), or null
+  int tiles_u;         // tiles of every utterance when prefix == null
+  int B;
+  int min_quota;       // lower bound of q
+};
+SETK_HD inline int sched_tiles_of(int frames, int TT) { return frames > 0 ? (frames + TT - 1) / TT : 1; }
+__device__ __forceinline__ int sched_prefix(const TileSched& s, int b) {
+  return s.prefix ? s.prefix[b] : b * s.tiles_u;
+}
+__device__ __forceinline__ int sched_quota(const TileSched& s, int n_ctas) {
+  const int total = sched_prefix(s, s.B);
+  return imax((total + n_ctas - 1) / n_ctas, imax(s.min_quota, 1));
+}
+// utterance that holds tile x (0 <= x < total)
+__device__ __forceinline__ int sched_find(const TileSched& s, int x) {
+  if (!s.prefix) return x / s.tiles_u;
+  int lo = 0, hi = s.B;                 // prefix[lo] <= x < prefix[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (s.prefix[mid] <= x) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+// slots of per-utterance partial results a launch with n_ctas CTA slots needs
+SETK_HD inline int sched_slots(int n_ctas, int B) {
+  int s = (n_ctas + B - 1) / B + 3;
+  return s < 4 ? 4 : (s > 18 ? 18 : s);
+}
+SETK_HD inline int sched_min_quota(int tiles_max, int slots) { return (tiles_max + slots - 3) / (slots - 2); }
+// CTAs to launch for at most total_max tiles
+SETK_HD inline int sched_grid(int total_max, int n_ctas, int min_quota) {
+  int q = (total_max + n_ctas - 1) / n_ctas;
+  if (q < min_quota) q = min_quota;
+  if (q < 1) q = 1;
+  return (total_max + q - 1) / q;
+}
+
 // Shared-memory carve-up common to both fused kernels.
 template <int C, int TT>
 struct TileSmem {
@@ -118,39 +165,39 @@ __device__ __forceinline__ void stage_tile_scalar(const TileSmem<C, TT>& sm, int
   }
 }
 
-// Forward FFT of every (frame, channel) of the tile by warps 0..7, reading
-// audio[buf].  All threads of warps 0..7 must call it; hop must be even.
+// Forward FFT of every (frame, channel) of the tile by warps 0..NW-1, reading
+// audio[buf].  All threads of those warps must call it; hop must be even.
 // amax accumulates max |sample| of everything the tile reads.
-template <int C, int TT>
+template <int C, int TT, bool TAB = false, int NW = 8>
 __device__ __forceinline__ void fft_tile(const TileSmem<C, TT>& sm, int buf, int nt, int hop,
-                                         float2 w1, float& amax) {
+                                         float2 w1, float& amax, const float2* twtab = nullptr) {
   constexpr int JOBS = TT * C;
   static_assert(JOBS % 2 == 0, "half-warp jobs must pair up per warp");
-  constexpr int ROUNDS = (JOBS + 15) / 16;
+  constexpr int ROUNDS = (JOBS + 2 * NW - 1) / (2 * NW);       // warps 0..NW-1 call this
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lane16 = lane & 15, half = lane >> 4;
 #pragma unroll
   for (int r = 0; r < ROUNDS; ++r) {
-    const int job = r * 16 + warp * 2 + half;
+    const int job = r * (2 * NW) + warp * 2 + half;
     if (job - half < JOBS) {                    // warp-uniform
       const int fr = job / C, ch = job - fr * C;
       float2 v[16];
       const float* src = sm.abuf(buf) + ch * sm.Lp + fr * hop + 2 * lane16;
       const float* wsrc = sm.win + 2 * lane16;
-      const bool live = fr < nt;
+      if (fr < nt) {                            // ONE branch per job (a dead frame only in a last tile)
 #pragma unroll
-      for (int m1 = 0; m1 < 16; ++m1) {
-        float2 x = make_float2(0.f, 0.f);
-        if (live) {
+        for (int m1 = 0; m1 < 16; ++m1) {
           const float2 s = *reinterpret_cast<const float2*>(src + 32 * m1);
           const float2 w = *reinterpret_cast<const float2*>(wsrc + 32 * m1);
           amax = fmaxf(amax, fmaxf(fabsf(s.x), fabsf(s.y)));
-          x = f2mul(s, w);
+          v[m1] = f2mul(s, w);
         }
-        v[m1] = x;
+      } else {
+#pragma unroll
+        for (int m1 = 0; m1 < 16; ++m1) v[m1] = make_float2(0.f, 0.f);
       }
       float2* zs = sm.z + job * SETK_ZSLOT;
-      halfwarp_fft256(v, zs, lane16, w1);
+      halfwarp_fft256<TAB>(v, zs, lane16, w1, twtab);
 #pragma unroll
       for (int s = 0; s < 16; ++s) zs[lane16 + 16 * kof(s)] = v[s];
     }
