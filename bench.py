@@ -352,7 +352,7 @@ def gpu_arm(args):
                        "unique_utterances_per_gpu": uniq},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": measured_traffic(B), "peak_source": peak_src,
-                         "kernel": "setk_stft_cov (stft_cov_kernel<4,4> + finalize)",
+                         "kernel": "setk_stft_cov (stft_cov_kernel<4,5> + finalize)",
                          "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms},
             "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_val, "unit": UNIT,

@@ -32,7 +32,7 @@ cudaError_t run_stft_cov_fused(setk_plan*, const float*, const int*, int, int, i
                                void*);
 bool apply_istft_fused_supported(const Geometry&);
 cudaError_t run_apply_istft_fused(setk_plan*, const float*, const int*, int, int, int, const void*, int,
-                                  const float*, int, int*, float*, unsigned*, const float*, unsigned*, void*);
+                                  const float*, int, int*, float*, unsigned*, void*);
 
 bool stft_spill_supported(const Geometry&);
 size_t stft_spill_bytes(const Geometry&, int, int);
@@ -238,7 +238,7 @@ int setk_stft_cov(setk_plan_t* pl, const float* audio, const int32_t* n_samples,
   if (!audio || !mask_s || !Rs || !Rn) return fail(SETK_EINVAL, "setk_stft_cov: null buffer");
   const Geometry& g = pl->geo;
   const int T = frames_of(N, g.n_fft, g.hop, g.pad);
-  cudaError_t e = ensure(&pl->d_peak, &pl->peak_bytes, sizeof(unsigned) * 3 * (size_t)pl->cfg.max_batch);
+  cudaError_t e = ensure(&pl->d_peak, &pl->peak_bytes, sizeof(unsigned) * 2 * (size_t)pl->cfg.max_batch);
   if (e != cudaSuccess) return cuda_fail(e, "setk_stft_cov(workspace)");
   unsigned* maxabs_bits = nullptr;
   if (maxabs) {
@@ -358,7 +358,7 @@ int setk_istft(setk_plan_t* pl, const void* enh, int32_t B, int32_t T, int32_t n
   const Geometry& g = pl->geo;
   const int T_used = T_used_for(g, T, n_out);
   cudaError_t e = ensure(&pl->d_frames_ws, &pl->frames_ws_bytes, sizeof(float) * (size_t)B * T_used * g.n_fft);
-  if (e == cudaSuccess) e = ensure(&pl->d_peak, &pl->peak_bytes, sizeof(unsigned) * 3 * (size_t)pl->cfg.max_batch);
+  if (e == cudaSuccess) e = ensure(&pl->d_peak, &pl->peak_bytes, sizeof(unsigned) * 2 * (size_t)pl->cfg.max_batch);
   if (e != cudaSuccess) return cuda_fail(e, "setk_istft(workspace)");
   unsigned* peak = norm ? pl->d_peak : nullptr;
   if (peak) {
@@ -380,7 +380,7 @@ int setk_apply_istft(setk_plan_t* pl, const float* audio, const int32_t* n_sampl
   if (n_out < 1) return fail(SETK_ESHAPE, "setk_apply_istft: n_out=%d", n_out);
   const Geometry& g = pl->geo;
   const int T = frames_of(N, g.n_fft, g.hop, g.pad);
-  cudaError_t e = ensure(&pl->d_peak, &pl->peak_bytes, sizeof(unsigned) * 3 * (size_t)pl->cfg.max_batch);
+  cudaError_t e = ensure(&pl->d_peak, &pl->peak_bytes, sizeof(unsigned) * 2 * (size_t)pl->cfg.max_batch);
   if (e != cudaSuccess) return cuda_fail(e, "setk_apply_istft(workspace)");
   unsigned* peak = norm ? pl->d_peak : nullptr;
   if (peak) {
@@ -391,16 +391,8 @@ int setk_apply_istft(setk_plan_t* pl, const float* audio, const int32_t* n_sampl
     if (n_samples)
       e = ensure(&pl->d_tile_prefix, &pl->tile_prefix_bytes, sizeof(int) * ((size_t)pl->cfg.max_batch + 1));
     if (e != cudaSuccess) return cuda_fail(e, "setk_apply_istft(workspace)");
-    // the fused kernel also applies the `norm` rescale (the CTA that completes an utterance)
-    unsigned* done = nullptr;
-    if (norm) {
-      done = pl->d_peak + 2 * (size_t)pl->cfg.max_batch;
-      e = cudaMemsetAsync(done, 0, sizeof(unsigned) * B, static_cast<cudaStream_t>(stream));
-      if (e != cudaSuccess) return cuda_fail(e, "setk_apply_istft(memset)");
-    }
     e = run_apply_istft_fused(pl, audio, n_samples, B, N, T, w, w_dtype, post_mask, n_out,
-                              pl->d_tile_prefix, wave, peak, norm, done, stream);
-    return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_apply_istft");
+                              pl->d_tile_prefix, wave, peak, stream);
   } else if (stft_spill_supported(g)) {
     // tile STFT into the bin-major workspace, y = w^H x over it, then the
     // frame-wise inverse FFT + overlap-add reading Y[b][t][f] in place

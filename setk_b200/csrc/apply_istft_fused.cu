@@ -7,7 +7,10 @@
 // the optional post-mask (apply_adaptive_beamformer.py:174-175) and
 // inverse_stft (libs/utils.py:142-173 -> librosa.istft: irfft, x window,
 // overlap-add, / window-sum-square, trim) up to the peak of |y| needed by the
-// `norm` rescale (utils.py:166-168), which peak_scale_kernel then applies.
+// `norm` rescale (utils.py:166-168), which peak_scale_kernel then applies (a
+// rescale by the CTA that completes an utterance was measured slower: the
+// utterance's first samples have left L2 by then, 17 % of the kernel's samples
+// sat in that loop).
 // C++ twin: Beamform (include/beamformer.cc:215-230) + InverseShortTimeFT
 // (include/stft.cc:154-198).
 //
@@ -47,8 +50,6 @@ struct ApplyIstftArgs {
   int n_out;
   float* wave;          // [B][n_out]
   unsigned* peak;       // [B] or null
-  const float* norm;    // [B] or null: rescale y * norm / (max|y| + eps) in this launch (needs peak, done)
-  unsigned* done;       // [B] tiles of each utterance finished so far (zeroed by the caller)
   int c0, c_total;      // this launch handles channels [c0, c0 + C) of c_total
   int accumulate;       // != 0: wave += this block's contribution (iSTFT is linear)
 };
@@ -69,7 +70,6 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
   float2* s_w = reinterpret_cast<float2*>(sm.end());          // [C][kWPitch]
   float2* s_zi = s_w + C * kWPitch;                           // [TT][SETK_ZSLOT]
   float2* s_tw = s_zi + TT * SETK_ZSLOT;                      // [130] split twiddles (129 used)
-  int& s_last = *reinterpret_cast<int*>(s_tw + NPAIR);        // spare slot: "this CTA completed the utterance"
   float* s_frames = reinterpret_cast<float*>(s_tw + NPAIR + 1);   // [TT][512]
   float* s_wsyn = s_frames + TT * kNfft;                      // [512] window / 512
   float* s_wsq = s_wsyn + kNfft;                              // [512]
@@ -364,34 +364,6 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
       if (lane == 0 && peak > 0.f) atomicMax(a.peak + b, __float_as_uint(peak));
       peak = 0.f;
     }
-    // ---- `norm` rescale (utils.py:166-168) by whichever CTA completes the utterance:
-    // its 4 n_out bytes are still in L2, so the separate pass over HBM disappears ----
-    if (a.norm) {
-      __threadfence();                 // this thread's samples and peak are visible device-wide
-      __syncthreads();
-      if (tid == 0) {
-        const unsigned mine = (unsigned)(seg_end - cur_tile);
-        s_last = (atomicAdd(a.done + b, mine) + mine == (unsigned)(pe - pb)) ? 1 : 0;
-      }
-      __syncthreads();
-      if (s_last) {
-        __threadfence();
-        const float nm = a.norm[b];
-        if (nm != 0.f) {                // "if norm:"
-          const float den = __uint_as_float(*reinterpret_cast<volatile unsigned*>(a.peak + b)) + SETK_EPS32;
-          if (out_vec) {
-            float4* y4 = reinterpret_cast<float4*>(yb);
-            for (int qq = tid; qq < (a.n_out >> 2); qq += blockDim.x) {
-              float4 v = y4[qq];
-              v.x = (v.x * nm) / den; v.y = (v.y * nm) / den; v.z = (v.z * nm) / den; v.w = (v.w * nm) / den;
-              y4[qq] = v;
-            }
-          } else {
-            for (int qq = tid; qq < a.n_out; qq += blockDim.x) yb[qq] = (yb[qq] * nm) / den;
-          }
-        }
-      }
-    }
     cur_tile = seg_end;
   }
 }
@@ -431,8 +403,7 @@ cudaError_t run_tile_prefix(const int* n_samples, int B, const Geometry& g, int 
 
 cudaError_t run_apply_istft_fused(setk_plan* pl, const float* audio, const int* n_samples, int B, int N,
                                   int T, const void* w, int w_dtype, const float* post_mask, int n_out,
-                                  int* tile_prefix, float* wave, unsigned* peak, const float* norm,
-                                  unsigned* done, void* stream) {
+                                  int* tile_prefix, float* wave, unsigned* peak, void* stream) {
   constexpr int TT = 4;
   ApplyIstftArgs a;
   a.g = pl->geo;
@@ -466,8 +437,6 @@ cudaError_t run_apply_istft_fused(setk_plan* pl, const float* audio, const int* 
     a.c0 = c0;
     a.accumulate = c0 > 0;
     a.peak = (c0 + cb >= Ctot) ? peak : nullptr;
-    a.norm = (a.peak && done) ? norm : nullptr;      // the block that sees the complete sums rescales
-    a.done = done;
     switch (cb) {
       case 1: e = run_apply_istft_t<1, TT>(a, n_ctas, stream); break;
       case 2: e = run_apply_istft_t<2, TT>(a, n_ctas, stream); break;

@@ -394,14 +394,23 @@ bool stft_cov_fused_supported(const Geometry& g) {
 size_t stft_cov_partial_floats(const Geometry& g) { return (size_t)(2 * g.C * g.C + 2) * g.F; }
 
 int stft_cov_pick_chunks(const setk_plan* pl, int B, int T) {
-  // aim for >= 2 waves of (2 CTAs / SM) with at most 16 chunks per utterance
+  // (chunk, utterance) grids of the workspace routes: all CTAs are equally long, so
+  // the launch costs ceil(CTAs / slots) waves of frames-per-chunk each.  Pick the
+  // chunk count (<= 16 per utterance) that minimises that product -- "two waves
+  // or more" alone left up to a third of the last wave empty.
   const int slots = 2 * pl->sm_count;
-  int chunks = (2 * slots + B - 1) / B;
-  if (chunks < 1) chunks = 1;
-  if (chunks > 16) chunks = 16;
-  const int max_chunks = (T + 3) / 4;
-  if (chunks > max_chunks) chunks = max_chunks;
-  return chunks < 1 ? 1 : chunks;
+  int max_chunks = (T + 3) / 4;
+  if (max_chunks > 16) max_chunks = 16;
+  if (max_chunks < 1) max_chunks = 1;
+  int best = 1;
+  long long best_cost = -1;
+  for (int c = 1; c <= max_chunks; ++c) {
+    const long long waves = ((long long)B * c + slots - 1) / slots;
+    const int fpc = (((T + c - 1) / c + 3) / 4) * 4 + 4;     // + per-chunk prologue
+    const long long cost = waves * fpc;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c; }
+  }
+  return best;
 }
 
 // CTA slots of the fused kernels (2 CTAs per SM resident: registers and shared memory)

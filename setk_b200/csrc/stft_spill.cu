@@ -41,7 +41,7 @@ struct StftSpillArgs {
 };
 
 template <int CG, int TT>
-__global__ void __maxnreg__(112) stft_spill_kernel(StftSpillArgs a) {
+__global__ void __maxnreg__(96) stft_spill_kernel(StftSpillArgs a) {
   SETK_DYN_SMEM(float, smem);
   const int hop = a.g.hop, pad = a.g.pad, C = a.g.C;
   TileSmem<CG, TT> sm;
