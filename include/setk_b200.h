@@ -263,6 +263,43 @@ int setk_cgmm_stft(const void* stft, int32_t B, int32_t C, int32_t F, int32_t T,
 int setk_wpe_stft(const void* stft, int32_t B, int32_t C, int32_t F, int32_t T, int32_t taps, int32_t delay,
                   int32_t context, int32_t num_iters, void* out, uint32_t* status, void* stream);
 
+/* ---- spatial features on explicit STFTs: scripts/sptk/libs/spatial.py ---- */
+
+/* ipd(si, sj, cos, sin): spatial.py:163-181.  si, sj c64 [rows][F] (rows = B*T);
+ *   mode 0: np.mod(angle(si) - angle(sj) + pi, 2 pi) - pi   -> out f32 [rows][F]
+ *   mode 1: cos(angle(si) - angle(sj))                      -> out f32 [rows][F]
+ *   mode 2: [cos | sin]                                     -> out f32 [rows][2F] */
+int setk_ipd(const void* si, const void* sj, int64_t rows, int32_t F, int32_t mode, float* out,
+             void* stream);
+
+/* directional_feats(spectrogram, steer_vector, df_pair): spatial.py:184-208.
+ *   stft   c64  [B][M][F][T]
+ *   steer  c128 [M][F] (steer_batched == 0) or [B][M][F]
+ *   pairs  i32  [n_pairs][2] or NULL (all i < j)
+ *   out    f64  [B][T][F] = mean over pairs of cos((arg x_i - arg x_j) - (arg d_i - arg d_j)) */
+int setk_directional_feats(const void* stft, const void* steer, int32_t steer_batched,
+                           const int32_t* pairs, int32_t n_pairs, int32_t B, int32_t M, int32_t F,
+                           int32_t T, double* out, void* stream);
+
+/* gcc_phat_linear / gcc_phat_diag: spatial.py:37-92 (the caller supplies the TDOA grid that
+ * linear_tdoa_grid, 11-34, or the circular-array formula, 78-80, produce).
+ *   si, sj c64 [T][F];  omega f64 [F] (rad/s);  tau f64 [D] (s)
+ *   spectrum = Re(exp(j (angle si - angle sj)) @ exp(-j outer(omega, tau)))      [T][D]
+ *   normalize:   spectrum /= max(max |spectrum|, eps32);  apply_floor: max(spectrum, 0)
+ *   accumulate != 0: out += spectrum (srp_phat_linear, 95-123, sums the pairs) else out = spectrum
+ *   work   f64 [setk_gcc_phat_work_doubles(T, F, D)] scratch;  out f64 [T][D] */
+int64_t setk_gcc_phat_work_doubles(int32_t T, int32_t F, int32_t D);
+int setk_gcc_phat(const void* si, const void* sj, int32_t T, int32_t F, const double* omega,
+                  const double* tau, int32_t D, int32_t normalize, int32_t apply_floor,
+                  int32_t accumulate, double* work, double* out, void* stream);
+
+/* msc(spectrogram, context, normalize): spatial.py:126-160, as written (the diagonal terms
+ * enter as their grand total, np.sum without an axis at :153).
+ *   spec c64 [N][T][F];  work f64 [setk_msc_work_doubles(T, F)];  out f64 [T][F] */
+int64_t setk_msc_work_doubles(int32_t T, int32_t F);
+int setk_msc(const void* spec, int32_t N, int32_t T, int32_t F, int32_t context, int32_t normalize,
+             double* work, double* out, void* stream);
+
 /* floor(y * 32768) clipped to int16: the PCM_16 conversion of
  * WaveWriter.write -> write_wav -> soundfile (data_handler.py:600-605,
  * utils.py:45-62; SURVEY.md finding 3).  wave f32 [n], pcm i16 [n]. */

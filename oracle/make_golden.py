@@ -341,11 +341,102 @@ def wpe_cases(ref, report):
     np.savez_compressed(os.path.join(GOLD, "ref_wpe.npz"), **out)
 
 
+def spatial_cases(ref, report):
+    """
+    libs/spatial.py run by the REFERENCE on STFTs of small seeded mixtures (complex64, as
+    SpectrogramReader feeds it): ipd (3 modes), directional_feats (all pairs / given pairs),
+    gcc_phat_linear (DOA and TDOA grids), gcc_phat_diag, srp_phat_linear (2 and 4 mics),
+    msc (context 0..2).  The restatement must reproduce every array exactly.
+    """
+    from oracle import spatial_oracle as sp
+    rng = np.random.default_rng(20240927)
+    out = {}
+    worst = 0.0
+
+    def pin(key, got_ref, got_oracle):
+        nonlocal worst
+        out[key] = got_ref
+        worst = max(worst, float(np.max(np.abs(np.asarray(got_ref) - np.asarray(got_oracle)))))
+
+    for name, C, N, fl, hop in (("c4_512", 4, 9000, 512, 256), ("c3_256", 3, 5000, 256, 128),
+                                ("c2_1024", 2, 12000, 1024, 256)):
+        mix, _, _ = synth_case(rng, C, N)
+        kw = dict(frame_len=fl, frame_hop=hop, window="hann", center=True, transpose=False)
+        obs = ref_multichannel_stft(ref, mix, round_power_of_two=True, **kw)        # c64 C x F x T
+        F = obs.shape[1]
+        S = np.ascontiguousarray(np.transpose(obs, (0, 2, 1)))                      # C x T x F
+        out[name + "/mix"] = mix
+        out[name + "/cfg"] = np.array([fl, hop], dtype=np.int64)
+        pin(name + "/ipd", ref.spatial.ipd(S[0], S[1]), sp.ipd(S[0], S[1]))
+        pin(name + "/ipd_cos", ref.spatial.ipd(S[0], S[1], cos=True), sp.ipd(S[0], S[1], cos=True))
+        pin(name + "/ipd_cos_sin", ref.spatial.ipd(S[0], S[C - 1], cos=True, sin=True),
+            sp.ipd(S[0], S[C - 1], cos=True, sin=True))
+        steer = np.exp(-1j * rng.uniform(0, 2 * np.pi, size=(C, F)))                # complex128
+        out[name + "/steer"] = steer
+        pin(name + "/df", ref.spatial.directional_feats(obs, steer), sp.directional_feats(obs, steer))
+        pairs = [(0, C - 1), (C - 1, 0)] if C > 2 else [(1, 0)]
+        out[name + "/df_pairs"] = np.array(pairs, dtype=np.int32)
+        pin(name + "/df_given_pairs", ref.spatial.directional_feats(obs, steer, df_pair=pairs),
+            sp.directional_feats(obs, steer, df_pair=pairs))
+        gk = dict(num_bins=F, num_doa=37)
+        pin(name + "/gcc", ref.spatial.gcc_phat_linear(S[0], S[1], 0.07, **gk),
+            sp.gcc_phat_linear(S[0], S[1], 0.07, **gk))
+        pin(name + "/gcc_tdoa_raw",
+            ref.spatial.gcc_phat_linear(S[0], S[1], -0.05, normalize=False, apply_floor=False,
+                                        samp_doa=False, **gk),
+            sp.gcc_phat_linear(S[0], S[1], -0.05, normalize=False, apply_floor=False, samp_doa=False,
+                               **gk))
+        pin(name + "/gcc_diag", ref.spatial.gcc_phat_diag(S[0], S[1], 0.3, 0.1, num_doas=25, num_bins=F),
+            sp.gcc_phat_diag(S[0], S[1], 0.3, 0.1, num_doas=25, num_bins=F))
+        d = [0.04 * i for i in range(C)]
+        out[name + "/topo"] = np.array(d)
+        pin(name + "/srp", ref.spatial.srp_phat_linear(S, d, **gk), sp.srp_phat_linear(S, d, **gk))
+        for ctx in (0, 1, 2):
+            pin(name + f"/msc_ctx{ctx}", ref.spatial.msc(S, context=ctx), sp.msc(S, context=ctx))
+        pin(name + "/msc_raw", ref.spatial.msc(S, context=1, normalize=False),
+            sp.msc(S, context=1, normalize=False))
+    report["spatial/oracle_vs_ref_maxabs"] = worst
+    np.savez_compressed(os.path.join(GOLD, "ref_spatial.npz"), **out)
+
+
+def fixed_cases(ref, report):
+    """
+    Geometry-based beamformers of libs/beamformer.py (106-212, 323-512) run by the REFERENCE:
+    weights of the DS / SD beamformers for linear and circular arrays, a beam pattern, and the
+    enhanced STFT of run(doa, obs) / FixedBeamformer.run(obs) on a seeded 4-channel mixture.
+    """
+    rng = np.random.default_rng(20240928)
+    bf = ref.beamformer
+    out = {}
+    mix, _, _ = synth_case(rng, 4, 7000)
+    kw = dict(frame_len=256, frame_hop=128, window="hann", center=True, transpose=False)
+    obs = ref_multichannel_stft(ref, mix, round_power_of_two=True, **kw)            # c64 4 x F x T
+    F = obs.shape[1]
+    out["mix"] = mix
+    topo = [0.0, 0.05, 0.1, 0.15]
+    for name, obj, doa in (("lin_ds", bf.LinearDSBeamformer(topo), 60.0),
+                           ("lin_sd", bf.LinearSDBeamformer(topo), 110.0),
+                           ("cir_ds", bf.CircularDSBeamformer(0.05, 4), 45.0),
+                           ("cir_sd", bf.CircularSDBeamformer(0.05, 3, center=True), 200.0)):
+        out[name + "/weight"] = obj.weight(doa, F)
+        out[name + "/enh"] = obj.run(doa, obs)
+        out[name + "/doa"] = np.array(doa)
+    out["cir_sd/distance_mat"] = bf.CircularSDBeamformer(0.05, 3, center=True).distance_mat
+    out["fixed/enh"] = bf.FixedBeamformer(out["lin_sd/weight"]).run(obs)
+    sv = np.stack([bf.linear_steer_vector(np.array(topo), d, F) for d in (0.0, 45.0, 90.0, 135.0)], axis=1)
+    out["pattern/sv"] = sv                                                           # F x D x N
+    out["pattern/single"] = bf.beam_pattern(out["lin_ds/weight"], sv)
+    out["pattern/multi"] = np.stack(bf.beam_pattern(np.stack([out["lin_ds/weight"], out["lin_sd/weight"]]), sv))
+    out["diffuse"] = bf.diffuse_covar(F, np.abs(np.subtract.outer(topo, topo)), diag_eps=0.01)
+    report["fixed/cases"] = sorted(out)
+    np.savez_compressed(os.path.join(GOLD, "ref_fixed_bf.npz"), **out)
+
+
 def main():
-    if len(sys.argv) > 1 and sys.argv[1] in ("cgmm", "wpe"):   # add one fixture only
+    if len(sys.argv) > 1 and sys.argv[1] in ("cgmm", "wpe", "spatial", "fixed"):   # add one fixture only
         ref = ref_shim.load_reference()
         report = {}
-        (cgmm_cases if sys.argv[1] == "cgmm" else wpe_cases)(ref, report)
+        {"cgmm": cgmm_cases, "wpe": wpe_cases, "spatial": spatial_cases, "fixed": fixed_cases}[sys.argv[1]](ref, report)
         path = os.path.join(GOLD, "PINNING.json")
         with open(path) as f:
             full = json.load(f)
@@ -369,6 +460,8 @@ def main():
     config_cases(ref, report)
     cgmm_cases(ref, report)
     wpe_cases(ref, report)
+    spatial_cases(ref, report)
+    fixed_cases(ref, report)
     with open(os.path.join(GOLD, "PINNING.json"), "w") as f:
         json.dump(report, f, indent=1, sort_keys=True)
     print(json.dumps(report, indent=1, sort_keys=True))

@@ -117,7 +117,7 @@ def _patch_numpy_scipy():
 def load_reference():
     """
     Returns a namespace with the reference's modules:
-      .utils .beamformer .cluster .wpe (and .data_handler if importable)
+      .utils .beamformer .cluster .wpe .spatial (and .data_handler if importable)
     """
     if not reference_available():
         raise RuntimeError(f"reference tree not found at {REFERENCE_SPTK}")
@@ -133,6 +133,10 @@ def load_reference():
         ns.wpe = importlib.import_module("libs.wpe")
     except Exception:  # nara_wpe-free file, but keep optional
         ns.wpe = None
+    try:
+        ns.spatial = importlib.import_module("libs.spatial")
+    except Exception:
+        ns.spatial = None
     try:
         ns.data_handler = importlib.import_module("libs.data_handler")
     except Exception:

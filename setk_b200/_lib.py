@@ -84,6 +84,15 @@ _PROTOTYPES = {
                                c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "setk_wpe_stft": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                               c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "setk_ipd": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
+    "setk_directional_feats": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32,
+                                       c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "setk_gcc_phat_work_doubles": (c_int64, [c_int32, c_int32, c_int32]),
+    "setk_gcc_phat": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32,
+                              c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "setk_msc_work_doubles": (c_int64, [c_int32, c_int32]),
+    "setk_msc": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                         c_void_p]),
     "setk_float_to_pcm16": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "setk_pcm16_to_float": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
 }

@@ -23,6 +23,14 @@ cudaError_t run_peak_scale(float*, int, int, const float*, const unsigned*, void
 cudaError_t run_float_to_pcm16(const float*, long long, int16_t*, void*);
 cudaError_t run_pcm16_to_float(const int16_t*, long long, float*, void*);
 
+cudaError_t run_ipd(const float2*, const float2*, long long, int, int, float*, void*);
+cudaError_t run_dirfeat(const float2*, const double2*, int, const int*, int, int, int, int, int, double*,
+                        void*);
+size_t gcc_phat_work_doubles(int, int, int);
+cudaError_t run_gcc_phat(const float2*, const float2*, int, int, const double*, const double*, int, int,
+                         int, int, double*, double*, void*);
+size_t msc_work_doubles(int, int);
+cudaError_t run_msc(const float2*, int, int, int, int, int, double*, double*, void*);
 bool stft_cov_fused_supported(const Geometry&);
 size_t stft_cov_partial_floats(const Geometry&);
 size_t stft_cov_partial_bytes(const setk_plan*, int, int);
@@ -538,6 +546,61 @@ int setk_pcm16_to_float(const int16_t* pcm, int64_t n, float* wave, void* stream
   if (n == 0) return SETK_OK;
   cudaError_t e = run_pcm16_to_float(pcm, n, wave, stream);
   return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_pcm16_to_float");
+}
+
+// ---- spatial features (spatial.cu) ----
+int setk_ipd(const void* si, const void* sj, int64_t rows, int32_t F, int32_t mode, float* out,
+             void* stream) {
+  if (!si || !sj || !out) return fail(SETK_EINVAL, "setk_ipd: null buffer");
+  if (rows < 1 || F < 1) return fail(SETK_ESHAPE, "setk_ipd: rows=%lld F=%d", (long long)rows, F);
+  if (mode < 0 || mode > 2) return fail(SETK_EINVAL, "setk_ipd: mode %d outside 0..2", mode);
+  cudaError_t e = run_ipd(static_cast<const float2*>(si), static_cast<const float2*>(sj), rows, F, mode,
+                          out, stream);
+  return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_ipd");
+}
+
+int setk_directional_feats(const void* stft, const void* steer, int32_t steer_batched,
+                           const int32_t* pairs, int32_t n_pairs, int32_t B, int32_t M, int32_t F,
+                           int32_t T, double* out, void* stream) {
+  if (!stft || !steer || !out) return fail(SETK_EINVAL, "setk_directional_feats: null buffer");
+  if (B < 1 || F < 1 || T < 1 || M < 2 || M > SETK_MAX_CHANNELS)
+    return fail(SETK_ESHAPE, "setk_directional_feats: bad shape B=%d M=%d F=%d T=%d", B, M, F, T);
+  if (pairs && n_pairs < 1) return fail(SETK_EINVAL, "setk_directional_feats: empty pair list");
+  cudaError_t e = run_dirfeat(static_cast<const float2*>(stft), static_cast<const double2*>(steer),
+                              steer_batched, pairs, n_pairs, B, M, F, T, out, stream);
+  return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_directional_feats");
+}
+
+int64_t setk_gcc_phat_work_doubles(int32_t T, int32_t F, int32_t D) {
+  if (T < 1 || F < 1 || D < 1) return -1;
+  return (int64_t)gcc_phat_work_doubles(T, F, D);
+}
+
+int setk_gcc_phat(const void* si, const void* sj, int32_t T, int32_t F, const double* omega,
+                  const double* tau, int32_t D, int32_t normalize, int32_t apply_floor,
+                  int32_t accumulate, double* work, double* out, void* stream) {
+  if (!si || !sj || !omega || !tau || !work || !out) return fail(SETK_EINVAL, "setk_gcc_phat: null buffer");
+  if (T < 1 || F < 1 || D < 1) return fail(SETK_ESHAPE, "setk_gcc_phat: T=%d F=%d D=%d", T, F, D);
+  if ((size_t)F * sizeof(double2) > 48 * 1024)
+    return fail(SETK_EUNSUPPORTED, "setk_gcc_phat: F=%d too large (<= 3072 bins)", F);
+  cudaError_t e = run_gcc_phat(static_cast<const float2*>(si), static_cast<const float2*>(sj), T, F, omega,
+                               tau, D, normalize, apply_floor, accumulate, work, out, stream);
+  return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_gcc_phat");
+}
+
+int64_t setk_msc_work_doubles(int32_t T, int32_t F) {
+  if (T < 1 || F < 1) return -1;
+  return (int64_t)msc_work_doubles(T, F);
+}
+
+int setk_msc(const void* spec, int32_t N, int32_t T, int32_t F, int32_t context, int32_t normalize,
+             double* work, double* out, void* stream) {
+  if (!spec || !work || !out) return fail(SETK_EINVAL, "setk_msc: null buffer");
+  if (N < 2 || N > SETK_MAX_CHANNELS || T < 1 || F < 1)
+    return fail(SETK_ESHAPE, "setk_msc: bad shape N=%d T=%d F=%d", N, T, F);
+  if (context < 0) return fail(SETK_EINVAL, "setk_msc: context %d < 0", context);
+  cudaError_t e = run_msc(static_cast<const float2*>(spec), N, T, F, context, normalize, work, out, stream);
+  return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_msc");
 }
 
 }  // extern "C"

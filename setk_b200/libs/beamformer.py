@@ -10,7 +10,13 @@ Same names, argument names, defaults and array axis orders as the reference
   Beamformer.beamform 220-234, SupervisedBeamformer 237-283,
   OnlineSupervisedBeamformer 286-320, MvdrBeamformer 515-539,
   MpdrBeamformer 542-590, PmwfBeamformer 593-659, GevdBeamformer 662-682,
-  OnlineGevdBeamformer 685-703, OnlineMvdrBeamformer 706-728.
+  OnlineGevdBeamformer 685-703, OnlineMvdrBeamformer 706-728;
+  geometry-based: beam_pattern 106-130, diffuse_covar 133-152,
+  plane/linear/circular_steer_vector 155-212, FixedBeamformer 323-340, DSBeamformer
+  343-377, Linear/CircularDSBeamformer 380-428, Linear/CircularSDBeamformer 431-512.
+  Their weights depend on the array geometry only (a few hundred constants per
+  direction, computed once on the host like the STFT window); the data path --
+  Beamformer.beamform on the observations -- is setk_apply.
 
 numpy in -> numpy out, torch in -> torch out (same device).  Every function
 accepts an optional leading batch dimension on its array arguments.
@@ -41,7 +47,10 @@ from .utils import EPSILON, _back, _to_tensor, cmat_abs  # noqa: F401
 __all__ = [
     "do_ban", "solve_pevd", "rank1_constraint", "compute_covar", "Beamformer",
     "SupervisedBeamformer", "OnlineSupervisedBeamformer", "MvdrBeamformer", "MpdrBeamformer",
-    "PmwfBeamformer", "GevdBeamformer", "OnlineGevdBeamformer", "OnlineMvdrBeamformer"
+    "PmwfBeamformer", "GevdBeamformer", "OnlineGevdBeamformer", "OnlineMvdrBeamformer",
+    "beam_pattern", "diffuse_covar", "plane_steer_vector", "linear_steer_vector",
+    "circular_steer_vector", "FixedBeamformer", "DSBeamformer", "LinearDSBeamformer",
+    "CircularDSBeamformer", "LinearSDBeamformer", "CircularSDBeamformer"
 ]
 
 
@@ -333,3 +342,157 @@ class OnlineMvdrBeamformer(OnlineSupervisedBeamformer):
 
     def weight(self, Rs, Rn):
         return _weights(_lib.BF_MVDR, Rs, Rn)
+
+
+# ---------------------------------------------------------------------------
+# geometry-based beamformers (beamformer.py:106-212, 323-512)
+# ---------------------------------------------------------------------------
+def beam_pattern(weight, steer_vector):
+    """
+    Beam pattern of a fixed beamformer (beamformer.py:106-130).
+        weight: B x F x N or F x N;  steer_vector: F x D x N
+    returns F x D (or a list of them, one per beam)
+    """
+    weight, steer_vector = np.asarray(weight), np.asarray(steer_vector)
+    if weight.shape[-1] != steer_vector.shape[-1] or weight.shape[-2] != steer_vector.shape[0]:
+        raise RuntimeError("Shape mismatch between weight and steer_vector")
+
+    def single_beam(w, sv):
+        return np.squeeze(np.abs(sv @ np.expand_dims(w.conj(), -1)))
+
+    if weight.ndim == 2:
+        return single_beam(weight, steer_vector)
+    elif weight.ndim == 3:
+        return [single_beam(w, steer_vector) for w in weight]
+    raise RuntimeError(f"Expect 2/3D beam weights, got {weight.ndim}")
+
+
+def diffuse_covar(num_bins, dist_mat, sr=16000, c=340, diag_eps=0.1):
+    """Covariance of the spherically isotropic noise field, F x N x N (beamformer.py:133-152)."""
+    N, _ = dist_mat.shape
+    omega = np.pi * np.arange(num_bins) * sr / (num_bins - 1)
+    return np.sinc(dist_mat[None] * omega[:, None, None] / c) + np.eye(N) * diag_eps
+
+
+def plane_steer_vector(distance, num_bins, c=340, sr=16000):
+    """Steer vector F x N for projected distances on the DoA (beamformer.py:155-167)."""
+    omega = np.pi * np.arange(num_bins) * sr / (num_bins - 1)
+    return np.exp(-1j * np.outer(omega, np.asarray(distance) / c))
+
+
+def linear_steer_vector(topo, doa, num_bins, c=340, sr=16000):
+    """Steer vector of a linear array, doa in degrees (beamformer.py:170-186)."""
+    return plane_steer_vector(np.cos(doa * np.pi / 180) * np.asarray(topo), num_bins, c=c, sr=sr)
+
+
+def circular_steer_vector(redius, num_arounded, doa, num_bins, c=349, sr=16000, center=False):
+    """Steer vector of a circular array (optionally with a centre microphone), beamformer.py:189-212."""
+    dirc = np.arange(num_arounded) * 2 * np.pi / num_arounded
+    dist = np.cos(dirc - doa * np.pi / 180) * redius
+    if center:
+        dist = np.concatenate([np.array([0]), dist])
+    return plane_steer_vector(-dist, num_bins, c=c, sr=sr)
+
+
+class FixedBeamformer(Beamformer):
+    """Fixed beamformer with predefined weights F x N (beamformer.py:323-340)."""
+
+    def __init__(self, weight):
+        super().__init__()
+        self.weight = weight
+
+    def run(self, obs):
+        """obs N x F x T -> F x T"""
+        return self.beamform(self.weight, obs)
+
+
+class DSBeamformer(Beamformer):
+    """Base delay-and-sum beamformer (beamformer.py:343-377)."""
+
+    def __init__(self, num_mics):
+        super().__init__()
+        self.num_mics = num_mics
+
+    def weight(self, doa, num_bins, c=340, sr=16000):
+        raise NotImplementedError
+
+    def run(self, doa, obs, c=340, sr=16000):
+        """doa in degrees, obs N x F x T -> F x T"""
+        if obs.shape[-3] != self.num_mics:
+            raise ValueError("Shape of obs do not match with number" +
+                             f"of microphones, {self.num_mics} vs {obs.shape[-3]}")
+        weight = self.weight(doa, obs.shape[-2], c=c, sr=sr)
+        return self.beamform(weight, obs)
+
+
+class LinearDSBeamformer(DSBeamformer):
+    """Delay and sum beamformer for a linear array (beamformer.py:380-398)."""
+
+    def __init__(self, linear_topo):
+        super().__init__(len(linear_topo))
+        self.linear_topo = np.array(linear_topo)
+
+    def weight(self, doa, num_bins, c=340, sr=16000):
+        return linear_steer_vector(self.linear_topo, doa, num_bins, c=c, sr=sr) / self.num_mics
+
+
+class CircularDSBeamformer(DSBeamformer):
+    """Delay and sum beamformer for a circular array (beamformer.py:401-428)."""
+
+    def __init__(self, radius, num_arounded, center=False):
+        super().__init__(num_arounded + 1 if center else num_arounded)
+        self.radius = radius
+        self.center = center
+        self.num_arounded = num_arounded
+
+    def weight(self, doa, num_bins, c=340, sr=16000):
+        sv = circular_steer_vector(self.radius, self.num_arounded, doa, num_bins, c=c, sr=sr,
+                                   center=self.center)
+        return sv / self.num_mics
+
+
+def _superdirective(steer_vector, Rn):
+    """w = Rn^-1 d / (d^H Rn^-1 d) per bin (beamformer.py:453-456, 508-512)."""
+    numerator = np.linalg.solve(Rn, steer_vector[..., None])[..., 0]    # stack-of-vectors semantics
+    denominator = np.einsum("...d,...d->...", steer_vector.conj(), numerator)
+    return numerator / np.expand_dims(denominator, axis=-1)
+
+
+class LinearSDBeamformer(LinearDSBeamformer):
+    """Linear super-directive beamformer in a diffuse noise field (beamformer.py:431-456)."""
+
+    def __init__(self, linear_topo):
+        super().__init__(linear_topo)
+        mat = np.tile(self.linear_topo, (self.num_mics, 1))
+        self.distance_mat = np.abs(mat - np.transpose(mat))
+
+    def weight(self, doa, num_bins, c=340, sr=16000, diag_eps=0.1):
+        steer_vector = super().weight(doa, num_bins, c=c, sr=sr)
+        Rn = diffuse_covar(num_bins, self.distance_mat, sr=sr, c=c, diag_eps=diag_eps)
+        return _superdirective(steer_vector, Rn)
+
+
+class CircularSDBeamformer(CircularDSBeamformer):
+    """Circular super-directive beamformer in a diffuse noise field (beamformer.py:459-512)."""
+
+    def __init__(self, radius, num_arounded, center=False):
+        super().__init__(radius, num_arounded, center=center)
+        self.distance_mat = self._compute_distance_mat()
+
+    def _compute_distance_mat(self):
+        distance_mat = np.zeros((self.num_mics, self.num_mics))
+        raw = 0
+        if self.center:
+            distance_mat[0, 1:] = self.radius
+            raw = 1
+        ang = np.pi / self.num_arounded
+        for r in range(raw, self.num_mics):
+            for c in range(r + 1, self.num_mics):
+                distance_mat[r, c] = np.abs(np.sin((c - r) * ang) * 2 * self.radius)
+        distance_mat += distance_mat.T
+        return distance_mat
+
+    def weight(self, doa, num_bins, c=340, sr=16000, diag_eps=1e-5):
+        steer_vector = super().weight(doa, num_bins, c=c, sr=sr)
+        Rn = diffuse_covar(num_bins, self.distance_mat, sr=sr, c=c, diag_eps=diag_eps)
+        return _superdirective(steer_vector, Rn)

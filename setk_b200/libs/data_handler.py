@@ -297,20 +297,30 @@ class Writer(object):
     """Directory-of-files writer with an optional `key<TAB>path` script."""
 
     def __init__(self, obj_path_or_dir, scp_path=None, is_dir=False):
-        if not is_dir:
-            raise NotImplementedError("archive writers are outside the beamformer hot path")
-        self.path_or_dir = Path(obj_path_or_dir).absolute()
-        self.path_or_dir.mkdir(exist_ok=True, parents=True)
         self.scp_path = scp_path
+        if obj_path_or_dir == "-" and scp_path:        # data_handler.py:278-281
+            warnings.warn("Ignore script output discriptor cause dump archives to stdout")
+            self.scp_path = None
+        self.dump_out_dir = is_dir
+        if is_dir:
+            self.path_or_dir = Path(obj_path_or_dir).absolute()
+            self.path_or_dir.mkdir(exist_ok=True, parents=True)
+        else:
+            self.path_or_dir = "-" if obj_path_or_dir == "-" else os.path.abspath(obj_path_or_dir)
         self.scp_file = None
+        self.ark_file = None
 
     def __enter__(self):
+        if not self.dump_out_dir:                       # "wb" is important
+            self.ark_file = sys.stdout.buffer if self.path_or_dir == "-" else open(self.path_or_dir, "wb")
         if self.scp_path:
             self.scp_file = sys.stdout if self.scp_path == "-" else open(self.scp_path, "w",
                                                                          encoding="utf-8")
         return self
 
     def __exit__(self, *exc):
+        if self.ark_file is not None and self.ark_file is not sys.stdout.buffer:
+            self.ark_file.close()
         if self.scp_file is not None and self.scp_file is not sys.stdout:
             self.scp_file.close()
 
@@ -352,3 +362,48 @@ class NumpyWriter(Writer):
         target = self.path_or_dir / f"{key}.npy"
         np.save(target, obj)
         self._record(key, target)
+
+
+def write_kaldi_matrix(fd, mat):
+    """
+    Kaldi binary float matrix / vector (kaldi_io.py:156-168, 218-229, 351-361):
+    token FM|DM (FV|DV), then \\4 + int32 sizes, then the raw row-major data.
+    """
+    if not isinstance(mat, np.ndarray):
+        raise TypeError(f"Unsupport type: {type(mat)}")
+    if mat.dtype not in (np.float32, np.float64):
+        raise AssertionError("kaldi archives hold float32 / float64 data")
+    double = mat.dtype == np.float64
+    if mat.ndim == 2:
+        fd.write(b"DM " if double else b"FM ")
+        fd.write(b"\x04" + struct.pack("i", mat.shape[0]))
+        fd.write(b"\x04" + struct.pack("i", mat.shape[1]))
+    elif mat.ndim == 1:
+        fd.write(b"DV " if double else b"FV ")
+        fd.write(b"\x04" + struct.pack("i", mat.size))
+    else:
+        raise RuntimeError(f"Only support 2D matrix, but got {mat.ndim:d}")
+    fd.write(np.ascontiguousarray(mat).tobytes())
+
+
+class ArchiveWriter(Writer):
+    """
+    Writer for kaldi's scripts && archive (BaseFloat matrix): data_handler.py:564-587.
+    Each entry is `key ` + `\\0B` + the binary matrix; the script line points at the
+    offset of the binary marker (`key<TAB>path:offset`).
+    """
+
+    def __init__(self, ark_path, scp_path=None, dtype=np.float32):
+        if not ark_path:
+            raise RuntimeError("Seem configure path of archives as None")
+        super().__init__(ark_path, scp_path)
+        self.dtype = dtype
+
+    def write(self, key, obj):
+        self.check_args(obj)
+        self.ark_file.write(str.encode(key + " "))
+        offset = self.ark_file.tell() if self.path_or_dir != "-" else 0
+        self.ark_file.write(b"\0B")
+        write_kaldi_matrix(self.ark_file, obj.astype(self.dtype))
+        if self.scp_file is not None:
+            self.scp_file.write(f"{key}\t{self.path_or_dir}:{offset:d}\n")

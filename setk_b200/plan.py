@@ -401,3 +401,101 @@ def pcm16_to_float(pcm):
         _lib.check(_lib.library().setk_pcm16_to_float(_lib.ptr(pcm), pcm.numel(), _lib.ptr(wave),
                                                       _lib.current_stream(pcm.device)))
     return wave
+
+
+# ---------------------------------------------------------------------------
+# spatial features on explicit STFTs (libs/spatial.py of the reference; csrc/spatial.cu)
+# ---------------------------------------------------------------------------
+def _c64(t, device=None):
+    t = torch.as_tensor(t) if device is None else torch.as_tensor(t, device=device)
+    if t.dtype != torch.complex64:
+        t = t.to(torch.complex64)
+    return t.contiguous()
+
+
+def ipd(si, sj, mode=0):
+    """spatial.ipd: si, sj (..., T, F) complex64 -> float32 (..., T, F) (mode 0/1) or (..., T, 2F)."""
+    si, sj = _c64(si), _c64(sj, si.device if torch.is_tensor(si) else None)
+    if si.shape != sj.shape or si.dim() < 2:
+        raise ValueError(f"ipd: shapes {tuple(si.shape)} / {tuple(sj.shape)}")
+    F = si.shape[-1]
+    rows = si.numel() // F
+    shape = list(si.shape)
+    if mode == 2:
+        shape[-1] = 2 * F
+    out = torch.empty(shape, dtype=torch.float32, device=si.device)
+    with _ctx(si.device):
+        _lib.check(_lib.library().setk_ipd(_lib.ptr(si), _lib.ptr(sj), rows, F, int(mode),
+                                           _lib.ptr(out), _lib.current_stream(si.device)))
+    return out
+
+
+def directional_feats(stft, steer, pairs=None):
+    """
+    spatial.directional_feats batched: stft (B,M,F,T) complex64, steer (M,F) or (B,M,F)
+    complex -> (B,T,F) float64.  pairs: list of (i, j) or None (all i < j).
+    """
+    stft = _c64(stft)
+    if stft.dim() != 4:
+        raise ValueError(f"stft must be (B, M, F, T), got {tuple(stft.shape)}")
+    B, M, F, T = stft.shape
+    steer = torch.as_tensor(steer, device=stft.device).to(torch.complex128).contiguous()
+    batched = steer.dim() == 3
+    if tuple(steer.shape[-2:]) != (M, F) or (batched and steer.shape[0] != B):
+        raise ValueError(f"steer vector must be ({M}, {F}) or ({B}, {M}, {F}), got {tuple(steer.shape)}")
+    p_t, n_pairs = None, 0
+    if pairs is not None:
+        p_t = torch.as_tensor(pairs, dtype=torch.int32, device=stft.device).reshape(-1, 2).contiguous()
+        n_pairs = p_t.shape[0]
+        if n_pairs == 0 or int(p_t.min()) < 0 or int(p_t.max()) >= M:
+            raise ValueError(f"df_pair entries must lie in [0, {M})")
+    out = torch.empty((B, T, F), dtype=torch.float64, device=stft.device)
+    with _ctx(stft.device):
+        _lib.check(_lib.library().setk_directional_feats(
+            _lib.ptr(stft), _lib.ptr(steer), int(batched), _lib.ptr(p_t), n_pairs, B, M, F, T,
+            _lib.ptr(out), _lib.current_stream(stft.device)))
+    return out
+
+
+def gcc_phat(si, sj, omega, tau, normalize=True, apply_floor=True, out=None):
+    """
+    One microphone pair of gcc_phat_linear / gcc_phat_diag: si, sj (T,F) complex64, omega (F,)
+    and tau (D,) float64 -> (T,D) float64.  With `out` given the pair is ADDED to it
+    (srp_phat_linear).
+    """
+    si = _c64(si)
+    sj = _c64(sj, si.device)
+    if si.dim() != 2 or si.shape != sj.shape:
+        raise ValueError(f"gcc_phat: si/sj must be (T, F), got {tuple(si.shape)} / {tuple(sj.shape)}")
+    T, F = si.shape
+    omega = torch.as_tensor(omega, dtype=torch.float64, device=si.device).contiguous()
+    tau = torch.as_tensor(tau, dtype=torch.float64, device=si.device).contiguous()
+    if omega.numel() != F:
+        raise ValueError(f"gcc_phat: {omega.numel()} frequencies for {F} bins")
+    D = tau.numel()
+    lib = _lib.library()
+    work = torch.empty((int(lib.setk_gcc_phat_work_doubles(T, F, D)),), dtype=torch.float64,
+                       device=si.device)
+    accumulate = out is not None
+    if out is None:
+        out = torch.empty((T, D), dtype=torch.float64, device=si.device)
+    with _ctx(si.device):
+        _lib.check(lib.setk_gcc_phat(_lib.ptr(si), _lib.ptr(sj), T, F, _lib.ptr(omega), _lib.ptr(tau), D,
+                                     int(bool(normalize)), int(bool(apply_floor)), int(accumulate),
+                                     _lib.ptr(work), _lib.ptr(out), _lib.current_stream(si.device)))
+    return out
+
+
+def msc(spec, context=1, normalize=True):
+    """spatial.msc: spec (N,T,F) complex64 -> (T,F) float64."""
+    spec = _c64(spec)
+    if spec.dim() != 3:
+        raise ValueError(f"msc: spectrogram must be (N, T, F), got {tuple(spec.shape)}")
+    N, T, F = spec.shape
+    lib = _lib.library()
+    work = torch.empty((int(lib.setk_msc_work_doubles(T, F)),), dtype=torch.float64, device=spec.device)
+    out = torch.empty((T, F), dtype=torch.float64, device=spec.device)
+    with _ctx(spec.device):
+        _lib.check(lib.setk_msc(_lib.ptr(spec), N, T, F, int(context), int(bool(normalize)),
+                                _lib.ptr(work), _lib.ptr(out), _lib.current_stream(spec.device)))
+    return out

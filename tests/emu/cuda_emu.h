@@ -235,6 +235,13 @@ static inline int atomicMax(int* a, int v) {
   return old;
 }
 static inline unsigned atomicOr(unsigned* a, unsigned v) { return __atomic_fetch_or(a, v, __ATOMIC_RELAXED); }
+static inline unsigned long long atomicMax(unsigned long long* a, unsigned long long v) {
+  unsigned long long old = __atomic_load_n(a, __ATOMIC_RELAXED);
+  while (old < v && !__atomic_compare_exchange_n(a, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+  return old;
+}
+static inline long long __double_as_longlong(double f) { long long u; memcpy(&u, &f, 8); return u; }
+static inline double __longlong_as_double(long long u) { double f; memcpy(&f, &u, 8); return f; }
 static inline unsigned atomicAdd(unsigned* a, unsigned v) { return __atomic_fetch_add(a, v, __ATOMIC_RELAXED); }
 static inline int atomicAdd(int* a, int v) { return __atomic_fetch_add(a, v, __ATOMIC_RELAXED); }
 static inline unsigned long long atomicAdd(unsigned long long* a, unsigned long long v) {

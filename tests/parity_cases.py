@@ -482,3 +482,155 @@ def check_wpe_fixture(device, name):
     err = bo.rel_inf(out[0].cpu().numpy(), g[name + "/derev"])
     assert err <= 1e-5, (name, err)      # the reference ran in complex64; both sit ~1e-8 from float64
     return err
+
+
+# ---------------------------------------------------------------------------
+# spatial features (csrc/spatial.cu) vs oracle/spatial_oracle.py
+#   phases are float32 like the reference (np.angle of complex64): atan2f / cosf on the
+#   device and in libm differ by a few ulp -> 5e-6 absolute on cos/sin/IPD (IPD compared
+#   modulo 2 pi: a last-bit difference may wrap the other way), 5e-6 of max|.| for GCC/SRP;
+#   MSC is float64 arithmetic on exact complex64 inputs -> 1e-9.
+# ---------------------------------------------------------------------------
+TOL_PHASE = 5e-6
+
+
+def _wrap_err(a, b):
+    d = np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(np.mod(d + np.pi, 2 * np.pi) - np.pi)))
+
+
+def spatial_compare(device, S, obs, steer, pairs, topo, expect):
+    """
+    Run every spatial entry point on S (C x T x F complex64) / obs (C x F x T) and compare
+    with `expect` (dict of arrays: the oracle's or the reference's).  Returns worst errors.
+    """
+    C, T, F = S.shape
+    St = torch.from_numpy(S).to(device)
+    res = {}
+    res["ipd"] = _wrap_err(P.ipd(St[0], St[1], 0).cpu().numpy(), expect["ipd"])
+    res["ipd_cos"] = float(np.max(np.abs(P.ipd(St[0], St[1], 1).cpu().numpy() - expect["ipd_cos"])))
+    got = P.ipd(St[0], St[C - 1], 2).cpu().numpy()
+    assert got.shape == (T, 2 * F) and got.dtype == np.float32
+    res["ipd_cos_sin"] = float(np.max(np.abs(got - expect["ipd_cos_sin"])))
+    ot = torch.from_numpy(obs).to(device)[None]
+    res["df"] = float(np.max(np.abs(P.directional_feats(ot, torch.from_numpy(steer).to(device))[0]
+                                    .cpu().numpy() - expect["df"])))
+    res["df_given_pairs"] = float(np.max(np.abs(
+        P.directional_feats(ot, torch.from_numpy(steer).to(device)[None], pairs=pairs)[0].cpu().numpy()
+        - expect["df_given_pairs"])))
+    for k in ("ipd", "ipd_cos", "ipd_cos_sin", "df", "df_given_pairs"):
+        assert res[k] <= TOL_PHASE, (k, res[k])
+    from oracle import spatial_oracle as sp
+
+    def rel(got, ref):
+        return float(np.max(np.abs(got - ref)) / max(np.max(np.abs(ref)), 1e-30))
+
+    gk = dict(num_bins=F, num_doa=37)
+    om, tau = sp.tdoa_grid(0.07, **gk)
+    res["gcc"] = rel(P.gcc_phat(St[0], St[1], om, tau).cpu().numpy(), expect["gcc"])
+    om, tau = sp.tdoa_grid(-0.05, samp_doa=False, **gk)
+    res["gcc_tdoa_raw"] = rel(P.gcc_phat(St[0], St[1], om, tau, normalize=False, apply_floor=False)
+                              .cpu().numpy(), expect["gcc_tdoa_raw"])
+    tau = np.cos(0.3 - np.linspace(0, np.pi * 2, 25)) * 0.1 / 343
+    om = np.linspace(0, 16000 / 2, F) * 2 * np.pi
+    res["gcc_diag"] = rel(P.gcc_phat(St[0], St[1], om, tau).cpu().numpy(), expect["gcc_diag"])
+    if C == 2:
+        om, tau = sp.tdoa_grid(topo[1] - topo[0], **gk)
+        srp = P.gcc_phat(St[0], St[1], om, tau)
+    else:
+        srp = torch.zeros((T, 37), dtype=torch.float64, device=device)
+        for i in range(C):
+            for j in range(i + 1, C):
+                om, tau = sp.tdoa_grid(topo[j] - topo[i], **gk)
+                P.gcc_phat(St[i], St[j], om, tau, out=srp)
+        srp = srp * 2 / (C * (C - 1))
+    res["srp"] = rel(srp.cpu().numpy(), expect["srp"])
+    for k in ("gcc", "gcc_tdoa_raw", "gcc_diag", "srp"):
+        assert res[k] <= TOL_PHASE, (k, res[k])
+    for ctx in (0, 1, 2):
+        res[f"msc_ctx{ctx}"] = rel(P.msc(St, context=ctx).cpu().numpy(), expect[f"msc_ctx{ctx}"])
+    res["msc_raw"] = rel(P.msc(St, context=1, normalize=False).cpu().numpy(), expect["msc_raw"])
+    for k in ("msc_ctx0", "msc_ctx1", "msc_ctx2", "msc_raw"):
+        assert res[k] <= 1e-9, (k, res[k])
+    return res
+
+
+def check_spatial(device, rng, C, N, frame_len=256, hop=128):
+    """Every spatial kernel vs oracle/spatial_oracle.py on a seeded mixture."""
+    from oracle import spatial_oracle as sp
+    x = structured_audio(rng, 1, C, N)[0]
+    obs = oracle_stft(x, frame_len, hop, True, "hann", dtype=np.complex64)           # C x F x T
+    S = np.ascontiguousarray(np.transpose(obs, (0, 2, 1)))
+    F = obs.shape[1]
+    steer = np.exp(-1j * rng.uniform(0, 2 * np.pi, size=(C, F)))
+    pairs = [(0, C - 1), (C - 1, 0)] if C > 2 else [(1, 0)]
+    topo = [0.04 * i for i in range(C)]
+    gk = dict(num_bins=F, num_doa=37)
+    expect = {
+        "ipd": sp.ipd(S[0], S[1]), "ipd_cos": sp.ipd(S[0], S[1], cos=True),
+        "ipd_cos_sin": sp.ipd(S[0], S[C - 1], cos=True, sin=True),
+        "df": sp.directional_feats(obs, steer),
+        "df_given_pairs": sp.directional_feats(obs, steer, df_pair=pairs),
+        "gcc": sp.gcc_phat_linear(S[0], S[1], 0.07, **gk),
+        "gcc_tdoa_raw": sp.gcc_phat_linear(S[0], S[1], -0.05, normalize=False, apply_floor=False,
+                                           samp_doa=False, **gk),
+        "gcc_diag": sp.gcc_phat_diag(S[0], S[1], 0.3, 0.1, num_doas=25, num_bins=F),
+        "srp": sp.srp_phat_linear(S, topo, **gk),
+        "msc_raw": sp.msc(S, context=1, normalize=False),
+    }
+    for ctx in (0, 1, 2):
+        expect[f"msc_ctx{ctx}"] = sp.msc(S, context=ctx)
+    return spatial_compare(device, S, obs, steer, pairs, topo, expect)
+
+
+def check_spatial_fixture(device, name):
+    """The same entry points against the REFERENCE's own outputs (tests/golden/ref_spatial.npz)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_spatial.npz"))
+    fl, hop = (int(v) for v in g[name + "/cfg"])
+    obs = oracle_stft(g[name + "/mix"], fl, hop, True, "hann", dtype=np.complex64)
+    S = np.ascontiguousarray(np.transpose(obs, (0, 2, 1)))
+    expect = {k.split("/", 1)[1]: g[k] for k in g.files if k.startswith(name + "/")}
+    pairs = [tuple(int(v) for v in p) for p in g[name + "/df_pairs"]]
+    return spatial_compare(device, S, obs, g[name + "/steer"], pairs, list(g[name + "/topo"]), expect)
+
+
+def check_fixed_beamformers(device):
+    """
+    Geometry-based beamformers of setk_b200.libs.beamformer against the REFERENCE's own weights
+    and enhanced STFTs (tests/golden/ref_fixed_bf.npz): weights are host constants (<= 1e-12),
+    the enhanced STFT comes from setk_apply (complex64 storage: 2e-6).
+    """
+    import os
+    from setk_b200.libs import beamformer as BF
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_fixed_bf.npz"))
+    obs = oracle_stft(g["mix"], 256, 128, True, "hann", dtype=np.complex64)         # 4 x F x T
+    F = obs.shape[1]
+    topo = [0.0, 0.05, 0.1, 0.15]
+    objs = {"lin_ds": BF.LinearDSBeamformer(topo), "lin_sd": BF.LinearSDBeamformer(topo),
+            "cir_ds": BF.CircularDSBeamformer(0.05, 4), "cir_sd": BF.CircularSDBeamformer(0.05, 3, center=True)}
+    worst = 0.0
+    for name, obj in objs.items():
+        doa = float(g[name + "/doa"])
+        w = obj.weight(doa, F)
+        assert w.shape == g[name + "/weight"].shape
+        assert np.max(np.abs(w - g[name + "/weight"])) <= 1e-12 * max(1.0, np.max(np.abs(w))), name
+        enh = obj.run(doa, torch.from_numpy(obs).to(device))
+        assert torch.is_tensor(enh)
+        err = bo.rel_inf(enh.cpu().numpy(), g[name + "/enh"])
+        assert err <= 2e-6, (name, err)
+        worst = max(worst, err)
+    assert np.array_equal(objs["cir_sd"].distance_mat, g["cir_sd/distance_mat"])
+    enh = BF.FixedBeamformer(g["lin_sd/weight"]).run(torch.from_numpy(obs).to(device)).cpu().numpy()
+    assert bo.rel_inf(enh, g["fixed/enh"]) <= 2e-6
+    assert np.allclose(BF.beam_pattern(g["lin_ds/weight"], g["pattern/sv"]), g["pattern/single"], rtol=0, atol=1e-12)
+    multi = BF.beam_pattern(np.stack([g["lin_ds/weight"], g["lin_sd/weight"]]), g["pattern/sv"])
+    assert isinstance(multi, list) and np.allclose(np.stack(multi), g["pattern/multi"], rtol=0, atol=1e-12)
+    assert np.allclose(BF.diffuse_covar(F, np.abs(np.subtract.outer(topo, topo)), diag_eps=0.01), g["diffuse"],
+                       rtol=0, atol=1e-15)
+    import pytest
+    with pytest.raises(ValueError):
+        objs["lin_ds"].run(30.0, torch.from_numpy(obs[:3]).to(device))
+    with pytest.raises(RuntimeError):
+        BF.beam_pattern(g["lin_ds/weight"][:, :3], g["pattern/sv"])
+    return worst

@@ -148,6 +148,31 @@ def test_wpe_argument_errors(emu):
     assert int(st[0]) != 0
 
 
+def test_spatial_features(emu):
+    rng = np.random.default_rng(95)
+    pc.check_spatial(emu, rng, 3, 2200, 128, 64)
+    pc.check_spatial(emu, rng, 2, 1500, 64, 32)
+
+
+def test_spatial_argument_errors(emu):
+    from setk_b200 import plan as P
+    a = torch.zeros((5, 9), dtype=torch.complex64)
+    with pytest.raises(ValueError):
+        P.ipd(a, torch.zeros((5, 8), dtype=torch.complex64))
+    with pytest.raises(ValueError):
+        P.directional_feats(torch.zeros((1, 3, 9, 5), dtype=torch.complex64),
+                            torch.zeros((2, 9), dtype=torch.complex128))
+    with pytest.raises(ValueError):
+        P.directional_feats(torch.zeros((1, 3, 9, 5), dtype=torch.complex64),
+                            torch.zeros((3, 9), dtype=torch.complex128), pairs=[(0, 3)])
+    with pytest.raises(ValueError):
+        P.gcc_phat(a, a, np.zeros(8), np.zeros(4))
+    with pytest.raises(Exception):
+        P.msc(torch.zeros((1, 5, 9), dtype=torch.complex64))       # one channel: N (N - 1) = 0
+    # silence: 0 / 0 like the reference (NaN everywhere, no crash)
+    assert bool(torch.isnan(P.msc(torch.zeros((2, 4, 5), dtype=torch.complex64))).all())
+
+
 def test_cov_generic(emu):
     pc.check_cov_generic(emu, np.random.default_rng(7), 2, 6, 9, 70)
 

@@ -317,3 +317,46 @@ def test_wpe_reference_fixtures(cuda):
     """libs/wpe.py wpe() run by the reference (tests/golden/ref_wpe.npz)"""
     for name in ("c3_t4", "c4_t10", "c2_t6_ctx0"):
         pc.check_wpe_fixture(cuda, name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,N,fl,hop", [(4, 20000, 512, 256), (2, 9000, 1024, 256), (7, 6000, 256, 64)])
+def test_spatial_features(cuda, C, N, fl, hop):
+    """ipd / directional_feats / gcc_phat / srp / msc kernels vs oracle/spatial_oracle.py"""
+    pc.check_spatial(cuda, np.random.default_rng(500 + C), C, N, fl, hop)
+
+
+@pytest.mark.gpu
+def test_spatial_reference_fixtures(cuda):
+    """libs/spatial.py run by the reference (tests/golden/ref_spatial.npz)"""
+    for name in ("c4_512", "c3_256", "c2_1024"):
+        pc.check_spatial_fixture(cuda, name)
+
+
+@pytest.mark.gpu
+def test_spatial_libs_mirror_numpy(cuda):
+    """setk_b200.libs.spatial: the reference's names and axes, numpy in -> numpy out"""
+    from oracle import spatial_oracle as sp
+    from setk_b200.libs import spatial as gs
+    rng = np.random.default_rng(77)
+    S = (rng.standard_normal((3, 40, 129)) + 1j * rng.standard_normal((3, 40, 129))).astype(np.complex64)
+    d = [0.0, 0.05, 0.1]
+    kw = dict(num_bins=129, num_doa=19)
+    got = gs.srp_phat_linear(S, d, **kw)
+    ref = sp.srp_phat_linear(S, d, **kw)
+    assert isinstance(got, np.ndarray) and got.dtype == np.float64 and got.shape == ref.shape
+    assert np.max(np.abs(got - ref)) <= 5e-6 * np.max(np.abs(ref))
+    assert np.max(np.abs(gs.ipd(S[0], S[1], cos=True, sin=True) - sp.ipd(S[0], S[1], cos=True, sin=True))) <= 5e-6
+    assert np.max(np.abs(gs.msc(S) - sp.msc(S))) <= 1e-9
+    obs = np.ascontiguousarray(np.transpose(S, (0, 2, 1)))
+    sv = np.exp(1j * rng.uniform(0, 6.28, size=(3, 129)))
+    assert np.max(np.abs(gs.directional_feats(obs, sv) - sp.directional_feats(obs, sv))) <= 5e-6
+    assert np.array_equal(gs.linear_tdoa_grid(0.1, **kw), np.exp(-1j * np.outer(*sp.tdoa_grid(0.1, **kw))))
+    with pytest.raises(ValueError):
+        gs.srp_phat_linear(S, np.array(d))
+
+
+@pytest.mark.gpu
+def test_geometry_based_beamformers(cuda):
+    """DS / SD / fixed beamformers (host weights, setk_apply on the observations) vs ref_fixed_bf.npz"""
+    pc.check_fixed_beamformers(cuda)

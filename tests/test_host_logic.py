@@ -255,6 +255,136 @@ def test_wpe_mirror_and_cli(tmp_path, emu, emu_library_path):
     assert d.max() <= 1
 
 
+def test_archive_writer_and_spatial_cli(tmp_path, emu, emu_library_path):
+    """
+    ArchiveWriter (Kaldi ark + scp, data_handler.py:564-587), the libs.spatial mirror (reference
+    names / axes) and scripts/sptk/compute_ipd_and_linear_srp.py on the CPU execution model.
+    """
+    import struct
+    from oracle import spatial_oracle as sp
+    from setk_b200.libs import utils
+    from setk_b200.libs import spatial as gs
+    from setk_b200.libs.data_handler import ArchiveWriter, ScriptReader
+    import parity_cases as pc
+    utils.set_default_device("cpu")
+    # ---- writer: the bytes the reference's kaldi_io writers produce, read back by ScriptReader ----
+    a = np.arange(6, dtype=np.float64).reshape(2, 3) / 7
+    v = np.linspace(0, 1, 5)
+    with ArchiveWriter(str(tmp_path / "a.ark"), str(tmp_path / "a.scp")) as w:
+        w.write("m1", a)
+        w.write("v1", v)
+        with pytest.raises(RuntimeError):
+            w.write("bad", [1, 2, 3])
+    raw = (tmp_path / "a.ark").read_bytes()
+    expect = (b"m1 \0BFM \x04" + struct.pack("i", 2) + b"\x04" + struct.pack("i", 3) +
+              a.astype(np.float32).tobytes() + b"v1 \0BFV \x04" + struct.pack("i", 5) +
+              v.astype(np.float32).tobytes())
+    assert raw == expect
+    lines = (tmp_path / "a.scp").read_text().splitlines()
+    assert lines[0] == f"m1\t{tmp_path / 'a.ark'}:3" and lines[1].startswith("v1\t")
+    rd = ScriptReader(str(tmp_path / "a.scp"))
+    assert np.array_equal(rd["m1"], a.astype(np.float32)) and np.array_equal(rd["v1"], v.astype(np.float32))
+    with pytest.raises(RuntimeError):
+        ArchiveWriter("")
+    # ---- libs.spatial mirror: numpy in -> numpy out, reference dtypes ----
+    rng = np.random.default_rng(31)
+    x = pc.structured_audio(rng, 1, 3, 2400)[0]
+    x = so.float_from_pcm16(so.pcm16_from_float(x))
+    kw = dict(frame_len=128, frame_hop=64, center=True, window="hann", round_power_of_two=True,
+              transpose=False)
+    obs = so.multichannel_stft(x, out_dtype=np.complex64, **kw)                    # C x F x T
+    S = np.ascontiguousarray(np.transpose(obs, (0, 2, 1)))                          # C x T x F
+    F = S.shape[-1]
+    topo = (0.0, 0.1, 0.25)
+    gk = dict(num_bins=F, num_doa=21)
+    srp = gs.srp_phat_linear(S, topo, **gk)
+    ref_srp = sp.srp_phat_linear(S, topo, **gk)
+    assert isinstance(srp, np.ndarray) and srp.dtype == ref_srp.dtype and srp.shape == ref_srp.shape
+    assert np.max(np.abs(srp - ref_srp)) <= 5e-6 * np.max(np.abs(ref_srp))
+    two = gs.srp_phat_linear(S[:2], topo[:2], normalize=False, **gk)               # N == 2: defaults win
+    assert np.max(np.abs(two - sp.srp_phat_linear(S[:2], topo[:2], normalize=False, **gk))) <= 5e-6
+    got = gs.ipd(S[0], S[2])
+    assert got.dtype == np.float32 and pc._wrap_err(got, sp.ipd(S[0], S[2])) <= 5e-6
+    assert np.max(np.abs(gs.msc(S, context=2) - sp.msc(S, context=2))) <= 1e-9
+    sv = np.exp(1j * rng.uniform(0, 6.28, size=(3, F)))
+    assert np.max(np.abs(gs.directional_feats(obs, sv, df_pair=[(0, 2)]) -
+                         sp.directional_feats(obs, sv, df_pair=[(0, 2)]))) <= 5e-6
+    t = gs.gcc_phat_diag(torch.from_numpy(S[0]), torch.from_numpy(S[1]), 0.4, 0.08, num_doas=13, num_bins=F)
+    assert torch.is_tensor(t)
+    assert np.max(np.abs(t.numpy() - sp.gcc_phat_diag(S[0], S[1], 0.4, 0.08, num_doas=13, num_bins=F))) <= 5e-6
+    with pytest.raises(ValueError):
+        gs.srp_phat_linear(S, np.array(topo))
+    with pytest.raises(ValueError):
+        gs.srp_phat_linear(S, (0.0, 0.1))
+    # ---- the CLI, the reference's flags, all three feature types ----
+    _write_wav(str(tmp_path / "utt1.wav"), x)
+    (tmp_path / "wav.scp").write_text(f"utt1 {tmp_path / 'utt1.wav'}\n")
+    env = dict(os.environ, SETK_B200_TEST_LIBRARY=emu_library_path, PYTHONPATH=ROOT)
+    runner = (
+        "import os, sys, runpy; sys.argv = sys.argv[1:];"
+        "from setk_b200 import _lib; _lib.use_library(os.environ['SETK_B200_TEST_LIBRARY']);"
+        "from setk_b200.libs import utils; utils.set_default_device('cpu');"
+        "runpy.run_path(sys.argv[0], run_name='__main__')")
+    script = os.path.join(ROOT, "scripts", "sptk", "compute_ipd_and_linear_srp.py")
+    base = [sys.executable, "-c", runner, script, "--frame-len", "128", "--frame-hop", "64",
+            "--center", "true"]
+    cases = {
+        "srp": (["--type", "srp", "--srp.topo", "0,0.1,0.25", "--srp.num_doa", "21"], ref_srp),
+        "ipd": (["--type", "ipd", "--ipd.pair", "0,1;0,2", "--ipd.cos", "true"],
+                np.hstack([sp.ipd(S[0], S[1], cos=True), sp.ipd(S[0], S[2], cos=True)])),
+        "msc": (["--type", "msc", "--msc.ctx", "2"], sp.msc(S, context=2)),
+    }
+    for name, (flags, ref) in cases.items():
+        ark, scp = tmp_path / f"{name}.ark", tmp_path / f"{name}.scp"
+        subprocess.run(base + flags + ["--scp", str(scp), str(tmp_path / "wav.scp"), str(ark)], check=True,
+                       env=env, capture_output=True)
+        feats = ScriptReader(str(scp))["utt1"]
+        assert feats.dtype == np.float32 and feats.shape == ref.shape, (name, feats.shape, ref.shape)
+        assert np.max(np.abs(feats - ref)) <= 1e-5 * max(1.0, np.max(np.abs(ref))), name
+    utils.set_default_device(None)
+
+
+def test_geometry_based_beamformers(libs, tmp_path, emu_library_path):
+    """DS / SD / fixed beamformers and beam_pattern vs the reference's own outputs (ref_fixed_bf.npz),
+    and scripts/sptk/apply_fixed_beamformer.py (single and multiple beams) vs the oracle."""
+    import parity_cases as pc
+    from setk_b200.libs import beamformer as BF
+    pc.check_fixed_beamformers(torch.device("cpu"))
+    rng = np.random.default_rng(17)
+    x = pc.structured_audio(rng, 1, 3, 3000)[0]
+    x = so.float_from_pcm16(so.pcm16_from_float(x))
+    kw = dict(frame_len=256, frame_hop=128, center=True, window="hann", round_power_of_two=True,
+              transpose=False)
+    obs = so.multichannel_stft(x, out_dtype=np.complex64, **kw)                    # 3 x F x T
+    F = obs.shape[1]
+    w0 = BF.LinearSDBeamformer([0.0, 0.06, 0.12]).weight(70.0, F)
+    w1 = BF.LinearDSBeamformer([0.0, 0.06, 0.12]).weight(120.0, F)
+    np.save(str(tmp_path / "w_single.npy"), w0)
+    np.save(str(tmp_path / "w_multi.npy"), np.stack([w0, w1]))
+    _write_wav(str(tmp_path / "utt1.wav"), x)
+    (tmp_path / "wav.scp").write_text(f"utt1 {tmp_path / 'utt1.wav'}\n")
+    (tmp_path / "beam.scp").write_text("utt1 1\n")
+    env = dict(os.environ, SETK_B200_TEST_LIBRARY=emu_library_path, PYTHONPATH=ROOT)
+    runner = (
+        "import os, sys, runpy; sys.argv = sys.argv[1:];"
+        "from setk_b200 import _lib; _lib.use_library(os.environ['SETK_B200_TEST_LIBRARY']);"
+        "from setk_b200.libs import utils; utils.set_default_device('cpu');"
+        "runpy.run_path(sys.argv[0], run_name='__main__')")
+    script = os.path.join(ROOT, "scripts", "sptk", "apply_fixed_beamformer.py")
+    base = [sys.executable, "-c", runner, script, "--frame-len", "256", "--frame-hop", "128", "--center", "true"]
+    import scipy.io.wavfile as wavfile
+    for tag, wfile, extra, w in (("single", "w_single.npy", [], w0),
+                                 ("multi", "w_multi.npy", ["--beam", str(tmp_path / "beam.scp")], w1)):
+        subprocess.run(base + extra + [str(tmp_path / "wav.scp"), str(tmp_path / wfile), str(tmp_path / tag)],
+                       check=True, env=env, capture_output=True)
+        sr, y = wavfile.read(str(tmp_path / tag / "utt1.wav"))
+        enh = np.einsum("fn,nft->ft", w.conj(), obs.astype(np.complex128))
+        yo = so.inverse_stft(enh, frame_len=256, frame_hop=128, center=True, window="hann", transpose=False,
+                             norm=float(np.max(np.abs(x))))
+        d = np.abs(y.astype(np.int64) - so.pcm16_from_float(yo).astype(np.int64))
+        assert sr == 16000 and y.dtype == np.int16 and d.max() <= 1, (tag, int(d.max()))
+
+
 def test_permu_aligner_restores_a_scrambled_mask():
     from setk_b200.libs.cluster import permu_aligner
     rng = np.random.default_rng(12)

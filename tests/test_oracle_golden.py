@@ -181,3 +181,37 @@ def test_restatement_against_live_reference():
         e_ref = bf.run(mask, obs, ban=(kind == "gevd"))
         e_or = bo.run_supervised(kind, mask, obs, ban=(kind == "gevd"))
         assert bo.rel_inf(bo.align_phase(e_or, e_ref)[0], e_ref) <= 1e-10
+
+
+def test_spatial_oracle_pinned_to_reference():
+    """libs/spatial.py run by the reference on complex64 STFTs (ref_spatial.npz): bit for bit."""
+    from oracle import spatial_oracle as sp
+    from oracle import stft_oracle as so
+    g = np.load(os.path.join(GOLD, "ref_spatial.npz"))
+    for name in ("c4_512", "c3_256", "c2_1024"):
+        fl, hop = (int(v) for v in g[name + "/cfg"])
+        mix = g[name + "/mix"]
+        obs = np.stack([so.stft(mix[c], fl, hop, fl, window="hann", center=True, out_dtype=np.complex64)
+                        for c in range(mix.shape[0])])
+        S = np.ascontiguousarray(np.transpose(obs, (0, 2, 1)))
+        C, _, F = S.shape
+        steer = g[name + "/steer"]
+        pairs = [tuple(int(v) for v in p) for p in g[name + "/df_pairs"]]
+        gk = dict(num_bins=F, num_doa=37)
+        got = {
+            "ipd": sp.ipd(S[0], S[1]), "ipd_cos": sp.ipd(S[0], S[1], cos=True),
+            "ipd_cos_sin": sp.ipd(S[0], S[C - 1], cos=True, sin=True),
+            "df": sp.directional_feats(obs, steer),
+            "df_given_pairs": sp.directional_feats(obs, steer, df_pair=pairs),
+            "gcc": sp.gcc_phat_linear(S[0], S[1], 0.07, **gk),
+            "gcc_tdoa_raw": sp.gcc_phat_linear(S[0], S[1], -0.05, normalize=False, apply_floor=False,
+                                               samp_doa=False, **gk),
+            "gcc_diag": sp.gcc_phat_diag(S[0], S[1], 0.3, 0.1, num_doas=25, num_bins=F),
+            "srp": sp.srp_phat_linear(S, list(g[name + "/topo"]), **gk),
+            "msc_ctx0": sp.msc(S, context=0), "msc_ctx1": sp.msc(S, context=1),
+            "msc_ctx2": sp.msc(S, context=2), "msc_raw": sp.msc(S, context=1, normalize=False),
+        }
+        for k, v in got.items():
+            ref = g[name + "/" + k]
+            assert v.shape == ref.shape and v.dtype == ref.dtype, (name, k, v.dtype, ref.dtype)
+            assert np.array_equal(v, ref), (name, k, float(np.max(np.abs(v - ref))))
