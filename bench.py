@@ -360,6 +360,8 @@ def gpu_arm(args):
                     "d2h_bytes_per_step": wave.numel() * 4, "steps": e2e_steps,
                     "how": "pinned host f32 audio+mask -> H2D -> BeamformPipeline.run -> D2H wave, "
                            "every step; 2 lanes (streams) so copies overlap kernels",
+                    "h2d_GBps": e2e_val / world * (audio.numel() + mask.numel()) * 4 / B / 1e9,
+                    "bound": "host->device link (PCIe): the kernels need 1/12 of the step",
                     "pcm16_audio_variant": {"value": e2e_pcm16, "unit": UNIT,
                                             "h2d_bytes_per_step": audio.numel() * 2 + mask.numel() * 4}},
             "gpu_launches": int(launches),

@@ -251,3 +251,16 @@ def get_logger(name, format_str=default_format_str, date_format="%Y-%m-%d %H:%M:
             logger.addHandler(get_handler(logging.FileHandler(name)))
         logger.addHandler(get_handler(logging.StreamHandler()))
     return logger
+
+
+def check_doa(geometry, doa, online=False):
+    """Check value of the DoA (utils.py:248-263)."""
+    doas = doa if online else [doa]
+    for doa in doas:
+        if doa < 0:
+            return False
+        if geometry == "linear" and doa > 180:
+            return False
+        if geometry == "circular" and doa >= 360:
+            return False
+    return True

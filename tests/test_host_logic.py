@@ -341,6 +341,33 @@ def test_archive_writer_and_spatial_cli(tmp_path, emu, emu_library_path):
         feats = ScriptReader(str(scp))["utt1"]
         assert feats.dtype == np.float32 and feats.shape == ref.shape, (name, feats.shape, ref.shape)
         assert np.max(np.abs(feats - ref)) <= 1e-5 * max(1.0, np.max(np.abs(ref))), name
+    # ---- directional features from given steer vectors / from a TF-mask ----
+    A = np.exp(1j * rng.uniform(0, 6.28, size=(3, 3, F)))                          # A x M x F
+    np.save(str(tmp_path / "sv.npy"), A)
+    script = os.path.join(ROOT, "scripts", "sptk", "compute_df_on_geometry.py")
+    base = [sys.executable, "-c", runner, script, "--frame-len", "128", "--frame-hop", "64", "--center", "true"]
+    ark, scp = tmp_path / "dfg.ark", tmp_path / "dfg.scp"
+    subprocess.run(base + ["--doa-idx", "0,2", "--df-pair", "0,1;0,2", "--scp", str(scp),
+                           str(tmp_path / "wav.scp"), str(tmp_path / "sv.npy"), str(ark)],
+                   check=True, env=env, capture_output=True)
+    dfs = np.stack([sp.directional_feats(obs, A[i], df_pair=[(0, 1), (0, 2)]) for i in (0, 2)])
+    ref = dfs.transpose(1, 0, 2).reshape(dfs.shape[1], -1)
+    feats = ScriptReader(str(scp))["utt1"]
+    assert feats.shape == ref.shape and np.max(np.abs(feats - ref)) <= 1e-5
+    mask = rng.uniform(0.05, 1.0, size=(S.shape[1], F)).astype(np.float32)         # T x F
+    np.save(str(tmp_path / "mask.npy"), mask)
+    (tmp_path / "mask.scp").write_text(f"utt1 {tmp_path / 'mask.npy'}\n")
+    script = os.path.join(ROOT, "scripts", "sptk", "compute_df_on_mask.py")
+    base = [sys.executable, "-c", runner, script, "--frame-len", "128", "--frame-hop", "64", "--center", "true"]
+    ark, scp = tmp_path / "dfm.ark", tmp_path / "dfm.scp"
+    subprocess.run(base + ["--mask-format", "numpy", "--df-pair", "0,2", "--scp", str(scp),
+                           str(tmp_path / "wav.scp"), str(tmp_path / "mask.scp"), str(ark)],
+                   check=True, env=env, capture_output=True)
+    Rs = bo.compute_covar(obs.astype(np.complex128), mask.astype(np.float64))
+    sv = bo.solve_pevd(Rs)                                                          # F x N (phase: arbitrary)
+    ref = sp.directional_feats(obs, sv.T, df_pair=[(0, 2)])      # phase differences: sign/phase invariant
+    feats = ScriptReader(str(scp))["utt1"]
+    assert feats.shape == ref.shape and np.max(np.abs(feats - ref)) <= 2e-4
     utils.set_default_device(None)
 
 
@@ -383,6 +410,33 @@ def test_geometry_based_beamformers(libs, tmp_path, emu_library_path):
                              norm=float(np.max(np.abs(x))))
         d = np.abs(y.astype(np.int64) - so.pcm16_from_float(yo).astype(np.int64))
         assert sr == 16000 and y.dtype == np.int16 and d.max() <= 1, (tag, int(d.max()))
+    # scripts/sptk/apply_classic_beamformer.py: SD for a linear array (one DoA per utterance) and
+    # DS in chunks (online: one DoA per --chunk-len frames), --normalize true
+    script = os.path.join(ROOT, "scripts", "sptk", "apply_classic_beamformer.py")
+    base = [sys.executable, "-c", runner, script, "--frame-len", "256", "--frame-hop", "128", "--center", "true",
+            "--linear-topo", "0,0.06,0.12", "--normalize", "true"]
+    T = obs.shape[-1]
+    (tmp_path / "utt2doa").write_text("utt1 70\n")
+    half = (T + 1) // 2
+    runs = (("sd", ["--beamformer", "sd", "--utt2doa", str(tmp_path / "utt2doa")],
+             np.einsum("fn,nft->ft", BF.LinearSDBeamformer([0.0, 0.06, 0.12]).weight(70.0, F, c=343).conj(),
+                       obs.astype(np.complex128))),
+            ("ds_online", ["--beamformer", "ds", "--chunk-len", str(half), "--doa", "30"], None))
+    for tag, extra, enh in runs:
+        if enh is None:
+            (tmp_path / "utt2doa2").write_text("utt1 30 150\n")
+            extra = ["--beamformer", "ds", "--chunk-len", str(half), "--utt2doa", str(tmp_path / "utt2doa2")]
+            ds = BF.LinearDSBeamformer([0.0, 0.06, 0.12])
+            o = obs.astype(np.complex128)
+            enh = np.hstack([np.einsum("fn,nft->ft", ds.weight(30.0, F, c=343).conj(), o[:, :, :half]),
+                             np.einsum("fn,nft->ft", ds.weight(150.0, F, c=343).conj(), o[:, :, half:])])
+        subprocess.run(base + extra + [str(tmp_path / "wav.scp"), str(tmp_path / tag)], check=True, env=env,
+                       capture_output=True)
+        sr, y = wavfile.read(str(tmp_path / tag / "utt1.wav"))
+        yo = so.inverse_stft(enh, frame_len=256, frame_hop=128, center=True, window="hann", transpose=False,
+                             norm=float(np.max(np.abs(x))))
+        d = np.abs(y.astype(np.int64) - so.pcm16_from_float(yo).astype(np.int64))
+        assert sr == 16000 and d.max() <= 1, (tag, int(d.max()))
 
 
 def test_permu_aligner_restores_a_scrambled_mask():
