@@ -144,7 +144,27 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
     const bool last_tile = (p_t0 + p_nt == T_used);
     const float* cin = s_carry + cur * carry_len;
     float* cout = s_carry + (cur ^ 1) * carry_len;
-    if (fast_hop) {
+    // interior tile of a 50 %-overlap transform: every row is owned, inside the output, has two
+    // frames and a following tile takes the last half frame -- one check per tile, none per sample
+    const bool interior = fast_hop && out_vec && !a.accumulate && p_nt == TT && !last_tile &&
+                          p_t0 >= 1 && p_t0 + p_nt < T_used && p_tile >= own_begin && p_tile >= pad &&
+                          p_tile - pad + p_nt * kM <= a.n_out;
+    if (interior) {
+      static_assert((TT + 1) * (kM / 4) == kApplyThreads, "one flush item per thread");
+      const int jj = tid >> 6, r = (tid & 63) * 4;
+      float4 val = jj >= 1 ? *reinterpret_cast<const float4*>(s_frames + (jj - 1) * kNfft + kM + r)
+                           : *reinterpret_cast<const float4*>(cin + r);
+      if (jj < TT) {
+        const float4 f = *reinterpret_cast<const float4*>(s_frames + jj * kNfft + r);
+        const float4 rw = *reinterpret_cast<const float4*>(s_rw + r);
+        val.x = (val.x + f.x) * rw.x; val.y = (val.y + f.y) * rw.y;
+        val.z = (val.z + f.z) * rw.z; val.w = (val.w + f.w) * rw.w;
+        *reinterpret_cast<float4*>(yb + (p_tile - pad + jj * kM + r)) = val;
+        peak = fmaxf(peak, fmaxf(fmaxf(fabsf(val.x), fabsf(val.y)), fmaxf(fabsf(val.z), fabsf(val.w))));
+      } else {
+        *reinterpret_cast<float4*>(cout + r) = val;
+      }
+    } else if (fast_hop) {
       // rows of 256 positions; row jj gets frame jj (n = r) and frame jj-1 (n = r + 256).
       // Four consecutive positions per thread: 16-byte shared loads and (when the
       // output rows allow it) 16-byte global stores; pad and own_begin are multiples

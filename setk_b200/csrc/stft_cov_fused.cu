@@ -166,10 +166,9 @@ __global__ void __maxnreg__(SETK_SC_REGS) stft_cov_kernel(StftCovArgs a) {
       const float2* z = sm.z + (j * C + c) * SETK_ZSLOT;
       x[c] = split_bin(z[zk], z[zn], tw);
     }
-    if (bin == 0 || bin == kM) {
-#pragma unroll
-      for (int c = 0; c < C; ++c) x[c].y = 0.f;               // DC / Nyquist are real
-    }
+    // DC / Nyquist need no special case: with Zk == Zn the split's difference has an
+    // exactly zero real part, its sum an exactly zero imaginary part, and the bin's
+    // twiddle is (-0, -+1), so Im X comes out as an exact (signed) zero
     const float m_raw = s_mask[(2 * j) * MPITCH + bin];
     const float m_s = clip ? fminf(m_raw, 1.0f) : m_raw;
     const float m_n = has_mn ? s_mask[(2 * j + 1) * MPITCH + bin] : 1.0f - m_s;
@@ -235,11 +234,19 @@ __global__ void __maxnreg__(SETK_SC_REGS) stft_cov_kernel(StftCovArgs a) {
       } else if (!nyq) {
         const float* mps = a.mask_s + mbase + (long long)t0 * mstride;
         const float* mpn = has_mn ? a.mask_n + mbase + (long long)t0 * mstride : nullptr;
+        if (nt == TT) {
 #pragma unroll
-        for (int j = 0; j < TT; ++j) {
-          if (j < nt) {
+          for (int j = 0; j < TT; ++j) {
             cp_async_f32(s_mask + (2 * j) * MPITCH + bin, mps + j * mstride);
             if (has_mn) cp_async_f32(s_mask + (2 * j + 1) * MPITCH + bin, mpn + j * mstride);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < TT; ++j) {
+            if (j < nt) {
+              cp_async_f32(s_mask + (2 * j) * MPITCH + bin, mps + j * mstride);
+              if (has_mn) cp_async_f32(s_mask + (2 * j + 1) * MPITCH + bin, mpn + j * mstride);
+            }
           }
         }
       } else if (lane < nt) {
@@ -258,9 +265,14 @@ __global__ void __maxnreg__(SETK_SC_REGS) stft_cov_kernel(StftCovArgs a) {
       // ---- covariance ----
       if (cov_idle) {
       } else if (!nyq) {
+        if (nt == TT) {          // every tile but an utterance's last: straight-line code
 #pragma unroll
-        for (int j = 0; j < TT; ++j)
-          if (j < nt) accumulate(j);
+          for (int j = 0; j < TT; ++j) accumulate(j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < TT; ++j)
+            if (j < nt) accumulate(j);
+        }
       } else if (lane < nt) {
         accumulate(lane);
       }

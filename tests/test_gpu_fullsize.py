@@ -103,3 +103,48 @@ def test_mvdr_distortionless_and_oracle_sample(cuda, batch):
     for b in (3, 200):
         err = pc.mvdr_end_to_end(cuda, audio[b:b + 1].cpu().numpy(), mask[b:b + 1].cpu().numpy())
         assert err <= pc.TOL_E2E, err
+
+
+def test_persistent_schedule_batch_compositions(cuda):
+    """
+    The fused kernels cut the batch's (utterance, tile) sequence into equal runs per CTA, so where
+    an utterance is cut depends on the batch around it.  An utterance's results must not: the
+    enhanced audio is bit-identical (every sample is the same arithmetic wherever the cut falls),
+    the covariances agree to fp32 summation order, for batches of 1, 3, 37 and 300 utterances,
+    ragged lengths from one frame to the full 10 s, and an utterance too short for one frame.
+    """
+    from setk_b200 import plan as P, synth
+    dev = cuda
+    a, m = synth.make_batch(4, C, N, device=dev)
+    T = m.shape[1]
+    for Bx in (1, 3, 37, 300):
+        pl = P.StftPlan(C, 512, 256, True, True, "hann", Bx, N, dev)
+        idx = torch.arange(Bx, device=dev) % 4
+        audio = (a[idx] * torch.linspace(0.3, 1.0, Bx, device=dev)[:, None, None]).contiguous()
+        mask = m[idx].contiguous()
+        lens = torch.full((Bx,), N, dtype=torch.int32, device=dev)
+        if Bx >= 3:
+            lens[1] = 700                       # three frames
+            lens[2] = 100                       # too short for reflect padding: no frame at all
+            for b in range(3, Bx):
+                lens[b] = int(N * (0.05 + 0.95 * ((b * 7919) % 101) / 100.0))
+        Rs, Rn, mx = pl.stft_cov(audio, mask, n_samples=lens)
+        w = torch.zeros((Bx, 257, C), dtype=torch.complex64, device=dev)
+        w[:, :, 0] = 0.75
+        w[:, :, 2] = 0.25j
+        y = pl.apply_istft(audio, w, n_samples=lens)
+        assert torch.isfinite(Rs).all() and torch.isfinite(y).all()
+        for b in sorted({0, 1, 2, Bx // 2, Bx - 1} & set(range(Bx))):
+            nb = int(lens[b])
+            one = P.StftPlan(C, 512, 256, True, True, "hann", 1, N, dev)
+            Rs1, Rn1, mx1 = one.stft_cov(audio[b:b + 1], mask[b:b + 1], n_samples=lens[b:b + 1])
+            y1 = one.apply_istft(audio[b:b + 1], w[b:b + 1], n_samples=lens[b:b + 1])
+            one.close()
+            assert torch.equal(y[b], y1[0]), (Bx, b)
+            scale = float(Rs1.abs().amax()) or 1.0
+            assert float((Rs[b] - Rs1[0]).abs().amax()) <= 5e-6 * scale, (Bx, b)
+            assert float((Rn[b] - Rn1[0]).abs().amax()) <= 5e-6 * max(float(Rn1.abs().amax()), 1e-30), (Bx, b)
+            assert float(mx[b]) == float(mx1[0])
+            if nb == 100:                       # no frame: zero covariances, silent output
+                assert float(Rs[b].abs().amax()) == 0.0 and float(y[b].abs().amax()) == 0.0
+        pl.close()
