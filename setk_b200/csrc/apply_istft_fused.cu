@@ -120,11 +120,15 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
     const int job = (warp - 8) * 2 + half;         // frame inside the tile
     float2 v[16];
     float2* zi = s_zi + job * SETK_ZSLOT;
+    if (job < p_nt) {                              // ONE branch per job, not one per load
 #pragma unroll
-    for (int m1 = 0; m1 < 16; ++m1) {
-      float2 x = make_float2(0.f, 0.f);
-      if (job < p_nt) { x = zi[16 * m1 + lane16]; x.y = -x.y; }
-      v[m1] = x;
+      for (int m1 = 0; m1 < 16; ++m1) {
+        const float2 x = zi[16 * m1 + lane16];
+        v[m1] = make_float2(x.x, -x.y);
+      }
+    } else {
+#pragma unroll
+      for (int m1 = 0; m1 < 16; ++m1) v[m1] = make_float2(0.f, 0.f);
     }
     __syncwarp();                                  // slot is free: reuse it as the exchange tile
     halfwarp_fft256(v, zi, lane16, w1);
@@ -324,7 +328,8 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
         float2 wk[C], wm[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) { wk[c] = s_w[c * kWPitch + k]; wm[c] = s_w[c * kWPitch + km]; }
-        for (int j = g; j < nt; j += 2) {
+        // one (pair, frame) item; a full tile is two straight-line items per thread (frames g, g + 2)
+        auto item = [&](int j) {
           float2 yk = make_float2(0.f, 0.f), ym = make_float2(0.f, 0.f);
 #pragma unroll
           for (int c = 0; c < C; ++c) {
@@ -356,6 +361,12 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
               zi[km] = make_float2(qq.x, -qq.y);
             }
           }
+        };
+        if (nt == TT) {
+          item(g);
+          item(g + 2);
+        } else {
+          for (int j = g; j < nt; j += 2) item(j);
         }
       }
       // ---- phase B: flush of the previous tile (its frames were made in phase A) ----

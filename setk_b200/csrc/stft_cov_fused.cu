@@ -171,7 +171,10 @@ __global__ void __maxnreg__(SETK_SC_REGS) stft_cov_kernel(StftCovArgs a) {
     // twiddle is (-0, -+1), so Im X comes out as an exact (signed) zero
     const float m_raw = s_mask[(2 * j) * MPITCH + bin];
     const float m_s = clip ? fminf(m_raw, 1.0f) : m_raw;
-    const float m_n = has_mn ? s_mask[(2 * j + 1) * MPITCH + bin] : 1.0f - m_s;
+    // the second row is loaded whether or not it was filled (a select, not a branch, keeps the
+    // frames of a tile in one basic block for the scheduler)
+    const float m_n_row = s_mask[(2 * j + 1) * MPITCH + bin];
+    const float m_n = has_mn ? m_n_row : 1.0f - m_s;
     const float2 msn = make_float2(m_s, m_n);
     const float2 mss = make_float2(m_s, m_s), mnn = make_float2(m_n, m_n);
     sm2 = f2add(sm2, msn);
