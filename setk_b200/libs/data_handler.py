@@ -238,6 +238,36 @@ class SpectrogramReader(WaveReader):
         return self.stft(self.read(key))
 
 
+def _read_compressed_matrix(fd, token):
+    """
+    Kaldi CompressedMatrix (kaldi_io.py:248-318): global header {min, range, rows, cols};
+    CM  = per-column header of four uint16 percentiles + one uint8 per element (column major),
+    CM2 = uint16 per element, CM3 = uint8 per element (row major).  Same float32 arithmetic
+    as the reference's uncompress().
+    """
+    min_val, prange, num_rows, num_cols = struct.unpack("<ffii", fd.read(16))
+    if token == "CM":
+        raw = fd.read(num_cols * (8 + num_rows))
+        if len(raw) != num_cols * (8 + num_rows):
+            raise RuntimeError("truncated compressed Kaldi matrix")
+        pch = np.frombuffer(raw[:8 * num_cols], dtype="<u2").astype(np.float32)
+        pch = np.transpose(pch.reshape(num_cols, 4))
+        pch = pch * prange / 65535.0 + min_val
+        u8 = np.frombuffer(raw[8 * num_cols:], dtype=np.uint8).astype(np.float32)
+        u8 = np.transpose(u8.reshape(num_cols, num_rows))
+        return np.where(
+            u8 <= 64, u8 * (pch[1] - pch[0]) / 64.0 + pch[0],
+            np.where(u8 >= 193, (u8 - 192) * (pch[3] - pch[2]) / 63.0 + pch[2],
+                     (u8 - 64) * (pch[2] - pch[1]) / 128.0 + pch[1]))
+    if token == "CM2":
+        seq = np.frombuffer(fd.read(2 * num_rows * num_cols), dtype="<u2").astype(np.float32)
+        inc = float(prange / 65535.0)
+    else:
+        seq = np.frombuffer(fd.read(num_rows * num_cols), dtype=np.uint8).astype(np.float32)
+        inc = float(prange / 255.0)
+    return min_val + seq.reshape(num_rows, num_cols) * inc
+
+
 def read_kaldi_matrix(fd):
     """
     One uncompressed Kaldi float/double matrix or vector from a binary stream
@@ -252,8 +282,8 @@ def read_kaldi_matrix(fd):
             break
         token += ch
     token = token.decode()
-    if token.startswith("CM"):
-        raise NotImplementedError("compressed Kaldi matrices are not supported")
+    if token in ("CM", "CM2", "CM3"):
+        return _read_compressed_matrix(fd, token)
     if token not in ("FM", "DM", "FV", "DV"):
         raise RuntimeError(f"Unknown Kaldi object token: {token}")
     dtype = np.dtype("<f4" if token[0] == "F" else "<f8")

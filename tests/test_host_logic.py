@@ -368,6 +368,17 @@ def test_archive_writer_and_spatial_cli(tmp_path, emu, emu_library_path):
     ref = sp.directional_feats(obs, sv.T, df_pair=[(0, 2)])      # phase differences: sign/phase invariant
     feats = ScriptReader(str(scp))["utt1"]
     assert feats.shape == ref.shape and np.max(np.abs(feats - ref)) <= 2e-4
+    # ---- SRP for a circular array: mean of the diagonal pairs' GCC-PHAT ----
+    script = os.path.join(ROOT, "scripts", "sptk", "compute_circular_srp.py")
+    base = [sys.executable, "-c", runner, script, "--frame-len", "128", "--frame-hop", "64", "--center", "true"]
+    ark, scp = tmp_path / "csrp.ark", tmp_path / "csrp.scp"
+    subprocess.run(base + ["--n", "3", "--d", "0.08", "--diag-pair", "0,2;1,2", "--num-doas", "17",
+                           "--scp", str(scp), str(tmp_path / "wav.scp"), str(ark)],
+                   check=True, env=env, capture_output=True)
+    ref = np.average(np.stack([sp.gcc_phat_diag(S[i], S[j], min(i, j) * np.pi * 2 / 3, 0.08, num_bins=F,
+                                                sr=16000, num_doas=17) for i, j in ((0, 2), (1, 2))]), axis=0)
+    feats = ScriptReader(str(scp))["utt1"]
+    assert feats.shape == ref.shape and np.max(np.abs(feats - ref)) <= 1e-5
     utils.set_default_device(None)
 
 
@@ -472,6 +483,53 @@ def test_kaldi_matrix_reader(tmp_path):
     (tmp_path / "m.scp").write_text(f"utt1 {path}:{off}\n")
     rd = ScriptReader(str(tmp_path / "m.scp"))
     assert "utt1" in rd and np.array_equal(rd["utt1"], mat)
+
+
+def test_kaldi_compressed_matrix_reader(tmp_path):
+    """CM / CM2 / CM3 archives (kaldi_io.py:248-318): hand-built bytes, and the reference's own reader
+    on the same bytes when the reference tree is present."""
+    import io
+    import struct
+    from setk_b200.libs.data_handler import ScriptReader, read_kaldi_matrix
+    rng = np.random.default_rng(5)
+    rows, cols = 7, 5
+    blobs = {}
+    pch = np.sort(rng.integers(0, 65535, size=(cols, 4)), axis=1).astype("<u2")
+    u8 = rng.integers(0, 256, size=(cols, rows)).astype(np.uint8)
+    u8[0, :3] = (64, 65, 193)                                    # the three segments' edges
+    blobs["CM"] = (b"\0BCM " + struct.pack("<ffii", -3.0, 9.5, rows, cols) + pch.tobytes() + u8.tobytes())
+    u16 = rng.integers(0, 65536, size=(rows, cols)).astype("<u2")
+    blobs["CM2"] = b"\0BCM2 " + struct.pack("<ffii", 0.25, 4.0, rows, cols) + u16.tobytes()
+    u8b = rng.integers(0, 256, size=(rows, cols)).astype(np.uint8)
+    blobs["CM3"] = b"\0BCM3 " + struct.pack("<ffii", -1.0, 2.0, rows, cols) + u8b.tobytes()
+    # expected values, straight from Kaldi's definition
+    p = pch.astype(np.float32).T * np.float32(9.5) / 65535.0 + np.float32(-3.0)
+    v = u8.astype(np.float32).T
+    exp_cm = np.where(v <= 64, v * (p[1] - p[0]) / 64.0 + p[0],
+                      np.where(v >= 193, (v - 192) * (p[3] - p[2]) / 63.0 + p[2], (v - 64) * (p[2] - p[1]) / 128.0 + p[1]))
+    expect = {"CM": exp_cm, "CM2": 0.25 + u16.astype(np.float32) * float(4.0 / 65535.0),
+              "CM3": -1.0 + u8b.astype(np.float32) * float(2.0 / 255.0)}
+    ref_io = None
+    try:
+        from oracle import ref_shim
+        if ref_shim.reference_available():
+            ref_shim.load_reference()
+            import importlib
+            ref_io = importlib.import_module("libs.kaldi_io")
+    except Exception:
+        ref_io = None
+    with open(tmp_path / "c.ark", "wb") as f, open(tmp_path / "c.scp", "w") as scp:
+        for key, blob in blobs.items():
+            f.write(key.encode() + b" ")
+            scp.write(f"{key} {tmp_path / 'c.ark'}:{f.tell()}\n")
+            f.write(blob)
+    rd = ScriptReader(str(tmp_path / "c.scp"))
+    for key, blob in blobs.items():
+        got = read_kaldi_matrix(io.BytesIO(blob))
+        assert got.shape == (rows, cols) and np.allclose(got, expect[key], rtol=1e-6, atol=1e-6), key
+        assert np.array_equal(rd[key], got)
+        if ref_io is not None:
+            assert np.array_equal(ref_io.read_float_mat_vec(io.BufferedReader(io.BytesIO(blob)), direct_access=True), got), key
 
 
 def test_config3_fixture_cgmm_mask_gev(emu):
