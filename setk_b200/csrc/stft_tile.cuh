@@ -168,7 +168,7 @@ __device__ __forceinline__ void stage_tile_scalar(const TileSmem<C, TT>& sm, int
 // Forward FFT of every (frame, channel) of the tile by warps 0..NW-1, reading
 // audio[buf].  All threads of those warps must call it; hop must be even.
 // amax accumulates max |sample| of everything the tile reads.
-template <int C, int TT, bool TAB = false, int NW = 8>
+template <int C, int TT, bool TAB = false, int NW = 8, bool FULL = false>
 __device__ __forceinline__ void fft_tile(const TileSmem<C, TT>& sm, int buf, int nt, int hop,
                                          float2 w1, float& amax, const float2* twtab = nullptr) {
   constexpr int JOBS = TT * C;
@@ -184,7 +184,7 @@ __device__ __forceinline__ void fft_tile(const TileSmem<C, TT>& sm, int buf, int
       float2 v[16];
       const float* src = sm.abuf(buf) + ch * sm.Lp + fr * hop + 2 * lane16;
       const float* wsrc = sm.win + 2 * lane16;
-      if (fr < nt) {                            // ONE branch per job (a dead frame only in a last tile)
+      if (FULL || fr < nt) {                    // ONE branch per job (a dead frame only in a last tile)
 #pragma unroll
         for (int m1 = 0; m1 < 16; ++m1) {
           const float2 s = *reinterpret_cast<const float2*>(src + 32 * m1);

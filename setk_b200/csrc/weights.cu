@@ -94,8 +94,13 @@ __device__ inline bool all_finite(const CVec<C>& v) {
   return ok;
 }
 
+// resident CTAs of 128 threads per SM the register allocation must allow (2 -> 255 registers)
+#ifndef SETK_W_MINBLOCKS
+#define SETK_W_MINBLOCKS 2
+#endif
+
 template <int C>
-__global__ void __launch_bounds__(128) weights_kernel(WeightsArgs a) {
+__global__ void __launch_bounds__(128, SETK_W_MINBLOCKS) weights_kernel(WeightsArgs a) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)a.B * a.F) return;
   int b = (int)(idx / a.F);
