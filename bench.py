@@ -189,6 +189,9 @@ def gpu_arm(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # stdout carries ONE JSON line: keep NCCL's "NCCL version ..." banner off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     # CPU baseline first (rank 0, N=1 only): before the GPU gets busy
