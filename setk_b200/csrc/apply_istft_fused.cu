@@ -34,6 +34,7 @@
 // are recomputed as a halo tile.
 // Algorithmic bytes per utterance: 4*C*N (audio) + 8*F*C (w) + 4*n_out (wave)
 // (+ 4*T*F with a post-mask).
+#include <type_traits>
 #include "common.cuh"
 #include "stft_tile.cuh"
 
@@ -53,6 +54,14 @@ struct ApplyIstftArgs {
   int c0, c_total;      // this launch handles channels [c0, c0 + C) of c_total
   int accumulate;       // != 0: wave += this block's contribution (iSTFT is linear)
 };
+
+// a separate forward-FFT instantiation for full tiles (no dead-frame test): 2 % faster, but ptxas
+// schedules the two instantiations differently enough that an utterance's samples then depend
+// (in the last bit) on where the batch cut its tiles -- off, so the output stays bit-identical
+// across batch compositions (tests/test_gpu_fullsize.py)
+#ifndef SETK_AI_FULLFFT
+#define SETK_AI_FULLFFT 0
+#endif
 
 constexpr int kApplyThreads = 320;
 constexpr int kWPitch = 260;          // float2 pitch of the per-channel weight rows
@@ -312,6 +321,10 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
       }
       // ---- phase A: forward FFT of this tile || inverse FFT of the previous one ----
       if (warp < 8) {
+#if SETK_AI_FULLFFT
+        if (nt == TT) fft_tile<C, TT, false, 8, true>(sm, buf, nt, hop, w1, amax_unused);
+        else
+#endif
         fft_tile<C, TT>(sm, buf, nt, hop, w1, amax_unused);
       } else if (prev_nt > 0) {
         ifft_tile(prev_nt);
@@ -329,7 +342,7 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
 #pragma unroll
         for (int c = 0; c < C; ++c) { wk[c] = s_w[c * kWPitch + k]; wm[c] = s_w[c * kWPitch + km]; }
         // one (pair, frame) item; a full tile is two straight-line items per thread (frames g, g + 2)
-        auto item = [&](int j) {
+        auto item = [&](int j, auto pm_tag) {      // pm_tag: post-mask or not, decided per tile, not per item
           float2 yk = make_float2(0.f, 0.f), ym = make_float2(0.f, 0.f);
 #pragma unroll
           for (int c = 0; c < C; ++c) {
@@ -340,7 +353,7 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
             yk = cmad_conjw(wk[c], xk, yk);                    // += conj(w) x: two packed instructions
             ym = cmad_conjw(wm[c], xm, ym);
           }
-          if (a.post_mask) {
+          if constexpr (decltype(pm_tag)::value) {
             const float* pm = a.post_mask + ((long long)b * a.T + (t0 + j)) * F;
             const float mk = pm[k], mm = pm[km];
             yk = f2mul(yk, make_float2(mk, mk)); ym = f2mul(ym, make_float2(mm, mm));
@@ -362,11 +375,13 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
             }
           }
         };
-        if (nt == TT) {
-          item(g);
-          item(g + 2);
+        if (nt == TT && !a.post_mask) {
+          item(g, std::false_type{});
+          item(g + 2, std::false_type{});
+        } else if (a.post_mask) {
+          for (int j = g; j < nt; j += 2) item(j, std::true_type{});
         } else {
-          for (int j = g; j < nt; j += 2) item(j);
+          for (int j = g; j < nt; j += 2) item(j, std::false_type{});
         }
       }
       // ---- phase B: flush of the previous tile (its frames were made in phase A) ----
