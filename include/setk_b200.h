@@ -263,6 +263,19 @@ int setk_cgmm_stft(const void* stft, int32_t B, int32_t C, int32_t F, int32_t T,
 int setk_wpe_stft(const void* stft, int32_t B, int32_t C, int32_t F, int32_t T, int32_t taps, int32_t delay,
                   int32_t context, int32_t num_iters, void* out, uint32_t* status, void* stream);
 
+/* One WPE step with a caller-supplied variance: the dereverberation stage of facted_wpd
+ * (libs/wpe.py:113-177; wpe_step 58-77 with lambda from the previous WPD output, 150-153).
+ *   stft        c64 [B][C][F][T]
+ *   lambda_enh  c64 [B][F][T] or NULL: lambda = max(|lambda_enh|^2, eps32); NULL: compute_lambda(stft, context)
+ *               (then the call equals setk_wpe_stft with num_iters = 1)
+ *   out         c64 [B][C][F][T]   dereverberated observations
+ *   inv_lambda  f32 [B][T][F] or NULL: 1 / lambda, the frame weights of Rd (wpe.py:165) in the layout
+ *               setk_cov takes as a mask
+ *   status      u32 [B] or NULL (SETK_ST_SINGULAR like setk_wpe_stft) */
+int setk_wpe_step(const void* stft, const void* lambda_enh, int32_t B, int32_t C, int32_t F, int32_t T,
+                  int32_t taps, int32_t delay, int32_t context, void* out, float* inv_lambda,
+                  uint32_t* status, void* stream);
+
 /* ---- spatial features on explicit STFTs: scripts/sptk/libs/spatial.py ---- */
 
 /* ipd(si, sj, cos, sin): spatial.py:163-181.  si, sj c64 [rows][F] (rows = B*T);

@@ -432,11 +432,39 @@ def fixed_cases(ref, report):
     np.savez_compressed(os.path.join(GOLD, "ref_fixed_bf.npz"), **out)
 
 
+def wpd_cases(ref, report):
+    """
+    libs/wpe.py facted_wpd() run by the REFERENCE (complex64 observations, as apply_wpd.py feeds
+    it) on small mixtures: the final 2-class mask and the enhanced spectrum.
+    """
+    from oracle import wpe_oracle as wo
+    rng = np.random.default_rng(20240929)
+    out = {}
+    for name, C, N, fl, hop, taps, delay, ctx, ci, wi in (("c3", 3, 6000, 256, 64, 3, 2, 1, 4, 2),
+                                                        ("c4", 4, 9000, 256, 128, 4, 3, 1, 3, 3)):
+        mix, _, _ = synth_case(rng, C, N)
+        kw = dict(frame_len=fl, frame_hop=hop, window="hann", center=True, transpose=True)
+        obs = ref_multichannel_stft(ref, mix, round_power_of_two=True, **kw)        # c64 C x T x F
+        tf_mask, enh = ref.wpe.facted_wpd(obs, cgmm_iters=ci, wpd_iters=wi, taps=taps, delay=delay,
+                                          context=ctx)
+        out[name + "/mix"] = mix
+        out[name + "/cfg"] = np.array([fl, hop, taps, delay, ctx, ci, wi], dtype=np.int64)
+        out[name + "/tf_mask"] = tf_mask.astype(np.float32)                          # T x F x 2
+        out[name + "/enh"] = enh.astype(np.complex64)                                # T x F
+        for tag, dt in (("c64", np.complex64), ("c128", np.complex128)):
+            m, e = wo.facted_wpd(obs, cgmm_iters=ci, wpd_iters=wi, taps=taps, delay=delay, context=ctx, dtype=dt)
+            ea, _ = bo.align_phase(e.T, enh.T)                                       # per bin
+            report[f"wpd/{name}/oracle_{tag}_enh_vs_ref_relinf"] = bo.rel_inf(ea, enh.T)
+            report[f"wpd/{name}/oracle_{tag}_mask_vs_ref_maxabs"] = float(np.max(np.abs(m - tf_mask)))
+    np.savez_compressed(os.path.join(GOLD, "ref_wpd.npz"), **out)
+
+
 def main():
-    if len(sys.argv) > 1 and sys.argv[1] in ("cgmm", "wpe", "spatial", "fixed"):   # add one fixture only
+    if len(sys.argv) > 1 and sys.argv[1] in ("cgmm", "wpe", "spatial", "fixed", "wpd"):   # add one fixture only
         ref = ref_shim.load_reference()
         report = {}
-        {"cgmm": cgmm_cases, "wpe": wpe_cases, "spatial": spatial_cases, "fixed": fixed_cases}[sys.argv[1]](ref, report)
+        {"cgmm": cgmm_cases, "wpe": wpe_cases, "spatial": spatial_cases, "fixed": fixed_cases,
+         "wpd": wpd_cases}[sys.argv[1]](ref, report)
         path = os.path.join(GOLD, "PINNING.json")
         with open(path) as f:
             full = json.load(f)
@@ -462,6 +490,7 @@ def main():
     wpe_cases(ref, report)
     spatial_cases(ref, report)
     fixed_cases(ref, report)
+    wpd_cases(ref, report)
     with open(os.path.join(GOLD, "PINNING.json"), "w") as f:
         json.dump(report, f, indent=1, sort_keys=True)
     print(json.dumps(report, indent=1, sort_keys=True))

@@ -67,3 +67,46 @@ def wpe(reverb, taps=10, delay=3, context=1, num_iters=3, dtype=np.complex128, r
         G = np.linalg.solve(R, r)
         z = x - np.einsum("...na,...nb->...ab", G.conj(), yt)
     return (z, G) if return_filters else z
+
+
+def wpe_step(x, yt, lam):
+    """wpe.py:58-77 for a given variance lam (F x T): one weighted least-squares prediction step."""
+    yn = yt / lam[:, None, :]
+    R = np.einsum("...mt,...nt->...mn", yn, yt.conj())
+    r = np.einsum("...mt,...nt->...mn", yn, x.conj())
+    G = np.linalg.solve(R, r)
+    return x - np.einsum("...na,...nb->...ab", G.conj(), yt)
+
+
+def facted_wpd(obs, cgmm_iters=10, wpd_iters=3, taps=10, delay=3, context=1, update_alpha=False,
+               dtype=np.complex128):
+    """
+    wpe.py:113-177 (factored WPD: joint dereverberation and denoising).  obs N x T x F complex.
+    Per iteration: one WPE step (variance = compute_lambda of the observations, then |previous
+    output|^2, floored at EPSILON), a 2-class CGMM on the dereverberated channels, Rd = sum_t
+    der der^H / lambda / T, Rs = compute_covar(der, mask), sv = principal eigenvector of Rs,
+    w = Rd^-1 sv / (sv^H Rd^-1 sv), output = w^H der.
+    Returns (tf_mask T x F x 2, wpd_enh T x F) like the reference.  `dtype` = the precision of the
+    dereverberation stage (np.complex64 follows the reference's dtype flow for complex64 input).
+    """
+    from oracle import beamformer_oracle as bo
+    from oracle import cgmm_oracle as co
+    x = np.einsum("ntf->fnt", np.asarray(obs)).astype(dtype)             # F x N x T
+    yt = tap_matrix(x, taps, delay)
+    enh, gamma = None, None
+    for i in range(wpd_iters):
+        lam = frame_variance(x, ctx=context) if i == 0 else np.abs(enh) ** 2
+        lam = np.maximum(lam, EPSILON)
+        der = wpe_step(x, yt, lam)                                        # F x N x T
+        der_r = np.einsum("fnt->nft", der)
+        _, hist = co.cgmm_masks(der_r, 2, cgmm_iters, update_alpha=update_alpha, return_all=True,
+                                start_dtype=np.complex64 if dtype == np.complex64 else np.complex128)
+        gamma = hist[-1]                                                  # K x F x T
+        Rd = np.einsum("...nt,...mt->...nm", der / lam[:, None], der.conj()) / der.shape[-1]
+        Rs = bo.compute_covar(der_r, gamma[0].T)
+        sv = bo.solve_pevd(Rs)
+        Rd_inv_sv = np.linalg.solve(Rd, sv[..., None])[..., 0]
+        den = np.einsum("...d,...d->...", sv.conj(), Rd_inv_sv)
+        weight = Rd_inv_sv / den[:, None]
+        enh = np.einsum("...n,...nt->...t", weight.conj(), der)           # F x T
+    return gamma.T, enh.T

@@ -84,6 +84,8 @@ _PROTOTYPES = {
                                c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "setk_wpe_stft": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                               c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "setk_wpe_step": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                              c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "setk_ipd": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "setk_directional_feats": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32,
                                        c_int32, c_int32, c_int32, c_void_p, c_void_p]),

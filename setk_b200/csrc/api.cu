@@ -53,7 +53,8 @@ cudaError_t run_cgmm(const CgCtx*, const float2*, int, double*, const int*, int,
 cudaError_t run_bcft_to_spill(const float2*, int, int, int, int, int, float2*, void*);
 bool wpe_supported(int, int, int, int);
 size_t wpe_workspace_bytes(int, int, int, int);
-cudaError_t run_wpe(const float2*, int, int, int, int, int, int, int, int, int, double*, float2*, unsigned*, void*);
+cudaError_t run_wpe(const float2*, int, int, int, int, int, int, int, int, int, double*, float2*, unsigned*,
+                    const float2*, float*, void*);
 cudaError_t run_apply_spill(setk_plan*, const float2*, const void*, int, const float*, int, int, float2*, void*);
 cudaError_t run_istft_strided(const setk_plan*, const float2*, long long, long long, long long, int, int, int,
                               const int*, float*, float*, unsigned*, void*);
@@ -506,32 +507,47 @@ int setk_cgmm_stft(const void* stft, int32_t B, int32_t C, int32_t F, int32_t T,
   return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_cgmm_stft");
 }
 
-int setk_wpe_stft(const void* stft, int32_t B, int32_t C, int32_t F, int32_t T, int32_t taps, int32_t delay,
-                  int32_t context, int32_t num_iters, void* out, uint32_t* status, void* stream) {
-  if (!stft || !out) return fail(SETK_EINVAL, "setk_wpe_stft: null buffer");
+static int wpe_entry(const char* who, const void* stft, const void* lambda_enh, int32_t B, int32_t C, int32_t F,
+                     int32_t T, int32_t taps, int32_t delay, int32_t context, int32_t num_iters, void* out,
+                     float* inv_lambda, uint32_t* status, void* stream) {
+  if (!stft || !out) return fail(SETK_EINVAL, "%s: null buffer", who);
   if (B < 1 || F < 1 || T < 1 || C < 1 || C > SETK_MAX_CHANNELS || (long long)B * F > 2000000000LL)
-    return fail(SETK_ESHAPE, "setk_wpe_stft: bad shape B=%d C=%d F=%d T=%d", B, C, F, T);
+    return fail(SETK_ESHAPE, "%s: bad shape B=%d C=%d F=%d T=%d", who, B, C, F, T);
   if (taps < 1 || delay < 0 || context < 0 || num_iters < 1)
-    return fail(SETK_EINVAL, "setk_wpe_stft: taps=%d delay=%d context=%d num_iters=%d", taps, delay, context,
+    return fail(SETK_EINVAL, "%s: taps=%d delay=%d context=%d num_iters=%d", who, taps, delay, context,
                 num_iters);
   if (!wpe_supported(C, T, taps, delay))
-    return fail(SETK_EUNSUPPORTED, "setk_wpe_stft: %d channels x %d taps over %d frames exceeds the kernels' "
-                "shared-memory budget", C, taps, T);
+    return fail(SETK_EUNSUPPORTED, "%s: %d channels x %d taps over %d frames exceeds the kernels' "
+                "shared-memory budget", who, C, taps, T);
   const int P = (F + 7) & ~7;
   const size_t x_bytes = sizeof(float2) * (size_t)B * T * C * P;
   const size_t w_bytes = wpe_workspace_bytes(B, C, F, taps);
   char* ws = nullptr;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&ws), x_bytes + w_bytes + 256, st);
-  if (e != cudaSuccess) return cuda_fail(e, "setk_wpe_stft(workspace)");
+  if (e != cudaSuccess) return cuda_fail(e, who);
   float2* X = reinterpret_cast<float2*>(ws);
   double* dw = reinterpret_cast<double*>(ws + ((x_bytes + 255) / 256) * 256);
   e = run_bcft_to_spill(static_cast<const float2*>(stft), B, C, F, T, P, X, stream);
   if (e == cudaSuccess)
-    e = run_wpe(X, P, B, C, F, T, taps, delay, context, num_iters, dw, static_cast<float2*>(out), status, stream);
+    e = run_wpe(X, P, B, C, F, T, taps, delay, context, num_iters, dw, static_cast<float2*>(out), status,
+                static_cast<const float2*>(lambda_enh), inv_lambda, stream);
   cudaError_t ef = cudaFreeAsync(ws, st);
   if (e == cudaSuccess) e = ef;
-  return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_wpe_stft");
+  return e == cudaSuccess ? SETK_OK : cuda_fail(e, who);
+}
+
+int setk_wpe_stft(const void* stft, int32_t B, int32_t C, int32_t F, int32_t T, int32_t taps, int32_t delay,
+                  int32_t context, int32_t num_iters, void* out, uint32_t* status, void* stream) {
+  return wpe_entry("setk_wpe_stft", stft, nullptr, B, C, F, T, taps, delay, context, num_iters, out, nullptr,
+                   status, stream);
+}
+
+int setk_wpe_step(const void* stft, const void* lambda_enh, int32_t B, int32_t C, int32_t F, int32_t T,
+                  int32_t taps, int32_t delay, int32_t context, void* out, float* inv_lambda,
+                  uint32_t* status, void* stream) {
+  return wpe_entry("setk_wpe_step", stft, lambda_enh, B, C, F, T, taps, delay, context, 1, out, inv_lambda,
+                   status, stream);
 }
 
 int setk_float_to_pcm16(const float* wave, int64_t n, int16_t* pcm, void* stream) {

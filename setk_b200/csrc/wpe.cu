@@ -33,6 +33,9 @@ struct WpeArgs {
   double* Raug;                  // [B*F][NK][NK + C] complex
   float2* out;                   // filter: [B][C][F][T]
   unsigned* status;              // [B]
+  const float2* lam_src;         // corr, first pass only: lambda = max(|e|^2, eps) of this [B][F][T]
+                                 // spectrum (facted_wpd, wpe.py:150-153) instead of compute_lambda
+  float* linv_out;               // corr: 1 / lambda -> [B][T][F] f32 (weights of Rd, wpe.py:165), or null
 };
 
 // shared memory: xs [C][Tp] cd | linv [T] | L [T] | Gs [NK][C] cd
@@ -97,11 +100,19 @@ __global__ void __launch_bounds__(512) wpe_corr_kernel(WpeArgs a) {
   }
   __syncthreads();
   for (int t = tid; t < a.T; t += blockDim.x) {
-    double s = 0.0;
-    int cnt = 0;
-    for (int c = -a.ctx; c <= a.ctx; ++c)
-      if (t + c >= 0 && t + c < a.T) { s += L[t + c]; ++cnt; }
-    linv[t] = 1.0 / fmax(s / (double)cnt, SETK_EPS32_D);
+    double lam;
+    if (a.lam_src && !a.use_filter) {
+      const float2 e = a.lam_src[((long long)b * a.F + f) * a.T + t];
+      lam = (double)e.x * (double)e.x + (double)e.y * (double)e.y;
+    } else {
+      double s = 0.0;
+      int cnt = 0;
+      for (int c = -a.ctx; c <= a.ctx; ++c)
+        if (t + c >= 0 && t + c < a.T) { s += L[t + c]; ++cnt; }
+      lam = s / (double)cnt;
+    }
+    linv[t] = 1.0 / fmax(lam, SETK_EPS32_D);
+    if (a.linv_out) a.linv_out[((long long)b * a.T + t) * a.F + f] = (float)linv[t];
   }
   __syncthreads();
   // ---- [R | r]: 4 x 4 tiles (I, J >= I) of the NK x (NK + C) augmented matrix ----
@@ -251,8 +262,10 @@ size_t wpe_workspace_bytes(int B, int C, int F, int taps) {
 
 // reverb -> dereverberated STFT, both [B][C][F][T] c64; X is the bin-major copy of reverb
 cudaError_t run_wpe(const float2* X, int P, int B, int C, int F, int T, int taps, int delay, int ctx,
-                    int num_iters, double* ws, float2* out, unsigned* status, void* stream) {
+                    int num_iters, double* ws, float2* out, unsigned* status, const float2* lam_src,
+                    float* linv_out, void* stream) {
   WpeArgs a;
+  a.lam_src = lam_src; a.linv_out = linv_out;
   a.X = X; a.P = P; a.B = B; a.C = C; a.F = F; a.T = T;
   a.taps = taps; a.delay = delay; a.ctx = ctx;
   a.NK = C * taps;

@@ -301,6 +301,32 @@ def wpe_from_stft(stft, taps=10, delay=3, context=1, num_iters=3):
     return out, status
 
 
+def wpe_step(stft, lambda_enh=None, taps=10, delay=3, context=1, want_inv_lambda=True):
+    """
+    One WPE step with the variance of facted_wpd (libs/wpe.py:147-155): stft (B,C,F,T) complex64,
+    lambda_enh (B,F,T) complex64 or None (first iteration: compute_lambda of the observations).
+    Returns (dereverberated (B,C,F,T) complex64, 1/lambda (B,T,F) float32 or None, status (B,) int32).
+    """
+    stft = stft.contiguous()
+    if stft.dtype != torch.complex64:
+        stft = stft.to(torch.complex64)
+    if stft.dim() != 4:
+        raise ValueError(f"stft must be (B, C, F, T), got {tuple(stft.shape)}")
+    B, C, F, T = stft.shape
+    if lambda_enh is not None:
+        lambda_enh = torch.as_tensor(lambda_enh, device=stft.device).to(torch.complex64).contiguous()
+        if tuple(lambda_enh.shape) != (B, F, T):
+            raise ValueError(f"lambda_enh must be {(B, F, T)}, got {tuple(lambda_enh.shape)}")
+    out = torch.empty_like(stft)
+    inv = torch.empty((B, T, F), dtype=torch.float32, device=stft.device) if want_inv_lambda else None
+    status = torch.zeros((B,), dtype=torch.int32, device=stft.device)
+    with _ctx(stft.device):
+        _lib.check(_lib.library().setk_wpe_step(
+            _lib.ptr(stft), _lib.ptr(lambda_enh), B, C, F, T, int(taps), int(delay), int(context),
+            _lib.ptr(out), _lib.ptr(inv), _lib.ptr(status), _lib.current_stream(stft.device)))
+    return out, inv, status
+
+
 def covariance(stft, mask, clip_mask=False, mask_ft=False):
     """compute_covar batched: stft (B,C,F,T) c64, mask (B,T,F) -> (B,F,C,C) c64."""
     stft = stft.contiguous()

@@ -634,3 +634,31 @@ def check_fixed_beamformers(device):
     with pytest.raises(RuntimeError):
         BF.beam_pattern(g["lin_ds/weight"][:, :3], g["pattern/sv"])
     return worst
+
+
+def check_wpd_fixture(device, name, enh_tol=1e-4, mask_mean_tol=1e-5):
+    """
+    libs.wpe.facted_wpd (setk_wpe_step -> setk_cgmm_stft -> setk_cov x2 -> setk_weights -> setk_apply)
+    against the REFERENCE's facted_wpd output (tests/golden/ref_wpd.npz).  The enhanced spectrum is
+    compared after per-bin phase alignment (the principal eigenvector's phase is LAPACK's in the
+    reference, SURVEY.md finding 4).  Observed on the CPU execution model: 7e-7 on the spectrum,
+    mask differences 1e-7 mean / 3e-5 max; the bounds leave room for the CGMM's ill-conditioned
+    cells (an eigenvalue at its floor) without letting a wrong stage through.
+    """
+    import os
+    from setk_b200.libs import utils
+    from setk_b200.libs.wpe import facted_wpd
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_wpd.npz"))
+    fl, hop, taps, delay, ctx, ci, wi = (int(v) for v in g[name + "/cfg"])
+    obs = oracle_stft(g[name + "/mix"], fl, hop, True, "hann", dtype=np.complex64)      # C x F x T
+    x = torch.from_numpy(np.ascontiguousarray(np.transpose(obs, (0, 2, 1)))).to(device)  # C x T x F
+    tf_mask, enh = facted_wpd(x, cgmm_iters=ci, wpd_iters=wi, taps=taps, delay=delay, context=ctx)
+    tf_mask, enh = tf_mask.cpu().numpy(), enh.cpu().numpy()
+    ref_mask, ref_enh = g[name + "/tf_mask"], g[name + "/enh"]
+    assert tf_mask.shape == ref_mask.shape and enh.shape == ref_enh.shape
+    ea, _ = bo.align_phase(enh.T, ref_enh.T)                                              # per bin
+    err = bo.rel_inf(ea, ref_enh.T)
+    md = np.abs(tf_mask - ref_mask)
+    assert err <= enh_tol, (name, err)
+    assert float(md.mean()) <= mask_mean_tol and float((md > 1e-3).mean()) <= 0.01, (name, md.mean(), md.max())
+    return err, float(md.mean()), float(md.max())

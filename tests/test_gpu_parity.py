@@ -360,3 +360,15 @@ def test_spatial_libs_mirror_numpy(cuda):
 def test_geometry_based_beamformers(cuda):
     """DS / SD / fixed beamformers (host weights, setk_apply on the observations) vs ref_fixed_bf.npz"""
     pc.check_fixed_beamformers(cuda)
+
+
+@pytest.mark.gpu
+def test_facted_wpd_reference_fixtures(cuda):
+    """libs/wpe.py facted_wpd() run by the reference (tests/golden/ref_wpd.npz)"""
+    from setk_b200.libs import utils
+    utils.set_default_device(cuda)
+    try:
+        for name in ("c3", "c4"):
+            pc.check_wpd_fixture(cuda, name)
+    finally:
+        utils.set_default_device(None)

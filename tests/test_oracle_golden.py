@@ -215,3 +215,21 @@ def test_spatial_oracle_pinned_to_reference():
             ref = g[name + "/" + k]
             assert v.shape == ref.shape and v.dtype == ref.dtype, (name, k, v.dtype, ref.dtype)
             assert np.array_equal(v, ref), (name, k, float(np.max(np.abs(v - ref))))
+
+
+def test_wpd_oracle_pinned_to_reference():
+    """libs/wpe.py facted_wpd() run by the reference on complex64 STFTs (ref_wpd.npz)."""
+    from oracle import stft_oracle as so
+    from oracle import wpe_oracle as wo
+    g = np.load(os.path.join(GOLD, "ref_wpd.npz"))
+    for name in ("c3", "c4"):
+        fl, hop, taps, delay, ctx, ci, wi = (int(v) for v in g[name + "/cfg"])
+        mix = g[name + "/mix"]
+        obs = np.stack([so.stft(mix[c], fl, hop, fl, window="hann", center=True, out_dtype=np.complex64)
+                        for c in range(mix.shape[0])])
+        x = np.ascontiguousarray(np.transpose(obs, (0, 2, 1)))                       # C x T x F
+        for dt in (np.complex64, np.complex128):
+            m, e = wo.facted_wpd(x, cgmm_iters=ci, wpd_iters=wi, taps=taps, delay=delay, context=ctx, dtype=dt)
+            ea, _ = bo.align_phase(e.T, g[name + "/enh"].T)
+            assert bo.rel_inf(ea, g[name + "/enh"].T) <= 5e-6, (name, dt)
+            assert np.max(np.abs(m - g[name + "/tf_mask"])) <= 2e-5, (name, dt)
