@@ -437,3 +437,110 @@ class ArchiveWriter(Writer):
         write_kaldi_matrix(self.ark_file, obj.astype(self.dtype))
         if self.scp_file is not None:
             self.scp_file.write(f"{key}\t{self.path_or_dir}:{offset:d}\n")
+
+
+# ------------------------------------------------- remaining table readers / writers ---
+def read_kaldi_archive(fd):
+    """(key, matrix | vector) for every entry of a binary Kaldi archive stream (kaldi_io.py:364-376)."""
+    while True:
+        token = bytearray()
+        while True:
+            ch = fd.read(1)
+            if ch in (b" ", b""):
+                break
+            token += ch
+        if not token:
+            return
+        yield token.decode().strip(), read_kaldi_matrix(fd)
+
+
+class ArchiveReader(object):
+    """Sequential reader of a Kaldi archive: a path, "-" (stdin) or "command |" (data_handler.py:311-323)."""
+
+    def __init__(self, ark_or_pipe):
+        self.ark_or_pipe = ark_or_pipe
+
+    def __iter__(self):
+        with _Source(self.ark_or_pipe, binary=True) as fd:
+            yield from read_kaldi_archive(fd)
+
+
+class DirReader(Reader):
+    """Every `<obj_dir>/*.<prefix>` file, keyed by its file name (data_handler.py:256-267)."""
+
+    def __init__(self, obj_dir, prefix):
+        from .utils import filekey
+        obj_dir = Path(obj_dir)
+        if not obj_dir.is_dir():
+            raise RuntimeError("DirReader expect directory as input")
+        super().__init__({filekey(f): f for f in glob.glob((obj_dir / f"*.{prefix}").as_posix())})
+
+
+class SegmentWaveReader(ScpReader):
+    """`segments` file (key wav-key begin end) over a wav.scp (data_handler.py:416-436)."""
+
+    def __init__(self, wav_scp, segments, sr=None, normalize=True):
+        super().__init__(segments, num_tokens=4,
+                         value_processor=lambda x: {"wav": x[0], "beg": float(x[1]), "end": float(x[2])})
+        self.wav_reader = WaveReader(wav_scp, sr=sr, normalize=normalize)
+
+    def _load(self, key):
+        info = self.index_dict[key]
+        return self.wav_reader.read(info["wav"], beg=int(info["beg"]), end=int(info["end"]))
+
+
+class PickleReader(ScpReader):
+    """key -> pickle.load(path) (data_handler.py:451-462)."""
+
+    def _load(self, key):
+        import pickle
+        with open(self.index_dict[key], "rb") as f:
+            return pickle.load(f)
+
+
+class MatReader(ScpReader):
+    """key -> scipy.io.loadmat(path)[name] (data_handler.py:465-480)."""
+
+    def __init__(self, mat_scp, key):
+        super().__init__(mat_scp)
+        self.key = key
+
+    def _load(self, key):
+        import scipy.io as sio
+        mat_dict = sio.loadmat(self.index_dict[key])
+        if self.key not in mat_dict:
+            raise KeyError(f"Could not find \'{self.key}\' in python dictionary")
+        return mat_dict[self.key]
+
+
+class BinaryReader(ScpReader):
+    """key -> numpy.fromfile(path, dtype), optionally of a fixed length (data_handler.py:538-561)."""
+
+    _TYPES = {"float32": np.float32, "float64": np.float64, "int32": np.int32, "int64": np.int64}
+
+    def __init__(self, bin_scp, length=None, data_type="float32"):
+        super().__init__(bin_scp)
+        if data_type not in self._TYPES:
+            raise RuntimeError(f"Unsupported data type: {data_type}")
+        self.fmt = self._TYPES[data_type]
+        self.length = length
+
+    def _load(self, key):
+        obj = np.fromfile(self.index_dict[key], dtype=self.fmt)
+        if self.length is not None and obj.size != self.length:
+            raise RuntimeError(f"Expect length {self.length:d}, but got {obj.size:d}")
+        return obj
+
+
+class MatWriter(Writer):
+    """<dump_dir>/<key>.mat with the array under "data" (data_handler.py:624-637)."""
+
+    def __init__(self, dump_dir, scp_path=None):
+        super().__init__(dump_dir, scp_path, is_dir=True)
+
+    def write(self, key, obj):
+        import scipy.io as sio
+        self.check_args(obj)
+        target = self.path_or_dir / f"{key}.mat"
+        sio.savemat(target, {"data": obj})
+        self._record(key, target)

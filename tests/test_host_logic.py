@@ -579,6 +579,42 @@ def test_kaldi_compressed_matrix_reader(tmp_path):
             assert np.array_equal(ref_io.read_float_mat_vec(io.BufferedReader(io.BytesIO(blob)), direct_access=True), got), key
 
 
+def test_remaining_table_readers(tmp_path):
+    """ArchiveReader (file / pipe), DirReader, SegmentWaveReader, BinaryReader, PickleReader, Mat* round trips."""
+    import pickle
+    from setk_b200.libs.data_handler import (ArchiveReader, ArchiveWriter, BinaryReader, DirReader, MatReader,
+                                             MatWriter, PickleReader, SegmentWaveReader)
+    a, v = np.arange(12, dtype=np.float32).reshape(3, 4), np.arange(5, dtype=np.float32)
+    with ArchiveWriter(str(tmp_path / "x.ark")) as w:
+        w.write("a", a)
+        w.write("v", v)
+    for spec in (str(tmp_path / "x.ark"), f"cat {tmp_path / 'x.ark'} |"):
+        got = dict(ArchiveReader(spec))
+        assert list(got) == ["a", "v"] and np.array_equal(got["a"], a) and np.array_equal(got["v"], v)
+    x = (np.arange(2 * 4000, dtype=np.float32).reshape(2, 4000) % 200 - 100) / 32768.0
+    _write_wav(str(tmp_path / "u1.wav"), x)
+    (tmp_path / "wav.scp").write_text(f"u1 {tmp_path / 'u1.wav'}\n")
+    (tmp_path / "segments").write_text("u1-a u1 100 1100\nu1-b u1 2000 2500\n")
+    seg = SegmentWaveReader(str(tmp_path / "wav.scp"), str(tmp_path / "segments"), sr=16000)
+    assert len(seg) == 2 and np.array_equal(seg["u1-a"], x[:, 100:1100]) and seg["u1-b"].shape == (2, 500)
+    d = DirReader(str(tmp_path), "wav")
+    assert list(d.index_keys) == ["u1"]
+    v.tofile(str(tmp_path / "v.bin"))
+    (tmp_path / "bin.scp").write_text(f"v {tmp_path / 'v.bin'}\n")
+    assert np.array_equal(BinaryReader(str(tmp_path / "bin.scp"), length=5)["v"], v)
+    with pytest.raises(RuntimeError):
+        BinaryReader(str(tmp_path / "bin.scp"), length=4)["v"]
+    with open(tmp_path / "o.pkl", "wb") as f:
+        pickle.dump({"k": 1}, f)
+    (tmp_path / "pkl.scp").write_text(f"o {tmp_path / 'o.pkl'}\n")
+    assert PickleReader(str(tmp_path / "pkl.scp"))["o"] == {"k": 1}
+    with MatWriter(str(tmp_path / "mats"), str(tmp_path / "mat.scp")) as w:
+        w.write("m", a)
+    assert np.array_equal(MatReader(str(tmp_path / "mat.scp"), "data")["m"], a)
+    with pytest.raises(KeyError):
+        MatReader(str(tmp_path / "mat.scp"), "nope")["m"]
+
+
 def test_config3_fixture_cgmm_mask_gev(emu):
     """config 3 (8 ch, 1024-pt, reference CGMM mask -> GEV) on the CPU execution model."""
     import parity_cases as pc
