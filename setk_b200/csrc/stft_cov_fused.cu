@@ -7,13 +7,14 @@
 // 87-103); C++ twin: ShortTimeFTComputer::Compute (include/stft.cc:28-66) +
 // EstimatePsd (include/beamformer.cc:91-120).
 //
-// Mapping (template <C, 512-point frames, TT frames per tile>), 288 threads:
+// Mapping (template <C, 512-point frames, TT frames per tile>), 320 threads at TT = 5 (even C)
+// or 288 at TT = 4, 96 registers, two CTAs per SM:
 //   grid = 2 x SMs persistent CTAs; the (utterance, tile) sequence of the batch is
 //   cut into equal runs (TileSched, stft_tile.cuh), so a CTA owns a run of frames
 //   of one to three consecutive utterances and there is no partial last wave.
 //   per tile of TT frames
-//     stage   (TT-1)*hop + n_fft samples x C channels -> smem, 16-byte loads;
-//             reflect padding / ragged ends resolved here; running max|x|
+//     stage   (TT-1)*hop + n_fft samples x C channels -> smem by TMA bulk copies one
+//             tile ahead; reflect padding / ragged ends element-wise; running max|x|
 //     FFT     one half-warp per (frame, channel): 512-point real FFT as a
 //             256-point complex FFT, 16 values per lane in registers, one
 //             conflict-free smem exchange (fft16.cuh); Z stays in smem
