@@ -55,14 +55,6 @@ struct ApplyIstftArgs {
   int accumulate;       // != 0: wave += this block's contribution (iSTFT is linear)
 };
 
-// a separate forward-FFT instantiation for full tiles (no dead-frame test): 2 % faster, but ptxas
-// schedules the two instantiations differently enough that an utterance's samples then depend
-// (in the last bit) on where the batch cut its tiles -- off, so the output stays bit-identical
-// across batch compositions (tests/test_gpu_fullsize.py)
-#ifndef SETK_AI_FULLFFT
-#define SETK_AI_FULLFFT 0
-#endif
-
 constexpr int kApplyThreads = 320;
 constexpr int kWPitch = 260;          // float2 pitch of the per-channel weight rows
 
@@ -321,10 +313,6 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
       }
       // ---- phase A: forward FFT of this tile || inverse FFT of the previous one ----
       if (warp < 8) {
-#if SETK_AI_FULLFFT
-        if (nt == TT) fft_tile<C, TT, false, 8, true>(sm, buf, nt, hop, w1, amax_unused);
-        else
-#endif
         fft_tile<C, TT>(sm, buf, nt, hop, w1, amax_unused);
       } else if (prev_nt > 0) {
         ifft_tile(prev_nt);

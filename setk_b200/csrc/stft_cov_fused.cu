@@ -262,10 +262,7 @@ __global__ void __maxnreg__(SETK_SC_REGS) stft_cov_kernel(StftCovArgs a) {
         mbar_wait(&sm.bar[buf], (par >> buf) & 1u);
         par ^= 1u << buf;
       }
-      if (warp < NW) {
-        if (nt == TT) fft_tile<C, TT, SETK_SC_TAB != 0, NW, true>(sm, buf, nt, hop, w1, amax, s_twtab);
-        else fft_tile<C, TT, SETK_SC_TAB != 0, NW, false>(sm, buf, nt, hop, w1, amax, s_twtab);
-      }
+      if (warp < NW) fft_tile<C, TT, SETK_SC_TAB != 0, NW>(sm, buf, nt, hop, w1, amax, s_twtab);
       async_cur = async_next;
       cp_async_wait_all();
       __syncthreads();

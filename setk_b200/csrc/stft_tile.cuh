@@ -168,7 +168,7 @@ __device__ __forceinline__ void stage_tile_scalar(const TileSmem<C, TT>& sm, int
 // Forward FFT of every (frame, channel) of the tile by warps 0..NW-1, reading
 // audio[buf].  All threads of those warps must call it; hop must be even.
 // amax accumulates max |sample| of everything the tile reads.
-template <int C, int TT, bool TAB = false, int NW = 8, bool FULL = false>
+template <int C, int TT, bool TAB = false, int NW = 8>
 __device__ __forceinline__ void fft_tile(const TileSmem<C, TT>& sm, int buf, int nt, int hop,
                                          float2 w1, float& amax, const float2* twtab = nullptr) {
   constexpr int JOBS = TT * C;
@@ -181,20 +181,19 @@ __device__ __forceinline__ void fft_tile(const TileSmem<C, TT>& sm, int buf, int
     const int job = r * (2 * NW) + warp * 2 + half;
     if (job - half < JOBS) {                    // warp-uniform
       const int fr = job / C, ch = job - fr * C;
+      // a dead frame (fr >= nt, only in an utterance's last tile) re-transforms the last live one:
+      // its spectrum is never read, max|x| sees nothing new, and every tile runs ONE straight-line
+      // path -- no zero-fill branch, no second instantiation whose rounding could differ
+      const int fr_src = imin(fr, nt - 1);
       float2 v[16];
-      const float* src = sm.abuf(buf) + ch * sm.Lp + fr * hop + 2 * lane16;
+      const float* src = sm.abuf(buf) + ch * sm.Lp + fr_src * hop + 2 * lane16;
       const float* wsrc = sm.win + 2 * lane16;
-      if (FULL || fr < nt) {                    // ONE branch per job (a dead frame only in a last tile)
 #pragma unroll
-        for (int m1 = 0; m1 < 16; ++m1) {
-          const float2 s = *reinterpret_cast<const float2*>(src + 32 * m1);
-          const float2 w = *reinterpret_cast<const float2*>(wsrc + 32 * m1);
-          amax = fmaxf(amax, fmaxf(fabsf(s.x), fabsf(s.y)));
-          v[m1] = f2mul(s, w);
-        }
-      } else {
-#pragma unroll
-        for (int m1 = 0; m1 < 16; ++m1) v[m1] = make_float2(0.f, 0.f);
+      for (int m1 = 0; m1 < 16; ++m1) {
+        const float2 s = *reinterpret_cast<const float2*>(src + 32 * m1);
+        const float2 w = *reinterpret_cast<const float2*>(wsrc + 32 * m1);
+        amax = fmaxf(amax, fmaxf(fabsf(s.x), fabsf(s.y)));
+        v[m1] = f2mul(s, w);
       }
       float2* zs = sm.z + job * SETK_ZSLOT;
       halfwarp_fft256<TAB>(v, zs, lane16, w1, twtab);
