@@ -19,33 +19,59 @@ struct alignas(8) MBar {
 
 #ifdef SETK_EMU
 
-// layout of the emulated barrier word: [63:48] magic, [47:32] phase, [31:0] pending bytes
-#define SETK_EMU_MBAR_MAGIC 0xBA55ull
-__device__ inline void mbar_check(const MBar* b) {
-  if ((__atomic_load_n(&b->v, __ATOMIC_SEQ_CST) >> 48) != SETK_EMU_MBAR_MAGIC)
+// layout of the emulated barrier word: [63:56] magic, [55:48] arrival count of a phase,
+// [47:40] arrivals still pending, [39:32] phase, [31:0] transaction bytes still pending
+#define SETK_EMU_MBAR_MAGIC 0xB5ull
+__device__ inline unsigned long long mbar_load(const MBar* b) {
+  const unsigned long long v = __atomic_load_n(&b->v, __ATOMIC_SEQ_CST);
+  if ((v >> 56) != SETK_EMU_MBAR_MAGIC)
     emu::die("mbarrier used before mbar_init (missing __syncthreads after init?)");
+  return v;
 }
-__device__ inline void mbar_init(MBar* b, int) {
-  __atomic_store_n(&b->v, SETK_EMU_MBAR_MAGIC << 48, __ATOMIC_SEQ_CST);
+__device__ inline void mbar_init(MBar* b, int count) {
+  if (count < 1 || count > 255) emu::die("mbar_init: count");
+  __atomic_store_n(&b->v, (SETK_EMU_MBAR_MAGIC << 56) | ((unsigned long long)count << 48) |
+                              ((unsigned long long)count << 40), __ATOMIC_SEQ_CST);
+}
+// apply (arrivals, bytes) to the barrier; completes the phase when both reach zero
+__device__ inline void mbar_update(MBar* b, int arrivals, long long bytes) {
+  for (;;) {
+    unsigned long long v = mbar_load(b);
+    long long pend = (long long)((v >> 40) & 0xff) - arrivals;
+    long long tx = (long long)(int)(v & 0xffffffffull) + bytes;
+    if (pend < 0) emu::die("mbarrier: more arrivals than its count");
+    unsigned long long phase = (v >> 32) & 0xff;
+    const unsigned long long count = (v >> 48) & 0xff;
+    if (pend == 0 && tx == 0) { phase = (phase + 1) & 0xff; pend = (long long)count; }
+    const unsigned long long nv = (SETK_EMU_MBAR_MAGIC << 56) | (count << 48) |
+                                  ((unsigned long long)pend << 40) | (phase << 32) |
+                                  ((unsigned long long)(unsigned)(int)tx);
+    if (__atomic_compare_exchange_n(&b->v, &v, nv, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) return;
+  }
 }
 __device__ inline void fence_proxy_async() {}
-__device__ inline void mbar_expect_tx(MBar* b, unsigned bytes) {
-  mbar_check(b);
-  __atomic_fetch_add(&b->v, (unsigned long long)bytes, __ATOMIC_SEQ_CST);
-}
+__device__ inline void mbar_expect_tx(MBar* b, unsigned bytes) { mbar_update(b, 1, (long long)bytes); }
+__device__ inline void mbar_arrive(MBar* b) { mbar_update(b, 1, 0); }
 __device__ inline void bulk_g2s(void* dst, const void* src, unsigned bytes, MBar* b) {
-  mbar_check(b);
+  mbar_load(b);
   if ((bytes & 15u) || (reinterpret_cast<uintptr_t>(dst) & 15u) || (reinterpret_cast<uintptr_t>(src) & 15u))
     emu::die("cp.async.bulk needs 16-byte aligned addresses and size");
   memcpy(dst, src, bytes);
-  unsigned long long after = __atomic_sub_fetch(&b->v, (unsigned long long)bytes, __ATOMIC_SEQ_CST);
-  if ((after & 0xffffffffull) == 0) __atomic_fetch_add(&b->v, 1ull << 32, __ATOMIC_SEQ_CST);  // phase++
+  mbar_update(b, 0, -(long long)bytes);
 }
+// returns once the phase with the given parity has completed (a fresh barrier has
+// "completed" the phase of parity 1, as on the device)
 __device__ inline void mbar_wait(MBar* b, unsigned parity) {
-  mbar_check(b);
-  while ((((__atomic_load_n(&b->v, __ATOMIC_SEQ_CST)) >> 32) & 1ull) == (unsigned long long)parity)
+  long long spins = 0;
+  while (((mbar_load(b) >> 32) & 1ull) == (unsigned long long)(parity & 1u)) {
     std::this_thread::yield();
+    if (++spins > 400000000LL) emu::die("mbar_wait: no progress (deadlock in the kernel's protocol?)");
+  }
 }
+// named barriers (bar.sync id, n) and the register re-budgeting of warp-specialised kernels
+__device__ inline void named_bar_sync(int id, int nthreads) { emu::named_sync(id, nthreads); }
+template <int R> __device__ inline void setmaxnreg_inc() {}
+template <int R> __device__ inline void setmaxnreg_dec() {}
 // 4-byte cp.async (LDGSTS): global -> shared without a register round trip
 __device__ inline void cp_async_f32(float* dst, const float* src) { *dst = *src; }
 __device__ inline void cp_async_8(void* dst, const void* src) { memcpy(dst, src, 8); }
@@ -69,6 +95,20 @@ __device__ __forceinline__ void fence_proxy_async() {
 __device__ __forceinline__ void mbar_expect_tx(MBar* b, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(MBar* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+// named barrier among nthreads threads (a multiple of 32) of the CTA; id 1..15
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// warp-group register re-budgeting (SASS USETMAXREG); all warps of the warpgroup execute it
+template <int R> __device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R));
+}
+template <int R> __device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R));
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, MBar* b) {
   asm volatile(

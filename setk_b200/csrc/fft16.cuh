@@ -133,4 +133,22 @@ __device__ __forceinline__ void halfwarp_fft256(float2 (&v)[16], float2* xch, in
   dft16(v);
 }
 
+// The same transform in two halves, for kernels that must wait for the exchange
+// tile to become free between them (stft_cov_ws.cu: the tile is a ring slot):
+//   a: first radix-16 pass + inter-pass twiddles, registers only
+//   b: exchange through xch + second radix-16 pass
+__device__ __forceinline__ void halfwarp_fft256_a(float2 (&v)[16], const float2* tab, int lane16) {
+  dft16(v);
+  twiddle_pass1_tab(v, tab, lane16);
+}
+__device__ __forceinline__ void halfwarp_fft256_b(float2 (&v)[16], float2* xch, int lane16) {
+#pragma unroll
+  for (int s = 0; s < 16; ++s) xch[kof(s) * SETK_XPITCH + lane16] = v[s];
+  __syncwarp();
+#pragma unroll
+  for (int m2 = 0; m2 < 16; ++m2) v[m2] = xch[lane16 * SETK_XPITCH + m2];
+  __syncwarp();
+  dft16(v);
+}
+
 }  // namespace setk

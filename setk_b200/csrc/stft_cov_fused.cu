@@ -29,6 +29,7 @@
 #include <cstdlib>
 #include "common.cuh"
 #include "stft_tile.cuh"
+#include "stft_cov_args.cuh"
 
 namespace setk {
 
@@ -47,24 +48,6 @@ namespace setk {
 #ifndef SETK_SC_TAB
 #define SETK_SC_TAB 1
 #endif
-
-template <int C>
-struct CovAcc {
-  static constexpr int NOFF = C * (C - 1) / 2;
-  static constexpr int NACC = C * C;  // C real diagonals + NOFF complex
-};
-
-struct StftCovArgs {
-  Geometry g;
-  const float* audio; const int* n_samples; int N;
-  const float* mask_s; const float* mask_n; unsigned flags;
-  int T;                 // frames of an N-sample utterance (mask leading dim)
-  TileSched sched;       // which (utterance, tile) pairs this CTA owns
-  int slots;             // partial-sum slots per utterance
-  const float* window;   // [n_fft]
-  float* partials;       // [B][slots][2*C*C + 2][F]
-  unsigned* maxabs_bits; // [B] or null
-};
 
 // tiles before every utterance of a ragged batch (one CTA; B is small)
 __global__ void tile_prefix_kernel(const int* __restrict__ n_samples, int B, Geometry g, int TT,
@@ -376,6 +359,24 @@ __global__ void cov_finalize_kernel(const float* __restrict__ partials, int B, i
 
 cudaError_t run_bits_to_float(const unsigned* bits, int n, float* out, void* stream);
 
+template <int C>
+static cudaError_t run_cov_finalize_t(const float* partials, int B, int F, TileSched sched, int n_ctas,
+                                      int slots, float2* Rs, float2* Rn, void* stream) {
+  const long long n = (long long)B * F;
+  return launch(cov_finalize_kernel<C>, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, stream, true,
+                partials, B, F, sched, n_ctas, slots, Rs, Rn);
+}
+cudaError_t run_cov_finalize(int C, const float* partials, int B, int F, TileSched sched, int n_ctas,
+                             int slots, float2* Rs, float2* Rn, void* stream) {
+  switch (C) {
+    case 1: return run_cov_finalize_t<1>(partials, B, F, sched, n_ctas, slots, Rs, Rn, stream);
+    case 2: return run_cov_finalize_t<2>(partials, B, F, sched, n_ctas, slots, Rs, Rn, stream);
+    case 3: return run_cov_finalize_t<3>(partials, B, F, sched, n_ctas, slots, Rs, Rn, stream);
+    case 4: return run_cov_finalize_t<4>(partials, B, F, sched, n_ctas, slots, Rs, Rn, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 template <int C, int TT>
 static size_t stft_cov_smem_bytes(int hop) {
   return sizeof(float) * (TileSmem<C, TT>::floats(hop) + (size_t)TT * 2 * 260 + 2 * 256);
@@ -390,9 +391,7 @@ static cudaError_t run_stft_cov_t(setk_plan* pl, StftCovArgs a, int B, int n_cta
   if (e != cudaSuccess) return e;
   e = launch(stft_cov_kernel<C, TT>, dim3(n_ctas), dim3(TT > 4 ? 320 : 288), smem, stream, false, a);
   if (e != cudaSuccess) return e;
-  const long long n = (long long)B * a.g.F;
-  e = launch(cov_finalize_kernel<C>, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, stream, true,
-             (const float*)a.partials, B, a.g.F, a.sched, n_ctas, a.slots, Rs, Rn);
+  e = run_cov_finalize_t<C>(a.partials, B, a.g.F, a.sched, n_ctas, a.slots, Rs, Rn, stream);
   if (e != cudaSuccess) return e;
   if (maxabs) e = run_bits_to_float(a.maxabs_bits, B, maxabs, stream);
   return e;
@@ -455,10 +454,25 @@ size_t stft_cov_partial_bytes(const setk_plan* pl, int B, int T) {
   return sizeof(float) * stft_cov_partial_floats(pl->geo) * (size_t)slots * B;
 }
 
+bool stft_cov_ws_supported(const Geometry& g);
+cudaError_t run_stft_cov_ws(setk_plan*, const float*, const int*, int, int, int, const float*, const float*,
+                            unsigned, int*, float*, unsigned*, float2*, float2*, float*, void*);
+
+// which build of the fused kernel serves this geometry: the warp-specialised one
+// (stft_cov_ws.cu) where it exists, unless SETK_SC_IMPL=classic (measurement knob)
+static bool use_ws(const Geometry& g) {
+  static const char* env = getenv("SETK_SC_IMPL");
+  if (env && env[0] == 'c') return false;
+  return stft_cov_ws_supported(g);
+}
+
 cudaError_t run_stft_cov_fused(setk_plan* pl, const float* audio, const int* n_samples, int B, int N,
                                int T, const float* mask_s, const float* mask_n, unsigned flags,
                                int* tile_prefix, float* partials, unsigned* maxabs_bits, float2* Rs,
                                float2* Rn, float* maxabs, void* stream) {
+  if (use_ws(pl->geo))
+    return run_stft_cov_ws(pl, audio, n_samples, B, N, T, mask_s, mask_n, flags, tile_prefix, partials,
+                           maxabs_bits, Rs, Rn, maxabs, stream);
   const int TT = sc_tt(pl->geo.C);
   StftCovArgs a;
   a.g = pl->geo;

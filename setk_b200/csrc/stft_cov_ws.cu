@@ -1,0 +1,526 @@
+// stft_cov_ws.cu -- THE METRIC KERNEL, warp-specialised build (round 2): multichannel
+// STFT fused with the mask-weighted spatial covariance; the STFT never touches HBM.
+//
+// Replaces (scripts/sptk): SpectrogramReader._load (libs/data_handler.py:492-503,
+// forward_stft per channel, libs/utils.py:96-138 -> librosa.stft) followed by
+// SupervisedBeamformer.run's two compute_covar calls (libs/beamformer.py:279-281,
+// 87-103); C++ twin: ShortTimeFTComputer::Compute (include/stft.cc:28-66) +
+// EstimatePsd (include/beamformer.cc:91-120).
+//
+// Same maths, schedule (TileSched) and outputs as stft_cov_fused.cu; what changed is who
+// does what.  There every thread carried the FFT's 32 values AND 34 covariance
+// accumulators (96 registers, 20 warps / SM) and the two phases alternated behind two
+// CTA-wide barriers per tile.  Here the roles live in different warps with their own
+// register budgets (setmaxnreg) and meet only through a ring of Z tiles:
+//
+//   384 threads = 4 covariance warps (112 registers) + 8 FFT warps (64 registers);
+//   launched at 80 registers ⇒ two CTAs per SM (24 warps)
+//   tile = 16 half-warp FFT jobs = TT frames x C channels (C = 4: 4 frames)
+//
+//   FFT warps   wait audio tile (TMA bulk copy, mbarrier) -> 16 samples x window per lane
+//               -> named barrier among the FFT warps (the single audio buffer is free:
+//               one thread issues the bulk copy of the NEXT tile) -> first radix-16 pass +
+//               twiddles in registers -> wait z_empty[slot] -> exchange + second pass in
+//               the slot itself -> Z -> arrive z_full[slot]
+//   cov warps   thread k owns the bin PAIR (k, 256-k), k = 0..127 (k = 0: DC and Nyquist):
+//               one split serves both bins and every Z value is read once.  Per tile:
+//               masks of the next tile by cp.async (each thread fetches exactly the mask
+//               values it will read itself: no barrier), wait z_full[slot], TT rank-1
+//               updates of 2 x (Rs, Rn) upper triangles in 68 fp32 registers, arrive
+//               z_empty[slot].  The 129th job -- bin 128, its own mirror -- goes to lanes
+//               0..TT-1 (one frame each) of cov warp (tile mod 4); its accumulators live in
+//               shared memory, one row per (warp, lane), summed in fixed order at the end.
+//   end of an utterance's run: partial sums -> workspace [B][slot][acc][F], reduced by
+//   cov_finalize_kernel exactly as before (deterministic, no float atomics).
+//
+// Algorithmic bytes per utterance: 4*C*N + 4*T*F (+4*T*F with mask_n) + 2*8*F*C^2.
+#include <cstdlib>
+#include "common.cuh"
+#include "stft_tile.cuh"
+#include "stft_cov_args.cuh"
+
+namespace setk {
+
+// Register budgets.  The CTA's pool is what it was launched with (80 x 384 = 30 720, two
+// CTAs per SM); after the re-budgeting 8 x 32 x 64 + 4 x 32 x 112 = 30 720 exactly.
+#ifndef SETK_WS_FFT_REGS
+#define SETK_WS_FFT_REGS 64
+#endif
+#ifndef SETK_WS_COV_REGS
+#define SETK_WS_COV_REGS 112
+#endif
+#define SETK_WS_LAUNCH_REGS 80
+
+constexpr int kWsCovThreads = 128, kWsFftThreads = 256, kWsThreads = 384;
+constexpr int kWsBarFft = 1, kWsBarCov = 2;   // named barriers (0 is __syncthreads)
+constexpr int kWsMaskPitch = 260;             // 257 bins + the two bin-128 side columns (257, 258)
+
+template <int C>
+struct WsShape {
+  static_assert(16 % C == 0, "16 half-warp jobs per tile");
+  static constexpr int TT = 16 / C;                 // frames per tile
+  static constexpr int NOFF = C * (C - 1) / 2;
+  static constexpr int NACC = C * C;
+  static constexpr int NPAIR = C + 2 * NOFF + 1;    // float2 accumulators of one bin
+  static constexpr int ROWS128 = 4 * TT;            // (cov warp, lane) rows of bin 128
+};
+
+// Shared-memory carve-up (C = 4, hop 256: 104 768 B, 113 088 B with mask_n rows).
+template <int C>
+struct WsSmem {
+  static constexpr int TT = WsShape<C>::TT;
+  MBar* bar_audio;   // [1]  bulk copy of the audio tile
+  MBar* z_full;      // [2]  8 arrivals: one per FFT warp
+  MBar* z_empty;     // [2]  4 arrivals: one per covariance warp
+  float* win;        // [512] analysis window x 0.5
+  float2* twtab;     // [256] W256^{lane16 k}
+  float* audio;      // [C][Lp]
+  float2* z;         // [2][16][SETK_ZSLOT]
+  float* mask;       // [2][TT][mrows][kWsMaskPitch]
+  float2* acc128;    // [ROWS128][NPAIR]
+  int Lp, mrows;
+  SETK_HD static int staged_len(int hop) { return ((TT - 1) * hop + kNfft + 3) & ~3; }
+  SETK_HD static size_t bytes(int hop, int mrows) {
+    return 64 + sizeof(float) * kNfft + sizeof(float2) * 256 + sizeof(float) * C * staged_len(hop) +
+           sizeof(float2) * 2 * 16 * SETK_ZSLOT + sizeof(float) * 2 * TT * mrows * kWsMaskPitch +
+           sizeof(float2) * WsShape<C>::ROWS128 * WsShape<C>::NPAIR;
+  }
+  __device__ void carve(float* base, int hop, int mrows_) {
+    Lp = staged_len(hop);
+    mrows = mrows_;
+    MBar* bars = reinterpret_cast<MBar*>(base);
+    bar_audio = bars; z_full = bars + 1; z_empty = bars + 3;
+    win = base + 16;
+    twtab = reinterpret_cast<float2*>(win + kNfft);
+    audio = reinterpret_cast<float*>(twtab + 256);
+    z = reinterpret_cast<float2*>(audio + C * Lp);
+    mask = reinterpret_cast<float*>(z + 2 * 16 * SETK_ZSLOT);
+    acc128 = reinterpret_cast<float2*>(mask + 2 * TT * mrows * kWsMaskPitch);
+  }
+};
+
+// Where a linear tile index lives: utterance b, the tiles before it / before the next one.
+struct WsCursor {
+  int b, pb, pe, nb, Tb;
+  __device__ __forceinline__ void load(const StftCovArgs& a) {
+    nb = a.n_samples ? a.n_samples[b] : a.N;
+    Tb = frames_of(nb, kNfft, a.g.hop, a.g.pad);
+  }
+  __device__ __forceinline__ void seek(const StftCovArgs& a, int x) {
+    b = sched_find(a.sched, x);
+    pb = sched_prefix(a.sched, b);
+    pe = sched_prefix(a.sched, b + 1);
+    load(a);
+  }
+  __device__ __forceinline__ void advance(const StftCovArgs& a, int x) {   // x >= pb
+    if (x >= pe) {
+      do { ++b; pb = pe; pe = sched_prefix(a.sched, b + 1); } while (x >= pe);
+      load(a);
+    }
+  }
+  // live frames of tile x (0 for the empty tile of a too-short utterance)
+  __device__ __forceinline__ int frames(int x, int TT) const { return imax(0, imin(TT, Tb - (x - pb) * TT)); }
+};
+
+// ---- audio staging by the FFT warps (threads 128..383) ----
+template <int C>
+__device__ __forceinline__ void ws_stage_bulk(const WsSmem<C>& sm, const float* __restrict__ xb, int N,
+                                              int t0, int nt, int hop, int pad) {   // ONE thread
+  const int need = (nt - 1) * hop + kNfft;
+  const int i0 = t0 * hop - pad;
+  fence_proxy_async();
+  mbar_expect_tx(sm.bar_audio, (unsigned)(C * need * sizeof(float)));
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    bulk_g2s(sm.audio + c * sm.Lp, xb + (long long)c * N + i0, (unsigned)(need * sizeof(float)),
+             sm.bar_audio);
+}
+template <int C>
+__device__ __forceinline__ void ws_stage_scalar(const WsSmem<C>& sm, const float* __restrict__ xb, int N,
+                                                int nb, int t0, int nt, int hop, int pad, int ftid) {
+  const int p0 = t0 * hop;
+  const int need = (nt - 1) * hop + kNfft;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float* src = xb + (long long)c * N;
+    for (int q = ftid; q < need; q += kWsFftThreads) {
+      const int i = pad ? reflect_index(p0 + q, pad, nb) : (p0 + q);
+      sm.audio[c * sm.Lp + q] = src[i];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// FFT role: threads 128..383, half-warp job = (thread - 128) / 16 = frame * C + channel
+// ---------------------------------------------------------------------------
+template <int C>
+__device__ __forceinline__ void ws_fft_role(const StftCovArgs& a, const WsSmem<C>& sm, int lo, int hi,
+                                            bool vec_ok) {
+  constexpr int TT = WsShape<C>::TT;
+  const int ftid = (int)threadIdx.x - kWsCovThreads;
+  const int lane = ftid & 31, lane16 = lane & 15;
+  const int job = ftid >> 4;
+  const int fr = job / C, ch = job - fr * C;
+  const int hop = a.g.hop, pad = a.g.pad;
+  float amax = 0.f;
+
+  WsCursor cur;
+  cur.seek(a, lo);
+  bool async_cur = false;
+  {
+    const int nt = cur.frames(lo, TT);
+    if (nt > 0) {
+      const int t0 = (lo - cur.pb) * TT;
+      const float* xb = a.audio + (long long)cur.b * C * a.N;
+      if (tile_bulk_ok(t0, nt, hop, pad, cur.nb, vec_ok)) {
+        if (ftid == 0) ws_stage_bulk<C>(sm, xb, a.N, t0, nt, hop, pad);
+        async_cur = true;
+      } else {
+        ws_stage_scalar<C>(sm, xb, a.N, cur.nb, t0, nt, hop, pad, ftid);
+        named_bar_sync(kWsBarFft, kWsFftThreads);
+      }
+    }
+  }
+  unsigned apar = 0;
+  for (int x = lo, n = 0; x < hi; ++x, ++n) {
+    const int nt = cur.frames(x, TT);
+    float2 v[16];
+    if (nt > 0) {
+      if (async_cur) { mbar_wait(sm.bar_audio, apar); apar ^= 1u; }
+      // a dead frame (fr >= nt, only in an utterance's last tile) re-transforms the last live
+      // one: its spectrum is never read and max|x| sees nothing new
+      const int fr_src = imin(fr, nt - 1);
+      const float* src = sm.audio + ch * sm.Lp + fr_src * hop + 2 * lane16;
+      const float* wsrc = sm.win + 2 * lane16;
+#pragma unroll
+      for (int m1 = 0; m1 < 16; ++m1) {
+        const float2 s = *reinterpret_cast<const float2*>(src + 32 * m1);
+        const float2 w = *reinterpret_cast<const float2*>(wsrc + 32 * m1);
+        amax = fmaxf(amax, fmaxf(fabsf(s.x), fabsf(s.y)));
+        v[m1] = f2mul(s, w);
+      }
+    }
+    named_bar_sync(kWsBarFft, kWsFftThreads);   // every FFT warp holds its samples: the buffer is free
+    WsCursor nxt = cur;
+    bool async_next = false, scalar_next = false;
+    if (x + 1 < hi) {
+      nxt.advance(a, x + 1);
+      const int ntn = nxt.frames(x + 1, TT);
+      if (ntn > 0) {
+        const int t0n = (x + 1 - nxt.pb) * TT;
+        const float* xbn = a.audio + (long long)nxt.b * C * a.N;
+        if (tile_bulk_ok(t0n, ntn, hop, pad, nxt.nb, vec_ok)) {
+          if (ftid == 0) ws_stage_bulk<C>(sm, xbn, a.N, t0n, ntn, hop, pad);
+          async_next = true;
+        } else {
+          ws_stage_scalar<C>(sm, xbn, a.N, nxt.nb, t0n, ntn, hop, pad, ftid);
+          scalar_next = true;
+        }
+      }
+    }
+    if (nt > 0) halfwarp_fft256_a(v, sm.twtab, lane16);
+    const int s = n & 1;
+    mbar_wait(&sm.z_empty[s], ((unsigned)(n >> 1) & 1u) ^ 1u);
+    if (nt > 0) {
+      float2* zs = sm.z + (s * 16 + job) * SETK_ZSLOT;
+      halfwarp_fft256_b(v, zs, lane16);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) zs[lane16 + 16 * kof(q)] = v[q];
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.z_full[s]);
+
+    // end of this utterance's part of the CTA's run: max|x| (SpectrogramReader.maxabs)
+    const int seg_end = imin(hi, cur.pe);
+    if (x + 1 == seg_end && a.maxabs_bits) {
+      if (seg_end == cur.pe) {      // center=False leaves a tail no frame covers
+        const int covered = (cur.Tb > 0 ? (cur.Tb - 1) * hop + kNfft - 2 * pad : 0);
+        const float* xb = a.audio + (long long)cur.b * C * a.N;
+        for (int c = 0; c < C; ++c)
+          for (int i = imax(covered, 0) + ftid; i < cur.nb; i += kWsFftThreads)
+            amax = fmaxf(amax, fabsf(xb[(long long)c * a.N + i]));
+      }
+      for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      if (lane == 0 && amax > 0.f) atomicMax(a.maxabs_bits + cur.b, __float_as_uint(amax));
+      amax = 0.f;
+    }
+    if (scalar_next) named_bar_sync(kWsBarFft, kWsFftThreads);
+    cur = nxt;
+    async_cur = async_next;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// covariance role: threads 0..127, thread k owns bins (k, 256 - k)
+// ---------------------------------------------------------------------------
+// one frame of one bin: A += m x x^H for (m_s, m_n); A = [diag | off_s | off_n | mask sums]
+template <int C>
+__device__ __forceinline__ void ws_update(float2* A, const float2* x, float ms, float mn) {
+  constexpr int NOFF = WsShape<C>::NOFF;
+  const float2 msn = make_float2(ms, mn);
+  const float2 mss = make_float2(ms, ms), mnn = make_float2(mn, mn);
+  A[C + 2 * NOFF] = f2add(A[C + 2 * NOFF], msn);
+  int o = 0;
+#pragma unroll
+  for (int i = 0; i < C; ++i) {
+    const float pii = x[i].x * x[i].x + x[i].y * x[i].y;
+    A[i] = f2fma(msn, make_float2(pii, pii), A[i]);
+#pragma unroll
+    for (int k = i + 1; k < C; ++k) {
+      const float2 pr = cmul_conj(x[i], x[k]);          // x_i conj(x_k): two packed instructions
+      A[C + o] = f2fma(pr, mss, A[C + o]);
+      A[C + NOFF + o] = f2fma(pr, mnn, A[C + NOFF + o]);
+      ++o;
+    }
+  }
+}
+// accumulator p of a bin -> its two rows in the partial-sum workspace [2*NACC + 2][F]
+template <int C>
+__device__ __forceinline__ void ws_store_pair(float* pp, int p, float2 v) {
+  constexpr int NOFF = WsShape<C>::NOFF, NACC = WsShape<C>::NACC, F = kBins;
+  int i0, i1;
+  if (p < C) { i0 = p; i1 = NACC + p; }
+  else if (p < C + NOFF) { i0 = C + 2 * (p - C); i1 = i0 + 1; }
+  else if (p < C + 2 * NOFF) { i0 = NACC + C + 2 * (p - C - NOFF); i1 = i0 + 1; }
+  else { i0 = 2 * NACC; i1 = i0 + 1; }
+  pp[(long long)i0 * F] = v.x;
+  pp[(long long)i1 * F] = v.y;
+}
+
+template <int C>
+__device__ __forceinline__ void ws_cov_role(const StftCovArgs& a, const WsSmem<C>& sm, int lo, int hi,
+                                            int q) {
+  constexpr int TT = WsShape<C>::TT, NPAIR = WsShape<C>::NPAIR, NACC = WsShape<C>::NACC;
+  constexpr int ROWS128 = WsShape<C>::ROWS128, F = kBins, MP = kWsMaskPitch;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bk = tid, bm = kM - tid;                       // the pair's bins
+  const int zk = tid, zn = (kM - tid) & (kM - 1);          // their half-size spectrum entries
+  const float2 tw = split_twiddle(tid);
+  const bool has_mn = a.mask_n != nullptr;
+  const bool clip = (a.flags & SETK_F_CLIP_MASK) != 0;
+  const bool mask_ft = (a.flags & SETK_F_MASK_FT) != 0;
+  const int mrows = sm.mrows;
+  const int mn_off = has_mn ? MP : 0;
+  float2 ak[NPAIR], am[NPAIR];
+  float2* my128 = sm.acc128 + (warp * TT + imin(lane, TT - 1)) * NPAIR;
+
+  // masks of tile x (frames t0.., local tile number n) -> mask slot n & 1.  Every thread
+  // fetches exactly what it reads itself, so cp.async.wait_group is all the sync needed.
+  auto prefetch = [&](const WsCursor& c, int x, int n) {
+    const int nt = c.frames(x, TT);
+    if (nt <= 0) return;
+    const int t0 = (x - c.pb) * TT;
+    const long long mstride = mask_ft ? 1 : F;
+    const long long base = mask_ft ? (long long)c.b * F * a.T + t0 : ((long long)c.b * a.T + t0) * F;
+    const long long fmul = mask_ft ? a.T : 1;
+    float* dst = sm.mask + (n & 1) * TT * mrows * MP;
+    const float* ps = a.mask_s + base;
+    const float* pn = has_mn ? a.mask_n + base : nullptr;
+#pragma unroll
+    for (int j = 0; j < TT; ++j) {
+      if (j < nt) {
+        cp_async_f32(dst + (j * mrows) * MP + bk, ps + j * mstride + bk * fmul);
+        cp_async_f32(dst + (j * mrows) * MP + bm, ps + j * mstride + bm * fmul);
+        if (has_mn) {
+          cp_async_f32(dst + (j * mrows + 1) * MP + bk, pn + j * mstride + bk * fmul);
+          cp_async_f32(dst + (j * mrows + 1) * MP + bm, pn + j * mstride + bm * fmul);
+        }
+      }
+    }
+    // bin 128 of frame `lane`: fetched by the warp that will process it, into a side column that
+    // alternates every second tile (the reader of tile n-1 is a different warp than the writer of n+1)
+    if (warp == (n & 3) && lane < nt) {
+      const int col = kBins + ((n >> 1) & 1);
+      cp_async_f32(dst + (lane * mrows) * MP + col, ps + lane * mstride + 128 * fmul);
+      if (has_mn) cp_async_f32(dst + (lane * mrows + 1) * MP + col, pn + lane * mstride + 128 * fmul);
+    }
+  };
+
+  // frame j of the pair: one split, two rank-1 updates
+  auto accumulate = [&](int j, const float2* zt, const float* mt) {
+    float2 xk[C], xm[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float2* z = zt + (j * C + c) * SETK_ZSLOT;
+      split_pair(z[zk], z[zn], tw, xk[c], xm[c]);
+    }
+    const float* mr = mt + (j * mrows) * MP;
+    const float rk = mr[bk], rm = mr[bm];
+    const float msk = clip ? fminf(rk, 1.0f) : rk, msm = clip ? fminf(rm, 1.0f) : rm;
+    // the second row is a select, not a branch (one basic block per tile for the scheduler)
+    const float nk = mr[mn_off + bk], nm = mr[mn_off + bm];
+    const float mnk = has_mn ? nk : 1.0f - msk, mnm = has_mn ? nm : 1.0f - msm;
+    ws_update<C>(ak, xk, msk, mnk);
+    ws_update<C>(am, xm, msm, mnm);
+  };
+
+  WsCursor cur;
+  cur.seek(a, lo);
+  prefetch(cur, lo, 0);
+  cp_async_commit();
+  for (int x = lo, n = 0; x < hi; ++x, ++n) {
+    cur.advance(a, x);
+    const int nt = cur.frames(x, TT);
+    const int seg_begin = imax(lo, cur.pb), seg_end = imin(hi, cur.pe);
+    if (x == seg_begin) {
+#pragma unroll
+      for (int p = 0; p < NPAIR; ++p) { ak[p] = make_float2(0.f, 0.f); am[p] = make_float2(0.f, 0.f); }
+      if (lane < TT) {
+#pragma unroll
+        for (int p = 0; p < NPAIR; ++p) my128[p] = make_float2(0.f, 0.f);
+      }
+    }
+    if (x + 1 < hi) {
+      WsCursor nx = cur;
+      nx.advance(a, x + 1);
+      prefetch(nx, x + 1, n + 1);
+    }
+    cp_async_commit();
+    cp_async_wait_group1();                         // this tile's masks have landed
+    const int s = n & 1;
+    mbar_wait(&sm.z_full[s], (unsigned)(n >> 1) & 1u);
+    const float2* zt = sm.z + s * 16 * SETK_ZSLOT;
+    const float* mt = sm.mask + s * TT * mrows * MP;
+    if (nt == TT) {                                 // every tile but an utterance's last: straight-line
+#pragma unroll
+      for (int j = 0; j < TT; ++j) accumulate(j, zt, mt);
+    } else {
+#pragma unroll
+      for (int j = 0; j < TT; ++j)
+        if (j < nt) accumulate(j, zt, mt);
+    }
+    if (warp == (n & 3) && lane < nt) {             // bin 128, frame `lane`
+      float2 x128[C];
+      const float2 tw128 = make_float2(-1.0f, -0.0f);     // split_twiddle(128)
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float2 z = zt[(lane * C + c) * SETK_ZSLOT + 128];
+        x128[c] = split_bin(z, z, tw128);
+      }
+      const int col = kBins + ((n >> 1) & 1);
+      const float* mr = mt + (lane * mrows) * MP;
+      const float r = mr[col];
+      const float ms = clip ? fminf(r, 1.0f) : r;
+      const float mn = has_mn ? mr[mn_off + col] : 1.0f - ms;
+      ws_update<C>(my128, x128, ms, mn);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.z_empty[s]);
+
+    if (x + 1 == seg_end) {
+      // ---- partial sums of this segment -> slot ----
+      const int slot = (int)blockIdx.x - cur.pb / q;
+      float* pp = a.partials + (((long long)cur.b * a.slots + slot) * (2 * NACC + 2)) * F;
+#pragma unroll
+      for (int p = 0; p < NPAIR; ++p) {
+        ws_store_pair<C>(pp + bk, p, ak[p]);
+        ws_store_pair<C>(pp + bm, p, am[p]);
+      }
+      named_bar_sync(kWsBarCov, kWsCovThreads);     // every warp's bin-128 rows are final
+      if (tid < NPAIR) {
+        float2 sum = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < ROWS128; ++r) sum = f2add(sum, sm.acc128[r * NPAIR + tid]);
+        ws_store_pair<C>(pp + 128, tid, sum);
+      }
+      named_bar_sync(kWsBarCov, kWsCovThreads);     // rows may be zeroed again
+    }
+  }
+}
+
+template <int C>
+__global__ void __maxnreg__(SETK_WS_LAUNCH_REGS) stft_cov_ws_kernel(StftCovArgs a, int mrows) {
+  SETK_DYN_SMEM(float, smem);
+  WsSmem<C> sm;
+  sm.carve(smem, a.g.hop, mrows);
+  const int tid = threadIdx.x;
+
+  // this CTA's run of the (utterance, tile) sequence
+  const int q = sched_quota(a.sched, gridDim.x);
+  const int total = sched_prefix(a.sched, a.sched.B);
+  const int lo = blockIdx.x * q;
+  const int hi = imin(lo + q, total);
+  if (lo >= hi) return;
+
+  for (int n = tid; n < kNfft; n += kWsThreads) sm.win[n] = 0.5f * a.window[n];
+  twiddle_table_fill(sm.twtab, tid, kWsThreads);
+  if (tid == 0) {
+    mbar_init(sm.bar_audio, 1);
+    mbar_init(&sm.z_full[0], kWsFftThreads / 32);
+    mbar_init(&sm.z_full[1], kWsFftThreads / 32);
+    mbar_init(&sm.z_empty[0], kWsCovThreads / 32);
+    mbar_init(&sm.z_empty[1], kWsCovThreads / 32);
+  }
+  __syncthreads();
+  if (tid < kWsCovThreads) {
+    setmaxnreg_inc<SETK_WS_COV_REGS>();
+    ws_cov_role<C>(a, sm, lo, hi, q);
+  } else {
+    setmaxnreg_dec<SETK_WS_FFT_REGS>();
+    const bool vec_ok = ((a.N & 3) == 0) && ((a.g.hop & 3) == 0) && ((a.g.pad & 3) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(a.audio) & 15) == 0);
+    ws_fft_role<C>(a, sm, lo, hi, vec_ok);
+  }
+}
+
+// ---- host side ----
+cudaError_t run_bits_to_float(const unsigned* bits, int n, float* out, void* stream);
+cudaError_t run_tile_prefix(const int* n_samples, int B, const Geometry& g, int TT, int T_cap,
+                            int* prefix, void* stream);
+cudaError_t run_cov_finalize(int C, const float* partials, int B, int F, TileSched sched, int n_ctas,
+                             int slots, float2* Rs, float2* Rn, void* stream);
+void fused_schedule(const setk_plan* pl, int B, int T, int TT, int* n_ctas, int* slots, int* min_quota);
+
+bool stft_cov_ws_supported(const Geometry& g) {
+  if (g.n_fft != 512 || g.C != 4) return false;
+  if (g.hop < 2 || g.hop > 512 || (g.hop & 1)) return false;
+  return true;
+}
+int stft_cov_ws_tt(int C) { return 16 / C; }
+
+template <int C>
+static cudaError_t run_ws_t(StftCovArgs a, int B, int n_ctas, float2* Rs, float2* Rn, float* maxabs,
+                            void* stream) {
+  const int mrows = a.mask_n ? 2 : 1;
+  const size_t smem = WsSmem<C>::bytes(a.g.hop, mrows);
+  cudaError_t e = cudaFuncSetAttribute(stft_cov_ws_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
+  if (e != cudaSuccess) return e;
+  e = launch(stft_cov_ws_kernel<C>, dim3(n_ctas), dim3(kWsThreads), smem, stream, false, a, mrows);
+  if (e != cudaSuccess) return e;
+  e = run_cov_finalize(C, a.partials, B, a.g.F, a.sched, n_ctas, a.slots, Rs, Rn, stream);
+  if (e != cudaSuccess) return e;
+  if (maxabs) e = run_bits_to_float(a.maxabs_bits, B, maxabs, stream);
+  return e;
+}
+
+cudaError_t run_stft_cov_ws(setk_plan* pl, const float* audio, const int* n_samples, int B, int N, int T,
+                            const float* mask_s, const float* mask_n, unsigned flags, int* tile_prefix,
+                            float* partials, unsigned* maxabs_bits, float2* Rs, float2* Rn, float* maxabs,
+                            void* stream) {
+  const int TT = stft_cov_ws_tt(pl->geo.C);
+  StftCovArgs a;
+  a.g = pl->geo;
+  a.audio = audio; a.n_samples = n_samples; a.N = N;
+  a.mask_s = mask_s; a.mask_n = mask_n; a.flags = flags;
+  a.T = T;
+  int n_ctas;
+  fused_schedule(pl, B, T, TT, &n_ctas, &a.slots, &a.sched.min_quota);
+  a.sched.B = B;
+  a.sched.tiles_u = sched_tiles_of(T, TT);
+  a.sched.prefix = nullptr;
+  if (n_samples) {     // ragged batch: the lengths live on the device
+    cudaError_t e = run_tile_prefix(n_samples, B, pl->geo, TT, 0x7fffffff, tile_prefix, stream);
+    if (e != cudaSuccess) return e;
+    a.sched.prefix = tile_prefix;
+  }
+  a.window = pl->d_window;
+  a.partials = partials;
+  a.maxabs_bits = maxabs_bits;
+  switch (pl->geo.C) {
+    case 4: return run_ws_t<4>(a, B, n_ctas, Rs, Rn, maxabs, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace setk

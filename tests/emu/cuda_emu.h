@@ -132,6 +132,8 @@ struct Ctx {
   int nthreads = 0;
   Barrier cta;
   std::vector<Barrier> warps;
+  Barrier named[16];              // bar.sync id, n (id 1..15)
+  std::mutex named_m;
   std::vector<uint64_t> slots;
   unsigned char* dyn = nullptr;
   bool serial = false;
@@ -192,6 +194,18 @@ void launch(dim3 grid, dim3 block, size_t smem, bool serial, F&& body) {
 inline void sync_cta() {
   if (g_ctx->serial) die("__syncthreads in a kernel launched as barrier-free");
   g_ctx->cta.wait();
+}
+// bar.sync id, nthreads: the first arrival fixes the participant count
+inline void named_sync(int id, int nthreads) {
+  if (g_ctx->serial) die("named barrier in a kernel launched as barrier-free");
+  if (id < 1 || id > 15) die("named barrier id");
+  Barrier& b = g_ctx->named[id];
+  {
+    std::unique_lock<std::mutex> lk(g_ctx->named_m);
+    if (b.expected == 0) b.init(nthreads);
+    else if (b.expected != nthreads) die("named barrier used with two different thread counts");
+  }
+  b.wait();
 }
 inline void sync_warp() {
   if (g_ctx->serial) die("__syncwarp in a kernel launched as barrier-free");

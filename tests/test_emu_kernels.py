@@ -50,6 +50,26 @@ def test_stft_cov_fused_ragged(emu):
     pc.check_stft_cov(emu, np.random.default_rng(4), 3, 4, 3000, n_samples=ns)
 
 
+@pytest.mark.parametrize("B,N,hop,center,with_mn,clip,mask_ft", [
+    (11, 1500, 256, True, True, True, True),     # many short utterances: CTAs own several segments
+    (3, 5200, 130, True, False, False, False),   # hop % 4 != 0: every tile staged element-wise
+    (2, 4100, 128, False, False, True, False),   # center=False tail feeds max|x|
+    (5, 2300, 512, True, True, False, False),    # hop = n_fft (no overlap), mask_n rows
+])
+def test_stft_cov_ws_protocol(emu, B, N, hop, center, with_mn, clip, mask_ft):
+    # the warp-specialised build (stft_cov_ws.cu): ring of Z tiles, named barriers, bin 128 rows
+    pc.check_stft_cov(emu, np.random.default_rng(7), B, 4, N, 512, hop, center, "hann",
+                      with_mask_n=with_mn, clip=clip, mask_ft=mask_ft)
+
+
+def test_stft_cov_ws_ragged_short(emu):
+    # utterances too short for one frame get an empty tile; others end mid-tile
+    ns = torch.tensor([3000, 200, 1701, 513, 2999, 256, 257, 1024], dtype=torch.int32)
+    pc.check_stft_cov(emu, np.random.default_rng(8), 8, 4, 3000, n_samples=ns)
+    pc.check_stft_cov(emu, np.random.default_rng(9), 8, 4, 3000, 512, 256, False, "hamming",
+                      n_samples=ns, with_mask_n=True)
+
+
 def test_stft_cov_generic_route(emu):
     # C = 5 and n_fft = 256 have no fused instantiation: explicit STFT + covariance
     pc.check_stft_cov(emu, np.random.default_rng(5), 1, 5, 1500, 512, 256, True, "hann")
