@@ -51,7 +51,7 @@ size_t cgmm_workspace_bytes(const CgCtx*, int, int, int, int);
 cudaError_t run_cgmm(const CgCtx*, const float2*, int, double*, const int*, int, int, int, int, int, const float*,
                      int, float*, unsigned*, void*);
 cudaError_t run_bcft_to_spill(const float2*, int, int, int, int, int, float2*, void*);
-bool wpe_supported(int, int, int, int);
+bool wpe_supported(int, int, int, int, int);
 size_t wpe_workspace_bytes(int, int, int, int);
 cudaError_t run_wpe(const float2*, int, int, int, int, int, int, int, int, int, double*, float2*, unsigned*,
                     const float2*, float*, void*);
@@ -516,9 +516,9 @@ static int wpe_entry(const char* who, const void* stft, const void* lambda_enh, 
   if (taps < 1 || delay < 0 || context < 0 || num_iters < 1)
     return fail(SETK_EINVAL, "%s: taps=%d delay=%d context=%d num_iters=%d", who, taps, delay, context,
                 num_iters);
-  if (!wpe_supported(C, T, taps, delay))
-    return fail(SETK_EUNSUPPORTED, "%s: %d channels x %d taps over %d frames exceeds the kernels' "
-                "shared-memory budget", who, C, taps, T);
+  if (!wpe_supported(C, T, taps, delay, context))
+    return fail(SETK_EUNSUPPORTED, "%s: %d channels x %d taps (context %d) exceeds the kernels' "
+                "shared-memory budget", who, C, taps, context);
   const int P = (F + 7) & ~7;
   const size_t x_bytes = sizeof(float2) * (size_t)B * T * C * P;
   const size_t w_bytes = wpe_workspace_bytes(B, C, F, taps);

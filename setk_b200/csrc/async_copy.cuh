@@ -51,6 +51,7 @@ __device__ inline void mbar_update(MBar* b, int arrivals, long long bytes) {
 }
 __device__ inline void fence_proxy_async() {}
 __device__ inline void mbar_expect_tx(MBar* b, unsigned bytes) { mbar_update(b, 1, (long long)bytes); }
+__device__ inline void mbar_add_tx(MBar* b, unsigned bytes) { mbar_update(b, 0, (long long)bytes); }
 __device__ inline void mbar_arrive(MBar* b) { mbar_update(b, 1, 0); }
 __device__ inline void bulk_g2s(void* dst, const void* src, unsigned bytes, MBar* b) {
   mbar_load(b);
@@ -99,6 +100,11 @@ __device__ __forceinline__ void mbar_expect_tx(MBar* b, unsigned bytes) {
 __device__ __forceinline__ void mbar_arrive(MBar* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
+// more transaction bytes for the current phase WITHOUT arriving (the caller arrives later itself)
+__device__ __forceinline__ void mbar_add_tx(MBar* b, unsigned bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes)
+               : "memory");
+}
 // named barrier among nthreads threads (a multiple of 32) of the CTA; id 1..15
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -117,18 +123,44 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
       "l"(src), "r"(bytes), "r"(smem_u32(b))
       : "memory");
 }
-__device__ __forceinline__ void mbar_wait(MBar* b, unsigned parity) {
+// One try: true when the phase with the given parity has completed.  The thread may be
+// suspended by the hardware for up to `hint_ns` while it waits (it wakes when the phase
+// completes), which keeps a long wait from burning issue slots in a polling loop.
+__device__ __forceinline__ bool mbar_try_wait(MBar* b, unsigned parity, unsigned hint_ns) {
+  unsigned ok;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(smem_u32(b)),
-      "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(b)), "r"(parity), "r"(hint_ns)
       : "memory");
+  return ok != 0;
+}
+#ifndef SETK_MBAR_HINT_NS
+#define SETK_MBAR_HINT_NS 20000
+#endif
+__device__ __forceinline__ bool mbar_try_wait_nohint(MBar* b, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(b)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(MBar* b, unsigned parity) {
+#if SETK_MBAR_HINT_NS > 0
+  while (!mbar_try_wait(b, parity, SETK_MBAR_HINT_NS)) {}
+#else
+  while (!mbar_try_wait_nohint(b, parity)) {}
+#endif
 }
 
 // 4-byte cp.async (LDGSTS): global -> shared without a register round trip

@@ -13,7 +13,8 @@
 // CTA-wide barriers per tile.  Here the roles live in different warps with their own
 // register budgets (setmaxnreg) and meet only through a ring of Z tiles:
 //
-//   384 threads = 4 covariance warps (112 registers) + 8 FFT warps (64 registers);
+//   384 threads = 8 FFT warps (64 registers) + 4 covariance warps (112 registers, the
+//   highest warp ids: the issue arbiter favours them and they are the critical role);
 //   launched at 80 registers ⇒ two CTAs per SM (24 warps)
 //   tile = 16 half-warp FFT jobs = TT frames x C channels (C = 4: 4 frames)
 //
@@ -22,12 +23,16 @@
 //               one thread issues the bulk copy of the NEXT tile) -> first radix-16 pass +
 //               twiddles in registers -> wait z_empty[slot] -> exchange + second pass in
 //               the slot itself -> Z -> arrive z_full[slot]
+//   masks       the TT mask rows of a tile are one contiguous run of a [B][T][F] array: the
+//               FFT warps' elected thread fetches them with ONE bulk copy per tile (rounded
+//               out to 16-byte boundaries) that completes on z_full[slot] together with the
+//               Z tile -- no per-thread cp.async, no address arithmetic in the covariance
+//               warps.  (F,T)-layout masks, unaligned arrays and an utterance's last,
+//               partial tile are read by the covariance threads with plain loads instead.
 //   cov warps   thread k owns the bin PAIR (k, 256-k), k = 0..127 (k = 0: DC and Nyquist):
 //               one split serves both bins and every Z value is read once.  Per tile:
-//               masks of the next tile by cp.async (each thread fetches exactly the mask
-//               values it will read itself: no barrier), wait z_full[slot], TT rank-1
-//               updates of 2 x (Rs, Rn) upper triangles in 68 fp32 registers, arrive
-//               z_empty[slot].  The 129th job -- bin 128, its own mirror -- goes to lanes
+//               wait z_full[slot], TT rank-1 updates of 2 x (Rs, Rn) upper triangles in 68
+//               fp32 registers, arrive z_empty[slot].  The 129th job -- bin 128, its own mirror -- goes to lanes
 //               0..TT-1 (one frame each) of cov warp (tile mod 4); its accumulators live in
 //               shared memory, one row per (warp, lane), summed in fixed order at the end.
 //   end of an utterance's run: partial sums -> workspace [B][slot][acc][F], reduced by
@@ -50,10 +55,15 @@ namespace setk {
 #define SETK_WS_COV_REGS 112
 #endif
 #define SETK_WS_LAUNCH_REGS 80
+// measurement knob: 1 puts the covariance warps at the LOW warp ids (first hardware pass)
+#ifndef SETK_WS_COV_FIRST
+#define SETK_WS_COV_FIRST 0
+#endif
 
 constexpr int kWsCovThreads = 128, kWsFftThreads = 256, kWsThreads = 384;
 constexpr int kWsBarFft = 1, kWsBarCov = 2;   // named barriers (0 is __syncthreads)
-constexpr int kWsMaskPitch = 260;             // 257 bins + the two bin-128 side columns (257, 258)
+constexpr int kWsMaskRegion = 1036;           // floats of one mask tile in shared memory: 4 x 257 rounded
+                                              // out to 16-byte boundaries at both ends (<= 1032), padded
 
 template <int C>
 struct WsShape {
@@ -65,7 +75,7 @@ struct WsShape {
   static constexpr int ROWS128 = 4 * TT;            // (cov warp, lane) rows of bin 128
 };
 
-// Shared-memory carve-up (C = 4, hop 256: 104 768 B, 113 088 B with mask_n rows).
+// Shared-memory carve-up (C = 4, hop 256: 104 736 B, 108 880 B with mask_n rows).
 template <int C>
 struct WsSmem {
   static constexpr int TT = WsShape<C>::TT;
@@ -76,13 +86,13 @@ struct WsSmem {
   float2* twtab;     // [256] W256^{lane16 k}
   float* audio;      // [C][Lp]
   float2* z;         // [2][16][SETK_ZSLOT]
-  float* mask;       // [2][TT][mrows][kWsMaskPitch]
+  float* mask;       // [2][mrows][kWsMaskRegion]
   float2* acc128;    // [ROWS128][NPAIR]
   int Lp, mrows;
   SETK_HD static int staged_len(int hop) { return ((TT - 1) * hop + kNfft + 3) & ~3; }
   SETK_HD static size_t bytes(int hop, int mrows) {
     return 64 + sizeof(float) * kNfft + sizeof(float2) * 256 + sizeof(float) * C * staged_len(hop) +
-           sizeof(float2) * 2 * 16 * SETK_ZSLOT + sizeof(float) * 2 * TT * mrows * kWsMaskPitch +
+           sizeof(float2) * 2 * 16 * SETK_ZSLOT + sizeof(float) * 2 * mrows * kWsMaskRegion +
            sizeof(float2) * WsShape<C>::ROWS128 * WsShape<C>::NPAIR;
   }
   __device__ void carve(float* base, int hop, int mrows_) {
@@ -95,7 +105,7 @@ struct WsSmem {
     audio = reinterpret_cast<float*>(twtab + 256);
     z = reinterpret_cast<float2*>(audio + C * Lp);
     mask = reinterpret_cast<float*>(z + 2 * 16 * SETK_ZSLOT);
-    acc128 = reinterpret_cast<float2*>(mask + 2 * TT * mrows * kWsMaskPitch);
+    acc128 = reinterpret_cast<float2*>(mask + 2 * mrows * kWsMaskRegion);
   }
 };
 
@@ -122,7 +132,23 @@ struct WsCursor {
   __device__ __forceinline__ int frames(int x, int TT) const { return imax(0, imin(TT, Tb - (x - pb) * TT)); }
 };
 
-// ---- audio staging by the FFT warps (threads 128..383) ----
+// Can the TT mask rows of tile (b, frames t0..) arrive as one bulk copy?  They are TT * F
+// consecutive floats of a [B][T][F] array starting at float index `first`; the copy starts at
+// the 16-byte boundary below (`shift` floats earlier) and ends at the one above, which must
+// still lie inside the array.
+__device__ __forceinline__ bool ws_mask_bulk(const StftCovArgs& a, int b, int t0, int nt, int TT,
+                                             long long& first, int& shift) {
+  first = ((long long)b * a.T + t0) * kBins;
+  shift = (int)(first & 3);
+  if (nt != TT || (a.flags & SETK_F_MASK_FT)) return false;
+  if ((reinterpret_cast<uintptr_t>(a.mask_s) & 15) ||
+      (a.mask_n && (reinterpret_cast<uintptr_t>(a.mask_n) & 15)))
+    return false;
+  const long long end = first + (long long)TT * kBins;
+  return ((end + 3) & ~3LL) <= (long long)a.sched.B * a.T * kBins;
+}
+
+// ---- audio staging by the FFT warps (threads 0..255) ----
 template <int C>
 __device__ __forceinline__ void ws_stage_bulk(const WsSmem<C>& sm, const float* __restrict__ xb, int N,
                                               int t0, int nt, int hop, int pad) {   // ONE thread
@@ -151,13 +177,13 @@ __device__ __forceinline__ void ws_stage_scalar(const WsSmem<C>& sm, const float
 }
 
 // ---------------------------------------------------------------------------
-// FFT role: threads 128..383, half-warp job = (thread - 128) / 16 = frame * C + channel
+// FFT role: threads 0..255, half-warp job = thread / 16 = frame * C + channel
 // ---------------------------------------------------------------------------
 template <int C>
 __device__ __forceinline__ void ws_fft_role(const StftCovArgs& a, const WsSmem<C>& sm, int lo, int hi,
                                             bool vec_ok) {
   constexpr int TT = WsShape<C>::TT;
-  const int ftid = (int)threadIdx.x - kWsCovThreads;
+  const int ftid = (int)threadIdx.x - (SETK_WS_COV_FIRST ? kWsCovThreads : 0);
   const int lane = ftid & 31, lane16 = lane & 15;
   const int job = ftid >> 4;
   const int fr = job / C, ch = job - fr * C;
@@ -221,6 +247,19 @@ __device__ __forceinline__ void ws_fft_role(const StftCovArgs& a, const WsSmem<C
     if (nt > 0) halfwarp_fft256_a(v, sm.twtab, lane16);
     const int s = n & 1;
     mbar_wait(&sm.z_empty[s], ((unsigned)(n >> 1) & 1u) ^ 1u);
+    if (nt > 0 && ftid == 0) {
+      // the slot is free (the covariance warps are done with tile n - 2): this tile's mask rows
+      long long first;
+      int shift;
+      if (ws_mask_bulk(a, cur.b, (x - cur.pb) * TT, nt, TT, first, shift)) {
+        const unsigned bytes = (unsigned)(((shift + TT * kBins + 3) & ~3) * sizeof(float));
+        float* dst = sm.mask + s * sm.mrows * kWsMaskRegion;
+        fence_proxy_async();
+        mbar_add_tx(&sm.z_full[s], bytes * (unsigned)sm.mrows);
+        bulk_g2s(dst, a.mask_s + (first - shift), bytes, &sm.z_full[s]);
+        if (sm.mrows > 1) bulk_g2s(dst + kWsMaskRegion, a.mask_n + (first - shift), bytes, &sm.z_full[s]);
+      }
+    }
     if (nt > 0) {
       float2* zs = sm.z + (s * 16 + job) * SETK_ZSLOT;
       halfwarp_fft256_b(v, zs, lane16);
@@ -251,7 +290,7 @@ __device__ __forceinline__ void ws_fft_role(const StftCovArgs& a, const WsSmem<C
 }
 
 // ---------------------------------------------------------------------------
-// covariance role: threads 0..127, thread k owns bins (k, 256 - k)
+// covariance role: threads 256..383, thread 256 + k owns bins (k, 256 - k)
 // ---------------------------------------------------------------------------
 // one frame of one bin: A += m x x^H for (m_s, m_n); A = [diag | off_s | off_n | mask sums]
 template <int C>
@@ -287,80 +326,77 @@ __device__ __forceinline__ void ws_store_pair(float* pp, int p, float2 v) {
   pp[(long long)i1 * F] = v.y;
 }
 
-template <int C>
+// The TT frames of one tile for this thread's bin pair (+ bin 128 on the handler lanes).
+//   BULK : masks from the tile's shared-memory copy (ms: frame t0, bin 0 of the m_s rows; the m_n
+//          rows kWsMaskRegion floats later), else from the registers g* (loaded by the caller)
+//   FULL : nt == TT (straight-line code)
+template <int C, bool HAS_MN, bool BULK, bool FULL>
+__device__ __forceinline__ void ws_cov_tile(float2* ak, float2* am, float2* my128, const float2* zt,
+                                            const float* ms, const float* gk, const float* gm,
+                                            const float* g128, int nt, bool clip, int bk, int bm, int zk,
+                                            int zn, float2 tw, bool handler, int lane) {
+  constexpr int TT = WsShape<C>::TT, F = kBins;
+  constexpr int NR = HAS_MN ? 2 : 1;
+#pragma unroll
+  for (int j = 0; j < TT; ++j) {
+    if (FULL || j < nt) {
+      float2 xk[C], xm[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float2* z = zt + (j * C + c) * SETK_ZSLOT;
+        split_pair(z[zk], z[zn], tw, xk[c], xm[c]);
+      }
+      const float rk = BULK ? ms[j * F + bk] : gk[j * NR];
+      const float rm = BULK ? ms[j * F + bm] : gm[j * NR];
+      const float msk = clip ? fminf(rk, 1.0f) : rk, msm = clip ? fminf(rm, 1.0f) : rm;
+      float mnk, mnm;
+      if (HAS_MN) {
+        mnk = BULK ? ms[kWsMaskRegion + j * F + bk] : gk[j * NR + 1];
+        mnm = BULK ? ms[kWsMaskRegion + j * F + bm] : gm[j * NR + 1];
+      } else {
+        mnk = 1.0f - msk;
+        mnm = 1.0f - msm;
+      }
+      ws_update<C>(ak, xk, msk, mnk);
+      ws_update<C>(am, xm, msm, mnm);
+    }
+  }
+  if (handler && lane < nt) {                       // bin 128, frame `lane`
+    float2 x128[C];
+    const float2 tw128 = make_float2(-1.0f, -0.0f);       // split_twiddle(128)
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float2 z = zt[(lane * C + c) * SETK_ZSLOT + 128];
+      x128[c] = split_bin(z, z, tw128);
+    }
+    const float r = BULK ? ms[lane * F + 128] : g128[0];
+    const float m1 = clip ? fminf(r, 1.0f) : r;
+    const float m2 = HAS_MN ? (BULK ? ms[kWsMaskRegion + lane * F + 128] : g128[1]) : 1.0f - m1;
+    ws_update<C>(my128, x128, m1, m2);
+  }
+}
+
+template <int C, bool HAS_MN>
 __device__ __forceinline__ void ws_cov_role(const StftCovArgs& a, const WsSmem<C>& sm, int lo, int hi,
                                             int q) {
   constexpr int TT = WsShape<C>::TT, NPAIR = WsShape<C>::NPAIR, NACC = WsShape<C>::NACC;
-  constexpr int ROWS128 = WsShape<C>::ROWS128, F = kBins, MP = kWsMaskPitch;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int ROWS128 = WsShape<C>::ROWS128, F = kBins;
+  constexpr int NR = HAS_MN ? 2 : 1;
+  const int tid = (int)threadIdx.x - (SETK_WS_COV_FIRST ? 0 : kWsFftThreads), lane = tid & 31, warp = tid >> 5;
   const int bk = tid, bm = kM - tid;                       // the pair's bins
   const int zk = tid, zn = (kM - tid) & (kM - 1);          // their half-size spectrum entries
   const float2 tw = split_twiddle(tid);
-  const bool has_mn = a.mask_n != nullptr;
   const bool clip = (a.flags & SETK_F_CLIP_MASK) != 0;
   const bool mask_ft = (a.flags & SETK_F_MASK_FT) != 0;
-  const int mrows = sm.mrows;
-  const int mn_off = has_mn ? MP : 0;
   float2 ak[NPAIR], am[NPAIR];
   float2* my128 = sm.acc128 + (warp * TT + imin(lane, TT - 1)) * NPAIR;
 
-  // masks of tile x (frames t0.., local tile number n) -> mask slot n & 1.  Every thread
-  // fetches exactly what it reads itself, so cp.async.wait_group is all the sync needed.
-  auto prefetch = [&](const WsCursor& c, int x, int n) {
-    const int nt = c.frames(x, TT);
-    if (nt <= 0) return;
-    const int t0 = (x - c.pb) * TT;
-    const long long mstride = mask_ft ? 1 : F;
-    const long long base = mask_ft ? (long long)c.b * F * a.T + t0 : ((long long)c.b * a.T + t0) * F;
-    const long long fmul = mask_ft ? a.T : 1;
-    float* dst = sm.mask + (n & 1) * TT * mrows * MP;
-    const float* ps = a.mask_s + base;
-    const float* pn = has_mn ? a.mask_n + base : nullptr;
-#pragma unroll
-    for (int j = 0; j < TT; ++j) {
-      if (j < nt) {
-        cp_async_f32(dst + (j * mrows) * MP + bk, ps + j * mstride + bk * fmul);
-        cp_async_f32(dst + (j * mrows) * MP + bm, ps + j * mstride + bm * fmul);
-        if (has_mn) {
-          cp_async_f32(dst + (j * mrows + 1) * MP + bk, pn + j * mstride + bk * fmul);
-          cp_async_f32(dst + (j * mrows + 1) * MP + bm, pn + j * mstride + bm * fmul);
-        }
-      }
-    }
-    // bin 128 of frame `lane`: fetched by the warp that will process it, into a side column that
-    // alternates every second tile (the reader of tile n-1 is a different warp than the writer of n+1)
-    if (warp == (n & 3) && lane < nt) {
-      const int col = kBins + ((n >> 1) & 1);
-      cp_async_f32(dst + (lane * mrows) * MP + col, ps + lane * mstride + 128 * fmul);
-      if (has_mn) cp_async_f32(dst + (lane * mrows + 1) * MP + col, pn + lane * mstride + 128 * fmul);
-    }
-  };
-
-  // frame j of the pair: one split, two rank-1 updates
-  auto accumulate = [&](int j, const float2* zt, const float* mt) {
-    float2 xk[C], xm[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const float2* z = zt + (j * C + c) * SETK_ZSLOT;
-      split_pair(z[zk], z[zn], tw, xk[c], xm[c]);
-    }
-    const float* mr = mt + (j * mrows) * MP;
-    const float rk = mr[bk], rm = mr[bm];
-    const float msk = clip ? fminf(rk, 1.0f) : rk, msm = clip ? fminf(rm, 1.0f) : rm;
-    // the second row is a select, not a branch (one basic block per tile for the scheduler)
-    const float nk = mr[mn_off + bk], nm = mr[mn_off + bm];
-    const float mnk = has_mn ? nk : 1.0f - msk, mnm = has_mn ? nm : 1.0f - msm;
-    ws_update<C>(ak, xk, msk, mnk);
-    ws_update<C>(am, xm, msm, mnm);
-  };
-
   WsCursor cur;
   cur.seek(a, lo);
-  prefetch(cur, lo, 0);
-  cp_async_commit();
   for (int x = lo, n = 0; x < hi; ++x, ++n) {
     cur.advance(a, x);
     const int nt = cur.frames(x, TT);
+    const int t0 = (x - cur.pb) * TT;
     const int seg_begin = imax(lo, cur.pb), seg_end = imin(hi, cur.pe);
     if (x == seg_begin) {
 #pragma unroll
@@ -370,40 +406,39 @@ __device__ __forceinline__ void ws_cov_role(const StftCovArgs& a, const WsSmem<C
         for (int p = 0; p < NPAIR; ++p) my128[p] = make_float2(0.f, 0.f);
       }
     }
-    if (x + 1 < hi) {
-      WsCursor nx = cur;
-      nx.advance(a, x + 1);
-      prefetch(nx, x + 1, n + 1);
+    const bool handler = warp == (n & 3);
+    long long first;
+    int shift;
+    const bool bulk = ws_mask_bulk(a, cur.b, t0, nt, TT, first, shift);
+    // masks the bulk copy does not bring: plain loads, issued before the wait for the Z tile
+    float gk[TT * NR], gm[TT * NR], g128[NR];
+    if (!bulk && nt > 0) {
+      const long long mstride = mask_ft ? 1 : F, fmul = mask_ft ? a.T : 1;
+      const long long base = mask_ft ? (long long)cur.b * F * a.T + t0 : first;
+#pragma unroll
+      for (int j = 0; j < TT; ++j) {
+        const long long o = base + imin(j, nt - 1) * mstride;
+        gk[j * NR] = a.mask_s[o + bk * fmul];
+        gm[j * NR] = a.mask_s[o + bm * fmul];
+        if (HAS_MN) { gk[j * NR + 1] = a.mask_n[o + bk * fmul]; gm[j * NR + 1] = a.mask_n[o + bm * fmul]; }
+      }
+      const long long o128 = base + imin(lane, nt - 1) * mstride + 128 * fmul;
+      g128[0] = a.mask_s[o128];
+      if (HAS_MN) g128[1] = a.mask_n[o128];
     }
-    cp_async_commit();
-    cp_async_wait_group1();                         // this tile's masks have landed
     const int s = n & 1;
     mbar_wait(&sm.z_full[s], (unsigned)(n >> 1) & 1u);
     const float2* zt = sm.z + s * 16 * SETK_ZSLOT;
-    const float* mt = sm.mask + s * TT * mrows * MP;
-    if (nt == TT) {                                 // every tile but an utterance's last: straight-line
-#pragma unroll
-      for (int j = 0; j < TT; ++j) accumulate(j, zt, mt);
-    } else {
-#pragma unroll
-      for (int j = 0; j < TT; ++j)
-        if (j < nt) accumulate(j, zt, mt);
-    }
-    if (warp == (n & 3) && lane < nt) {             // bin 128, frame `lane`
-      float2 x128[C];
-      const float2 tw128 = make_float2(-1.0f, -0.0f);     // split_twiddle(128)
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const float2 z = zt[(lane * C + c) * SETK_ZSLOT + 128];
-        x128[c] = split_bin(z, z, tw128);
-      }
-      const int col = kBins + ((n >> 1) & 1);
-      const float* mr = mt + (lane * mrows) * MP;
-      const float r = mr[col];
-      const float ms = clip ? fminf(r, 1.0f) : r;
-      const float mn = has_mn ? mr[mn_off + col] : 1.0f - ms;
-      ws_update<C>(my128, x128, ms, mn);
-    }
+    const float* ms = sm.mask + s * NR * kWsMaskRegion + shift;
+    if (bulk)
+      ws_cov_tile<C, HAS_MN, true, true>(ak, am, my128, zt, ms, gk, gm, g128, nt, clip, bk, bm, zk, zn, tw,
+                                         handler, lane);
+    else if (nt == TT)
+      ws_cov_tile<C, HAS_MN, false, true>(ak, am, my128, zt, ms, gk, gm, g128, nt, clip, bk, bm, zk, zn, tw,
+                                          handler, lane);
+    else if (nt > 0)
+      ws_cov_tile<C, HAS_MN, false, false>(ak, am, my128, zt, ms, gk, gm, g128, nt, clip, bk, bm, zk, zn, tw,
+                                           handler, lane);
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.z_empty[s]);
 
@@ -428,11 +463,11 @@ __device__ __forceinline__ void ws_cov_role(const StftCovArgs& a, const WsSmem<C
   }
 }
 
-template <int C>
-__global__ void __maxnreg__(SETK_WS_LAUNCH_REGS) stft_cov_ws_kernel(StftCovArgs a, int mrows) {
+template <int C, bool HAS_MN>
+__global__ void __maxnreg__(SETK_WS_LAUNCH_REGS) stft_cov_ws_kernel(StftCovArgs a) {
   SETK_DYN_SMEM(float, smem);
   WsSmem<C> sm;
-  sm.carve(smem, a.g.hop, mrows);
+  sm.carve(smem, a.g.hop, HAS_MN ? 2 : 1);
   const int tid = threadIdx.x;
 
   // this CTA's run of the (utterance, tile) sequence
@@ -452,9 +487,9 @@ __global__ void __maxnreg__(SETK_WS_LAUNCH_REGS) stft_cov_ws_kernel(StftCovArgs 
     mbar_init(&sm.z_empty[1], kWsCovThreads / 32);
   }
   __syncthreads();
-  if (tid < kWsCovThreads) {
+  if (SETK_WS_COV_FIRST ? tid < kWsCovThreads : tid >= kWsFftThreads) {
     setmaxnreg_inc<SETK_WS_COV_REGS>();
-    ws_cov_role<C>(a, sm, lo, hi, q);
+    ws_cov_role<C, HAS_MN>(a, sm, lo, hi, q);
   } else {
     setmaxnreg_dec<SETK_WS_FFT_REGS>();
     const bool vec_ok = ((a.N & 3) == 0) && ((a.g.hop & 3) == 0) && ((a.g.pad & 3) == 0) &&
@@ -478,15 +513,14 @@ bool stft_cov_ws_supported(const Geometry& g) {
 }
 int stft_cov_ws_tt(int C) { return 16 / C; }
 
-template <int C>
+template <int C, bool HAS_MN>
 static cudaError_t run_ws_t(StftCovArgs a, int B, int n_ctas, float2* Rs, float2* Rn, float* maxabs,
                             void* stream) {
-  const int mrows = a.mask_n ? 2 : 1;
-  const size_t smem = WsSmem<C>::bytes(a.g.hop, mrows);
-  cudaError_t e = cudaFuncSetAttribute(stft_cov_ws_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem);
+  const size_t smem = WsSmem<C>::bytes(a.g.hop, HAS_MN ? 2 : 1);
+  cudaError_t e = cudaFuncSetAttribute(stft_cov_ws_kernel<C, HAS_MN>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  e = launch(stft_cov_ws_kernel<C>, dim3(n_ctas), dim3(kWsThreads), smem, stream, false, a, mrows);
+  e = launch(stft_cov_ws_kernel<C, HAS_MN>, dim3(n_ctas), dim3(kWsThreads), smem, stream, false, a);
   if (e != cudaSuccess) return e;
   e = run_cov_finalize(C, a.partials, B, a.g.F, a.sched, n_ctas, a.slots, Rs, Rn, stream);
   if (e != cudaSuccess) return e;
@@ -518,7 +552,8 @@ cudaError_t run_stft_cov_ws(setk_plan* pl, const float* audio, const int* n_samp
   a.partials = partials;
   a.maxabs_bits = maxabs_bits;
   switch (pl->geo.C) {
-    case 4: return run_ws_t<4>(a, B, n_ctas, Rs, Rn, maxabs, stream);
+    case 4: return mask_n ? run_ws_t<4, true>(a, B, n_ctas, Rs, Rn, maxabs, stream)
+                          : run_ws_t<4, false>(a, B, n_ctas, Rs, Rn, maxabs, stream);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -269,13 +269,9 @@ cudaError_t weights_dispatch(const WeightsArgs& a, int C, void* stream) {
   }
 }
 
-// grow-only scratch for the PMWF automatic reference selection.  One process
-// drives one GPU and the scratch is only touched by kernels ordered on the
-// caller's stream; concurrent PMWF(ref<0) calls on *different* streams are not
-// supported (documented in include/setk_b200.h).
-static double* g_pmwf_ws = nullptr;
-static size_t g_pmwf_ws_bytes = 0;
-
+// Scratch of the PMWF automatic reference selection: allocated per call on the caller's
+// stream (cudaMallocAsync / cudaFreeAsync, like wpe_entry and setk_cgmm_stft), so calls on
+// different streams or devices never share it.
 cudaError_t weights_run(int kind, double beta, int ref_channel, int rank1, int ban, const void* Rs,
                         const void* Rn, const void* Ry, int r_dtype, int B, int F, int C, void* w,
                         int w_dtype, unsigned* status, int* ref_used, void* stream) {
@@ -284,20 +280,21 @@ cudaError_t weights_run(int kind, double beta, int ref_channel, int rank1, int b
   a.Rs = Rs; a.Rn = Rn; a.Ry = Ry; a.r_dtype = r_dtype; a.B = B; a.F = F;
   a.w = w; a.w_dtype = w_dtype; a.status = status; a.ref_used = ref_used;
   a.Wfull = nullptr; a.pows = nullptr;
+  double* ws = nullptr;
   if (kind == SETK_BF_PMWF && ref_channel < 0) {
     const size_t nW = (size_t)B * F * C * C * 2, nP = (size_t)B * F * C * 2;
-    const size_t want = sizeof(double) * (nW + nP);
-    if (g_pmwf_ws_bytes < want) {
-      if (g_pmwf_ws) { cudaDeviceSynchronize(); cudaFree(g_pmwf_ws); }
-      g_pmwf_ws = nullptr; g_pmwf_ws_bytes = 0;
-      cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&g_pmwf_ws), want);
-      if (e != cudaSuccess) return e;
-      g_pmwf_ws_bytes = want;
-    }
-    a.Wfull = g_pmwf_ws;
-    a.pows = g_pmwf_ws + nW;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&ws), sizeof(double) * (nW + nP),
+                                    static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return e;
+    a.Wfull = ws;
+    a.pows = ws + nW;
   }
-  return weights_dispatch(a, C, stream);
+  cudaError_t e = weights_dispatch(a, C, stream);
+  if (ws) {
+    cudaError_t e2 = cudaFreeAsync(ws, static_cast<cudaStream_t>(stream));
+    if (e == cudaSuccess) e = e2;
+  }
+  return e;
 }
 
 }  // namespace setk

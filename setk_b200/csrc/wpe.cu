@@ -6,9 +6,12 @@
 //   scripts/sptk/libs/wpe.py:82-110  wpe             (num_iters steps)
 //
 // Every bin is an independent problem of size NK = channels x taps, so a CTA
-// owns ONE (utterance, bin) and keeps that bin's whole time series in shared
-// memory as fp64 (converted once; rows padded by taps + delay zero frames, so
-// the delayed stack yt[k N + n, t] = x[n, t - k - delay] is just an offset):
+// owns ONE (utterance, bin) and keeps that bin's time series in shared memory
+// as fp64 (converted once; rows carry taps + delay frames of history, zeros
+// before frame 0, so the delayed stack yt[k N + n, t] = x[n, t - k - delay] is
+// just an offset).  An utterance that does not fit is walked in chunks of Tc
+// frames (each reloaded with its history and +-context halo); the sums run over
+// t in the same order either way, so chunking does not change a bit:
 //   wpe_corr_kernel    prologue: previous filter G -> z -> lambda (or lambda of x);
 //                      then [R | r] = sum_t a_i conj(a_j) / lambda, 4 x 4 register tiles
 //                      over the upper block triangle of the augmented matrix
@@ -17,6 +20,7 @@
 //   wpe_filter_kernel  z = x - G^H yt, written in the API layout [B][C][F][T]
 // All arithmetic is fp64 (the reference computes in the dtype of its input,
 // complex64; see oracle/wpe_oracle.py).
+#include <cstdlib>
 #include "common.cuh"
 #include "hermitian_solve.cuh"
 
@@ -27,7 +31,8 @@ struct WpeArgs {
   int B, C, F, T;
   int taps, delay, ctx;
   int NK;                        // C * taps
-  int Tp;                        // padded row length in shared memory: T + taps + delay
+  int Tc;                        // frames per chunk (>= T: the whole utterance at once)
+  int Wp;                        // row length in shared memory: Tc + 2 ctx + taps + delay
   int use_filter;                // corr: lambda from z = x - G^H yt (iterations > 0)
   const double* G;               // [B*F][NK][C] complex (interleaved)
   double* Raug;                  // [B*F][NK][NK + C] complex
@@ -38,39 +43,39 @@ struct WpeArgs {
   float* linv_out;               // corr: 1 / lambda -> [B][T][F] f32 (weights of Rd, wpe.py:165), or null
 };
 
-// shared memory: xs [C][Tp] cd | linv [T] | L [T] | Gs [NK][C] cd
+// shared memory: xs [C][Wp] cd | linv [Tc] | L [Tc + 2 ctx] | Gs [NK][C] cd
 __device__ __forceinline__ void wpe_carve(double* sm, const WpeArgs& a, cd*& xs, double*& linv, double*& L, cd*& Gs) {
   xs = reinterpret_cast<cd*>(sm);
-  linv = sm + 2 * (size_t)a.C * a.Tp;
-  L = linv + a.T;
-  Gs = reinterpret_cast<cd*>(L + a.T + (a.T & 1));
+  linv = sm + 2 * (size_t)a.C * a.Wp;
+  L = linv + a.Tc;
+  const int nl = a.Tc + 2 * a.ctx;
+  Gs = reinterpret_cast<cd*>(L + nl + ((a.Tc + nl) & 1));
 }
-SETK_HD inline size_t wpe_smem_bytes(int C, int T, int Tp, int NK) {
-  return sizeof(double) * (2 * (size_t)C * Tp + 2 * (size_t)T + (T & 1) + 2 * (size_t)NK * C);
+SETK_HD inline size_t wpe_smem_bytes(int C, int Tc, int ctx, int hist, int NK) {
+  const size_t nl = (size_t)Tc + 2 * ctx;
+  return sizeof(double) * (2 * (size_t)C * (nl + hist) + Tc + nl + ((Tc + nl) & 1) + 2 * (size_t)NK * C);
 }
 
-// bin (b, f) of the workspace -> xs (fp64, zero history in front of every row)
-__device__ __forceinline__ void wpe_load_bin(const WpeArgs& a, int b, int f, cd* xs) {
-  const int pad = a.Tp - a.T;
-  for (int q = threadIdx.x; q < a.C * a.Tp; q += blockDim.x) {
-    const int n = q / a.Tp, tt = q - n * a.Tp;
+// frames [base, base + Wp) of bin (b, f) of the workspace -> xs (fp64, zeros outside [0, T))
+__device__ __forceinline__ void wpe_load_bin(const WpeArgs& a, int b, int f, cd* xs, int base) {
+  for (int q = threadIdx.x; q < a.C * a.Wp; q += blockDim.x) {
+    const int n = q / a.Wp, g = base + (q - n * a.Wp);
     cd v = cd_make(0.0, 0.0);
-    if (tt >= pad) {
-      const float2 x = a.X[(((long long)b * a.T + (tt - pad)) * a.C + n) * a.P + f];
+    if (g >= 0 && g < a.T) {
+      const float2 x = a.X[(((long long)b * a.T + g) * a.C + n) * a.P + f];
       v = cd_make((double)x.x, (double)x.y);
     }
     xs[q] = v;
   }
 }
 
-// z_n[t] = x_n[t] - sum_m conj(G[m][n]) yt[m][t]   (wpe.py:78)
-__device__ __forceinline__ cd wpe_filtered(const WpeArgs& a, const cd* xs, const cd* Gs, int n, int t) {
-  const int pad = a.Tp - a.T;
-  cd z = xs[n * a.Tp + pad + t];
+// z_n[t] = x_n[t] - sum_m conj(G[m][n]) yt[m][t]   (wpe.py:78); p = position of frame t in xs
+__device__ __forceinline__ cd wpe_filtered(const WpeArgs& a, const cd* xs, const cd* Gs, int n, int p) {
+  cd z = xs[n * a.Wp + p];
   for (int k = 0; k < a.taps; ++k) {
-    const int tt = pad + t - k - a.delay;          // >= 0 thanks to the padding
+    const int pp = p - k - a.delay;                // >= 0: every row carries taps + delay frames of history
     for (int c = 0; c < a.C; ++c)
-      z = cd_sub(z, cd_mul(cd_conj(Gs[(k * a.C + c) * a.C + n]), xs[c * a.Tp + tt]));
+      z = cd_sub(z, cd_mul(cd_conj(Gs[(k * a.C + c) * a.C + n]), xs[c * a.Wp + pp]));
   }
   return z;
 }
@@ -81,76 +86,93 @@ __global__ void __launch_bounds__(512) wpe_corr_kernel(WpeArgs a) {
   wpe_carve(sm, a, xs, linv, L, Gs);
   const int bin = blockIdx.x, b = bin / a.F, f = bin - b * a.F;
   const int tid = threadIdx.x;
-  const int pad = a.Tp - a.T, C = a.C, NK = a.NK, NA = NK + C;
-  wpe_load_bin(a, b, f, xs);
+  const int hist = a.taps + a.delay, C = a.C, NK = a.NK, NA = NK + C;
   if (a.use_filter)
     for (int q = tid; q < NK * C; q += blockDim.x) {
       const double* g = a.G + ((long long)bin * NK * C + q) * 2;
       Gs[q] = cd_make(g[0], g[1]);
     }
-  __syncthreads();
-  // ---- lambda (wpe.py:33-56) ----
-  for (int t = tid; t < a.T; t += blockDim.x) {
-    double p = 0.0;
-    for (int n = 0; n < C; ++n) {
-      const cd z = a.use_filter ? wpe_filtered(a, xs, Gs, n, t) : xs[n * a.Tp + pad + t];
-      p += z.x * z.x + z.y * z.y;
-    }
-    L[t] = p / (double)C;
-  }
-  __syncthreads();
-  for (int t = tid; t < a.T; t += blockDim.x) {
-    double lam;
-    if (a.lam_src && !a.use_filter) {
-      const float2 e = a.lam_src[((long long)b * a.F + f) * a.T + t];
-      lam = (double)e.x * (double)e.x + (double)e.y * (double)e.y;
-    } else {
-      double s = 0.0;
-      int cnt = 0;
-      for (int c = -a.ctx; c <= a.ctx; ++c)
-        if (t + c >= 0 && t + c < a.T) { s += L[t + c]; ++cnt; }
-      lam = s / (double)cnt;
-    }
-    linv[t] = 1.0 / fmax(lam, SETK_EPS32_D);
-    if (a.linv_out) a.linv_out[((long long)b * a.T + t) * a.F + f] = (float)linv[t];
-  }
-  __syncthreads();
   // ---- [R | r]: 4 x 4 tiles (I, J >= I) of the NK x (NK + C) augmented matrix ----
   const int RT = (NK + 3) / 4, CT = (NA + 3) / 4;
   int I = 0, e = tid;
   while (I < RT && e >= CT - I) { e -= CT - I; ++I; }
-  if (I >= RT) return;                                    // (no barrier below)
+  const bool tile = I < RT;
   const int J = I + e;
   // row m of the augmented operand: m < NK -> x_{m % C} delayed by m / C + delay; else x_{m - NK}
+  // (offsets relative to the position of frame t)
   int oi[4], oj[4];
+  bool vi[4], vj[4];
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const int mi = 4 * I + u, mj = 4 * J + u;
-    oi[u] = mi < NK ? (mi % C) * a.Tp + pad - (mi / C) - a.delay : -1;
-    oj[u] = mj < NK ? (mj % C) * a.Tp + pad - (mj / C) - a.delay : (mj < NA ? (mj - NK) * a.Tp + pad : -1);
+    vi[u] = tile && mi < NK;
+    vj[u] = tile && mj < NA;
+    oi[u] = vi[u] ? (mi % C) * a.Wp - (mi / C) - a.delay : 0;
+    oj[u] = vj[u] ? (mj < NK ? (mj % C) * a.Wp - (mj / C) - a.delay : (mj - NK) * a.Wp) : 0;
   }
   double ar[4][4], ai[4][4];
 #pragma unroll
   for (int u = 0; u < 4; ++u)
 #pragma unroll
     for (int v = 0; v < 4; ++v) { ar[u][v] = 0.0; ai[u][v] = 0.0; }
-  for (int t = 0; t < a.T; ++t) {
-    const double w = linv[t];
-    cd p[4], q[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      p[u] = oi[u] >= 0 ? xs[oi[u] + t] : cd_make(0.0, 0.0);
-      q[u] = oj[u] >= 0 ? xs[oj[u] + t] : cd_make(0.0, 0.0);
-      p[u].x *= w; p[u].y *= w;
+
+  for (int t0 = 0; t0 < a.T; t0 += a.Tc) {
+    const int n = imin(a.Tc, a.T - t0);
+    const int base = t0 - a.ctx - hist;                   // frame at position 0 of xs
+    __syncthreads();                                       // the previous chunk is consumed
+    wpe_load_bin(a, b, f, xs, base);
+    __syncthreads();
+    // ---- lambda (wpe.py:33-56): channel-mean power of frames [t0 - ctx, t0 + n + ctx) ----
+    for (int u = tid; u < n + 2 * a.ctx; u += blockDim.x) {
+      const int t = t0 - a.ctx + u;
+      double p = 0.0;
+      if (t >= 0 && t < a.T)
+        for (int c = 0; c < C; ++c) {
+          const cd z = a.use_filter ? wpe_filtered(a, xs, Gs, c, u + hist) : xs[c * a.Wp + u + hist];
+          p += z.x * z.x + z.y * z.y;
+        }
+      L[u] = p / (double)C;
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-      for (int v = 0; v < 4; ++v) {                       // p conj(q)
-        ar[u][v] += p[u].x * q[v].x + p[u].y * q[v].y;
-        ai[u][v] += p[u].y * q[v].x - p[u].x * q[v].y;
+    __syncthreads();
+    for (int u = tid; u < n; u += blockDim.x) {
+      const int t = t0 + u;
+      double lam;
+      if (a.lam_src && !a.use_filter) {
+        const float2 ev = a.lam_src[((long long)b * a.F + f) * a.T + t];
+        lam = (double)ev.x * (double)ev.x + (double)ev.y * (double)ev.y;
+      } else {
+        double s = 0.0;
+        int cnt = 0;
+        for (int c = -a.ctx; c <= a.ctx; ++c)
+          if (t + c >= 0 && t + c < a.T) { s += L[u + a.ctx + c]; ++cnt; }
+        lam = s / (double)cnt;
       }
+      linv[u] = 1.0 / fmax(lam, SETK_EPS32_D);
+      if (a.linv_out) a.linv_out[((long long)b * a.T + t) * a.F + f] = (float)linv[u];
+    }
+    __syncthreads();
+    if (tile) {
+      const cd* xt = xs + a.ctx + hist;                    // position of frame t0
+      for (int u = 0; u < n; ++u) {
+        const double w = linv[u];
+        cd p[4], q[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          p[k] = vi[k] ? xt[oi[k] + u] : cd_make(0.0, 0.0);
+          q[k] = vj[k] ? xt[oj[k] + u] : cd_make(0.0, 0.0);
+          p[k].x *= w; p[k].y *= w;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {                     // p conj(q)
+            ar[k][v] += p[k].x * q[v].x + p[k].y * q[v].y;
+            ai[k][v] += p[k].y * q[v].x - p[k].x * q[v].y;
+          }
+      }
+    }
   }
+  if (!tile) return;
   double* R = a.Raug + (long long)bin * NK * NA * 2;
 #pragma unroll
   for (int u = 0; u < 4; ++u)
@@ -233,26 +255,41 @@ __global__ void __launch_bounds__(256) wpe_filter_kernel(WpeArgs a) {
   cd* xs; double* linv; double* L; cd* Gs;
   wpe_carve(sm, a, xs, linv, L, Gs);
   const int bin = blockIdx.x, b = bin / a.F, f = bin - b * a.F;
-  wpe_load_bin(a, b, f, xs);
+  const int hist = a.taps + a.delay;
   for (int q = threadIdx.x; q < a.NK * a.C; q += blockDim.x) {
     const double* g = a.G + ((long long)bin * a.NK * a.C + q) * 2;
     Gs[q] = cd_make(g[0], g[1]);
   }
-  __syncthreads();
-  for (int q = threadIdx.x; q < a.C * a.T; q += blockDim.x) {
-    const int n = q / a.T, t = q - n * a.T;
-    const cd z = wpe_filtered(a, xs, Gs, n, t);
-    a.out[(((long long)b * a.C + n) * a.F + f) * a.T + t] = make_float2((float)z.x, (float)z.y);
+  for (int t0 = 0; t0 < a.T; t0 += a.Tc) {
+    const int n = imin(a.Tc, a.T - t0);
+    __syncthreads();
+    wpe_load_bin(a, b, f, xs, t0 - a.ctx - hist);
+    __syncthreads();
+    for (int q = threadIdx.x; q < a.C * n; q += blockDim.x) {
+      const int c = q / n, u = q - c * n;
+      const cd z = wpe_filtered(a, xs, Gs, c, u + a.ctx + hist);
+      a.out[(((long long)b * a.C + c) * a.F + f) * a.T + t0 + u] = make_float2((float)z.x, (float)z.y);
+    }
   }
 }
 
 // ---------------------------------------------------------------------------
 // what the kernels can hold: tiles <= 512 threads, matrices within shared memory
-bool wpe_supported(int C, int T, int taps, int delay) {
+static const size_t kWpeSmemCap = 200 * 1024;
+// frames per chunk: the whole utterance when it fits, else the largest multiple of 32 that does
+static int wpe_chunk_frames(int C, int T, int taps, int delay, int ctx) {
+  const int NK = C * taps, hist = taps + delay;
+  if (wpe_smem_bytes(C, T, ctx, hist, NK) <= kWpeSmemCap) return T;
+  int tc = 32;
+  while (wpe_smem_bytes(C, tc + 32, ctx, hist, NK) <= kWpeSmemCap) tc += 32;
+  return tc;
+}
+bool wpe_supported(int C, int T, int taps, int delay, int ctx) {
+  (void)T;                       // any length: long utterances are walked in chunks
   const int NK = C * taps, NA = NK + C, RT = (NK + 3) / 4, CT = (NA + 3) / 4;
   if (NK > 128 || RT * CT - RT * (RT - 1) / 2 > 512) return false;
-  if (wpe_smem_bytes(C, T, T + taps + delay, NK) > 200 * 1024) return false;
-  return sizeof(double) * (2 * (size_t)NK * (NA + 1) + 16) + 64 <= 200 * 1024;
+  if (ctx < 0 || wpe_smem_bytes(C, 32, ctx, taps + delay, NK) > kWpeSmemCap) return false;
+  return sizeof(double) * (2 * (size_t)NK * (NA + 1) + 16) + 64 <= kWpeSmemCap;
 }
 
 size_t wpe_workspace_bytes(int B, int C, int F, int taps) {
@@ -269,12 +306,17 @@ cudaError_t run_wpe(const float2* X, int P, int B, int C, int F, int T, int taps
   a.X = X; a.P = P; a.B = B; a.C = C; a.F = F; a.T = T;
   a.taps = taps; a.delay = delay; a.ctx = ctx;
   a.NK = C * taps;
-  a.Tp = T + taps + delay;
+  a.Tc = wpe_chunk_frames(C, T, taps, delay, ctx);
+  if (const char* env = getenv("SETK_WPE_CHUNK")) {     // test knob: force chunking of short inputs
+    const int v = atoi(env);
+    if (v >= 1 && v < a.Tc) a.Tc = v;
+  }
+  a.Wp = a.Tc + 2 * ctx + taps + delay;
   a.Raug = ws;
   double* G = ws + 2 * (size_t)B * F * a.NK * (a.NK + C);
   a.G = G;
   a.out = out; a.status = status;
-  const size_t smem = wpe_smem_bytes(C, T, a.Tp, a.NK);
+  const size_t smem = wpe_smem_bytes(C, a.Tc, ctx, taps + delay, a.NK);
   const int NA = a.NK + C, RT = (a.NK + 3) / 4, CT = (NA + 3) / 4;
   const int ntiles = RT * CT - RT * (RT - 1) / 2;
   const int corr_threads = ((ntiles + 31) / 32) * 32;

@@ -467,7 +467,8 @@ def check_cgmm_documented(device, which):
 TOL_WPE = 2e-6           # fp64 kernels, complex64 output, vs the float64 oracle on the same STFT
 
 
-def check_wpe(device, rng, B, C, N, frame_len=512, hop=128, taps=4, delay=2, ctx=1, iters=2):
+def check_wpe(device, rng, B, C, N, frame_len=512, hop=128, taps=4, delay=2, ctx=1, iters=2,
+              return_out=False):
     """setk_wpe_stft vs oracle.wpe_oracle on the oracle's complex64 STFT."""
     from oracle import wpe_oracle as wo
     x = structured_audio(rng, B, C, N)
@@ -482,7 +483,7 @@ def check_wpe(device, rng, B, C, N, frame_len=512, hop=128, taps=4, delay=2, ctx
         err = bo.rel_inf(out[b], np.einsum("fnt->nft", ref))
         assert err <= TOL_WPE, f"wpe rel-inf {err}"
         worst = max(worst, err)
-    return worst
+    return out if return_out else worst
 
 
 def check_wpe_fixture(device, name):

@@ -153,6 +153,19 @@ def test_wpe(emu):
     pc.check_wpe(emu, rng, 1, 5, 4000, 256, 128, taps=3, delay=3, ctx=2, iters=3)   # NK = 15: ragged tiles
 
 
+def test_wpe_chunked_long_utterance_path(emu, monkeypatch):
+    # utterances whose bin does not fit in shared memory are walked in chunks (history +
+    # context halo reloaded per chunk); forcing tiny chunks must not change a bit
+    rng = np.random.default_rng(21)
+    ref = pc.check_wpe(emu, rng, 1, 3, 3000, 256, 64, taps=4, delay=2, ctx=1, iters=2, return_out=True)
+    for chunk in ("7", "40"):
+        monkeypatch.setenv("SETK_WPE_CHUNK", chunk)
+        rng = np.random.default_rng(21)
+        out = pc.check_wpe(emu, rng, 1, 3, 3000, 256, 64, taps=4, delay=2, ctx=1, iters=2,
+                           return_out=True)
+        assert np.array_equal(out, ref)
+
+
 def test_wpe_reference_fixture(emu):
     pc.check_wpe_fixture(emu, "c2_t6_ctx0")
 
