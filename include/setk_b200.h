@@ -216,6 +216,17 @@ int setk_apply_istft(setk_plan_t* plan, const float* audio, const int32_t* n_sam
                      const float* post_mask, int32_t n_out, const float* norm,
                      float* wave, void* stream);
 
+/* The same, through to the wav writer: the pass that applies inverse_stft's `norm`
+ * rescale (utils.py:166-168) also performs WaveWriter.write -> write_wav's float ->
+ * PCM-16 conversion (data_handler.py:600-605, utils.py:45-62; soundfile's default
+ * subtype = floor(y * 32768) clipped, SURVEY.md finding 3), so the float wave is
+ * never written out: bit-identical to setk_apply_istft + setk_float_to_pcm16.
+ *   norm  f32 [B] or NULL (no rescale)      pcm  i16 [B][n_out] */
+int setk_apply_istft_pcm16(setk_plan_t* plan, const float* audio, const int32_t* n_samples,
+                           int32_t B, int32_t N, const void* w, int32_t w_dtype,
+                           const float* post_mask, int32_t n_out, const float* norm,
+                           int16_t* pcm, void* stream);
+
 /*
  * CGMM time-frequency mask estimation from audio: the tile STFT, then
  * CgmmTrainer(stft, num_classes, gamma=init, update_alpha=...).train(num_iters)

@@ -77,6 +77,9 @@ _PROTOTYPES = {
     "setk_apply_istft": (c_int, [c_void_p, c_void_p, c_void_p, c_int32,
                                  c_int32, c_void_p, c_int32, c_void_p, c_int32,
                                  c_void_p, c_void_p, c_void_p]),
+    "setk_apply_istft_pcm16": (c_int, [c_void_p, c_void_p, c_void_p, c_int32,
+                                       c_int32, c_void_p, c_int32, c_void_p, c_int32,
+                                       c_void_p, c_void_p, c_void_p]),
     "setk_cgmm_masks": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                 c_int32, c_int32, c_void_p, c_int32, c_void_p,
                                 c_void_p, c_void_p]),

@@ -21,6 +21,7 @@ cudaError_t run_istft_generic(const setk_plan*, const float2*, int, int, int, in
                               unsigned*, void*);
 cudaError_t run_peak_scale(float*, int, int, const float*, const unsigned*, void*);
 cudaError_t run_float_to_pcm16(const float*, long long, int16_t*, void*);
+cudaError_t run_peak_scale_pcm16(const float*, int, int, const float*, const unsigned*, int16_t*, void*);
 cudaError_t run_pcm16_to_float(const int16_t*, long long, float*, void*);
 
 cudaError_t run_ipd(const float2*, const float2*, long long, int, int, float*, void*);
@@ -172,6 +173,7 @@ int setk_plan_destroy(setk_plan_t* pl) {
   if (pl->d_window) cudaFree(pl->d_window);
   if (pl->d_wsq) cudaFree(pl->d_wsq);
   if (pl->d_partials) cudaFree(pl->d_partials);
+  if (pl->d_wave_ws) cudaFree(pl->d_wave_ws);
   if (pl->d_stft_ws) cudaFree(pl->d_stft_ws);
   if (pl->d_enh_ws) cudaFree(pl->d_enh_ws);
   if (pl->d_frames_ws) cudaFree(pl->d_frames_ws);
@@ -380,16 +382,22 @@ int setk_istft(setk_plan_t* pl, const void* enh, int32_t B, int32_t T, int32_t n
   return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_istft");
 }
 
-int setk_apply_istft(setk_plan_t* pl, const float* audio, const int32_t* n_samples, int32_t B, int32_t N,
-                     const void* w, int32_t w_dtype, const float* post_mask, int32_t n_out,
-                     const float* norm, float* wave, void* stream) {
+// wave != null: float output (+ norm rescale in place); pcm != null: the float wave goes to a plan
+// workspace and the rescale pass writes PCM-16 instead
+static int apply_istft_impl(setk_plan_t* pl, const float* audio, const int32_t* n_samples, int32_t B,
+                            int32_t N, const void* w, int32_t w_dtype, const float* post_mask,
+                            int32_t n_out, const float* norm, float* wave, int16_t* pcm, void* stream) {
   int rc = check_batch(pl, B, N, "setk_apply_istft");
   if (rc) return rc;
-  if (!audio || !w || !wave) return fail(SETK_EINVAL, "setk_apply_istft: null buffer");
+  if (!audio || !w || (!wave && !pcm)) return fail(SETK_EINVAL, "setk_apply_istft: null buffer");
   if (n_out < 1) return fail(SETK_ESHAPE, "setk_apply_istft: n_out=%d", n_out);
   const Geometry& g = pl->geo;
   const int T = frames_of(N, g.n_fft, g.hop, g.pad);
   cudaError_t e = ensure(&pl->d_peak, &pl->peak_bytes, sizeof(unsigned) * 2 * (size_t)pl->cfg.max_batch);
+  if (e == cudaSuccess && pcm) {
+    e = ensure(&pl->d_wave_ws, &pl->wave_ws_bytes, sizeof(float) * (size_t)B * n_out);
+    wave = pl->d_wave_ws;
+  }
   if (e != cudaSuccess) return cuda_fail(e, "setk_apply_istft(workspace)");
   unsigned* peak = norm ? pl->d_peak : nullptr;
   if (peak) {
@@ -433,8 +441,25 @@ int setk_apply_istft(setk_plan_t* pl, const float* audio, const int32_t* n_sampl
       e = run_istft_generic(pl, pl->d_enh_ws, B, T, T_used, n_out, n_samples, pl->d_frames_ws, wave, peak,
                             stream);
   }
-  if (e == cudaSuccess && norm) e = run_peak_scale(wave, B, n_out, norm, peak, stream);
+  if (e == cudaSuccess && pcm) e = run_peak_scale_pcm16(wave, B, n_out, norm, peak, pcm, stream);
+  else if (e == cudaSuccess && norm) e = run_peak_scale(wave, B, n_out, norm, peak, stream);
   return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_apply_istft");
+}
+
+int setk_apply_istft(setk_plan_t* pl, const float* audio, const int32_t* n_samples, int32_t B, int32_t N,
+                     const void* w, int32_t w_dtype, const float* post_mask, int32_t n_out,
+                     const float* norm, float* wave, void* stream) {
+  if (!wave) return fail(SETK_EINVAL, "setk_apply_istft: null buffer");
+  return apply_istft_impl(pl, audio, n_samples, B, N, w, w_dtype, post_mask, n_out, norm, wave, nullptr,
+                          stream);
+}
+
+int setk_apply_istft_pcm16(setk_plan_t* pl, const float* audio, const int32_t* n_samples, int32_t B,
+                           int32_t N, const void* w, int32_t w_dtype, const float* post_mask,
+                           int32_t n_out, const float* norm, int16_t* pcm, void* stream) {
+  if (!pcm) return fail(SETK_EINVAL, "setk_apply_istft_pcm16: null buffer");
+  return apply_istft_impl(pl, audio, n_samples, B, N, w, w_dtype, post_mask, n_out, norm, nullptr, pcm,
+                          stream);
 }
 
 int setk_cgmm_masks(setk_plan_t* pl, const float* audio, const int32_t* n_samples, int32_t B, int32_t N,

@@ -127,5 +127,6 @@ struct setk_plan {
   unsigned* d_peak;      size_t peak_bytes;       // [B] max|y| as uint bits
   double* d_cgmm_ws;     size_t cgmm_ws_bytes;    // CGMM posteriors, partials, R^-1 (cgmm.cu)
   int* d_tile_prefix;   size_t tile_prefix_bytes;   // ragged batches: tiles before each utterance
+  float* d_wave_ws;     size_t wave_ws_bytes;       // un-normalised wave of the PCM-16 output path
   int sm_count;
 };

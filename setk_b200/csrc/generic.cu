@@ -222,6 +222,37 @@ __global__ void peak_scale_kernel(float* __restrict__ wave, int n_out, const flo
     y[q] = (y[q] * nm) / den;
 }
 
+// The same rescale fused with write_wav's float -> PCM-16 conversion (utils.py:45-62:
+// soundfile's default subtype, floor(y * 32768) clipped, SURVEY.md finding 3): the float wave
+// is read once and 2 bytes per sample are written.  norm == null or norm[b] == 0: no rescale.
+__global__ void peak_scale_pcm16_kernel(const float* __restrict__ wave, int n_out,
+                                        const float* __restrict__ norm, const unsigned* __restrict__ peak,
+                                        int16_t* __restrict__ pcm) {
+  const int b = blockIdx.y;
+  const float nm = norm ? norm[b] : 0.f;
+  const float den = nm != 0.f ? __uint_as_float(peak[b]) + SETK_EPS32 : 1.f;
+  const float* y = wave + (long long)b * n_out;
+  int16_t* o = pcm + (long long)b * n_out;
+  auto conv = [&](float v) {
+    if (nm != 0.f) v = (v * nm) / den;
+    v = floorf(v * 32768.0f);
+    return (int)fminf(fmaxf(v, -32768.0f), 32767.0f);
+  };
+  if ((n_out & 3) == 0 && (reinterpret_cast<uintptr_t>(wave) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(pcm) & 7) == 0) {
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    int2* o2 = reinterpret_cast<int2*>(o);
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < (n_out >> 2); q += gridDim.x * blockDim.x) {
+      const float4 v = y4[q];
+      const int a0 = conv(v.x), a1 = conv(v.y), a2 = conv(v.z), a3 = conv(v.w);
+      o2[q] = make_int2((a0 & 0xffff) | (a1 << 16), (a2 & 0xffff) | (a3 << 16));
+    }
+    return;
+  }
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_out; q += gridDim.x * blockDim.x)
+    o[q] = (int16_t)conv(y[q]);
+}
+
 // max |sample| over all channels of each utterance (data_handler.py:398-400)
 __global__ void maxabs_kernel(const float* __restrict__ audio, const int* __restrict__ n_samples, int C,
                               int N, unsigned* __restrict__ bits) {
@@ -335,6 +366,14 @@ cudaError_t maxabs_generic(const float* audio, const int* n_samples, int B, int 
   return run_bits_to_float(bits, B, out, stream);
 }
 
+cudaError_t run_peak_scale_pcm16(const float* wave, int B, int n_out, const float* norm,
+                                 const unsigned* peak, int16_t* pcm, void* stream) {
+  int gx = (n_out / 4 + 255) / 256;
+  if (gx < 1) gx = 1;
+  if (gx > 64) gx = 64;
+  return launch(peak_scale_pcm16_kernel, dim3(gx, B), dim3(256), 0, stream, true, wave, n_out, norm, peak,
+                pcm);
+}
 cudaError_t run_float_to_pcm16(const float* wave, long long n, int16_t* pcm, void* stream) {
   return launch(float_to_pcm16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, true,
                 wave, n, pcm);

@@ -62,6 +62,7 @@ namespace setk {
 
 constexpr int kWsCovThreads = 128, kWsFftThreads = 256, kWsThreads = 384;
 constexpr int kWsBarFft = 1, kWsBarCov = 2;   // named barriers (0 is __syncthreads)
+constexpr int kWsChunk = 128;                 // tile descriptors per fill of the CTA's table
 constexpr int kWsMaskRegion = 1036;           // floats of one mask tile in shared memory: 4 x 257 rounded
                                               // out to 16-byte boundaries at both ends (<= 1032), padded
 
@@ -75,10 +76,25 @@ struct WsShape {
   static constexpr int ROWS128 = 4 * TT;            // (cov warp, lane) rows of bin 128
 };
 
-// Shared-memory carve-up (C = 4, hop 256: 104 736 B, 108 880 B with mask_n rows).
+// What the two roles need to know about one tile of the CTA's run, computed once per tile by
+// one thread (table fill) instead of by every thread of both roles on every tile.
+enum : unsigned {
+  WS_NT = 0xfu,               // live frames (0 for the empty tile of a too-short utterance)
+  WS_AUDIO_BULK = 1u << 4,    // samples arrive by bulk copy (else element-wise: reflect padding, ragged end)
+  WS_MASK_BULK = 1u << 5,     // mask rows arrive by bulk copy (else plain loads in the covariance warps)
+  WS_SEG_BEGIN = 1u << 6,     // first tile of an utterance's part of this CTA's run: accumulators restart
+  WS_SEG_END = 1u << 7,       // last tile of that part: partial sums and max|x| are flushed
+  WS_UTT_END = 1u << 8,       // ... and it is also the utterance's last tile
+  WS_SHIFT_POS = 9,           // 2 bits: floats between the 16-byte aligned mask copy and frame t0, bin 0
+  WS_SLOT_POS = 16            // 8 bits: partial-sum slot of this CTA for the utterance
+};
+struct alignas(16) WsTile { int b, t0, nb; unsigned flags; };
+
+// Shared-memory carve-up (C = 4, hop 256: 110 960 B, 115 104 B with mask_n rows).
 template <int C>
 struct WsSmem {
   static constexpr int TT = WsShape<C>::TT;
+  WsTile* tiles;     // [kWsChunk + 1]
   MBar* bar_audio;   // [1]  bulk copy of the audio tile
   MBar* z_full;      // [2]  8 arrivals: one per FFT warp
   MBar* z_empty;     // [2]  4 arrivals: one per covariance warp
@@ -86,13 +102,15 @@ struct WsSmem {
   float2* twtab;     // [256] W256^{lane16 k}
   float* audio;      // [C][Lp]
   float2* z;         // [2][16][SETK_ZSLOT]
-  float* mask;       // [2][mrows][kWsMaskRegion]
+  float* mask;       // [mslots][mrows][kWsMaskRegion], mslots = 3 (2 with mask_n rows)
   float2* acc128;    // [ROWS128][NPAIR]
   int Lp, mrows;
   SETK_HD static int staged_len(int hop) { return ((TT - 1) * hop + kNfft + 3) & ~3; }
+  SETK_HD static int mask_slots(int mrows) { return mrows > 1 ? 2 : 3; }
   SETK_HD static size_t bytes(int hop, int mrows) {
-    return 64 + sizeof(float) * kNfft + sizeof(float2) * 256 + sizeof(float) * C * staged_len(hop) +
-           sizeof(float2) * 2 * 16 * SETK_ZSLOT + sizeof(float) * 2 * mrows * kWsMaskRegion +
+    return 64 + sizeof(WsTile) * (kWsChunk + 2) + sizeof(float) * kNfft + sizeof(float2) * 256 +
+           sizeof(float) * C * staged_len(hop) + sizeof(float2) * 2 * 16 * SETK_ZSLOT +
+           sizeof(float) * mask_slots(mrows) * mrows * kWsMaskRegion +
            sizeof(float2) * WsShape<C>::ROWS128 * WsShape<C>::NPAIR;
   }
   __device__ void carve(float* base, int hop, int mrows_) {
@@ -100,36 +118,14 @@ struct WsSmem {
     mrows = mrows_;
     MBar* bars = reinterpret_cast<MBar*>(base);
     bar_audio = bars; z_full = bars + 1; z_empty = bars + 3;
-    win = base + 16;
+    tiles = reinterpret_cast<WsTile*>(base + 16);
+    win = base + 16 + 4 * (kWsChunk + 2);
     twtab = reinterpret_cast<float2*>(win + kNfft);
     audio = reinterpret_cast<float*>(twtab + 256);
     z = reinterpret_cast<float2*>(audio + C * Lp);
     mask = reinterpret_cast<float*>(z + 2 * 16 * SETK_ZSLOT);
-    acc128 = reinterpret_cast<float2*>(mask + 2 * mrows * kWsMaskRegion);
+    acc128 = reinterpret_cast<float2*>(mask + mask_slots(mrows) * mrows * kWsMaskRegion);
   }
-};
-
-// Where a linear tile index lives: utterance b, the tiles before it / before the next one.
-struct WsCursor {
-  int b, pb, pe, nb, Tb;
-  __device__ __forceinline__ void load(const StftCovArgs& a) {
-    nb = a.n_samples ? a.n_samples[b] : a.N;
-    Tb = frames_of(nb, kNfft, a.g.hop, a.g.pad);
-  }
-  __device__ __forceinline__ void seek(const StftCovArgs& a, int x) {
-    b = sched_find(a.sched, x);
-    pb = sched_prefix(a.sched, b);
-    pe = sched_prefix(a.sched, b + 1);
-    load(a);
-  }
-  __device__ __forceinline__ void advance(const StftCovArgs& a, int x) {   // x >= pb
-    if (x >= pe) {
-      do { ++b; pb = pe; pe = sched_prefix(a.sched, b + 1); } while (x >= pe);
-      load(a);
-    }
-  }
-  // live frames of tile x (0 for the empty tile of a too-short utterance)
-  __device__ __forceinline__ int frames(int x, int TT) const { return imax(0, imin(TT, Tb - (x - pb) * TT)); }
 };
 
 // Can the TT mask rows of tile (b, frames t0..) arrive as one bulk copy?  They are TT * F
@@ -146,6 +142,38 @@ __device__ __forceinline__ bool ws_mask_bulk(const StftCovArgs& a, int b, int t0
     return false;
   const long long end = first + (long long)TT * kBins;
   return ((end + 3) & ~3LL) <= (long long)a.sched.B * a.T * kBins;
+}
+
+// Descriptor of linear tile x of the launch (x in this CTA's run [lo, hi); q = its quota).
+template <int C>
+__device__ __forceinline__ WsTile ws_describe(const StftCovArgs& a, int x, int lo, int hi, int q,
+                                              bool vec_ok) {
+  constexpr int TT = WsShape<C>::TT;
+  WsTile d;
+  const int b = sched_find(a.sched, x);
+  const int pb = sched_prefix(a.sched, b), pe = sched_prefix(a.sched, b + 1);
+  d.b = b;
+  d.nb = a.n_samples ? a.n_samples[b] : a.N;
+  d.t0 = (x - pb) * TT;
+  const int nt = imax(0, imin(TT, frames_of(d.nb, kNfft, a.g.hop, a.g.pad) - d.t0));
+  unsigned f = (unsigned)nt;
+  if (nt > 0 && tile_bulk_ok(d.t0, nt, a.g.hop, a.g.pad, d.nb, vec_ok)) f |= WS_AUDIO_BULK;
+  long long first;
+  int shift;
+  if (ws_mask_bulk(a, b, d.t0, nt, TT, first, shift)) f |= WS_MASK_BULK;
+  f |= (unsigned)shift << WS_SHIFT_POS;
+  if (x == imax(lo, pb)) f |= WS_SEG_BEGIN;
+  if (x + 1 == imin(hi, pe)) f |= WS_SEG_END;
+  if (x + 1 == pe) f |= WS_UTT_END;
+  f |= (unsigned)((int)blockIdx.x - pb / q) << WS_SLOT_POS;
+  d.flags = f;
+  return d;
+}
+// Both roles call this between two __syncthreads(): descriptors of tiles [c0, c0 + count).
+template <int C>
+__device__ __forceinline__ void ws_fill_table(const StftCovArgs& a, const WsSmem<C>& sm, int c0, int count,
+                                              int lo, int hi, int q, bool vec_ok) {
+  for (int i = threadIdx.x; i < count; i += kWsThreads) sm.tiles[i] = ws_describe<C>(a, c0 + i, lo, hi, q, vec_ok);
 }
 
 // ---- audio staging by the FFT warps (threads 0..255) ----
@@ -179,113 +207,117 @@ __device__ __forceinline__ void ws_stage_scalar(const WsSmem<C>& sm, const float
 // ---------------------------------------------------------------------------
 // FFT role: threads 0..255, half-warp job = thread / 16 = frame * C + channel
 // ---------------------------------------------------------------------------
-template <int C>
-__device__ __forceinline__ void ws_fft_role(const StftCovArgs& a, const WsSmem<C>& sm, int lo, int hi,
+template <int C, bool HAS_MN>
+__device__ __forceinline__ void ws_fft_role(const StftCovArgs& a, const WsSmem<C>& sm, int lo, int hi, int q,
                                             bool vec_ok) {
   constexpr int TT = WsShape<C>::TT;
+  constexpr int NR = HAS_MN ? 2 : 1, MS = HAS_MN ? 2 : 3;
   const int ftid = (int)threadIdx.x - (SETK_WS_COV_FIRST ? kWsCovThreads : 0);
   const int lane = ftid & 31, lane16 = lane & 15;
   const int job = ftid >> 4;
   const int fr = job / C, ch = job - fr * C;
   const int hop = a.g.hop, pad = a.g.pad;
   float amax = 0.f;
-
-  WsCursor cur;
-  cur.seek(a, lo);
-  bool async_cur = false;
-  {
-    const int nt = cur.frames(lo, TT);
-    if (nt > 0) {
-      const int t0 = (lo - cur.pb) * TT;
-      const float* xb = a.audio + (long long)cur.b * C * a.N;
-      if (tile_bulk_ok(t0, nt, hop, pad, cur.nb, vec_ok)) {
-        if (ftid == 0) ws_stage_bulk<C>(sm, xb, a.N, t0, nt, hop, pad);
-        async_cur = true;
-      } else {
-        ws_stage_scalar<C>(sm, xb, a.N, cur.nb, t0, nt, hop, pad, ftid);
-        named_bar_sync(kWsBarFft, kWsFftThreads);
-      }
-    }
-  }
   unsigned apar = 0;
-  for (int x = lo, n = 0; x < hi; ++x, ++n) {
-    const int nt = cur.frames(x, TT);
-    float2 v[16];
-    if (nt > 0) {
-      if (async_cur) { mbar_wait(sm.bar_audio, apar); apar ^= 1u; }
-      // a dead frame (fr >= nt, only in an utterance's last tile) re-transforms the last live
-      // one: its spectrum is never read and max|x| sees nothing new
-      const int fr_src = imin(fr, nt - 1);
-      const float* src = sm.audio + ch * sm.Lp + fr_src * hop + 2 * lane16;
-      const float* wsrc = sm.win + 2 * lane16;
-#pragma unroll
-      for (int m1 = 0; m1 < 16; ++m1) {
-        const float2 s = *reinterpret_cast<const float2*>(src + 32 * m1);
-        const float2 w = *reinterpret_cast<const float2*>(wsrc + 32 * m1);
-        amax = fmaxf(amax, fmaxf(fabsf(s.x), fabsf(s.y)));
-        v[m1] = f2mul(s, w);
-      }
+
+  // one thread: the mask rows of tile d (local number nn) -> mask slot nn % MS, completing on
+  // z_full[nn & 1] together with that tile's Z
+  auto issue_mask = [&](const WsTile& d, int nn, int mslot) {
+    const int shift = (int)(d.flags >> WS_SHIFT_POS) & 3;
+    const long long a0 = ((long long)d.b * a.T + d.t0) * kBins - shift;
+    const unsigned bytes = (unsigned)(((shift + TT * kBins + 3) & ~3) * sizeof(float));
+    float* dst = sm.mask + mslot * NR * kWsMaskRegion;
+    MBar* bar = &sm.z_full[nn & 1];
+    fence_proxy_async();
+    mbar_add_tx(bar, bytes * (unsigned)NR);
+    bulk_g2s(dst, a.mask_s + a0, bytes, bar);
+    if (HAS_MN) bulk_g2s(dst + kWsMaskRegion, a.mask_n + a0, bytes, bar);
+  };
+  auto stage = [&](const WsTile& d) -> bool {       // true: written with ordinary stores
+    const int nt = (int)(d.flags & WS_NT);
+    if (nt <= 0) return false;
+    const float* xb = a.audio + (long long)d.b * C * a.N;
+    if (d.flags & WS_AUDIO_BULK) {
+      if (ftid == 0) ws_stage_bulk<C>(sm, xb, a.N, d.t0, nt, hop, pad);
+      return false;
     }
-    named_bar_sync(kWsBarFft, kWsFftThreads);   // every FFT warp holds its samples: the buffer is free
-    WsCursor nxt = cur;
-    bool async_next = false, scalar_next = false;
-    if (x + 1 < hi) {
-      nxt.advance(a, x + 1);
-      const int ntn = nxt.frames(x + 1, TT);
-      if (ntn > 0) {
-        const int t0n = (x + 1 - nxt.pb) * TT;
-        const float* xbn = a.audio + (long long)nxt.b * C * a.N;
-        if (tile_bulk_ok(t0n, ntn, hop, pad, nxt.nb, vec_ok)) {
-          if (ftid == 0) ws_stage_bulk<C>(sm, xbn, a.N, t0n, ntn, hop, pad);
-          async_next = true;
-        } else {
-          ws_stage_scalar<C>(sm, xbn, a.N, nxt.nb, t0n, ntn, hop, pad, ftid);
-          scalar_next = true;
+    ws_stage_scalar<C>(sm, xb, a.N, d.nb, d.t0, nt, hop, pad, ftid);
+    return true;
+  };
+
+  int n = 0, m3 = 0;                               // local tile number, n % MS
+  for (int c0 = lo; c0 < hi; c0 += kWsChunk) {
+    const int cnt = imin(kWsChunk, hi - c0);
+    __syncthreads();                               // the previous table is consumed by both roles
+    ws_fill_table<C>(a, sm, c0, cnt + (c0 + cnt < hi ? 1 : 0), lo, hi, q, vec_ok);
+    __syncthreads();
+    if (c0 == lo) {                                // the run's first tile: nobody staged it yet
+      const WsTile d = sm.tiles[0];
+      if (stage(d)) named_bar_sync(kWsBarFft, kWsFftThreads);
+      if (MS == 3 && ftid == 0 && (d.flags & WS_MASK_BULK)) issue_mask(d, 0, 0);
+    }
+    for (int i = 0; i < cnt; ++i, ++n) {
+      const WsTile d = sm.tiles[i];
+      const int nt = (int)(d.flags & WS_NT);
+      float2 v[16];
+      if (nt > 0) {
+        if (d.flags & WS_AUDIO_BULK) { mbar_wait(sm.bar_audio, apar); apar ^= 1u; }
+        // a dead frame (fr >= nt, only in an utterance's last tile) re-transforms the last live
+        // one: its spectrum is never read and max|x| sees nothing new
+        const int fr_src = imin(fr, nt - 1);
+        const float* src = sm.audio + ch * sm.Lp + fr_src * hop + 2 * lane16;
+        const float* wsrc = sm.win + 2 * lane16;
+#pragma unroll
+        for (int m1 = 0; m1 < 16; ++m1) {
+          const float2 sx = *reinterpret_cast<const float2*>(src + 32 * m1);
+          const float2 w = *reinterpret_cast<const float2*>(wsrc + 32 * m1);
+          amax = fmaxf(amax, fmaxf(fabsf(sx.x), fabsf(sx.y)));
+          v[m1] = f2mul(sx, w);
         }
       }
-    }
-    if (nt > 0) halfwarp_fft256_a(v, sm.twtab, lane16);
-    const int s = n & 1;
-    mbar_wait(&sm.z_empty[s], ((unsigned)(n >> 1) & 1u) ^ 1u);
-    if (nt > 0 && ftid == 0) {
-      // the slot is free (the covariance warps are done with tile n - 2): this tile's mask rows
-      long long first;
-      int shift;
-      if (ws_mask_bulk(a, cur.b, (x - cur.pb) * TT, nt, TT, first, shift)) {
-        const unsigned bytes = (unsigned)(((shift + TT * kBins + 3) & ~3) * sizeof(float));
-        float* dst = sm.mask + s * sm.mrows * kWsMaskRegion;
-        fence_proxy_async();
-        mbar_add_tx(&sm.z_full[s], bytes * (unsigned)sm.mrows);
-        bulk_g2s(dst, a.mask_s + (first - shift), bytes, &sm.z_full[s]);
-        if (sm.mrows > 1) bulk_g2s(dst + kWsMaskRegion, a.mask_n + (first - shift), bytes, &sm.z_full[s]);
+      named_bar_sync(kWsBarFft, kWsFftThreads);    // every FFT warp holds its samples: the buffer is free
+      const bool has_next = c0 + i + 1 < hi;
+      bool scalar_next = false;
+      if (has_next) scalar_next = stage(sm.tiles[i + 1]);
+      if (nt > 0) halfwarp_fft256_a(v, sm.twtab, lane16);
+      const int s = n & 1;
+      mbar_wait(&sm.z_empty[s], ((unsigned)(n >> 1) & 1u) ^ 1u);
+      // the covariance warps are done with tile n - 2: its Z slot, and the mask slot tile n + 1
+      // (three mask slots) or tile n (two) will use, are free
+      if (ftid == 0) {
+        if (MS == 3) {
+          if (has_next && (sm.tiles[i + 1].flags & WS_MASK_BULK))
+            issue_mask(sm.tiles[i + 1], n + 1, m3 == 2 ? 0 : m3 + 1);
+        } else if (d.flags & WS_MASK_BULK) {
+          issue_mask(d, n, s);
+        }
       }
-    }
-    if (nt > 0) {
-      float2* zs = sm.z + (s * 16 + job) * SETK_ZSLOT;
-      halfwarp_fft256_b(v, zs, lane16);
+      if (nt > 0) {
+        float2* zs = sm.z + (s * 16 + job) * SETK_ZSLOT;
+        halfwarp_fft256_b(v, zs, lane16);
 #pragma unroll
-      for (int q = 0; q < 16; ++q) zs[lane16 + 16 * kof(q)] = v[q];
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.z_full[s]);
-
-    // end of this utterance's part of the CTA's run: max|x| (SpectrogramReader.maxabs)
-    const int seg_end = imin(hi, cur.pe);
-    if (x + 1 == seg_end && a.maxabs_bits) {
-      if (seg_end == cur.pe) {      // center=False leaves a tail no frame covers
-        const int covered = (cur.Tb > 0 ? (cur.Tb - 1) * hop + kNfft - 2 * pad : 0);
-        const float* xb = a.audio + (long long)cur.b * C * a.N;
-        for (int c = 0; c < C; ++c)
-          for (int i = imax(covered, 0) + ftid; i < cur.nb; i += kWsFftThreads)
-            amax = fmaxf(amax, fabsf(xb[(long long)c * a.N + i]));
+        for (int p = 0; p < 16; ++p) zs[lane16 + 16 * kof(p)] = v[p];
       }
-      for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-      if (lane == 0 && amax > 0.f) atomicMax(a.maxabs_bits + cur.b, __float_as_uint(amax));
-      amax = 0.f;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.z_full[s]);
+
+      // end of this utterance's part of the CTA's run: max|x| (SpectrogramReader.maxabs)
+      if ((d.flags & WS_SEG_END) && a.maxabs_bits) {
+        if (d.flags & WS_UTT_END) {                 // center=False leaves a tail no frame covers
+          const int Tb = frames_of(d.nb, kNfft, hop, pad);
+          const int covered = (Tb > 0 ? (Tb - 1) * hop + kNfft - 2 * pad : 0);
+          const float* xb = a.audio + (long long)d.b * C * a.N;
+          for (int c = 0; c < C; ++c)
+            for (int k = imax(covered, 0) + ftid; k < d.nb; k += kWsFftThreads)
+              amax = fmaxf(amax, fabsf(xb[(long long)c * a.N + k]));
+        }
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        if (lane == 0 && amax > 0.f) atomicMax(a.maxabs_bits + d.b, __float_as_uint(amax));
+        amax = 0.f;
+      }
+      if (scalar_next) named_bar_sync(kWsBarFft, kWsFftThreads);
+      m3 = (m3 == MS - 1) ? 0 : m3 + 1;
     }
-    if (scalar_next) named_bar_sync(kWsBarFft, kWsFftThreads);
-    cur = nxt;
-    async_cur = async_next;
   }
 }
 
@@ -378,10 +410,10 @@ __device__ __forceinline__ void ws_cov_tile(float2* ak, float2* am, float2* my12
 
 template <int C, bool HAS_MN>
 __device__ __forceinline__ void ws_cov_role(const StftCovArgs& a, const WsSmem<C>& sm, int lo, int hi,
-                                            int q) {
+                                            int q, bool vec_ok) {
   constexpr int TT = WsShape<C>::TT, NPAIR = WsShape<C>::NPAIR, NACC = WsShape<C>::NACC;
   constexpr int ROWS128 = WsShape<C>::ROWS128, F = kBins;
-  constexpr int NR = HAS_MN ? 2 : 1;
+  constexpr int NR = HAS_MN ? 2 : 1, MS = HAS_MN ? 2 : 3;
   const int tid = (int)threadIdx.x - (SETK_WS_COV_FIRST ? 0 : kWsFftThreads), lane = tid & 31, warp = tid >> 5;
   const int bk = tid, bm = kM - tid;                       // the pair's bins
   const int zk = tid, zn = (kM - tid) & (kM - 1);          // their half-size spectrum entries
@@ -391,74 +423,76 @@ __device__ __forceinline__ void ws_cov_role(const StftCovArgs& a, const WsSmem<C
   float2 ak[NPAIR], am[NPAIR];
   float2* my128 = sm.acc128 + (warp * TT + imin(lane, TT - 1)) * NPAIR;
 
-  WsCursor cur;
-  cur.seek(a, lo);
-  for (int x = lo, n = 0; x < hi; ++x, ++n) {
-    cur.advance(a, x);
-    const int nt = cur.frames(x, TT);
-    const int t0 = (x - cur.pb) * TT;
-    const int seg_begin = imax(lo, cur.pb), seg_end = imin(hi, cur.pe);
-    if (x == seg_begin) {
+  int n = 0, m3 = 0;                                       // local tile number, n % MS
+  for (int c0 = lo; c0 < hi; c0 += kWsChunk) {
+    const int cnt = imin(kWsChunk, hi - c0);
+    __syncthreads();
+    ws_fill_table<C>(a, sm, c0, cnt + (c0 + cnt < hi ? 1 : 0), lo, hi, q, vec_ok);
+    __syncthreads();
+    for (int i = 0; i < cnt; ++i, ++n) {
+      const WsTile d = sm.tiles[i];
+      const int nt = (int)(d.flags & WS_NT);
+      if (d.flags & WS_SEG_BEGIN) {
 #pragma unroll
-      for (int p = 0; p < NPAIR; ++p) { ak[p] = make_float2(0.f, 0.f); am[p] = make_float2(0.f, 0.f); }
-      if (lane < TT) {
+        for (int p = 0; p < NPAIR; ++p) { ak[p] = make_float2(0.f, 0.f); am[p] = make_float2(0.f, 0.f); }
+        if (lane < TT) {
 #pragma unroll
-        for (int p = 0; p < NPAIR; ++p) my128[p] = make_float2(0.f, 0.f);
+          for (int p = 0; p < NPAIR; ++p) my128[p] = make_float2(0.f, 0.f);
+        }
       }
-    }
-    const bool handler = warp == (n & 3);
-    long long first;
-    int shift;
-    const bool bulk = ws_mask_bulk(a, cur.b, t0, nt, TT, first, shift);
-    // masks the bulk copy does not bring: plain loads, issued before the wait for the Z tile
-    float gk[TT * NR], gm[TT * NR], g128[NR];
-    if (!bulk && nt > 0) {
-      const long long mstride = mask_ft ? 1 : F, fmul = mask_ft ? a.T : 1;
-      const long long base = mask_ft ? (long long)cur.b * F * a.T + t0 : first;
+      const bool handler = warp == (n & 3);
+      const bool bulk = (d.flags & WS_MASK_BULK) != 0;
+      // masks the bulk copy does not bring: plain loads, issued before the wait for the Z tile
+      float gk[TT * NR], gm[TT * NR], g128[NR];
+      if (!bulk && nt > 0) {
+        const long long mstride = mask_ft ? 1 : F, fmul = mask_ft ? a.T : 1;
+        const long long base = mask_ft ? (long long)d.b * F * a.T + d.t0 : ((long long)d.b * a.T + d.t0) * F;
 #pragma unroll
-      for (int j = 0; j < TT; ++j) {
-        const long long o = base + imin(j, nt - 1) * mstride;
-        gk[j * NR] = a.mask_s[o + bk * fmul];
-        gm[j * NR] = a.mask_s[o + bm * fmul];
-        if (HAS_MN) { gk[j * NR + 1] = a.mask_n[o + bk * fmul]; gm[j * NR + 1] = a.mask_n[o + bm * fmul]; }
+        for (int j = 0; j < TT; ++j) {
+          const long long o = base + imin(j, nt - 1) * mstride;
+          gk[j * NR] = a.mask_s[o + bk * fmul];
+          gm[j * NR] = a.mask_s[o + bm * fmul];
+          if (HAS_MN) { gk[j * NR + 1] = a.mask_n[o + bk * fmul]; gm[j * NR + 1] = a.mask_n[o + bm * fmul]; }
+        }
+        const long long o128 = base + imin(lane, nt - 1) * mstride + 128 * fmul;
+        g128[0] = a.mask_s[o128];
+        if (HAS_MN) g128[1] = a.mask_n[o128];
       }
-      const long long o128 = base + imin(lane, nt - 1) * mstride + 128 * fmul;
-      g128[0] = a.mask_s[o128];
-      if (HAS_MN) g128[1] = a.mask_n[o128];
-    }
-    const int s = n & 1;
-    mbar_wait(&sm.z_full[s], (unsigned)(n >> 1) & 1u);
-    const float2* zt = sm.z + s * 16 * SETK_ZSLOT;
-    const float* ms = sm.mask + s * NR * kWsMaskRegion + shift;
-    if (bulk)
-      ws_cov_tile<C, HAS_MN, true, true>(ak, am, my128, zt, ms, gk, gm, g128, nt, clip, bk, bm, zk, zn, tw,
-                                         handler, lane);
-    else if (nt == TT)
-      ws_cov_tile<C, HAS_MN, false, true>(ak, am, my128, zt, ms, gk, gm, g128, nt, clip, bk, bm, zk, zn, tw,
-                                          handler, lane);
-    else if (nt > 0)
-      ws_cov_tile<C, HAS_MN, false, false>(ak, am, my128, zt, ms, gk, gm, g128, nt, clip, bk, bm, zk, zn, tw,
-                                           handler, lane);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.z_empty[s]);
+      const int s = n & 1;
+      mbar_wait(&sm.z_full[s], (unsigned)(n >> 1) & 1u);
+      const float2* zt = sm.z + s * 16 * SETK_ZSLOT;
+      const float* ms = sm.mask + m3 * NR * kWsMaskRegion + ((d.flags >> WS_SHIFT_POS) & 3);
+      if (bulk)
+        ws_cov_tile<C, HAS_MN, true, true>(ak, am, my128, zt, ms, gk, gm, g128, nt, clip, bk, bm, zk, zn,
+                                           tw, handler, lane);
+      else if (nt == TT)
+        ws_cov_tile<C, HAS_MN, false, true>(ak, am, my128, zt, ms, gk, gm, g128, nt, clip, bk, bm, zk, zn,
+                                            tw, handler, lane);
+      else if (nt > 0)
+        ws_cov_tile<C, HAS_MN, false, false>(ak, am, my128, zt, ms, gk, gm, g128, nt, clip, bk, bm, zk, zn,
+                                             tw, handler, lane);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.z_empty[s]);
 
-    if (x + 1 == seg_end) {
-      // ---- partial sums of this segment -> slot ----
-      const int slot = (int)blockIdx.x - cur.pb / q;
-      float* pp = a.partials + (((long long)cur.b * a.slots + slot) * (2 * NACC + 2)) * F;
+      if (d.flags & WS_SEG_END) {
+        // ---- partial sums of this segment -> slot ----
+        const int slot = (int)(d.flags >> WS_SLOT_POS) & 0xff;
+        float* pp = a.partials + (((long long)d.b * a.slots + slot) * (2 * NACC + 2)) * F;
 #pragma unroll
-      for (int p = 0; p < NPAIR; ++p) {
-        ws_store_pair<C>(pp + bk, p, ak[p]);
-        ws_store_pair<C>(pp + bm, p, am[p]);
-      }
-      named_bar_sync(kWsBarCov, kWsCovThreads);     // every warp's bin-128 rows are final
-      if (tid < NPAIR) {
-        float2 sum = make_float2(0.f, 0.f);
+        for (int p = 0; p < NPAIR; ++p) {
+          ws_store_pair<C>(pp + bk, p, ak[p]);
+          ws_store_pair<C>(pp + bm, p, am[p]);
+        }
+        named_bar_sync(kWsBarCov, kWsCovThreads);     // every warp's bin-128 rows are final
+        if (tid < NPAIR) {
+          float2 sum = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int r = 0; r < ROWS128; ++r) sum = f2add(sum, sm.acc128[r * NPAIR + tid]);
-        ws_store_pair<C>(pp + 128, tid, sum);
+          for (int r = 0; r < ROWS128; ++r) sum = f2add(sum, sm.acc128[r * NPAIR + tid]);
+          ws_store_pair<C>(pp + 128, tid, sum);
+        }
+        named_bar_sync(kWsBarCov, kWsCovThreads);     // rows may be zeroed again
       }
-      named_bar_sync(kWsBarCov, kWsCovThreads);     // rows may be zeroed again
+      m3 = (m3 == MS - 1) ? 0 : m3 + 1;
     }
   }
 }
@@ -487,14 +521,14 @@ __global__ void __maxnreg__(SETK_WS_LAUNCH_REGS) stft_cov_ws_kernel(StftCovArgs 
     mbar_init(&sm.z_empty[1], kWsCovThreads / 32);
   }
   __syncthreads();
+  const bool vec_ok = ((a.N & 3) == 0) && ((a.g.hop & 3) == 0) && ((a.g.pad & 3) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(a.audio) & 15) == 0);
   if (SETK_WS_COV_FIRST ? tid < kWsCovThreads : tid >= kWsFftThreads) {
     setmaxnreg_inc<SETK_WS_COV_REGS>();
-    ws_cov_role<C, HAS_MN>(a, sm, lo, hi, q);
+    ws_cov_role<C, HAS_MN>(a, sm, lo, hi, q, vec_ok);
   } else {
     setmaxnreg_dec<SETK_WS_FFT_REGS>();
-    const bool vec_ok = ((a.N & 3) == 0) && ((a.g.hop & 3) == 0) && ((a.g.pad & 3) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(a.audio) & 15) == 0);
-    ws_fft_role<C>(a, sm, lo, hi, vec_ok);
+    ws_fft_role<C, HAS_MN>(a, sm, lo, hi, q, vec_ok);
   }
 }
 

@@ -81,11 +81,12 @@ class BeamformPipeline(object):
                        out_dtype=torch.complex64)
 
     def run(self, audio, mask_s, mask_n=None, n_samples=None, clip_mask=None,
-            normalize=True, n_out=None):
+            normalize=True, n_out=None, pcm16_out=False):
         """
         audio (B,C,N) f32, mask_s (B,T,F) f32 [, mask_n].  Returns
         (wave (B,N_out) f32, status (B,) int32 device tensor).  `normalize`
-        applies inverse_stft's norm=max|x| rescale (CLI behaviour).
+        applies inverse_stft's norm=max|x| rescale (CLI behaviour); `pcm16_out`
+        returns the int16 samples WaveWriter would write (floor(y * 32768)).
         """
         Rs, Rn, maxabs = self.covariances(audio, mask_s, mask_n, n_samples, clip_mask)
         Ry = None
@@ -103,7 +104,7 @@ class BeamformPipeline(object):
                 post = torch.clamp(post, max=1.0)
         wave = self.plan.apply_istft(audio, w, post_mask=post, n_out=n_out,
                                      norm=maxabs if normalize else None,
-                                     n_samples=n_samples)
+                                     n_samples=n_samples, pcm16=pcm16_out)
         return wave, status
 
     def run_pcm16(self, audio_pcm16, mask_s, **kw):

@@ -223,8 +223,11 @@ class StftPlan(object):
                                                  _lib.ptr(norm_t), _lib.ptr(wave), self._stream()))
         return wave
 
-    def apply_istft(self, audio, weight, post_mask=None, n_out=None, norm=None, n_samples=None):
-        """Fused beamform + iSTFT from audio.  weight (B,F,C) complex."""
+    def apply_istft(self, audio, weight, post_mask=None, n_out=None, norm=None, n_samples=None,
+                    pcm16=False):
+        """Fused beamform + iSTFT from audio.  weight (B,F,C) complex.
+        pcm16=True: the `norm` rescale pass writes what WaveWriter would put in the wav file
+        (int16 = floor(y * 32768) clipped, utils.py:45-62) instead of float32."""
         audio = self._check_audio(audio)
         B, C, N = audio.shape
         T = self.num_frames(N)
@@ -239,9 +242,11 @@ class StftPlan(object):
             n_out = self.istft_length(T)
         norm_t = None if norm is None else _f32(norm, self.device).reshape(B)
         ns = self._nsamp(n_samples, B)
-        wave = torch.empty((B, int(n_out)), dtype=torch.float32, device=self.device)
+        wave = torch.empty((B, int(n_out)), dtype=torch.int16 if pcm16 else torch.float32,
+                           device=self.device)
+        fn = _lib.library().setk_apply_istft_pcm16 if pcm16 else _lib.library().setk_apply_istft
         with self._device_ctx():
-            _lib.check(_lib.library().setk_apply_istft(
+            _lib.check(fn(
                 self._h, _lib.ptr(audio), _lib.ptr(ns), B, N, _lib.ptr(weight), _dtype_code(weight),
                 _lib.ptr(post_mask), int(n_out), _lib.ptr(norm_t), _lib.ptr(wave), self._stream()))
         return wave
