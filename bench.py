@@ -8,27 +8,29 @@ center, batch = 256 utterances per GPU per step.  A "step" is one pass of the
 hot path over one resident batch:
 
     setk_stft_cov (fused STFT + Rs/Rn) -> setk_weights (fp64 MVDR) ->
-    setk_apply_istft (fused beamform + iSTFT + peak normalisation)
+    setk_apply_istft_pcm16 (fused beamform + iSTFT + peak normalisation + the wav
+    writer's float -> PCM-16 conversion)
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 N > 1 is launched by torch.distributed.run, one rank per GPU; utterances shard
-across ranks with no data-path collective ("scaling": "weak"); the timed region
-ends with ONE NCCL gather of the last batch's enhanced audio to rank 0.
+across ranks with no data-path collective ("scaling": "weak").  EVERY batch's
+enhanced audio (PCM-16, what the wav files would hold) is gathered to rank 0 by
+NCCL inside the timed region, asynchronously to the kernels.
 
 Prints one JSON line (rank 0).  Keys beyond the base contract:
   roofline      the dominant kernel (fused STFT+covariance): algorithmic bytes
                 per launch / CUDA-event time of that call, vs MEASURED_PEAKS.json
-  cpu_baseline  the oracle's numpy restatement of the reference path timed on
-                this box's host cores (bounded sample), beside the GPU number
-  e2e           same metric through the public API with HOST (pinned) buffers:
-                H2D of audio+mask and D2H of the enhanced audio inside the
-                timed region
-`--impl reference` times the reference's CPU implementation of the path (the
-oracle port: /root/reference does not exist on the GPU box) with all host
-cores, and prints the same JSON line with "impl": "reference".
+  cpu_baseline  the reference's CPU path (oracle port; the reference's own modules
+                when its tree is present) on this box's host cores (N = 1 only)
+  e2e           same metric through the public API with HOST (pinned) buffers: PCM-16
+                audio + float32 masks in, PCM-16 enhanced audio out, every step
+  configs       the other BASELINE.json configurations (3, 4, 5) at this GPU count
+`--impl reference` times the reference's CPU implementation of the path with all
+host cores and prints the same JSON line with "impl": "reference".
 """
 import argparse
+import collections
 import json
 import os
 import subprocess
@@ -46,10 +48,21 @@ C, N, FRAME_LEN, HOP, NFFT = 4, 160000, 512, 256, 512
 BATCH = 256
 F = NFFT // 2 + 1
 T = 1 + N // HOP            # center=True
+WORKLOAD = "cfg2: 4-ch MVDR, IRM mask, 16 kHz x 10 s, 512/256 hann center, batch 256 per GPU"
 
 
-def algorithmic_bytes_stft_cov(c=C, n=N, t=T, f=F):
+def config_dict(world, batch=BATCH):
+    """The workload both arms are measured on (identical in both JSON lines)."""
+    return {"workload": WORKLOAD, "batch_per_gpu": batch, "global_batch": batch * world,
+            "parallelism": f"utterance-sharded x{world}, no data-path collective; every batch's "
+                           f"PCM-16 result gathered to rank 0 inside the timed region",
+            "l2": f"inputs {batch * (C * N + T * F) * 4 / 1e6:.0f} MB per step exceed the 126 MB L2 "
+                  f"(no flush needed)"}
+
+
+def algorithmic_bytes_stft_cov(c=C, n=N, n_fft=NFFT, hop=HOP):
     """audio f32 + mask f32 + Rs,Rn c64, per utterance."""
+    f, t = n_fft // 2 + 1, 1 + n // hop
     return 4 * c * n + 4 * t * f + 2 * 8 * f * c * c
 
 
@@ -65,17 +78,17 @@ def measured_peaks():
 def measured_traffic(batch):
     """
     dram__bytes_read + dram__bytes_write of the dominant kernel per launch, from the
-    committed `ncu --set full` capture (profiles/r1_traffic.json); only valid for the
+    committed `ncu --set full` capture (profiles/r2_traffic.json); only valid for the
     batch it was captured on, else null.
     """
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    try:
-        with open(path) as fh:
-            d = json.load(fh)
-        if batch * algorithmic_bytes_stft_cov() == d["algorithmic_bytes_per_launch"]:
-            return d["traffic_bytes_per_launch"]
-    except Exception:
-        pass
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as fh:
+                d = json.load(fh)
+            if batch * algorithmic_bytes_stft_cov() == d["algorithmic_bytes_per_launch"]:
+                return d["traffic_bytes_per_launch"]
+        except Exception:
+            continue
     return None
 
 
@@ -122,45 +135,12 @@ class ClockSampler(threading.Thread):
             except Exception:
                 continue
         sm.sort()
-        med = sm[len(sm) // 2] if sm else None
+        # median over the upper half of the samples = the clock under load (the sampler also
+        # sees the idle gaps between the timed phases)
+        busy = sm[len(sm) // 2:] if sm else []
+        med = busy[len(busy) // 2] if busy else None
         return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
                 "samples": len(sm)}
-
-
-# ------------------------------------------------------------------ CPU arm ---
-def run_cpu_arm(n_utts_per_worker, workers, seed=20240923):
-    """Reference CPU path (oracle port) on `workers` processes; returns utts/s."""
-    from oracle import cpu_bench
-    return cpu_bench.throughput(C, N, n_utts_per_worker, workers, seed)
-
-
-def reference_arm(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    from oracle.cpu_bench import usable_cores
-    cores = usable_cores()
-    # a "step" of this arm = one utterance per worker process (a bounded sample of
-    # the 256-utterance GPU step); each worker warms up on one utterance first
-    # (oracle/cpu_bench.py), then times `per_worker` utterances back to back
-    per_worker = max(4, min(args.steps, 24))
-    t0 = time.time()
-    val = run_cpu_arm(per_worker, cores)
-    sample = (f"{per_worker} steps x {cores} utterances of the workload "
-              f"({cores} single-threaded worker processes like run.pl nj={cores}), compute only")
-    line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT,
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1000.0 * BATCH / val, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg2: 4-ch MVDR, IRM mask, 16 kHz x 10 s, 512/256 hann center, "
-                               "batch 256 per GPU", "cpu": cpu_model()},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": sample},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "wall_s": time.time() - t0,
-    }
-    print(json.dumps(line), flush=True)
 
 
 def cpu_model():
@@ -174,12 +154,91 @@ def cpu_model():
     return "unknown"
 
 
+# ------------------------------------------------------------------ CPU arm ---
+def cpu_steps(steps, warmup, budget_s, cores):
+    """
+    The reference's CPU path for `steps` steps.  A step is the GPU step's 256 utterances when
+    the whole run fits `budget_s` at ~20 utterances/s/core, else a bounded sample of it (a
+    multiple of the worker count); the line says which.
+    """
+    from oracle import cpu_bench
+    fit = int(budget_s * 20.0 * cores / max(1, steps + warmup))
+    ups = BATCH if fit >= BATCH else max(cores, (fit // cores) * cores)
+    return cpu_bench.run_steps(C, N, steps, warmup, ups, cores)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.cpu_bench import usable_cores
+    cores = usable_cores()
+    t0 = time.time()
+    r = cpu_steps(args.steps, args.warmup, args.cpu_budget, cores)
+    sample = (f"each step = {r['utts_per_step']} utterances of the {BATCH}-utterance GPU step"
+              f"{'' if r['utts_per_step'] == BATCH else ' (bounded sample)'}, spread over {r['workers']} "
+              f"single-threaded worker processes (run.pl nj={r['workers']}), distinct utterances, "
+              f"compute only")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"], "utts_per_step": r["utts_per_step"],
+        "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (STFT/cov/apply), f64 (per-bin weight solve)",
+        "data": "synthetic",
+        "config": config_dict(max(1, args.gpus), args.batch),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": cores, "kind": r["kind"],
+                         "sample": sample, "cpu": cpu_model(), "reference_root": r["reference_root"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "timed_s": r["seconds"], "wall_s": time.time() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------- NUMA binding ---
+def numa_bind(dev_index):
+    """
+    Pin this rank to the CPUs of its GPU's NUMA node BEFORE any pinned host allocation, so that
+    the staging buffers are node-local (first touch) and the ranks of an 8-GPU box do not
+    fight over one socket's memory controller.  Returns what was done, for the JSON line.
+    """
+    info = {"bound": False}
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(dev_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as fh:
+            node = int(fh.read().strip())
+        info["gpu_pci"] = bdf
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            spec = fh.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info["bound"] = True
+            info["cpus"] = len(cpus)
+    except Exception as e:          # no sysfs / no permission: run unbound and say so
+        info["error"] = f"{type(e).__name__}: {e}"
+    return info
+
+
 # ------------------------------------------------------------------ GPU arm ---
 def gpu_arm(args):
     import torch
     import torch.distributed as dist
     from setk_b200 import _lib, synth
-    from setk_b200.engine import BeamformPipeline
+    from setk_b200 import plan as P_
+    from setk_b200.engine import BeamformPipeline, HostBatchStreamer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -187,6 +246,21 @@ def gpu_arm(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+
+    # CPU baseline first (rank 0, N=1 only): before the GPU gets busy and before the rank is
+    # bound to one NUMA node
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.cpu_bench import usable_cores
+        cores = usable_cores()
+        r = cpu_steps(2, 1, 20.0, cores)
+        cpu_base = {"value": r["value"], "unit": UNIT, "cores": cores, "kind": r["kind"],
+                    "sample": f"2 steps x {r['utts_per_step']} utterances of the same synthetic workload "
+                              f"({r['workers']} single-threaded processes, distinct utterances), compute "
+                              f"only, {r['seconds']:.1f} s",
+                    "cpu": cpu_model()}
+
+    numa = numa_bind(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # stdout carries ONE JSON line: keep NCCL's "NCCL version ..." banner off it
@@ -194,24 +268,21 @@ def gpu_arm(args):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
-    # CPU baseline first (rank 0, N=1 only): before the GPU gets busy
-    cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle.cpu_bench import usable_cores
-        cores = usable_cores()
-        if args.cpu_utts <= 0:
-            args.cpu_utts = 16 * cores
-        per_worker = max(1, args.cpu_utts // cores)
-        v = run_cpu_arm(per_worker, cores)
-        cpu_base = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                    "sample": f"{per_worker * cores} utterances of the same synthetic workload "
-                              f"({cores} processes x {per_worker}), oracle numpy path, compute only",
-                    "cpu": cpu_model()}
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     B = args.batch
     pipe = BeamformPipeline(C, "mvdr", frame_len=FRAME_LEN, frame_hop=HOP, center=True,
                             window="hann", max_batch=B, max_samples=N, device=dev)
-    # distinct synthetic utterances per rank; a few unique ones tiled to the batch
+    # distinct synthetic utterances per rank (tiled to the batch when --unique < batch)
     uniq = min(B, args.unique)
     a_u, m_u = synth.make_batch(uniq, C, N, device=dev, first=rank * uniq)
     reps = (B + uniq - 1) // uniq
@@ -221,22 +292,34 @@ def gpu_arm(args):
     torch.cuda.synchronize()
 
     def step():
-        return pipe.run(audio, mask)
+        return pipe.run(audio, mask, pcm16_out=True)
 
-    for _ in range(args.warmup):
-        wave, status = step()
-    if world > 1:
-        # warm the gather path too: NCCL sets up its P2P channels lazily on first use
-        g0 = [torch.empty_like(wave) for _ in range(world)] if rank == 0 else None
-        dist.gather(wave, g0, dst=0)
-        del g0
+    # ---- the result gather: every batch, PCM-16, asynchronous to the kernels ----
+    RING = 3
+    glists = None
+    if world > 1 and rank == 0:
+        n_out = pipe.plan.istft_length(T)
+        glists = [[torch.empty((B, n_out), dtype=torch.int16, device=dev) for _ in range(world)]
+                  for _ in range(RING)]
+
+    def run_steps(k):
+        works, keep = [], collections.deque(maxlen=RING + 1)
+        wave = status = None
+        for i in range(k):
+            wave, status = step()
+            if world > 1:
+                if i >= RING:
+                    works[i - RING].wait()          # that ring slot's gather has drained
+                keep.append(wave)
+                works.append(dist.gather(wave, glists[i % RING] if rank == 0 else None, dst=0,
+                                         async_op=True))
+        for w in works[-RING:]:
+            w.wait()
+        return wave, status
+
+    wave, status = run_steps(max(args.warmup, 1))
     torch.cuda.synchronize()
     assert int(status.abs().sum()) == 0, "solver reported failures on the synthetic batch"
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -246,99 +329,106 @@ def gpu_arm(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    for _ in range(args.steps):
-        wave, status = step()
-    gathered = None
-    if world > 1:
-        gathered = [torch.empty_like(wave) for _ in range(world)] if rank == 0 else None
-        dist.gather(wave, gathered, dst=0)
+    wave, status = run_steps(args.steps)
     ev1.record()
     barrier()
-    ms = ev0.elapsed_time(ev1)
     launches = _lib.launch_count() - launches0
-    if sampler:
-        sampler.stop()
-    t_ms = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms = float(t_ms.item())
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
     value = world * B * args.steps / (ms / 1000.0)
 
+    # ---- the gather alone (one batch from every rank into rank 0), for the record ----
+    gather = None
+    if world > 1:
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        g0.record()
+        for _ in range(3):
+            dist.gather(wave, glists[0] if rank == 0 else None, dst=0)
+        g1.record()
+        barrier()
+        g_ms = max_over_ranks(g0.elapsed_time(g1)) / 3
+        gbytes = (world - 1) * wave.numel() * 2
+        gather = {"payload": "int16 PCM, every batch of every rank -> rank 0 (dist.gather, async to the "
+                             "kernels, ring of 3)",
+                  "bytes_into_rank0_per_step": gbytes, "gather_ms_alone": g_ms,
+                  "gather_GBps": gbytes / (g_ms * 1e-3) / 1e9,
+                  "needed_GBps_at_value": gbytes / ((ms / args.steps) * 1e-3) / 1e9}
+    del glists
+
     # ---- roofline of the dominant kernel: fused STFT+cov, timed alone ----
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for _ in range(2):
-        pipe.covariances(audio, mask)
-    torch.cuda.synchronize()
-    reps_k = max(5, args.steps)
-    e0.record()
-    for _ in range(reps_k):
-        pipe.covariances(audio, mask)
-    e1.record()
-    torch.cuda.synchronize()
-    k_ms = e0.elapsed_time(e1) / reps_k
+    def timed(fn, n):
+        fn(); fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n, r
+
+    k_ms, (Rs, Rn, mx) = timed(lambda: pipe.covariances(audio, mask), max(10, min(args.steps, 50)))
     peak, peak_src = measured_peaks()
     alg = algorithmic_bytes_stft_cov() * B
     achieved = alg / (k_ms * 1e-3) / 1e9
+    w_ms, (w, _, _) = timed(lambda: pipe.solve(Rs, Rn), 5)
+    a_ms, _ = timed(lambda: pipe.plan.apply_istft(audio, w, norm=mx, pcm16=True), 5)
+    stage = {"stft_cov_ms": k_ms, "weights_ms": w_ms, "apply_istft_pcm16_ms": a_ms}
+    alg_apply = (4 * C * N + 8 * F * C + 2 * HOP * (T - 1)) * B
+    stage["apply_istft_GBps"] = alg_apply / (a_ms * 1e-3) / 1e9
+    del Rs, Rn, w
 
-    # ---- stage split (CUDA events, informational) ----
-    Rs, Rn, mx = pipe.covariances(audio, mask)
-    w = pipe.solve(Rs, Rn)[0]
-    stage = {}
-    for name, fn in (("weights", lambda: pipe.solve(Rs, Rn)),
-                     ("apply_istft", lambda: pipe.plan.apply_istft(audio, w, norm=mx))):
-        fn(); torch.cuda.synchronize()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        for _ in range(5):
-            fn()
-        s1.record(); torch.cuda.synchronize()
-        stage[name + "_ms"] = s0.elapsed_time(s1) / 5
-    stage["stft_cov_ms"] = k_ms
-
-    # ---- e2e: host pinned buffers in, enhanced audio out, every step ----
-    h_audio = torch.empty(audio.shape, dtype=audio.dtype, pin_memory=True)
+    # ---- e2e: host pinned buffers in and out, every step ----
+    h_pcm = torch.empty(audio.shape, dtype=torch.int16, pin_memory=True)
+    h_pcm.copy_(P_.float_to_pcm16(audio))
     h_mask = torch.empty(mask.shape, dtype=mask.dtype, pin_memory=True)
-    h_audio.copy_(audio); h_mask.copy_(mask)
-    h_outs = [torch.empty(wave.shape, dtype=wave.dtype, pin_memory=True) for _ in range(2)]
-    from setk_b200.engine import HostBatchStreamer
+    h_mask.copy_(mask)
+    n_out = wave.shape[1]
+    h_outs = [torch.empty((B, n_out), dtype=torch.int16, pin_memory=True) for _ in range(2)]
 
     def make_pipe():
         return BeamformPipeline(C, "mvdr", frame_len=FRAME_LEN, frame_hop=HOP, center=True,
                                 window="hann", max_batch=B, max_samples=N, device=dev)
 
-    def time_e2e(streamer, h_a, steps):
+    def time_e2e(streamer, h_a, h_o, steps):
         """H2D + hot path + D2H per step, two lanes so copies overlap compute."""
         for i in range(2):
-            streamer.submit(h_a, h_mask, h_outs[i % 2])
+            streamer.submit(h_a, h_mask, h_o[i % 2])
         streamer.synchronize()
         barrier()
         x0 = torch.cuda.Event(enable_timing=True)
         x0.record()
         for i in range(steps):
-            streamer.submit(h_a, h_mask, h_outs[i % 2], after=x0 if i < 2 else None)
+            streamer.submit(h_a, h_mask, h_o[i % 2], after=x0 if i < 2 else None)
         ends = streamer.record_all()
         streamer.synchronize()
         barrier()
-        e_ms = torch.tensor([max(x0.elapsed_time(e) for e in ends)], device=dev)
-        if world > 1:
-            dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+        e_ms = max_over_ranks(max(x0.elapsed_time(e) for e in ends))
         for lane in streamer.slots:
             assert int(lane["status"].abs().sum()) == 0
-        return world * B * steps / (float(e_ms.item()) / 1000.0)
+        return world * B * steps / (e_ms / 1000.0)
 
     e2e_steps = max(4, min(args.steps, 8))
     del pipe
     torch.cuda.empty_cache()
-    st_f32 = HostBatchStreamer(make_pipe, B, C, N, slots=2, pcm16=False, device=dev)
-    e2e_val = time_e2e(st_f32, h_audio, e2e_steps)
-    del st_f32
+    st = HostBatchStreamer(make_pipe, B, C, N, slots=2, pcm16=True, pcm16_out=True, device=dev)
+    e2e_val = time_e2e(st, h_pcm, h_outs, e2e_steps)
+    del st
     torch.cuda.empty_cache()
-    # the same with PCM-16 samples on the host (what wav files hold): half the audio bytes
-    h_pcm = torch.empty(audio.shape, dtype=torch.int16, pin_memory=True)
-    h_pcm.copy_(torch.clamp(torch.floor(audio * 32768.0), -32768, 32767).to(torch.int16))
-    st_i16 = HostBatchStreamer(make_pipe, B, C, N, slots=2, pcm16=True, device=dev)
-    e2e_pcm16 = time_e2e(st_i16, h_pcm, e2e_steps)
-    del st_i16
+    # variant: float32 samples on the host in both directions (round 1's e2e definition)
+    h_f32 = torch.empty(audio.shape, dtype=torch.float32, pin_memory=True)
+    h_f32.copy_(audio)
+    h_outs_f = [torch.empty((B, n_out), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+    st = HostBatchStreamer(make_pipe, B, C, N, slots=2, pcm16=False, pcm16_out=False, device=dev)
+    e2e_f32 = time_e2e(st, h_f32, h_outs_f, e2e_steps)
+    del st, h_f32, h_outs_f
+    h2d = h_pcm.numel() * 2 + h_mask.numel() * 4
+    d2h = B * n_out * 2
+    del audio, mask, h_pcm, h_mask, h_outs
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE.json configurations at this GPU count ----
+    configs = None if args.no_configs else other_configs(dev, world, rank, barrier, max_over_ranks, peak)
 
     if rank == 0:
         line = {
@@ -346,35 +436,125 @@ def gpu_arm(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (STFT/cov/apply), f64 (per-bin weight solve)", "data": "synthetic",
-            "config": {"workload": "cfg2: 4-ch MVDR, IRM mask, 16 kHz x 10 s, 512/256 hann center",
-                       "batch_per_gpu": B, "global_batch": B * world,
-                       "parallelism": f"utterance-sharded x{world}, no data-path collective; one "
-                                      f"NCCL gather of the last batch inside the timed region",
-                       "l2": f"inputs {(audio.numel() + mask.numel()) * 4 / 1e6:.0f} MB per step "
-                             f"exceed the 126 MB L2 (no flush needed)",
-                       "unique_utterances_per_gpu": uniq},
+            "config": config_dict(world, B),
+            "run": {"unique_utterances_per_gpu": uniq, "numa": numa},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": measured_traffic(B), "peak_source": peak_src,
-                         "kernel": "setk_stft_cov (stft_cov_kernel<4,5> + finalize)",
+                         "kernel": "setk_stft_cov (stft_cov_ws_kernel<4> + finalize)",
                          "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms},
             "cpu_baseline": cpu_base,
-            "e2e": {"value": e2e_val, "unit": UNIT,
-                    "h2d_bytes_per_step": (audio.numel() + mask.numel()) * 4,
-                    "d2h_bytes_per_step": wave.numel() * 4, "steps": e2e_steps,
-                    "how": "pinned host f32 audio+mask -> H2D -> BeamformPipeline.run -> D2H wave, "
-                           "every step; 2 lanes (streams) so copies overlap kernels",
-                    "h2d_GBps": e2e_val / world * (audio.numel() + mask.numel()) * 4 / B / 1e9,
-                    "bound": "host->device link (PCIe): the kernels need 1/12 of the step",
-                    "pcm16_audio_variant": {"value": e2e_pcm16, "unit": UNIT,
-                                            "h2d_bytes_per_step": audio.numel() * 2 + mask.numel() * 4}},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps,
+                    "how": "pinned host PCM-16 audio (what wav files hold) + f32 masks -> H2D -> "
+                           "int16/32768 on device -> BeamformPipeline.run -> floor(y*32768) on device -> "
+                           "D2H int16, every step; 2 lanes (streams) so copies overlap kernels",
+                    "h2d_GBps": e2e_val / world * h2d / B / 1e9,
+                    "bound": "host->device link (PCIe)",
+                    "f32_host_variant": {"value": e2e_f32, "unit": UNIT,
+                                         "h2d_bytes_per_step": B * (C * N + T * F) * 4,
+                                         "d2h_bytes_per_step": B * n_out * 4}},
+            "gather": gather,
             "gpu_launches": int(launches),
             "stages": stage,
+            "configs": configs,
             "clocks": sampler.summary() if sampler else None,
             "library": _lib.library_path(),
         }
+        if sampler:
+            sampler.stop()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_configs(dev, world, rank, barrier, max_over_ranks, peak):
+    """
+    BASELINE.json configs[2..4] (SURVEY.md section 8d shapes), device-resident, a few steps each:
+      cfg3  8-ch GEV, 1024-pt STFT, batch 256 per GPU (processed as 4 x 64)
+      cfg4  WPE(taps 10, delay 3, 3 iterations) + MVDR, 6 ch, batch 128 in TOTAL (strong scaling)
+      cfg5  MVDR 8 ch and 16 ch, 512-pt (4 ch is the headline line)
+    value = utterances of all ranks / max-over-ranks device time.
+    """
+    import torch
+    from setk_b200 import synth
+    from setk_b200 import plan as P_
+    from setk_b200.engine import BeamformPipeline
+
+    out = {}
+
+    def time_steps(fn, n):
+        fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / n
+
+    def beamform_cfg(name, ch, frame_len, kind, b, steps=5):
+        pipe = BeamformPipeline(ch, kind, frame_len=frame_len, frame_hop=HOP, max_batch=b,
+                                max_samples=N, device=dev)
+        nf = pipe.plan.n_fft
+        a, m = synth.make_batch(min(b, 8), ch, N, device=dev, frame_len=frame_len, n_fft=nf,
+                                first=1000 + 8 * rank)
+        reps = (b + a.shape[0] - 1) // a.shape[0]
+        audio = a.repeat(reps, 1, 1)[:b].contiguous()
+        mask = m.repeat(reps, 1, 1)[:b].contiguous()
+        del a, m
+        ms = time_steps(lambda: pipe.run(audio, mask, pcm16_out=True), steps)
+        k_ms = time_steps(lambda: pipe.covariances(audio, mask), steps)
+        Rs, Rn, mx = pipe.covariances(audio, mask)
+        w_ms = time_steps(lambda: pipe.solve(Rs, Rn), steps)
+        w = pipe.solve(Rs, Rn)[0]
+        a_ms = time_steps(lambda: pipe.plan.apply_istft(audio, w, norm=mx, pcm16=True), steps)
+        alg = algorithmic_bytes_stft_cov(ch, N, nf, HOP) * b
+        ach = alg / (k_ms * 1e-3) / 1e9
+        out[name] = {"channels": ch, "n_fft": nf, "beamformer": kind, "batch_per_gpu": b,
+                     "value": world * b / ms * 1e3, "unit": UNIT, "ms_per_batch": ms,
+                     "stages": {"stft_cov_ms": k_ms, "weights_ms": w_ms, "apply_istft_pcm16_ms": a_ms},
+                     "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                                  "frac": ach / peak, "algorithmic_bytes_per_launch": alg,
+                                  "kernel": "setk_stft_cov"}}
+        del pipe, audio, mask, Rs, Rn, w
+        torch.cuda.empty_cache()
+
+    beamform_cfg("cfg3_8ch_gev_1024", 8, 1024, "gevd", 64)
+    beamform_cfg("cfg5_8ch_mvdr_512", 8, 512, "mvdr", 64)
+    beamform_cfg("cfg5_16ch_mvdr_512", 16, 512, "mvdr", 32)
+
+    # cfg4: WPE -> MVDR on the dereverberated STFT, 128 utterances in total over the ranks
+    b = max(1, 128 // world)
+    ch = 6
+    pipe = BeamformPipeline(ch, "mvdr", frame_len=512, frame_hop=HOP, max_batch=b, max_samples=N,
+                            device=dev)
+    a, m = synth.make_batch(min(b, 4), ch, N, device=dev, first=2000 + 4 * rank)
+    reps = (b + a.shape[0] - 1) // a.shape[0]
+    audio = a.repeat(reps, 1, 1)[:b].contiguous()
+    mask = m.repeat(reps, 1, 1)[:b].contiguous()
+    del a, m
+    from setk_b200 import _lib
+
+    def wpe_mvdr():
+        S = pipe.plan.stft(audio)                                  # (B,C,F,T)
+        D, st = P_.wpe_from_stft(S, 10, 3, 1, 3)
+        Rs = P_.covariance(D, mask)
+        Rn = P_.covariance(D, 1.0 - mask)
+        w = P_.weights(_lib.BF_MVDR, Rs, Rn=Rn, out_dtype=torch.complex64)[0]
+        enh = P_.apply_weights(D, w)
+        return pipe.plan.istft(enh)
+
+    ms = time_steps(wpe_mvdr, 2)
+    S = pipe.plan.stft(audio)
+    wpe_ms = time_steps(lambda: P_.wpe_from_stft(S, 10, 3, 1, 3), 2)
+    out["cfg4_wpe_mvdr_6ch"] = {"channels": ch, "n_fft": 512, "beamformer": "wpe(10,3,1,3)+mvdr",
+                                "batch_total": b * world, "batch_per_gpu": b, "scaling": "strong",
+                                "value": world * b / ms * 1e3, "unit": UNIT, "ms_per_batch": ms,
+                                "stages": {"wpe_ms": wpe_ms}}
+    del pipe, audio, mask, S
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -384,11 +564,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--unique", type=int, default=32,
+    ap.add_argument("--unique", type=int, default=256,
                     help="distinct synthetic utterances per GPU (tiled to the batch)")
-    ap.add_argument("--cpu-utts", type=int, default=0,
-                    help="utterances for the cpu_baseline sample (0 = 16 per core)")
+    ap.add_argument("--cpu-budget", type=float, default=150.0,
+                    help="seconds of CPU work the --impl reference run may take")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

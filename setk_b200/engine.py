@@ -133,13 +133,21 @@ class HostBatchStreamer(object):
     batch i-1 proceed concurrently (PCIe is full duplex).  Host buffers must be
     pinned for the copies to be asynchronous.  This is the B200 answer to the
     reference's per-utterance soundfile reads.
+
+    pcm16:     the host audio is int16 PCM (what wav files hold; read_wav's int16/32768,
+               utils.py:80-92, happens on the device)
+    pcm16_out: the result is int16 PCM (what WaveWriter writes: floor(y * 32768),
+               utils.py:45-62), 2 bytes per sample over the link instead of 4
+    A batch may be ragged (`n_samples`, host int32) and shorter than the lane (`count`).
     """
 
     def __init__(self, make_pipeline, batch, num_channels, num_samples, slots=2, pcm16=False,
-                 device=None):
+                 pcm16_out=False, device=None, run_kwargs=None):
         self.device = torch.device(device if device is not None else "cuda")
         self.slots = []
         self.pcm16 = bool(pcm16)
+        self.pcm16_out = bool(pcm16_out)
+        self.run_kwargs = dict(run_kwargs or {})
         for _ in range(slots):
             pipe = make_pipeline()
             T, F = pipe.plan.num_frames(num_samples), pipe.plan.num_bins
@@ -150,27 +158,51 @@ class HostBatchStreamer(object):
                                      dtype=torch.int16 if pcm16 else torch.float32,
                                      device=self.device),
                 "mask": torch.empty((batch, T, F), dtype=torch.float32, device=self.device),
+                "mask_n": None,
+                "n_samples": torch.empty((batch,), dtype=torch.int32, device=self.device),
                 "status": None,
+                "done": torch.cuda.Event(),
             }
             self.slots.append(lane)
         self._i = 0
 
-    def submit(self, h_audio, h_mask, h_out, after=None):
-        """Enqueue one host batch; returns the lane used.  `after`: event to wait on first."""
+    def submit(self, h_audio, h_mask, h_out, after=None, n_samples=None, count=None, h_mask_n=None,
+               h_status=None):
+        """
+        Enqueue one host batch; returns the lane used.  `after`: event to wait on first.
+        h_out receives the enhanced samples (first `count` rows); h_status (pinned int32) the
+        per-utterance solver status.  lane["done"] is recorded after the last copy.
+        """
         lane = self.slots[self._i % len(self.slots)]
         self._i += 1
+        B = int(count) if count is not None else int(h_audio.shape[0])
         with torch.cuda.stream(lane["stream"]):
             if after is not None:
                 lane["stream"].wait_event(after)
-            lane["audio"].copy_(h_audio, non_blocking=True)
-            lane["mask"].copy_(h_mask, non_blocking=True)
+            audio, mask = lane["audio"][:B], lane["mask"][:B]
+            audio.copy_(h_audio[:B], non_blocking=True)
+            mask.copy_(h_mask[:B], non_blocking=True)
+            mask_n = None
+            if h_mask_n is not None:
+                if lane["mask_n"] is None:
+                    lane["mask_n"] = torch.empty_like(lane["mask"])
+                mask_n = lane["mask_n"][:B]
+                mask_n.copy_(h_mask_n[:B], non_blocking=True)
+            ns = None
+            if n_samples is not None:
+                ns = lane["n_samples"][:B]
+                ns.copy_(n_samples[:B], non_blocking=True)
             if self.pcm16:
-                wave, status = lane["pipe"].run_pcm16(lane["audio"], lane["mask"])
-            else:
-                wave, status = lane["pipe"].run(lane["audio"], lane["mask"])
-            h_out.copy_(wave, non_blocking=True)
+                from .plan import pcm16_to_float
+                audio = pcm16_to_float(audio)
+            wave, status = lane["pipe"].run(audio, mask, mask_n=mask_n, n_samples=ns,
+                                            pcm16_out=self.pcm16_out, **self.run_kwargs)
+            h_out[:B].copy_(wave, non_blocking=True)
+            if h_status is not None:
+                h_status[:B].copy_(status, non_blocking=True)
             lane["status"] = status
             lane["wave"] = wave           # keep alive until the D2H copy has run
+            lane["done"].record(lane["stream"])
         return lane
 
     def record_all(self):
