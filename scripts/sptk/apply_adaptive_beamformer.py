@@ -10,6 +10,14 @@ per-utterance numerics running on libsetk_b200's CUDA kernels:
 
     fused STFT + covariances  ->  fp64 per-bin weight solve  ->  fused apply + iSTFT
 
+The offline path (no --online.chunk-size, no --vad-proportion) does not process one
+utterance per launch: setk_b200/batch_cli.py sorts a look-ahead window of the scp by
+length, fills pinned PCM-16 staging buffers of up to --batch-size ragged utterances on
+a reader thread, runs them through a two-lane HostBatchStreamer (copies overlap
+kernels) and writes PCM-16 wav files on a writer thread.  --batch-size / --lookahead
+are the only flags the reference does not have.  Under torchrun every rank takes the
+keys rank::world of the scp (run.pl's nj shards).
+
 Deviations from the reference, all bug fixes:
   * --itf-mask is read from args.itf_mask (the reference opens args.tgt_mask);
   * the online path works (the reference passes normalize= to run(..., ban=));
@@ -89,7 +97,13 @@ def run(args):
         "center": bool(args.center),  # false to comparable with kaldi
     }
     dev = default_device()
-    wave_reader = WaveReader(args.wav_scp, sr=args.sr)
+    online = args.chunk_size > 0
+    batched = (not online) and not (0.5 < args.vad_proportion < 1) and args.batch_size > 0
+    if "LOCAL_RANK" in os.environ and dev.type == "cuda":
+        import torch as _t
+        dev = _t.device("cuda", int(os.environ["LOCAL_RANK"]))
+        _t.cuda.set_device(dev)
+    wave_reader = WaveReader(args.wav_scp, sr=args.sr, raw_pcm16=batched)
     MaskReader = {"numpy": NumpyReader, "kaldi": ScriptReader}
     tgt_mask_reader = MaskReader[args.fmt](args.tgt_mask)
     itf_mask_reader = MaskReader[args.fmt](args.itf_mask) if args.itf_mask else None
@@ -97,7 +111,13 @@ def run(args):
         logger.info(f"Using interfering masks from {args.itf_mask}")
     n_fft = nextpow2(args.frame_len) if args.round_power_of_two else args.frame_len
     num_bins = n_fft // 2 + 1
-    online = args.chunk_size > 0
+    if batched:
+        from setk_b200.batch_cli import run_batched
+        logger.info(f"Using offline {args.beamformer} beamformer, batches of <= {args.batch_size}")
+        num_done = run_batched(args, wave_reader, tgt_mask_reader, itf_mask_reader, stft_kwargs,
+                               num_bins, dev, logger)
+        logger.info(f"Processed {num_done:d} utterances " + f"out of {len(wave_reader):d}")
+        return
     if not online:
         logger.info(f"Using offline {args.beamformer} beamformer")
     else:
@@ -221,6 +241,11 @@ def get_parser():
                         help="If >= 64, using online beamformer instead")
     parser.add_argument("--online.channels", default=4, type=int, dest="channels",
                         help="Number of channels available")
+    parser.add_argument("--batch-size", default=64, type=int,
+                        help="[setk_b200] utterances per device batch of the offline path "
+                        "(0: one utterance per launch, like the reference's loop)")
+    parser.add_argument("--lookahead", default=256, type=int,
+                        help="[setk_b200] utterances read ahead and sorted by length before batching")
     return parser
 
 

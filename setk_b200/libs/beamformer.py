@@ -219,9 +219,10 @@ class OnlineSupervisedBeamformer(SupervisedBeamformer):
     Online version of SupervisedBeamformer  (beamformer.py:286-320)
     """
 
-    def __init__(self, num_bins, num_channels, alpha=0.8):
+    def __init__(self, num_bins, num_channels, alpha=0.8, normalized_update=False):
         super(OnlineSupervisedBeamformer, self).__init__(num_bins)
         self.covar_mat_shape = (num_bins, num_channels, num_channels)
+        self.normalized_update = bool(normalized_update)
         self.reset_stats(alpha=alpha)
 
     def reset_stats(self, alpha=0.8):
@@ -235,11 +236,16 @@ class OnlineSupervisedBeamformer(SupervisedBeamformer):
         Rs = self.compute_covar_mat(mask_s, obs)
         if tuple(Rs.shape[-3:]) != self.covar_mat_shape:
             raise ValueError(f"covariance shape {tuple(Rs.shape)} vs {self.covar_mat_shape}")
-        # update stats
-        phi = 1 if self.reset else (1 - self.alpha)
+        # update stats.  The reference never clears `reset` (beamformer.py:314-316), so its
+        # recursion is R <- alpha R + R_chunk for every chunk; that is the default here.
+        # normalized_update=True is the evidently intended R <- alpha R + (1 - alpha) R_chunk
+        # after the first chunk (the weights differ only by a per-bin scale of R for MVDR / GEV
+        # once the sum has converged, but not during the first chunks).
+        phi = 1 if (self.reset or not self.normalized_update) else (1 - self.alpha)
         self.Rs = phi * Rs if self.Rs is None else self.Rs * self.alpha + phi * Rs
         self.Rn = phi * Rn if self.Rn is None else self.Rn * self.alpha + phi * Rn
-        self.reset = False
+        if self.normalized_update:
+            self.reset = False
         # do beamforming
         weight = self.weight(self.Rs, self.Rn)
         return self.beamform(do_ban(weight, Rn) if ban else weight, obs)

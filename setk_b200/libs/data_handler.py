@@ -9,8 +9,8 @@ implementation is this repository's own.
 Host-side IO is not the accelerated part (SURVEY.md section 8a "boundary
 only").  What changes is SpectrogramReader: all channels of an utterance go
 through ONE setk_stft launch instead of one librosa call per channel.
-Kaldi archives: uncompressed float / double matrices and vectors (tokens FM, DM,
-FV, DV) are supported; compressed matrices (CM*) are not.
+Kaldi archives: float / double matrices and vectors (tokens FM, DM, FV, DV) and the
+compressed matrices CM / CM2 / CM3 (bit-identical to kaldi_io.py:248-318).
 """
 import glob
 import io
@@ -149,14 +149,16 @@ class WaveReader(ScpReader):
     read() returns float32 samples, N or C x N.
     """
 
-    def __init__(self, wav_scp, sr=16000, normalize=True):
+    def __init__(self, wav_scp, sr=16000, normalize=True, raw_pcm16=False):
         super().__init__(wav_scp)
         self.sr = sr
         self.normalize = normalize
+        self.raw_pcm16 = raw_pcm16        # PCM-16 files come back as int16 (batched device feed)
         self._archives = {}
 
     def _decode(self, source, beg=None, end=None):
-        return read_wav(source, beg=beg or 0, end=end, normalize=self.normalize, sr=self.sr)
+        return read_wav(source, beg=beg or 0, end=end, normalize=self.normalize, sr=self.sr,
+                        raw_pcm16=self.raw_pcm16)
 
     def read_internal(self, addr, beg=None, end=None):
         if isinstance(addr, str) and ":" in addr:

@@ -112,7 +112,9 @@ def write_wav(fname, samps, sr=16000, normalize=True):
     import scipy.io.wavfile as wavfile
     if isinstance(samps, torch.Tensor):
         samps = samps.detach().cpu().numpy()
-    samps = np.asarray(samps).astype("float32" if normalize else "int16")
+    samps = np.asarray(samps)
+    if samps.dtype != np.int16:          # int16 = PCM-16 already (setk_apply_istft_pcm16): written as is
+        samps = samps.astype("float32" if normalize else "int16")
     if samps.ndim != 1 and samps.shape[0] < samps.shape[1]:
         samps = np.transpose(samps)
         samps = np.squeeze(samps)
@@ -126,13 +128,16 @@ def write_wav(fname, samps, sr=16000, normalize=True):
     wavfile.write(str(fname), sr, pcm)
 
 
-def read_wav(fname, beg=0, end=None, normalize=True, sr=16000):
-    """utils.py:65-92: returns C x N (or N) float32."""
+def read_wav(fname, beg=0, end=None, normalize=True, sr=16000, raw_pcm16=False):
+    """utils.py:65-92: returns C x N (or N) float32.  raw_pcm16=True returns the int16 samples of a
+    PCM-16 file untouched (the int16/32768 conversion then happens on the device)."""
     import scipy.io.wavfile as wavfile
     ret_sr, data = wavfile.read(fname)
     if sr != ret_sr:
         raise RuntimeError(f"Expect sr={sr} of {fname}, get {ret_sr} instead")
     data = data[beg:end]
+    if raw_pcm16 and data.dtype == np.int16:
+        return np.ascontiguousarray(np.transpose(data)) if data.ndim != 1 else data
     if data.dtype == np.int16:
         samps = data.astype(np.float32) / np.float32(32768.0) if normalize else data.astype(
             np.float32)

@@ -282,7 +282,10 @@ def mvdr_end_to_end(device, x, mask, kind="mvdr", frame_len=512, hop=256, center
     y, status = pipe.run(tx, tm)
     assert int(status.abs().sum()) == 0
     Rs, Rn, _ = pipe.covariances(tx, tm)
-    w_ours = pipe.solve(Rs, Rn)[0].cpu().numpy().astype(np.complex128)
+    Ry = None
+    if kind in ("mpdr", "mpdr-whiten"):       # Ry: the all-ones mask (beamformer.py:575-590)
+        Ry = pipe.plan.stft_cov(tx, torch.ones_like(tm), None, want_maxabs=False)[0]
+    w_ours = pipe.solve(Rs, Rn, Ry)[0].cpu().numpy().astype(np.complex128)
     y = y.cpu().numpy()
     kw = stft_kwargs(frame_len, hop, center, window)
     worst = 0.0

@@ -100,11 +100,19 @@ def test_online_beamformer(libs):
     mask = rng.uniform(0, 1, (T, F)).astype(np.float32)
     bf = BF.OnlineMvdrBeamformer(F, C, alpha=0.8)
     out = [bf.run(mask[c:c + 32], np.ascontiguousarray(obs[:, :, c:c + 32])) for c in (0, 32)]
-    assert out[0].shape == (F, 32) and not bf.reset
+    assert out[0].shape == (F, 32)
     # first chunk equals the offline beamformer on that chunk
     ref = bo.run_supervised("mvdr", mask[:32].astype(np.float64),
                             obs[:, :, :32].astype(np.complex128))
     assert bo.rel_inf(bo.align_phase(out[0], ref)[0], ref) <= 2e-5
+    # second chunk: the reference's recursion R <- alpha R + R_chunk (phi stays 1,
+    # beamformer.py:314-316: `reset` is never cleared there)
+    m64, o128 = mask.astype(np.float64), obs.astype(np.complex128)
+    Rs = [bo.compute_covar(o128[:, :, c:c + 32], m64[c:c + 32]) for c in (0, 32)]
+    Rn = [bo.compute_covar(o128[:, :, c:c + 32], 1 - m64[c:c + 32]) for c in (0, 32)]
+    w = bo.mvdr_weight(0.8 * Rs[0] + Rs[1], 0.8 * Rn[0] + Rn[1])
+    ref2 = bo.beamform(w, o128[:, :, 32:])
+    assert bo.rel_inf(bo.align_phase(out[1], ref2)[0], ref2) <= 5e-5
 
 
 def test_pipeline_status_maps_to_linalgerror(emu):
@@ -150,6 +158,7 @@ def test_cli_end_to_end(tmp_path, emu_library_path):
         cmd = [sys.executable, "-c", runner,
                os.path.join(ROOT, "scripts", "sptk", "apply_adaptive_beamformer.py"),
                "--frame-len", "512", "--frame-hop", "256", "--mask-format", "numpy",
+               "--batch-size", "0",       # the batched feeder needs CUDA streams: tests/test_gpu_cli.py
                "--beamformer", bf, *extra, str(tmp_path / "wav.scp"), str(tmp_path / "mask.scp"),
                str(dst)]
         subprocess.run(cmd, check=True, env=env, capture_output=True)
@@ -163,6 +172,26 @@ def test_cli_end_to_end(tmp_path, emu_library_path):
         ref = so.pcm16_from_float(y)
         d = np.abs(out.astype(np.int64) - ref.astype(np.int64))
         assert d.max() <= 1 and np.mean(d > 0) <= 0.05
+
+
+def test_batch_planner_sorts_and_cuts():
+    """setk_b200/batch_cli.plan_batches: same channel count / dtype per batch, lengths sorted,
+    at most batch_size utterances (pure host logic of the batched CLI)."""
+    from setk_b200.batch_cli import plan_batches
+    rng = np.random.default_rng(3)
+    window = []
+    for i in range(37):
+        C = 4 if i % 5 else 2
+        n = int(rng.integers(1000, 9000))
+        dt = np.int16 if i % 7 else np.float32
+        window.append((f"k{i}", np.zeros((C, n), dtype=dt), np.zeros((3, 5), np.float32), None))
+    batches = plan_batches(list(window), 8)
+    assert sum(len(b) for b in batches) == 37
+    for b in batches:
+        assert len(b) <= 8
+        assert len({(it[1].shape[0], it[1].dtype) for it in b}) == 1
+        lens = [it[1].shape[1] for it in b]
+        assert lens == sorted(lens)
 
 
 def test_cgmm_trainer_mirror_and_cli(tmp_path, emu, emu_library_path):
