@@ -60,6 +60,7 @@ cudaError_t run_apply_spill(setk_plan*, const float2*, const void*, int, const f
 cudaError_t run_istft_strided(const setk_plan*, const float2*, long long, long long, long long, int, int, int,
                               const int*, float*, float*, unsigned*, void*);
 size_t cov_spill_partial_bytes(const Geometry&, int, int);
+int cov_spill_chunks(const setk_plan*, int, int);
 cudaError_t run_stft_spill(setk_plan*, const float*, const int*, int, int, int, int, float2*, unsigned*,
                            void*);
 cudaError_t run_cov_spill(setk_plan*, const float2*, const float*, const float*, unsigned, const int*,
@@ -273,9 +274,7 @@ int setk_stft_cov(setk_plan_t* pl, const float* audio, const int32_t* n_samples,
     const int groups = (g.C + 3) / 4;
     const int chunks_a = stft_cov_pick_chunks(pl, B * groups, T);
     // >= 16 short fp32 runs per utterance, combined in double by the finalize kernel
-    int chunks_b = stft_cov_pick_chunks(pl, B * g.C * ((g.F + 287) / 288), T);
-    if (chunks_b < 16) chunks_b = 16;
-    if (chunks_b > T) chunks_b = T;
+    const int chunks_b = cov_spill_chunks(pl, B, T);
     e = ensure(&pl->d_stft_ws, &pl->stft_ws_bytes, stft_spill_bytes(g, B, T));
     if (e == cudaSuccess)
       e = ensure(&pl->d_partials, &pl->partials_bytes, cov_spill_partial_bytes(g, B, chunks_b));

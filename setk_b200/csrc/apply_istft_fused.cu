@@ -92,6 +92,7 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
   const int T_cap = (a.n_out + 2 * pad + hop - 1) / hop;
   // per-segment state (set at the top of the segment loop)
   int b = 0, nb = 0, T_used = 0, own_begin = 0;
+  int n_lim = a.n_out;      // output samples of the current utterance (a ragged one ends earlier)
   float* yb = nullptr;
   float peak = 0.f;
 
@@ -153,7 +154,7 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
     // frames and a following tile takes the last half frame -- one check per tile, none per sample
     const bool interior = fast_hop && out_vec && !a.accumulate && p_nt == TT && !last_tile &&
                           p_t0 >= 1 && p_t0 + p_nt < T_used && p_tile >= own_begin && p_tile >= pad &&
-                          p_tile - pad + p_nt * kM <= a.n_out;
+                          p_tile - pad + p_nt * kM <= n_lim;
     if (interior) {
       static_assert((TT + 1) * (kM / 4) == kApplyThreads, "one flush item per thread");
       const int jj = tid >> 6, r = (tid & 63) * 4;
@@ -185,7 +186,7 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
         if (jj < p_nt || last_tile) {
           const int p = p_tile + jj * kM + r;
           const int q = p - pad;
-          if (p >= own_begin && q >= 0 && q < a.n_out) {
+          if (p >= own_begin && q >= 0 && q < n_lim) {
             const int t = p_t0 + jj;               // frame starting at this row
             float vv[4] = {val.x, val.y, val.z, val.w};
             if (t >= 1 && t < T_used) {
@@ -198,7 +199,7 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
                 if (wss > SETK_TINY32) vv[i] /= wss;
               }
             }
-            if (out_vec && q + 4 <= a.n_out) {
+            if (out_vec && q + 4 <= n_lim) {
               float4* dst = reinterpret_cast<float4*>(yb + q);
               if (a.accumulate) {
                 const float4 o = *dst;
@@ -209,7 +210,7 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
             } else {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                if (q + i < a.n_out) {
+                if (q + i < n_lim) {
                   float v1 = vv[i];
                   if (a.accumulate) v1 += yb[q + i];
                   yb[q + i] = v1;
@@ -241,7 +242,7 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
           if (rel < final_len) {
             const int p = p_tile + rel;
             const int q = p - pad;
-            if (p >= own_begin && q >= 0 && q < a.n_out) {
+            if (p >= own_begin && q >= 0 && q < n_lim) {
               if (wss > SETK_TINY32) val /= wss;
               if (a.accumulate) val += yb[q];
               yb[q] = val;
@@ -272,6 +273,9 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
     const int t_begin = (cur_tile - pb) * TT;
     const int t_end = imin((seg_end - pb) * TT, T_used);
     const int expected = T_used > 0 ? kNfft + hop * (T_used - 1) : 0;   // padded signal length
+    // a ragged utterance ends where its own istft(length=None) would (center: the trailing
+    // n_fft/2 is trimmed); what lies beyond is zero-filled and must not reach the peak
+    n_lim = a.n_samples ? imin(a.n_out, imax(expected - 2 * pad, 0)) : a.n_out;
     own_begin = t_begin * hop;
     yb = a.wave + (long long)b * a.n_out;
     const float* xb = a.audio + ((long long)b * a.c_total + a.c0) * a.N;
@@ -390,7 +394,7 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
 
     // zero-fill what no frame reaches (fix_length padding / too-short input)
     if (t_end >= T_used && !a.accumulate) {
-      const int q0 = imax(expected - pad, 0);
+      const int q0 = a.n_samples ? n_lim : imax(expected - pad, 0);
       for (int qq = q0 + tid; qq < a.n_out; qq += blockDim.x) yb[qq] = 0.f;
     }
     if (a.peak) {

@@ -180,7 +180,10 @@ __global__ void istft_ola_kernel(Geometry g, const float* __restrict__ frames,
   if (q < n_out) {
     const int p = q + g.pad;
     const int expected = Tu > 0 ? g.n_fft + g.hop * (Tu - 1) : 0;
-    if (p < expected) {
+    // a ragged utterance ends where its own istft(length=None) would (center: the trailing
+    // n_fft/2 is trimmed); what lies beyond is zero and must not reach the peak
+    const int limit = n_samples ? expected - g.pad : expected;
+    if (p < limit) {
       const int t_lo = (p >= g.n_fft) ? (p - g.n_fft) / g.hop + 1 : 0;
       const int t_hi = imin(Tu - 1, p / g.hop);
       float wss = 0.f;

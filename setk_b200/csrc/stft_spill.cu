@@ -18,8 +18,10 @@
 //       Hermitian fill.
 // Algorithmic bytes per utterance (as for the fused kernel) 4CN + 4TF + 16FC^2;
 // this route moves 2 * 8*C*F*T more (the spill), which DESIGN.md reports.
+#include <cstdlib>
 #include "common.cuh"
 #include "stft_tile.cuh"
+#include "cov_spill_args.cuh"
 
 namespace setk {
 
@@ -374,19 +376,6 @@ __global__ void __launch_bounds__(256) spill_to_bcft_kernel(const float2* __rest
   }
 }
 
-struct CovSpillArgs {
-  const float2* xws;     // [B][T][C][pitch]
-  int pitch;
-  const float* mask_s; const float* mask_n; unsigned flags;
-  const int* n_samples; int N; Geometry g;
-  int T, F;
-  int frames_per_chunk, n_chunks;
-  float* partials;       // [B][n_chunks][C rows][2 masks][2*C + 1][F]
-};
-
-// floats per (utterance, chunk): rows x masks x (C complex + sum m) x F
-SETK_HD inline size_t cov_spill_partial_floats(int C, int F) { return (size_t)C * 2 * (2 * C + 1) * F; }
-
 template <int C>
 __global__ void __launch_bounds__(288) cov_spill_kernel(CovSpillArgs a) {
   const int nbb = (a.F + blockDim.x - 1) / blockDim.x;      // bin blocks (2 when F = 513)
@@ -535,10 +524,43 @@ cudaError_t run_stft_spill(setk_plan* pl, const float* audio, const int* n_sampl
   }
 }
 
+int stft_cov_pick_chunks(const setk_plan*, int, int);
+bool cov_mma_supported(int C);
+int cov_mma_bins_per_cta(int C);
+cudaError_t run_cov_mma(const CovSpillArgs& a, int B, void* stream);
+
+// C >= 5: the covariance is a real dense contraction (2C x 2C Gram blocks over T frames) and runs
+// on the tensor cores (cov_mma.cu) unless SETK_COV_IMPL=cuda (measurement knob)
+static bool use_cov_mma(int C) {
+  static const char* env = getenv("SETK_COV_IMPL");
+  if (env && env[0] == 'c') return false;
+  return C >= 5 && cov_mma_supported(C);
+}
+
+// chunks of frames per utterance for the covariance pass over the workspace
+int cov_spill_chunks(const setk_plan* pl, int B, int T) {
+  const Geometry& g = pl->geo;
+  if (use_cov_mma(g.C)) {
+    // fp32 tensor-core accumulators run over the whole utterance unless the launch would leave
+    // the machine empty (small batches): then cut T so that ~4 CTAs per SM exist
+    const int nbb = (g.F + cov_mma_bins_per_cta(g.C) - 1) / cov_mma_bins_per_cta(g.C);
+    int chunks = (4 * pl->sm_count + B * nbb - 1) / (B * nbb);
+    if (chunks > 16) chunks = 16;
+    if (chunks > (T + 7) / 8) chunks = (T + 7) / 8;
+    return chunks < 1 ? 1 : chunks;
+  }
+  int chunks = stft_cov_pick_chunks(pl, B * g.C * ((g.F + 287) / 288), T);
+  if (chunks < 16) chunks = 16;
+  if (chunks > T) chunks = T;
+  return chunks;
+}
+
 template <int C>
 static cudaError_t run_cov_spill_t(const CovSpillArgs& a, int B, float2* Rs, float2* Rn, void* stream) {
   const int nbb = (a.F + 287) / 288;
-  cudaError_t e = launch(cov_spill_kernel<C>, dim3(a.n_chunks * nbb, C, B), dim3(288), 0, stream, true, a);
+  cudaError_t e = use_cov_mma(C) ? run_cov_mma(a, B, stream)
+                                 : launch(cov_spill_kernel<C>, dim3(a.n_chunks * nbb, C, B), dim3(288), 0,
+                                          stream, true, a);
   if (e != cudaSuccess) return e;
   const long long n = (long long)B * a.F * C;
   return launch(cov_spill_finalize_kernel<C>, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, stream,

@@ -135,6 +135,7 @@ struct Ctx {
   Barrier named[16];              // bar.sync id, n (id 1..15)
   std::mutex named_m;
   std::vector<uint64_t> slots;
+  std::vector<float> gather;      // [nthreads][8]: warp all-gather scratch (emulated mma.sync)
   unsigned char* dyn = nullptr;
   bool serial = false;
 };
@@ -172,6 +173,7 @@ void launch(dim3 grid, dim3 block, size_t smem, bool serial, F&& body) {
           int n = nthr - 32 * w; ctx.warps[w].init(n > 32 ? 32 : n);
         }
         ctx.slots.assign(nthr, 0);
+        ctx.gather.assign((size_t)nthr * 8, 0.f);
         memset(dyn, 0xCD, smem);   // shared memory starts as garbage, like on the device
         auto run = [&](int tid) {
           g_ctx = &ctx; g_tid = tid;
@@ -210,6 +212,18 @@ inline void named_sync(int id, int nthreads) {
 inline void sync_warp() {
   if (g_ctx->serial) die("__syncwarp in a kernel launched as barrier-free");
   g_ctx->warps[g_tid / 32].wait();
+}
+// every lane of the warp contributes n <= 8 floats; all[i * 32 + l] = value i of lane l
+inline void warp_allgather(const float* mine, int n, float* all) {
+  float* buf = g_ctx->gather.data();
+  for (int i = 0; i < n; ++i) buf[(size_t)g_tid * 8 + i] = mine[i];
+  sync_warp();
+  const int w0 = g_tid & ~31;
+  for (int l = 0; l < 32; ++l) {
+    const int src = w0 + l < g_ctx->nthreads ? w0 + l : g_tid;
+    for (int i = 0; i < n; ++i) all[i * 32 + l] = buf[(size_t)src * 8 + i];
+  }
+  sync_warp();
 }
 template <class T>
 inline T shfl_idx(T v, int src_lane) {
