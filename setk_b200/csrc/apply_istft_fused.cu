@@ -34,26 +34,13 @@
 // are recomputed as a halo tile.
 // Algorithmic bytes per utterance: 4*C*N (audio) + 8*F*C (w) + 4*n_out (wave)
 // (+ 4*T*F with a post-mask).
+#include <cstdlib>
 #include <type_traits>
 #include "common.cuh"
 #include "stft_tile.cuh"
+#include "apply_istft_args.cuh"
 
 namespace setk {
-
-struct ApplyIstftArgs {
-  Geometry g;
-  const float* audio; const int* n_samples; int N;
-  const void* w; int w_dtype;
-  const float* post_mask; int T;   // mask leading dimension (frames of N samples)
-  TileSched sched;      // which (utterance, tile) pairs this CTA owns
-  const float* window;  // [n_fft] analysis == synthesis window
-  const float* wsq;     // [n_fft]
-  int n_out;
-  float* wave;          // [B][n_out]
-  unsigned* peak;       // [B] or null
-  int c0, c_total;      // this launch handles channels [c0, c0 + C) of c_total
-  int accumulate;       // != 0: wave += this block's contribution (iSTFT is linear)
-};
 
 constexpr int kApplyThreads = 320;
 constexpr int kWPitch = 260;          // float2 pitch of the per-channel weight rows
@@ -436,6 +423,14 @@ bool apply_istft_fused_supported(const Geometry& g) {
 }
 
 void fused_schedule(const setk_plan* pl, int B, int T, int TT, int* n_ctas, int* slots, int* min_quota);
+bool apply_istft_ws_supported(const Geometry& g);
+cudaError_t run_apply_istft_ws(const ApplyIstftArgs& a, int n_ctas, void* stream);
+// SETK_AI_IMPL=classic keeps the classic kernel (measurement knob)
+static bool use_apply_ws(const Geometry& g) {
+  static const char* env = getenv("SETK_AI_IMPL");
+  if (env && env[0] == 'c') return false;
+  return apply_istft_ws_supported(g);
+}
 cudaError_t run_tile_prefix(const int* n_samples, int B, const Geometry& g, int TT, int T_cap,
                             int* prefix, void* stream);
 
@@ -470,6 +465,10 @@ cudaError_t run_apply_istft_fused(setk_plan* pl, const float* audio, const int* 
   // peak is taken by the last block (it sees the complete sums)
   const int Ctot = pl->geo.C;
   a.c_total = Ctot;
+  if (use_apply_ws(pl->geo)) {         // the warp-specialised build serves the metric geometry
+    a.c0 = 0; a.accumulate = 0; a.peak = peak;
+    return run_apply_istft_ws(a, n_ctas, stream);
+  }
   for (int c0 = 0; c0 < Ctot && e == cudaSuccess; c0 += 4) {
     const int cb = Ctot - c0 < 4 ? Ctot - c0 : 4;
     a.c0 = c0;

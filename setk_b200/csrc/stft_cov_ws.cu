@@ -62,7 +62,10 @@ namespace setk {
 
 constexpr int kWsCovThreads = 128, kWsFftThreads = 256, kWsThreads = 384;
 constexpr int kWsBarFft = 1, kWsBarCov = 2;   // named barriers (0 is __syncthreads)
-constexpr int kWsChunk = 128;                 // tile descriptors per fill of the CTA's table
+#ifndef SETK_TABLE_CHUNK
+#define SETK_TABLE_CHUNK 128       // tile descriptors per table fill (the CPU test tier builds with 8)
+#endif
+constexpr int kWsChunk = SETK_TABLE_CHUNK;
 constexpr int kWsMaskRegion = 1036;           // floats of one mask tile in shared memory: 4 x 257 rounded
                                               // out to 16-byte boundaries at both ends (<= 1032), padded
 

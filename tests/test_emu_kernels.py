@@ -62,6 +62,11 @@ def test_stft_cov_ws_protocol(emu, B, N, hop, center, with_mn, clip, mask_ft):
                       with_mask_n=with_mn, clip=clip, mask_ft=mask_ft)
 
 
+def test_stft_cov_ws_long_run(emu):
+    # one long utterance: every CTA refills its 8-entry tile table (CPU build) several times
+    pc.check_stft_cov(emu, np.random.default_rng(10), 1, 4, 40000)
+
+
 def test_stft_cov_ws_ragged_short(emu):
     # utterances too short for one frame get an empty tile; others end mid-tile
     ns = torch.tensor([3000, 200, 1701, 513, 2999, 256, 257, 1024], dtype=torch.int32)
@@ -230,6 +235,18 @@ def test_weights_c64_and_status(emu):
 def test_apply_istft_fused(emu, C, N, hop, center, pm, norm):
     pc.check_apply_istft(emu, np.random.default_rng(30), 2, C, N, 512, hop, center, "hann",
                          post_mask=pm, norm=norm)
+
+
+def test_apply_istft_ws_protocol(emu):
+    # the warp-specialised build (apply_istft_ws.cu): long runs (several fills of the 8-entry
+    # tile table of the CPU build, halo tiles), many short utterances (several segments per CTA),
+    # ragged lengths, post-mask, no centre padding
+    rng = np.random.default_rng(33)
+    pc.check_apply_istft(emu, rng, 1, 4, 30000)
+    pc.check_apply_istft(emu, rng, 13, 4, 1500, post_mask=True)
+    ns = torch.tensor([9000, 700, 5120, 200, 8999, 4097], dtype=torch.int32)
+    pc.check_apply_istft(emu, rng, 6, 4, 9000, n_samples=ns)
+    pc.check_apply_istft(emu, rng, 3, 4, 9000, 512, 256, False, "hamming", n_samples=ns[:3], norm=False)
 
 
 def test_apply_istft_nsamps_and_ragged(emu):
