@@ -127,8 +127,11 @@ int setk_plan_create(const setk_config_t* cfg, setk_plan_t** plan_out) {
     return fail(SETK_EINVAL, "frame_len %d / frame_hop %d must be positive", cfg->frame_len, cfg->frame_hop);
   if (cfg->n_fft < cfg->frame_len)
     return fail(SETK_EINVAL, "n_fft %d smaller than frame_len %d", cfg->n_fft, cfg->frame_len);
-  if (!is_pow2(cfg->n_fft) || cfg->n_fft < 32 || cfg->n_fft > 4096)
-    return fail(SETK_EUNSUPPORTED, "n_fft %d: only powers of two in [32, 4096] are supported", cfg->n_fft);
+  // powers of two run the FFT kernels; any other EVEN size (--round-power-of-two false,
+  // utils.py:115) the direct-DFT path of the generic kernels (librosa's istft itself derives
+  // n_fft = 2 (F - 1), i.e. it only round-trips even sizes)
+  if (cfg->n_fft < 32 || cfg->n_fft > 4096 || (cfg->n_fft & 1))
+    return fail(SETK_EUNSUPPORTED, "n_fft %d: only even sizes in [32, 4096] are supported", cfg->n_fft);
   if (!cfg->window_host) return fail(SETK_EINVAL, "window_host is null");
   if (cfg->max_batch < 1 || cfg->max_samples < 1)
     return fail(SETK_EINVAL, "max_batch / max_samples must be positive");
@@ -142,6 +145,7 @@ int setk_plan_create(const setk_config_t* cfg, setk_plan_t** plan_out) {
   g.n_fft = cfg->n_fft;
   g.log2n = 0;
   while ((1 << g.log2n) < g.n_fft) ++g.log2n;
+  if (!is_pow2(g.n_fft)) g.log2n = -1;     // marks the direct-DFT route
   g.hop = cfg->frame_hop;
   g.pad = cfg->center ? g.n_fft / 2 : 0;
   g.F = g.n_fft / 2 + 1;

@@ -39,6 +39,49 @@ __device__ __forceinline__ int bitrev(int v, int log2n) {
   return (int)(__brev((unsigned)v) >> (32 - log2n));
 }
 
+// ---------------------------------------------------------------------------
+// n_fft that is not a power of two (--round-power-of-two false, utils.py:115: n_fft =
+// frame_len, e.g. 400): direct real DFT / inverse real DFT by the CTA, O(n^2) with a
+// shared-memory twiddle table W[k] = exp(-2 pi i k / n) indexed by (f n) mod n.  A rarely
+// used option of a 0.1 ms kernel: simplicity over speed; fp32 sums of <= 4096 terms with
+// exactly reduced arguments (rel. error ~1e-6).  s holds n floats (signal) + n float2 (table).
+// ---------------------------------------------------------------------------
+__device__ inline void dft_table(float2* tab, int n) {
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    float sn, cs;
+    sincospif(2.0f * (float)k / (float)n, &sn, &cs);
+    tab[k] = make_float2(cs, -sn);
+  }
+}
+// X[f] = sum_n x[n] W^{f n}, f = 0 .. n/2
+__device__ inline float2 dft_bin(const float* x, const float2* tab, int n, int f) {
+  float re = 0.f, im = 0.f;
+  int idx = 0;
+  for (int i = 0; i < n; ++i) {
+    const float2 w = tab[idx];
+    re = fmaf(x[i], w.x, re);
+    im = fmaf(x[i], w.y, im);
+    idx += f;
+    if (idx >= n) idx -= n;
+  }
+  return make_float2(re, im);
+}
+// x[i] = (1/n) (Re X0 + (-1)^i Re X_{n/2} + 2 sum_{k=1}^{n/2-1} Re(X_k conj(W)^{k i}))   (n even)
+__device__ inline float idft_sample(const float2* X, const float2* tab, int n, int i) {
+  float acc = 0.f;
+  int idx = i % n;
+  const int step = idx;
+  for (int k = 1; k < n / 2; ++k) {
+    const float2 w = tab[idx];                 // W^{k i} = (cos, -sin): Re(X conj(W)) = Xr c - Xi s ... s = -w.y
+    acc = fmaf(X[k].x, w.x, acc);
+    acc = fmaf(X[k].y, w.y, acc);
+    idx += step;
+    if (idx >= n) idx -= n;
+  }
+  const float nyq = (i & 1) ? -X[n / 2].x : X[n / 2].x;
+  return (X[0].x + nyq + 2.0f * acc) / (float)n;
+}
+
 // forward_stft (utils.py:96-138) for every (frame, channel, utterance).
 // grid (T, C, B); dynamic smem n_fft * 8 B.
 __global__ void stft_generic_kernel(Geometry g, const float* __restrict__ audio,
@@ -54,6 +97,19 @@ __global__ void stft_generic_kernel(Geometry g, const float* __restrict__ audio,
     return;
   }
   const float* x = audio + ((long long)b * g.C + c) * N;
+  if (g.log2n < 0) {                       // n_fft is not a power of two: direct DFT
+    float2* tab = s;
+    float* xs = reinterpret_cast<float*>(s + g.n_fft);
+    dft_table(tab, g.n_fft);
+    for (int n = threadIdx.x; n < g.n_fft; n += blockDim.x) {
+      const int p = t * g.hop + n;
+      const int i = g.pad ? reflect_index(p, g.pad, nb) : p;
+      xs[n] = window[n] * x[i];
+    }
+    __syncthreads();
+    for (int f = threadIdx.x; f < g.F; f += blockDim.x) o[(long long)f * T] = dft_bin(xs, tab, g.n_fft, f);
+    return;
+  }
   for (int n = threadIdx.x; n < g.n_fft; n += blockDim.x) {
     const int p = t * g.hop + n;
     const int i = g.pad ? reflect_index(p, g.pad, nb) : p;
@@ -153,6 +209,16 @@ __global__ void istft_frames_kernel(Geometry g, const float2* __restrict__ enh, 
   const int t = blockIdx.x, b = blockIdx.y;
   const float2* e = enh + (long long)b * sb + (long long)t * st;
   const int n = g.n_fft;
+  if (g.log2n < 0) {                       // n_fft is not a power of two: direct inverse DFT
+    float2* tab = s;
+    float2* X = s + n;
+    dft_table(tab, n);
+    for (int k = threadIdx.x; k < g.F; k += blockDim.x) X[k] = e[(long long)k * sf];
+    __syncthreads();
+    float* o = frames + ((long long)b * T_used + t) * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) o[i] = window[i] * idft_sample(X, tab, n, i);
+    return;
+  }
   for (int k = threadIdx.x; k < g.F; k += blockDim.x) {
     float2 v = e[(long long)k * sf];
     if (k == 0 || k == n / 2) v.y = 0.f;      // c2r ignores these imaginary parts
@@ -313,7 +379,8 @@ cudaError_t run_stft_generic(const setk_plan* pl, const float* audio, const int*
                              int N, int T, float2* out, void* stream) {
   const Geometry& g = pl->geo;
   dim3 grid(T, g.C, B), block(imin(256, g.n_fft / 2));
-  return launch(stft_generic_kernel, grid, block, (size_t)g.n_fft * sizeof(float2), stream, false, g,
+  return launch(stft_generic_kernel, grid, block, (size_t)g.n_fft * sizeof(float2) * (g.log2n < 0 ? 2 : 1),
+                stream, false, g,
                 audio, n_samples, N, T, (const float*)pl->d_window, out);
 }
 
@@ -337,7 +404,8 @@ cudaError_t run_istft_strided(const setk_plan* pl, const float2* enh, long long 
                               float* frames_ws, float* wave, unsigned* peak, void* stream) {
   const Geometry& g = pl->geo;
   cudaError_t e = launch(istft_frames_kernel, dim3(T_used, B), dim3(imin(256, g.n_fft / 2)),
-                         (size_t)g.n_fft * sizeof(float2), stream, false, g, enh, sb, sf, st,
+                         (size_t)g.n_fft * sizeof(float2) * (g.log2n < 0 ? 2 : 1), stream, false, g, enh,
+                         sb, sf, st,
                          (const float*)pl->d_window, frames_ws, T_used);
   if (e != cudaSuccess) return e;
   return launch(istft_ola_kernel, dim3((n_out + 255) / 256, B), dim3(256), 0, stream, false, g,

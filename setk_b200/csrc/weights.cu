@@ -99,8 +99,13 @@ __device__ inline bool all_finite(const CVec<C>& v) {
 #define SETK_W_MINBLOCKS 2
 #endif
 
-template <int C>
-__global__ void __launch_bounds__(128, SETK_W_MINBLOCKS) weights_kernel(WeightsArgs a) {
+// KIND >= 0: an instantiation for ONE beamformer kind (the branches of the others fold away, and
+// with them their registers: MVDR at C = 4 drops from 255 to <= 128 registers, i.e. from 8 to 16
+// resident warps per SM for a kernel that is nothing but fp64 latency chains); KIND = -1: any kind.
+template <int C, int KIND, int MINB>
+__global__ void __launch_bounds__(128, MINB) weights_kernel(WeightsArgs a0) {
+  WeightsArgs a = a0;
+  if (KIND >= 0) { a.kind = KIND; if (KIND != SETK_BF_PMWF) a.rank1 = SETK_RANK1_NONE; }
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)a.B * a.F) return;
   int b = (int)(idx / a.F);
@@ -252,7 +257,13 @@ static cudaError_t launch_weights(const WeightsArgs& a, void* stream) {
   long long n = (long long)a.B * a.F;
   const int bs = 128;
   dim3 block(bs), grid((unsigned)((n + bs - 1) / bs));
-  cudaError_t e = launch(weights_kernel<C>, grid, block, 0, stream, /*barrier_free=*/true, a);
+  cudaError_t e;
+  if (C <= 4 && a.kind == SETK_BF_MVDR)
+    e = launch(weights_kernel<(C <= 4 ? C : 1), SETK_BF_MVDR, 4>, grid, block, 0, stream, true, a);
+  else if (C <= 4 && a.kind == SETK_BF_GEVD)
+    e = launch(weights_kernel<(C <= 4 ? C : 1), SETK_BF_GEVD, 4>, grid, block, 0, stream, true, a);
+  else
+    e = launch(weights_kernel<C, -1, SETK_W_MINBLOCKS>, grid, block, 0, stream, /*barrier_free=*/true, a);
   if (e != cudaSuccess) return e;
   if (a.kind == SETK_BF_PMWF && a.ref_channel < 0)
     e = launch(pmwf_select_kernel<C>, dim3(a.B), dim3(128), 0, stream, /*barrier_free=*/false, a);

@@ -60,10 +60,8 @@ def check_stft(device, rng, B, C, N, frame_len=512, hop=256, center=True, window
     assert S.dtype == np.complex64
     for b in range(B):
         nb = N if n_samples is None else int(n_samples[b])
-        if nb < (frame_len if not center else pl.n_fft // 2 + 1) or (center and nb + pl.n_fft < pl.n_fft):
-            # too short for one frame (librosa raises): the batch entry gets zero covariances
-            assert not Rs[b].any() and not Rn[b].any()
-            assert mx[b] == np.float32(np.max(np.abs(x[b, :, :nb])))
+        if nb < (frame_len if not center else pl.n_fft // 2 + 1):
+            assert not S[b].any()        # too short for one frame (librosa raises): zeros
             continue
         So = oracle_stft(x[b, :, :nb], frame_len, hop, center, window)
         Tb = So.shape[-1]
@@ -114,6 +112,43 @@ def check_stft_cov(device, rng, B, C, N, frame_len=512, hop=256, center=True, wi
         worst = max(worst, es, en)
     pl.close()
     return worst
+
+
+def check_non_power_of_two(device, rng, frame_len=400, hop=160, C=3, N=4000):
+    """
+    --round-power-of-two false (libs/opts.py:41, utils.py:115): n_fft = frame_len.  Bookkeeping
+    bit-exact, STFT / iSTFT round trip and the whole PMWF chain against the oracle.
+    """
+    from setk_b200.engine import BeamformPipeline
+    kw = dict(frame_len=frame_len, frame_hop=hop, center=True, window="hann", transpose=False)
+    pl = P.StftPlan(C, frame_len, hop, True, False, "hann", 2, N, device)
+    assert pl.n_fft == frame_len and pl.num_bins == frame_len // 2 + 1
+    for n in (N, N - 37, 2 * frame_len + 1):
+        T = so.num_frames(n, frame_len, hop, True)
+        assert pl.num_frames(n) == T
+        assert pl.istft_length(T) == so.istft_length(T, frame_len, hop, True)
+    x = rng_audio(rng, 2, C, N)
+    S = pl.stft(torch.from_numpy(x).to(device)).cpu().numpy()
+    for b in range(2):
+        So = so.multichannel_stft(x[b], round_power_of_two=False, **kw)
+        assert S[b].shape == So.shape
+        assert bo.rel_inf(S[b], So) <= TOL_F32
+    y = pl.istft(torch.from_numpy(S[:, 0]).to(device)).cpu().numpy()       # channel 0 round trip
+    n_rt = y.shape[1]
+    assert bo.rel_inf(y[:, frame_len:n_rt - frame_len], x[:, 0, frame_len:n_rt - frame_len]) <= TOL_F32
+    pl.close()
+    pipe = BeamformPipeline(C, "pmwf-0", frame_len=frame_len, frame_hop=hop, round_power_of_two=False,
+                            max_batch=2, max_samples=N, device=device)
+    T, F = pipe.plan.num_frames(N), pipe.plan.num_bins
+    m = rng.uniform(0.05, 0.95, (2, T, F)).astype(np.float32)
+    xs = structured_audio(rng, 2, C, N)
+    wave, st = pipe.run(torch.from_numpy(xs).to(device), torch.from_numpy(m).to(device))
+    assert int(st.abs().sum()) == 0
+    for b in range(2):
+        yo, _, _ = bo.enhance_utterance(xs[b], m[b], kind="pmwf", beta=0, frame_len=frame_len,
+                                        frame_hop=hop, round_power_of_two=False)
+        assert bo.rel_inf(wave[b].cpu().numpy(), yo) <= TOL_E2E
+    pipe.plan.close()
 
 
 def check_cov_generic(device, rng, B, C, F, T):

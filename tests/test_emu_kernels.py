@@ -28,6 +28,13 @@ def test_stft_generic(emu, C, N, fl, hop, center, window):
     pc.check_stft(emu, np.random.default_rng(1), 1, C, N, fl, hop, center, window)
 
 
+def test_non_power_of_two_n_fft(emu):
+    # --round-power-of-two false --frame-len 400: n_fft = 400 through the direct-DFT route
+    pc.check_non_power_of_two(emu, np.random.default_rng(12))
+    with pytest.raises(Exception):
+        pc.P.StftPlan(1, 401, 160, True, False, "hann", 1, 4000, emu)      # odd n_fft: librosa cannot either
+
+
 def test_stft_generic_ragged(emu):
     ns = torch.tensor([1500, 900], dtype=torch.int32)
     pc.check_stft(emu, np.random.default_rng(2), 2, 2, 1500, n_samples=ns)

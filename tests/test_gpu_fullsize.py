@@ -20,7 +20,8 @@ import torch
 import parity_cases as pc
 from oracle import beamformer_oracle as bo
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not torch.cuda.is_available(), reason="no CUDA device")]
 B, C, N = 256, 4, 160000
 
 

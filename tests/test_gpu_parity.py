@@ -125,6 +125,12 @@ def test_apply_istft_nsamps_and_ragged(cuda):
     pc.check_apply_istft(cuda, rng, 3, 4, 30000, n_samples=ns)
 
 
+def test_non_power_of_two_n_fft(cuda):
+    """--round-power-of-two false (utils.py:115, opts.py:41): n_fft = frame_len = 400 / 600."""
+    pc.check_non_power_of_two(cuda, np.random.default_rng(12))
+    pc.check_non_power_of_two(cuda, np.random.default_rng(13), frame_len=600, hop=200, C=5, N=9000)
+
+
 def test_generic_chain(cuda):
     rng = np.random.default_rng(32)
     pc.check_generic_chain(cuda, rng, 2, 5, 15000, 512, 256, True, "hann")
