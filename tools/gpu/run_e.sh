@@ -12,8 +12,12 @@ for rep in 1 2; do
   timeout 300 python tools/ab_fused.py setk_b200/libsetk_b200.so ai_ws_64_112 >> gpurun_out/e/ab.jsonl 2>> gpurun_out/e/ab.err
   timeout 300 python tools/ab_fused.py ab/libsetk_b200_aw7296.so ai_ws_72_96 >> gpurun_out/e/ab.jsonl 2>> gpurun_out/e/ab.err
 done
+for impl in dmma dfma; do
+  SETK_WPE_CORR=$impl timeout 600 python tools/bench_configs.py "cfg4" 3 wpe >> gpurun_out/e/wpe_$impl.jsonl 2>> gpurun_out/e/configs.err
+done
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/e/launches_wpe.csv python tools/bench_configs.py "cfg4" 1 wpe > gpurun_out/e/ncu_wpe.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:apply_istft_ws -s 2 -c 1 -o gpurun_out/e/aw_prof python tools/ab_fused.py > gpurun_out/e/ncu_aw.log 2>&1
-tail -25 gpurun_out/e/pytest.log; cat gpurun_out/e/ab.jsonl
+tail -25 gpurun_out/e/pytest.log; cat gpurun_out/e/ab.jsonl; cat gpurun_out/e/wpe_dmma.jsonl gpurun_out/e/wpe_dfma.jsonl | cut -c1-600
 python - <<'PY'
 import json
 for impl in ("mma","cuda"):
