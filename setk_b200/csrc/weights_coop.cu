@@ -8,8 +8,8 @@
 // parallel LU (partial pivoting), Cholesky and triangular solves with the same
 // operation order per element as hermitian_solve.cuh.
 //
-// Kinds: MVDR (beamformer.py:527-539), GEVD / PEVD (31-63, 674-682), with BAN
-// (14-28).  MPDR, PMWF and the rank-1 options stay on weights.cu.
+// Kinds: MVDR (beamformer.py:527-539), MPDR (555-573), GEVD / PEVD (31-63, 674-682), with BAN
+// (14-28).  MPDR-whiten, PMWF and the rank-1 options stay on weights.cu.
 #include "jacobi_coop.cuh"
 #include "weights_args.cuh"
 
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(WCfg<C>::THREADS) weights_coop_kernel(WeightsA
   const bool have_rn = a.Rn != nullptr;
   cd w = cd_make(0.0, 0.0);
 
-  if (a.kind == SETK_BF_MVDR || (a.kind == SETK_BF_PEVD && !have_rn)) {
+  if (a.kind == SETK_BF_MVDR || a.kind == SETK_BF_MPDR || (a.kind == SETK_BF_PEVD && !have_rn)) {
     if (row) load_lower_hermitian<C>(a.Rs, a.r_dtype, idx, A, r);
     __syncwarp();
     if (!jacobi_coop<C>(A, V, rot, r, active)) st |= SETK_ST_NO_CONVERGE;
@@ -180,8 +180,10 @@ __global__ void __launch_bounds__(WCfg<C>::THREADS) weights_coop_kernel(WeightsA
     if (a.kind == SETK_BF_PEVD) {
       w = d;
     } else {
+      // denominator matrix: Rn for MVDR, Ry (all-ones mask) for MPDR (beamformer.py:555-573)
+      const void* D = a.kind == SETK_BF_MPDR ? a.Ry : a.Rn;
       if (row) {
-        for (int j = 0; j < C; ++j) M[r * LD + j] = load_c(a.Rn, a.r_dtype, idx * (C * C) + r * C + j);
+        for (int j = 0; j < C; ++j) M[r * LD + j] = load_c(D, a.r_dtype, idx * (C * C) + r * C + j);
         M[r * LD + C] = d;
       }
       __syncwarp();
@@ -280,7 +282,8 @@ __global__ void __launch_bounds__(WCfg<C>::THREADS) weights_coop_kernel(WeightsA
 bool weights_coop_supported(const WeightsArgs& a, int C) {
   if (C <= 4) return false;                            // register-resident one-thread solve is faster
   if (a.rank1 != SETK_RANK1_NONE) return false;
-  return a.kind == SETK_BF_MVDR || a.kind == SETK_BF_GEVD || a.kind == SETK_BF_PEVD;
+  return a.kind == SETK_BF_MVDR || a.kind == SETK_BF_MPDR || a.kind == SETK_BF_GEVD ||
+         a.kind == SETK_BF_PEVD;
 }
 
 template <int C>
