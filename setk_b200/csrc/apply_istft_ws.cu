@@ -8,15 +8,19 @@
 // needed by the `norm` rescale.  C++ twin: Beamform (include/beamformer.cc:215-230) +
 // InverseShortTimeFT (include/stft.cc:154-198).
 //
-// 384 threads = 8 FFT warps (64 registers) + 4 BACK warps (112 registers, highest warp ids),
-// launched at 80 registers => two CTAs per SM.  A tile is 4 frames x 4 channels; its Z slot
-// (one of two) is re-used in place down the pipeline:
+// 512 threads = 8 FFT warps (64 registers) + 4 IFFT warps (48) + 4 BACK warps (80, highest warp
+// ids), launched at 64 => two CTAs per SM (32 warps).  A first build let two of the FFT warps run the inverse
+// transforms: they waited for the BACK warps' apply while the other six waited for them at the
+// audio barrier, the roles ran one after the other and the kernel was 35 % SLOWER than the classic
+// one (0.79 vs 0.57 ms, profiles/r2_apply_istft_ws_serialised_ncu.txt); the inverse FFT therefore
+// has warps of its own that meet nobody but the mbarriers.  A tile is 4 frames x 4 channels; its
+// Z slot (one of two) is re-used in place down the pipeline:
 //
 //   FFT warps   audio tile (TMA bulk copy) -> forward FFT -> Z[slot]        ... arrive z_full
 //   BACK warps  wait z_full: thread k applies the weights of bin pair (k, 256-k) to the four
 //               channels of each frame and writes the half-size inverse spectrum Zi over
 //               channel 0's part of the slot (it owns entries k, 256-k)     ... arrive zi_full
-//   FFT warps   (two of them, rotating with the tile number) wait zi_full: inverse FFT of the
+//   IFFT warps  (a pair per tile, the two pairs alternate) wait zi_full: inverse FFT of the
 //               four frames, x synthesis window -> frames over channel 1's part ... arrive fr_full
 //   BACK warps  wait fr_full (of the PREVIOUS tile, so the inverse FFT overlaps their apply):
 //               overlap-add with the carried half frame, / window-sum-square, trim, 16-byte
@@ -34,15 +38,11 @@
 
 namespace setk {
 
-#define SETK_AW_LAUNCH_REGS 80
-#ifndef SETK_AW_FFT_REGS
-#define SETK_AW_FFT_REGS 64
-#endif
-#ifndef SETK_AW_BACK_REGS
-#define SETK_AW_BACK_REGS 112
-#endif
+#define SETK_AW_LAUNCH_REGS 64
+#define SETK_AW_IFFT_REGS 48
+#define SETK_AW_BACK_REGS 80
 
-constexpr int kAwFftThreads = 256, kAwBackThreads = 128, kAwThreads = 384;
+constexpr int kAwFftThreads = 256, kAwIfftThreads = 128, kAwBackThreads = 128, kAwThreads = 512;
 constexpr int kAwBarFft = 1, kAwBarBack = 2;
 #ifndef SETK_TABLE_CHUNK
 #define SETK_TABLE_CHUNK 128       // tile descriptors per table fill (the CPU test tier builds with 8)
@@ -73,7 +73,7 @@ struct AwSmem {
   MBar* bar_audio;        // [1]
   MBar* z_full;           // [2] 8 FFT warps
   MBar* zi_full;          // [2] 4 BACK warps
-  MBar* fr_full;          // [2] 2 FFT warps
+  MBar* fr_full;          // [2] 2 IFFT warps
   MBar* z_empty;          // [2] 4 BACK warps
   float* win;             // [512] analysis window x 0.5
   float2* twtab;          // [256]
@@ -212,40 +212,7 @@ __device__ __forceinline__ void aw_fft_role(const ApplyIstftArgs& a, const AwSme
     aw_stage_scalar(sm, xb, a.N, nb, d.t0, nt, hop, pad, ftid);
     return true;
   };
-  // inverse FFT of the frames of tile m (slot m & 1) by the two warps whose turn it is
-  auto ifft = [&](int m, int nt_m) {
-    const int w0 = (2 * m) & 7;
-    if (fw != w0 && fw != w0 + 1) return;
-    const int s = m & 1;
-    mbar_wait(&sm.zi_full[s], (unsigned)(m >> 1) & 1u);
-    const int j = (fw - w0) * 2 + (lane >> 4);      // frame inside the tile
-    {
-      // a dead frame (j >= nt_m) transforms zeros: both half-warps run the same code
-      float2* zi = sm.z + (s * 16 + j * kAwC) * SETK_ZSLOT;
-      float2 v[16];
-      const bool live = j < nt_m;
-#pragma unroll
-      for (int m1 = 0; m1 < 16; ++m1) {
-        const float2 x = live ? zi[16 * m1 + lane16] : make_float2(0.f, 0.f);
-        v[m1] = make_float2(x.x, -x.y);
-      }
-      __syncwarp();                                 // the slot part is free: reuse it as the exchange tile
-      halfwarp_fft256_a(v, sm.twtab, lane16);
-      halfwarp_fft256_b(v, zi, lane16);
-      float* fo = reinterpret_cast<float*>(sm.z + (s * 16 + j * kAwC + 1) * SETK_ZSLOT);
-#pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const int mm = lane16 + 16 * kof(q);
-        const float2 ws = *reinterpret_cast<const float2*>(sm.wsyn + 2 * mm);
-        *reinterpret_cast<float2*>(fo + 2 * mm) = make_float2(v[q].x * ws.x, -v[q].y * ws.y);
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.fr_full[s]);
-  };
-
   int n = 0;                                         // local tile number
-  int nt_prev = 0;
   bool first_fill = true;
   for (;;) {
     __syncthreads();                                 // the previous table is consumed by both roles
@@ -288,17 +255,63 @@ __device__ __forceinline__ void aw_fft_role(const ApplyIstftArgs& a, const AwSme
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.z_full[s]);
-      if (n > 0) ifft(n - 1, nt_prev);               // overlaps the BACK warps' apply of tile n
-      nt_prev = nt;
       if (scalar_next) named_bar_sync(kAwBarFft, kAwFftThreads);
     }
     if (!more) break;
   }
-  if (n > 0) ifft(n - 1, nt_prev);
 }
 
 // ---------------------------------------------------------------------------
-// BACK role: threads 256..383 -- apply (bin pair per thread) and flush
+// IFFT role: threads 256..383; warps (0, 1) take the even tiles, (2, 3) the odd ones; a half-warp
+// per frame: conj . FFT256 . conj of the half-size inverse spectrum, x synthesis window
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void aw_ifft_role(const ApplyIstftArgs& a, const AwSmem& sm, int lo, int hi,
+                                             int T_cap, bool vec_ok) {
+  const int tid = (int)threadIdx.x - kAwFftThreads;
+  const int lane = tid & 31, lane16 = lane & 15, iw = tid >> 5;
+  int n = 0;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) aw_fill_table(a, sm, lo, hi, T_cap, vec_ok);
+    __syncthreads();
+    const int cnt = sm.gen->count;
+    const bool more = !sm.gen->done;
+    for (int i = 0; i < cnt; ++i, ++n) {
+      if ((n & 1) != (iw >> 1)) continue;            // the other pair's tile
+      const int nt_m = (int)(sm.tiles[i].flags & AW_NT);
+      const int s = n & 1;
+      mbar_wait(&sm.zi_full[s], (unsigned)(n >> 1) & 1u);
+      const int j = (iw & 1) * 2 + (lane >> 4);      // frame inside the tile
+      {
+        // a dead frame (j >= nt_m) transforms zeros: both half-warps run the same code
+        float2* zi = sm.z + (s * 16 + j * kAwC) * SETK_ZSLOT;
+        float2 v[16];
+        const bool live = j < nt_m;
+#pragma unroll
+        for (int m1 = 0; m1 < 16; ++m1) {
+          const float2 x = live ? zi[16 * m1 + lane16] : make_float2(0.f, 0.f);
+          v[m1] = make_float2(x.x, -x.y);
+        }
+        __syncwarp();                                // the slot part is free: reuse it as the exchange tile
+        halfwarp_fft256_a(v, sm.twtab, lane16);
+        halfwarp_fft256_b(v, zi, lane16);
+        float* fo = reinterpret_cast<float*>(sm.z + (s * 16 + j * kAwC + 1) * SETK_ZSLOT);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int mm = lane16 + 16 * kof(q);
+          const float2 ws = *reinterpret_cast<const float2*>(sm.wsyn + 2 * mm);
+          *reinterpret_cast<float2*>(fo + 2 * mm) = make_float2(v[q].x * ws.x, -v[q].y * ws.y);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.fr_full[s]);
+    }
+    if (!more) break;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// BACK role: threads 384..511 -- apply (bin pair per thread) and flush
 // ---------------------------------------------------------------------------
 struct AwSeg {            // what the flush of a tile needs to know about its utterance
   int b, T_used, own_begin, n_lim, expected;
@@ -307,7 +320,7 @@ struct AwSeg {            // what the flush of a tile needs to know about its ut
 __device__ __forceinline__ void aw_back_role(const ApplyIstftArgs& a, const AwSmem& sm, int lo, int hi,
                                              int T_cap, bool vec_ok) {
   constexpr int C = kAwC, TT = kAwTT, F = kBins;
-  const int tid = (int)threadIdx.x - kAwFftThreads, lane = tid & 31, warp = tid >> 5;
+  const int tid = (int)threadIdx.x - kAwFftThreads - kAwIfftThreads, lane = tid & 31, warp = tid >> 5;
   const int hop = a.g.hop, pad = a.g.pad;
   const int k = tid, km = kM - tid;
   const float2 tw = split_twiddle(tid);
@@ -542,11 +555,15 @@ __global__ void __maxnreg__(SETK_AW_LAUNCH_REGS) apply_istft_ws_kernel(ApplyIstf
   const bool vec_ok = ((a.N & 3) == 0) && ((a.g.hop & 3) == 0) && ((a.g.pad & 3) == 0) &&
                       ((reinterpret_cast<uintptr_t>(a.audio) & 15) == 0);
   __syncthreads();
-  if (tid >= kAwFftThreads) {
+  // 64 registers at launch; the inverse-FFT warpgroup hands 16 per thread to the BACK warpgroup
+  // (whose threads keep a bin pair's eight complex weights in registers)
+  if (tid >= kAwFftThreads + kAwIfftThreads) {
     setmaxnreg_inc<SETK_AW_BACK_REGS>();
     aw_back_role(a, sm, lo, hi, T_cap, vec_ok);
+  } else if (tid >= kAwFftThreads) {
+    setmaxnreg_dec<SETK_AW_IFFT_REGS>();
+    aw_ifft_role(a, sm, lo, hi, T_cap, vec_ok);
   } else {
-    setmaxnreg_dec<SETK_AW_FFT_REGS>();
     aw_fft_role(a, sm, lo, hi, T_cap, vec_ok);
   }
 }
