@@ -425,10 +425,11 @@ bool apply_istft_fused_supported(const Geometry& g) {
 void fused_schedule(const setk_plan* pl, int B, int T, int TT, int* n_ctas, int* slots, int* min_quota);
 bool apply_istft_ws_supported(const Geometry& g);
 cudaError_t run_apply_istft_ws(const ApplyIstftArgs& a, int n_ctas, void* stream);
-// SETK_AI_IMPL=classic keeps the classic kernel (measurement knob)
+// The warp-specialised build is opt-in (SETK_AI_IMPL=ws): measured on B200 at config 2 it is
+// still slower than this kernel (0.62 vs 0.57 ms; apply_istft_ws.cu says why)
 static bool use_apply_ws(const Geometry& g) {
-  static const char* env = getenv("SETK_AI_IMPL");
-  if (env && env[0] == 'c') return false;
+  const char* env = getenv("SETK_AI_IMPL");
+  if (!(env && env[0] == 'w')) return false;
   return apply_istft_ws_supported(g);
 }
 cudaError_t run_tile_prefix(const int* n_samples, int B, const Geometry& g, int TT, int T_cap,

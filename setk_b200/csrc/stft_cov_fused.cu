@@ -319,7 +319,7 @@ __global__ void __maxnreg__(SETK_SC_REGS) stft_cov_kernel(StftCovArgs a) {
 // One thread per (b, f).
 template <int C>
 __global__ void cov_finalize_kernel(const float* __restrict__ partials, int B, int F, TileSched sched,
-                                    int n_ctas, int slots, float2* __restrict__ Rs,
+                                    int n_ctas, int slots, float scale, float2* __restrict__ Rs,
                                     float2* __restrict__ Rn) {
   constexpr int NACC = CovAcc<C>::NACC;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -340,7 +340,8 @@ __global__ void cov_finalize_kernel(const float* __restrict__ partials, int B, i
 #pragma unroll
   for (int which = 0; which < 2; ++which) {
     const float* A = acc + which * NACC;
-    const float inv = 1.0f / fmaxf(acc[2 * NACC + which], 1e-6f);
+    // scale: the spectra behind the sums were scaled by 1 / sqrt(scale) (pair-sum window path)
+    const float inv = scale / fmaxf(acc[2 * NACC + which], 1e-6f);
     float2* R = (which == 0 ? Rs : Rn) + idx * (C * C);
     int o = C;
 #pragma unroll
@@ -361,18 +362,18 @@ cudaError_t run_bits_to_float(const unsigned* bits, int n, float* out, void* str
 
 template <int C>
 static cudaError_t run_cov_finalize_t(const float* partials, int B, int F, TileSched sched, int n_ctas,
-                                      int slots, float2* Rs, float2* Rn, void* stream) {
+                                      int slots, float scale, float2* Rs, float2* Rn, void* stream) {
   const long long n = (long long)B * F;
   return launch(cov_finalize_kernel<C>, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, stream, true,
-                partials, B, F, sched, n_ctas, slots, Rs, Rn);
+                partials, B, F, sched, n_ctas, slots, scale, Rs, Rn);
 }
 cudaError_t run_cov_finalize(int C, const float* partials, int B, int F, TileSched sched, int n_ctas,
-                             int slots, float2* Rs, float2* Rn, void* stream) {
+                             int slots, float scale, float2* Rs, float2* Rn, void* stream) {
   switch (C) {
-    case 1: return run_cov_finalize_t<1>(partials, B, F, sched, n_ctas, slots, Rs, Rn, stream);
-    case 2: return run_cov_finalize_t<2>(partials, B, F, sched, n_ctas, slots, Rs, Rn, stream);
-    case 3: return run_cov_finalize_t<3>(partials, B, F, sched, n_ctas, slots, Rs, Rn, stream);
-    case 4: return run_cov_finalize_t<4>(partials, B, F, sched, n_ctas, slots, Rs, Rn, stream);
+    case 1: return run_cov_finalize_t<1>(partials, B, F, sched, n_ctas, slots, scale, Rs, Rn, stream);
+    case 2: return run_cov_finalize_t<2>(partials, B, F, sched, n_ctas, slots, scale, Rs, Rn, stream);
+    case 3: return run_cov_finalize_t<3>(partials, B, F, sched, n_ctas, slots, scale, Rs, Rn, stream);
+    case 4: return run_cov_finalize_t<4>(partials, B, F, sched, n_ctas, slots, scale, Rs, Rn, stream);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -391,7 +392,7 @@ static cudaError_t run_stft_cov_t(setk_plan* pl, StftCovArgs a, int B, int n_cta
   if (e != cudaSuccess) return e;
   e = launch(stft_cov_kernel<C, TT>, dim3(n_ctas), dim3(TT > 4 ? 320 : 288), smem, stream, false, a);
   if (e != cudaSuccess) return e;
-  e = run_cov_finalize_t<C>(a.partials, B, a.g.F, a.sched, n_ctas, a.slots, Rs, Rn, stream);
+  e = run_cov_finalize_t<C>(a.partials, B, a.g.F, a.sched, n_ctas, a.slots, 1.0f, Rs, Rn, stream);
   if (e != cudaSuccess) return e;
   if (maxabs) e = run_bits_to_float(a.maxabs_bits, B, maxabs, stream);
   return e;
@@ -461,7 +462,7 @@ cudaError_t run_stft_cov_ws(setk_plan*, const float*, const int*, int, int, int,
 // which build of the fused kernel serves this geometry: the warp-specialised one
 // (stft_cov_ws.cu) where it exists, unless SETK_SC_IMPL=classic (measurement knob)
 static bool use_ws(const Geometry& g) {
-  static const char* env = getenv("SETK_SC_IMPL");
+  const char* env = getenv("SETK_SC_IMPL");
   if (env && env[0] == 'c') return false;
   return stft_cov_ws_supported(g);
 }
@@ -490,6 +491,7 @@ cudaError_t run_stft_cov_fused(setk_plan* pl, const float* audio, const int* n_s
     a.sched.prefix = tile_prefix;
   }
   a.window = pl->d_window;
+  a.win_pair_sum = 0.f;
   a.partials = partials;
   a.maxabs_bits = maxabs_bits;
   switch (pl->geo.C) {

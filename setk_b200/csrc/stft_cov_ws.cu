@@ -210,7 +210,7 @@ __device__ __forceinline__ void ws_stage_scalar(const WsSmem<C>& sm, const float
 // ---------------------------------------------------------------------------
 // FFT role: threads 0..255, half-warp job = thread / 16 = frame * C + channel
 // ---------------------------------------------------------------------------
-template <int C, bool HAS_MN>
+template <int C, bool HAS_MN, bool PAIRWIN>
 __device__ __forceinline__ void ws_fft_role(const StftCovArgs& a, const WsSmem<C>& sm, int lo, int hi, int q,
                                             bool vec_ok) {
   constexpr int TT = WsShape<C>::TT;
@@ -263,6 +263,7 @@ __device__ __forceinline__ void ws_fft_role(const StftCovArgs& a, const WsSmem<C
       const WsTile d = sm.tiles[i];
       const int nt = (int)(d.flags & WS_NT);
       float2 v[16];
+      float2 w8[8];                                  // PAIRWIN: window of the first half frame
       if (nt > 0) {
         if (d.flags & WS_AUDIO_BULK) { mbar_wait(sm.bar_audio, apar); apar ^= 1u; }
         // a dead frame (fr >= nt, only in an utterance's last tile) re-transforms the last live
@@ -273,16 +274,24 @@ __device__ __forceinline__ void ws_fft_role(const StftCovArgs& a, const WsSmem<C
 #pragma unroll
         for (int m1 = 0; m1 < 16; ++m1) {
           const float2 sx = *reinterpret_cast<const float2*>(src + 32 * m1);
-          const float2 w = *reinterpret_cast<const float2*>(wsrc + 32 * m1);
           amax = fmaxf(amax, fmaxf(fabsf(sx.x), fabsf(sx.y)));
-          v[m1] = f2mul(sx, w);
+          if (PAIRWIN) {
+            v[m1] = sx;                              // the window rides in the first butterflies
+            if (m1 < 8) w8[m1] = *reinterpret_cast<const float2*>(wsrc + 32 * m1);
+          } else {
+            const float2 w = *reinterpret_cast<const float2*>(wsrc + 32 * m1);
+            v[m1] = f2mul(sx, w);
+          }
         }
       }
       named_bar_sync(kWsBarFft, kWsFftThreads);    // every FFT warp holds its samples: the buffer is free
       const bool has_next = c0 + i + 1 < hi;
       bool scalar_next = false;
       if (has_next) scalar_next = stage(sm.tiles[i + 1]);
-      if (nt > 0) halfwarp_fft256_a(v, sm.twtab, lane16);
+      if (nt > 0) {
+        if (PAIRWIN) halfwarp_fft256_a_pairwin(v, w8, sm.twtab, lane16);
+        else halfwarp_fft256_a(v, sm.twtab, lane16);
+      }
       const int s = n & 1;
       mbar_wait(&sm.z_empty[s], ((unsigned)(n >> 1) & 1u) ^ 1u);
       // the covariance warps are done with tile n - 2: its Z slot, and the mask slot tile n + 1
@@ -500,7 +509,10 @@ __device__ __forceinline__ void ws_cov_role(const StftCovArgs& a, const WsSmem<C
   }
 }
 
-template <int C, bool HAS_MN>
+// PAIRWIN: the window has a constant pair sum K = w[n] + w[n + 256] (Hann: 1): the FFT warps load
+// half the window (scaled by 1 / K) and fold it into the first butterflies; the spectra come out
+// scaled by 2 / K, which cov_finalize_kernel takes back (K^2 / 4 on the sums).
+template <int C, bool HAS_MN, bool PAIRWIN>
 __global__ void __maxnreg__(SETK_WS_LAUNCH_REGS) stft_cov_ws_kernel(StftCovArgs a) {
   SETK_DYN_SMEM(float, smem);
   WsSmem<C> sm;
@@ -514,7 +526,8 @@ __global__ void __maxnreg__(SETK_WS_LAUNCH_REGS) stft_cov_ws_kernel(StftCovArgs 
   const int hi = imin(lo + q, total);
   if (lo >= hi) return;
 
-  for (int n = tid; n < kNfft; n += kWsThreads) sm.win[n] = 0.5f * a.window[n];
+  for (int n = tid; n < kNfft; n += kWsThreads)
+    sm.win[n] = PAIRWIN ? a.window[n] / a.win_pair_sum : 0.5f * a.window[n];
   twiddle_table_fill(sm.twtab, tid, kWsThreads);
   if (tid == 0) {
     mbar_init(sm.bar_audio, 1);
@@ -531,7 +544,7 @@ __global__ void __maxnreg__(SETK_WS_LAUNCH_REGS) stft_cov_ws_kernel(StftCovArgs 
     ws_cov_role<C, HAS_MN>(a, sm, lo, hi, q, vec_ok);
   } else {
     setmaxnreg_dec<SETK_WS_FFT_REGS>();
-    ws_fft_role<C, HAS_MN>(a, sm, lo, hi, q, vec_ok);
+    ws_fft_role<C, HAS_MN, PAIRWIN>(a, sm, lo, hi, q, vec_ok);
   }
 }
 
@@ -540,7 +553,7 @@ cudaError_t run_bits_to_float(const unsigned* bits, int n, float* out, void* str
 cudaError_t run_tile_prefix(const int* n_samples, int B, const Geometry& g, int TT, int T_cap,
                             int* prefix, void* stream);
 cudaError_t run_cov_finalize(int C, const float* partials, int B, int F, TileSched sched, int n_ctas,
-                             int slots, float2* Rs, float2* Rn, void* stream);
+                             int slots, float scale, float2* Rs, float2* Rn, void* stream);
 void fused_schedule(const setk_plan* pl, int B, int T, int TT, int* n_ctas, int* slots, int* min_quota);
 
 bool stft_cov_ws_supported(const Geometry& g) {
@@ -550,16 +563,18 @@ bool stft_cov_ws_supported(const Geometry& g) {
 }
 int stft_cov_ws_tt(int C) { return 16 / C; }
 
-template <int C, bool HAS_MN>
+template <int C, bool HAS_MN, bool PAIRWIN>
 static cudaError_t run_ws_t(StftCovArgs a, int B, int n_ctas, float2* Rs, float2* Rn, float* maxabs,
                             void* stream) {
   const size_t smem = WsSmem<C>::bytes(a.g.hop, HAS_MN ? 2 : 1);
-  cudaError_t e = cudaFuncSetAttribute(stft_cov_ws_kernel<C, HAS_MN>,
+  cudaError_t e = cudaFuncSetAttribute(stft_cov_ws_kernel<C, HAS_MN, PAIRWIN>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  e = launch(stft_cov_ws_kernel<C, HAS_MN>, dim3(n_ctas), dim3(kWsThreads), smem, stream, false, a);
+  e = launch(stft_cov_ws_kernel<C, HAS_MN, PAIRWIN>, dim3(n_ctas), dim3(kWsThreads), smem, stream, false,
+             a);
   if (e != cudaSuccess) return e;
-  e = run_cov_finalize(C, a.partials, B, a.g.F, a.sched, n_ctas, a.slots, Rs, Rn, stream);
+  const float scale = PAIRWIN ? 0.25f * a.win_pair_sum * a.win_pair_sum : 1.0f;
+  e = run_cov_finalize(C, a.partials, B, a.g.F, a.sched, n_ctas, a.slots, scale, Rs, Rn, stream);
   if (e != cudaSuccess) return e;
   if (maxabs) e = run_bits_to_float(a.maxabs_bits, B, maxabs, stream);
   return e;
@@ -586,11 +601,17 @@ cudaError_t run_stft_cov_ws(setk_plan* pl, const float* audio, const int* n_samp
     a.sched.prefix = tile_prefix;
   }
   a.window = pl->d_window;
+  const char* env_pw = getenv("SETK_WS_PAIRWIN");       // measurement knob: 0 = table window
+  a.win_pair_sum = (env_pw && env_pw[0] == '0') ? 0.f : pl->win_pair_sum;
   a.partials = partials;
   a.maxabs_bits = maxabs_bits;
+  const bool pw = a.win_pair_sum > 0.f;
   switch (pl->geo.C) {
-    case 4: return mask_n ? run_ws_t<4, true>(a, B, n_ctas, Rs, Rn, maxabs, stream)
-                          : run_ws_t<4, false>(a, B, n_ctas, Rs, Rn, maxabs, stream);
+    case 4:
+      if (mask_n) return pw ? run_ws_t<4, true, true>(a, B, n_ctas, Rs, Rn, maxabs, stream)
+                            : run_ws_t<4, true, false>(a, B, n_ctas, Rs, Rn, maxabs, stream);
+      return pw ? run_ws_t<4, false, true>(a, B, n_ctas, Rs, Rn, maxabs, stream)
+                : run_ws_t<4, false, false>(a, B, n_ctas, Rs, Rn, maxabs, stream);
     default: return cudaErrorInvalidValue;
   }
 }

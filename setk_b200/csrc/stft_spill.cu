@@ -532,7 +532,7 @@ cudaError_t run_cov_mma(const CovSpillArgs& a, int B, void* stream);
 // C >= 5: the covariance is a real dense contraction (2C x 2C Gram blocks over T frames) and runs
 // on the tensor cores (cov_mma.cu) unless SETK_COV_IMPL=cuda (measurement knob)
 static bool use_cov_mma(int C) {
-  static const char* env = getenv("SETK_COV_IMPL");
+  const char* env = getenv("SETK_COV_IMPL");
   if (env && env[0] == 'c') return false;
   return C >= 5 && cov_mma_supported(C);
 }

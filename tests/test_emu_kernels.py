@@ -178,6 +178,15 @@ def test_wpe_chunked_long_utterance_path(emu, monkeypatch):
         assert np.array_equal(out, ref)
 
 
+def test_wpe_tensor_core_correlation(emu, monkeypatch):
+    # SETK_WPE_CORR=dmma: the fp64 mma.sync build of the correlation pass (kept selectable; the
+    # CUDA-core kernel measured faster on B200 and is the default)
+    monkeypatch.setenv("SETK_WPE_CORR", "dmma")
+    rng = np.random.default_rng(22)
+    pc.check_wpe(emu, rng, 1, 3, 3000, 256, 64, taps=4, delay=2, ctx=1, iters=2)
+    pc.check_wpe_fixture(emu, "c2_t6_ctx0")
+
+
 def test_wpe_reference_fixture(emu):
     pc.check_wpe_fixture(emu, "c2_t6_ctx0")
 
@@ -244,7 +253,8 @@ def test_apply_istft_fused(emu, C, N, hop, center, pm, norm):
                          post_mask=pm, norm=norm)
 
 
-def test_apply_istft_ws_protocol(emu):
+def test_apply_istft_ws_protocol(emu, monkeypatch):
+    monkeypatch.setenv("SETK_AI_IMPL", "ws")          # opt-in build (read once per process)
     # the warp-specialised build (apply_istft_ws.cu): long runs (several fills of the 8-entry
     # tile table of the CPU build, halo tiles), many short utterances (several segments per CTA),
     # ragged lengths, post-mask, no centre padding

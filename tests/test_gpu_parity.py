@@ -125,6 +125,31 @@ def test_apply_istft_nsamps_and_ragged(cuda):
     pc.check_apply_istft(cuda, rng, 3, 4, 30000, n_samples=ns)
 
 
+def test_opt_in_builds(cuda, monkeypatch):
+    """Builds kept behind environment knobs stay correct: the warp-specialised apply+iSTFT, the
+    classic fused STFT+covariance, the table-window path of the ws kernel, CUDA-core covariance."""
+    rng = np.random.default_rng(41)
+    ns = torch.tensor([30000, 19000, 9000], dtype=torch.int32)
+    monkeypatch.setenv("SETK_AI_IMPL", "ws")
+    pc.check_apply_istft(cuda, rng, 3, 4, 30000, n_samples=ns)
+    pc.check_apply_istft(cuda, rng, 2, 4, 48000, post_mask=True)
+    monkeypatch.delenv("SETK_AI_IMPL")
+    for knob, val in (("SETK_SC_IMPL", "classic"), ("SETK_WS_PAIRWIN", "0")):
+        monkeypatch.setenv(knob, val)
+        pc.check_stft_cov(cuda, rng, 3, 4, 30000, n_samples=ns)
+        monkeypatch.delenv(knob)
+    monkeypatch.setenv("SETK_COV_IMPL", "cuda")
+    pc.check_stft_cov(cuda, rng, 2, 8, 20000)
+    monkeypatch.delenv("SETK_COV_IMPL")
+
+
+def test_wpe_tensor_core_correlation(cuda, monkeypatch):
+    """SETK_WPE_CORR=dmma: the mma.sync.m8n8k4.f64 build of wpe_step's R, r (libs/wpe.py:58-77)."""
+    monkeypatch.setenv("SETK_WPE_CORR", "dmma")
+    pc.check_wpe(cuda, np.random.default_rng(22), 2, 6, 16000, 512, 128, taps=10, delay=3, ctx=1, iters=2)
+    pc.check_wpe_fixture(cuda, "c2_t6_ctx0")
+
+
 def test_non_power_of_two_n_fft(cuda):
     """--round-power-of-two false (utils.py:115, opts.py:41): n_fft = frame_len = 400 / 600."""
     pc.check_non_power_of_two(cuda, np.random.default_rng(12))
