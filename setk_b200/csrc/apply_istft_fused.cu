@@ -424,6 +424,7 @@ bool apply_istft_fused_supported(const Geometry& g) {
 
 void fused_schedule(const setk_plan* pl, int B, int T, int TT, int* n_ctas, int* slots, int* min_quota);
 bool apply_istft_ws_supported(const Geometry& g);
+int apply_istft_ws_tt();
 cudaError_t run_apply_istft_ws(const ApplyIstftArgs& a, int n_ctas, void* stream);
 // The warp-specialised build is opt-in (SETK_AI_IMPL=ws): measured on B200 at config 2 it is
 // still slower than this kernel (0.62 vs 0.57 ms; apply_istft_ws.cu says why)
@@ -439,6 +440,8 @@ cudaError_t run_apply_istft_fused(setk_plan* pl, const float* audio, const int* 
                                   int T, const void* w, int w_dtype, const float* post_mask, int n_out,
                                   int* tile_prefix, float* wave, unsigned* peak, void* stream) {
   constexpr int TT = 4;
+  const bool ws = use_apply_ws(pl->geo);
+  const int TTs = ws ? apply_istft_ws_tt() : TT;      // frames per tile of the schedule
   ApplyIstftArgs a;
   a.g = pl->geo;
   a.audio = audio; a.n_samples = n_samples; a.N = N;
@@ -448,13 +451,13 @@ cudaError_t run_apply_istft_fused(setk_plan* pl, const float* audio, const int* 
   const int T_cap = (n_out + 2 * a.g.pad + a.g.hop - 1) / a.g.hop;
   const int T_used = T < T_cap ? T : T_cap;
   int n_ctas, slots_unused;
-  fused_schedule(pl, B, T_used, TT, &n_ctas, &slots_unused, &a.sched.min_quota);
+  fused_schedule(pl, B, T_used, TTs, &n_ctas, &slots_unused, &a.sched.min_quota);
   a.sched.B = B;
-  a.sched.tiles_u = sched_tiles_of(T_used, TT);
+  a.sched.tiles_u = sched_tiles_of(T_used, TTs);
   a.sched.prefix = nullptr;
   cudaError_t e = cudaSuccess;
   if (n_samples) {     // ragged batch: the lengths live on the device
-    e = run_tile_prefix(n_samples, B, pl->geo, TT, T_cap, tile_prefix, stream);
+    e = run_tile_prefix(n_samples, B, pl->geo, TTs, T_cap, tile_prefix, stream);
     if (e != cudaSuccess) return e;
     a.sched.prefix = tile_prefix;
   }
@@ -466,7 +469,7 @@ cudaError_t run_apply_istft_fused(setk_plan* pl, const float* audio, const int* 
   // peak is taken by the last block (it sees the complete sums)
   const int Ctot = pl->geo.C;
   a.c_total = Ctot;
-  if (use_apply_ws(pl->geo)) {         // the warp-specialised build serves the metric geometry
+  if (ws) {                            // the warp-specialised build (opt-in) for the metric geometry
     a.c0 = 0; a.accumulate = 0; a.peak = peak;
     return run_apply_istft_ws(a, n_ctas, stream);
   }

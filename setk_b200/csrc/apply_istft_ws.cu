@@ -8,20 +8,23 @@
 // needed by the `norm` rescale.  C++ twin: Beamform (include/beamformer.cc:215-230) +
 // InverseShortTimeFT (include/stft.cc:154-198).
 //
-// 512 threads = 8 FFT warps (64 registers) + 4 IFFT warps (48) + 4 BACK warps (80, highest warp
-// ids), launched at 64 => two CTAs per SM (32 warps).  A first build let two of the FFT warps run the inverse
-// transforms: they waited for the BACK warps' apply while the other six waited for them at the
-// audio barrier, the roles ran one after the other and the kernel was 35 % SLOWER than the classic
-// one (0.79 vs 0.57 ms, profiles/r2_apply_istft_ws_serialised_ncu.txt); the inverse FFT therefore
-// has warps of its own that meet nobody but the mbarriers.  A tile is 4 frames x 4 channels; its
-// Z slot (one of two) is re-used in place down the pipeline:
+// 512 threads = two FFT groups of 4 warps (64 registers) + 4 IFFT warps (48) + 4 BACK warps (80,
+// the highest warp ids), launched at 64 => two CTAs per SM (32 warps).  History (B200, config 2,
+// classic kernel 0.57 ms): a first build let two of the FFT warps run the inverse transforms --
+// they waited for the BACK warps' apply while the other six waited for them at the audio barrier,
+// the roles ran one after the other: 0.79 ms (profiles/r2_apply_istft_ws_serialised_ncu.txt);
+// inverse-FFT warps of their own: 0.62 ms, still bound by the ring: a tile passes four stages
+// (forward FFT -> apply -> inverse FFT -> flush) but only TWO slots existed, so a stage could start
+// only every (sum of the four) / 2.  This build cuts tiles to 2 frames x 4 channels and rings FOUR
+// slots in the same shared memory, one per stage; the two FFT groups take alternate tiles with an
+// audio buffer each, so nothing but mbarriers couples the stages.  A slot is re-used in place:
 //
-//   FFT warps   audio tile (TMA bulk copy) -> forward FFT -> Z[slot]        ... arrive z_full
+//   FFT group   audio tile (TMA bulk copy) -> forward FFT -> Z[slot]        ... arrive z_full
 //   BACK warps  wait z_full: thread k applies the weights of bin pair (k, 256-k) to the four
 //               channels of each frame and writes the half-size inverse spectrum Zi over
 //               channel 0's part of the slot (it owns entries k, 256-k)     ... arrive zi_full
-//   IFFT warps  (a pair per tile, the two pairs alternate) wait zi_full: inverse FFT of the
-//               four frames, x synthesis window -> frames over channel 1's part ... arrive fr_full
+//   IFFT warp   (tile mod 4) wait zi_full: inverse FFT of the two frames, x synthesis window
+//               -> frames over channel 1's part                             ... arrive fr_full
 //   BACK warps  wait fr_full (of the PREVIOUS tile, so the inverse FFT overlaps their apply):
 //               overlap-add with the carried half frame, / window-sum-square, trim, 16-byte
 //               stores, running peak                                        ... arrive z_empty
@@ -43,12 +46,15 @@ namespace setk {
 #define SETK_AW_BACK_REGS 80
 
 constexpr int kAwFftThreads = 256, kAwIfftThreads = 128, kAwBackThreads = 128, kAwThreads = 512;
-constexpr int kAwBarFft = 1, kAwBarBack = 2;
+constexpr int kAwGroupThreads = 128;           // one FFT group (4 warps = the 8 half-warp jobs of a tile)
+constexpr int kAwBarFft = 1, kAwBarBack = 3;   // named barriers 1, 2: the FFT groups; 3: BACK
+constexpr int kAwSlots = 4, kAwLook = 2;       // ring slots; look-ahead entries of the tile table
 #ifndef SETK_TABLE_CHUNK
 #define SETK_TABLE_CHUNK 128       // tile descriptors per table fill (the CPU test tier builds with 8)
 #endif
 constexpr int kAwChunk = SETK_TABLE_CHUNK;
-constexpr int kAwC = 4, kAwTT = 4;
+constexpr int kAwC = 4, kAwTT = 2;
+constexpr int kAwJobs = kAwC * kAwTT;         // half-warp FFT jobs (and Z parts) per slot
 constexpr int kAwWPitch = 260;
 
 enum : unsigned {
@@ -65,47 +71,47 @@ struct AwGen {            // generator of the CTA's tile sequence (one thread)
   int halo_done;          // the halo tile of the segment starting at x has been emitted
   int done;               // nothing left
   int count;              // entries of the current table fill (consumers read this)
+  int avail;              // count + valid look-ahead entries behind them
+  int pad_[3];
 };
 
 struct AwSmem {
-  AwTile* tiles;          // [kAwChunk + 1]
+  AwTile* tiles;          // [kAwChunk + kAwLook]
   AwGen* gen;
-  MBar* bar_audio;        // [1]
-  MBar* z_full;           // [2] 8 FFT warps
-  MBar* zi_full;          // [2] 4 BACK warps
-  MBar* fr_full;          // [2] 2 IFFT warps
-  MBar* z_empty;          // [2] 4 BACK warps
+  MBar* bar_audio;        // [2] one per FFT group
+  MBar* z_full;           // [4] 4 warps of an FFT group
+  MBar* zi_full;          // [4] 4 BACK warps
+  MBar* fr_full;          // [4] 1 IFFT warp
+  MBar* z_empty;          // [4] 4 BACK warps
   float* win;             // [512] analysis window x 0.5
   float2* twtab;          // [256]
   float* wsyn;            // [512] window / 512
-  float* wsq;             // [512]
   float* rw;              // [256] 1 / (wsq[r] + wsq[r + 256])
   float* carry;           // [2][256]
   float2* w;              // [4][kAwWPitch]
-  float* audio;           // [4][Lp]
-  float2* z;              // [2][16][SETK_ZSLOT]
+  float* audio;           // [2 groups][4][Lp]
+  float2* z;              // [kAwSlots][kAwJobs][SETK_ZSLOT]
   int Lp;
   SETK_HD static int staged_len(int hop) { return ((kAwTT - 1) * hop + kNfft + 3) & ~3; }
   SETK_HD static size_t bytes(int hop) {
-    return 128 + sizeof(AwTile) * (kAwChunk + 2) + sizeof(float) * (3 * kNfft + kM + 2 * kM) +
-           sizeof(float2) * (256 + kAwC * kAwWPitch) + sizeof(float) * kAwC * staged_len(hop) +
-           sizeof(float2) * 2 * 16 * SETK_ZSLOT;
+    return 256 + sizeof(AwTile) * (kAwChunk + kAwLook + 2) + sizeof(float) * (2 * kNfft + kM + 2 * kM) +
+           sizeof(float2) * (256 + kAwC * kAwWPitch) + sizeof(float) * 2 * kAwC * staged_len(hop) +
+           sizeof(float2) * kAwSlots * kAwJobs * SETK_ZSLOT;
   }
   __device__ void carve(float* base, int hop) {
     Lp = staged_len(hop);
     MBar* bars = reinterpret_cast<MBar*>(base);
-    bar_audio = bars; z_full = bars + 1; zi_full = bars + 3; fr_full = bars + 5; z_empty = bars + 7;
-    gen = reinterpret_cast<AwGen*>(bars + 10);                 // byte 80 .. 96
-    tiles = reinterpret_cast<AwTile*>(base + 32);              // byte 128
-    win = base + 32 + 4 * (kAwChunk + 2);
+    bar_audio = bars; z_full = bars + 2; zi_full = bars + 6; fr_full = bars + 10; z_empty = bars + 14;
+    gen = reinterpret_cast<AwGen*>(bars + 20);                 // byte 160 .. 192
+    tiles = reinterpret_cast<AwTile*>(base + 64);              // byte 256
+    win = base + 64 + 4 * (kAwChunk + kAwLook + 2);
     wsyn = win + kNfft;
-    wsq = wsyn + kNfft;
-    rw = wsq + kNfft;
+    rw = wsyn + kNfft;
     carry = rw + kM;
     twtab = reinterpret_cast<float2*>(carry + 2 * kM);
     w = twtab + 256;
     audio = reinterpret_cast<float*>(w + kAwC * kAwWPitch);
-    z = reinterpret_cast<float2*>(audio + kAwC * Lp);
+    z = reinterpret_cast<float2*>(audio + 2 * kAwC * Lp);
   }
 };
 
@@ -121,8 +127,8 @@ __device__ void aw_fill_table(const ApplyIstftArgs& a, const AwSmem& sm, int lo,
   AwGen g = *sm.gen;
   int n = 0;
   AwGen before_last = g;
-  while (n < kAwChunk + 1 && !g.done) {
-    if (n == kAwChunk) before_last = g;          // the look-ahead entry is generated again next time
+  while (n < kAwChunk + kAwLook && !g.done) {
+    if (n == kAwChunk) before_last = g;          // the look-ahead entries are generated again next time
     const int x = g.x;
     const int b = sched_find(a.sched, x);
     const int pb = sched_prefix(a.sched, b), pe = sched_prefix(a.sched, b + 1);
@@ -159,45 +165,48 @@ __device__ void aw_fill_table(const ApplyIstftArgs& a, const AwSmem& sm, int lo,
     sm.tiles[n++] = d;
   }
   int count = n;
-  if (n == kAwChunk + 1) { count = kAwChunk; g = before_last; }   // entry [kAwChunk] is the look-ahead only
+  if (n > kAwChunk) { count = kAwChunk; g = before_last; }   // entries >= kAwChunk are look-ahead only
   g.count = count;
+  g.avail = n;
   *sm.gen = g;
 }
 
-__device__ __forceinline__ void aw_stage_bulk(const AwSmem& sm, const float* __restrict__ xb, int N,
-                                              int t0, int nt, int hop, int pad) {   // ONE thread
+__device__ __forceinline__ void aw_stage_bulk(float* dst, int Lp, MBar* bar, const float* __restrict__ xb,
+                                              int N, int t0, int nt, int hop, int pad) {   // ONE thread
   const int need = (nt - 1) * hop + kNfft;
   const int i0 = t0 * hop - pad;
   fence_proxy_async();
-  mbar_expect_tx(sm.bar_audio, (unsigned)(kAwC * need * sizeof(float)));
+  mbar_expect_tx(bar, (unsigned)(kAwC * need * sizeof(float)));
 #pragma unroll
   for (int c = 0; c < kAwC; ++c)
-    bulk_g2s(sm.audio + c * sm.Lp, xb + (long long)c * N + i0, (unsigned)(need * sizeof(float)),
-             sm.bar_audio);
+    bulk_g2s(dst + c * Lp, xb + (long long)c * N + i0, (unsigned)(need * sizeof(float)), bar);
 }
-__device__ __noinline__ void aw_stage_scalar(const AwSmem& sm, const float* __restrict__ xb, int N, int nb,
-                                             int t0, int nt, int hop, int pad, int ftid) {
+__device__ __noinline__ void aw_stage_scalar(float* dst, int Lp, const float* __restrict__ xb, int N, int nb,
+                                             int t0, int nt, int hop, int pad, int gtid) {
   const int p0 = t0 * hop;
   const int need = (nt - 1) * hop + kNfft;
   for (int c = 0; c < kAwC; ++c) {
     const float* src = xb + (long long)c * N;
-    for (int q = ftid; q < need; q += kAwFftThreads) {
+    for (int q = gtid; q < need; q += kAwGroupThreads) {
       const int i = pad ? reflect_index(p0 + q, pad, nb) : (p0 + q);
-      sm.audio[c * sm.Lp + q] = src[i];
+      dst[c * Lp + q] = src[i];
     }
   }
 }
 
 // ---------------------------------------------------------------------------
-// FFT role: threads 0..255; forward job = thread / 16 = frame * 4 + channel
+// FFT role: threads 0..255 = two groups of 4 warps; group g transforms the tiles n = g (mod 2);
+// half-warp job = (thread in group) / 16 = frame * 4 + channel
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void aw_fft_role(const ApplyIstftArgs& a, const AwSmem& sm, int lo, int hi,
                                             int T_cap, bool vec_ok) {
-  const int ftid = threadIdx.x;
-  const int lane = ftid & 31, lane16 = lane & 15, fw = ftid >> 5;
-  const int job = ftid >> 4;
+  const int grp = (int)threadIdx.x >> 7, gtid = (int)threadIdx.x & (kAwGroupThreads - 1);
+  const int lane = gtid & 31, lane16 = lane & 15;
+  const int job = gtid >> 4;
   const int fr = job >> 2, ch = job & 3;
   const int hop = a.g.hop, pad = a.g.pad;
+  float* abuf = sm.audio + grp * kAwC * sm.Lp;
+  MBar* abar = sm.bar_audio + grp;
   unsigned apar = 0;
 
   auto stage = [&](const AwTile& d) -> bool {        // true: written with ordinary stores
@@ -205,33 +214,35 @@ __device__ __forceinline__ void aw_fft_role(const ApplyIstftArgs& a, const AwSme
     if (nt <= 0) return false;
     const float* xb = a.audio + ((long long)d.b * a.c_total + a.c0) * a.N;
     if (d.flags & AW_AUDIO_BULK) {
-      if (ftid == 0) aw_stage_bulk(sm, xb, a.N, d.t0, nt, hop, pad);
+      if (gtid == 0) aw_stage_bulk(abuf, sm.Lp, abar, xb, a.N, d.t0, nt, hop, pad);
       return false;
     }
     const int nb = a.n_samples ? a.n_samples[d.b] : a.N;
-    aw_stage_scalar(sm, xb, a.N, nb, d.t0, nt, hop, pad, ftid);
+    aw_stage_scalar(abuf, sm.Lp, xb, a.N, nb, d.t0, nt, hop, pad, gtid);
     return true;
   };
-  int n = 0;                                         // local tile number
+
+  int nbase = 0;                                     // local number of the table's first tile
   bool first_fill = true;
   for (;;) {
-    __syncthreads();                                 // the previous table is consumed by both roles
+    __syncthreads();                                 // the previous table is consumed by every role
     if (threadIdx.x == 0) aw_fill_table(a, sm, lo, hi, T_cap, vec_ok);
     __syncthreads();
-    const int cnt = sm.gen->count;
+    const int cnt = sm.gen->count, avail = sm.gen->avail;
     const bool more = !sm.gen->done;
     if (first_fill) {
       first_fill = false;
-      if (cnt > 0 && stage(sm.tiles[0])) named_bar_sync(kAwBarFft, kAwFftThreads);
+      if (grp < avail && stage(sm.tiles[grp])) named_bar_sync(kAwBarFft + grp, kAwGroupThreads);
     }
-    for (int i = 0; i < cnt; ++i, ++n) {
+    for (int i = grp; i < cnt; i += 2) {             // kAwChunk is even: i and n have the same parity
+      const int n = nbase + i;
       const AwTile d = sm.tiles[i];
       const int nt = (int)(d.flags & AW_NT);
       float2 v[16];
       if (nt > 0) {
-        if (d.flags & AW_AUDIO_BULK) { mbar_wait(sm.bar_audio, apar); apar ^= 1u; }
+        if (d.flags & AW_AUDIO_BULK) { mbar_wait(abar, apar); apar ^= 1u; }
         const int fr_src = imin(fr, nt - 1);         // a dead frame re-transforms the last live one
-        const float* src = sm.audio + ch * sm.Lp + fr_src * hop + 2 * lane16;
+        const float* src = abuf + ch * sm.Lp + fr_src * hop + 2 * lane16;
         const float* wsrc = sm.win + 2 * lane16;
 #pragma unroll
         for (int m1 = 0; m1 < 16; ++m1) {
@@ -240,51 +251,52 @@ __device__ __forceinline__ void aw_fft_role(const ApplyIstftArgs& a, const AwSme
           v[m1] = f2mul(sx, w);
         }
       }
-      named_bar_sync(kAwBarFft, kAwFftThreads);      // every FFT warp holds its samples: the buffer is free
-      const bool has_next = i + 1 < cnt || more;     // entry [cnt] is the look-ahead when more follow
+      named_bar_sync(kAwBarFft + grp, kAwGroupThreads);   // the group holds its samples: its buffer is free
       bool scalar_next = false;
-      if (has_next) scalar_next = stage(sm.tiles[i + 1]);
+      if (i + 2 < avail) scalar_next = stage(sm.tiles[i + 2]);   // this group's next tile
       if (nt > 0) halfwarp_fft256_a(v, sm.twtab, lane16);
-      const int s = n & 1;
-      mbar_wait(&sm.z_empty[s], ((unsigned)(n >> 1) & 1u) ^ 1u);   // tile n - 2 has been flushed
+      const int s = n & (kAwSlots - 1);
+      mbar_wait(&sm.z_empty[s], ((unsigned)(n >> 2) & 1u) ^ 1u);   // tile n - 4 has been flushed
       if (nt > 0) {
-        float2* zs = sm.z + (s * 16 + job) * SETK_ZSLOT;
+        float2* zs = sm.z + (s * kAwJobs + job) * SETK_ZSLOT;
         halfwarp_fft256_b(v, zs, lane16);
 #pragma unroll
         for (int p = 0; p < 16; ++p) zs[lane16 + 16 * kof(p)] = v[p];
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.z_full[s]);
-      if (scalar_next) named_bar_sync(kAwBarFft, kAwFftThreads);
+      if (scalar_next) named_bar_sync(kAwBarFft + grp, kAwGroupThreads);
     }
+    nbase += cnt;
     if (!more) break;
   }
 }
 
 // ---------------------------------------------------------------------------
-// IFFT role: threads 256..383; warps (0, 1) take the even tiles, (2, 3) the odd ones; a half-warp
-// per frame: conj . FFT256 . conj of the half-size inverse spectrum, x synthesis window
+// IFFT role: threads 256..383; warp w takes the tiles n = w (mod 4), a half-warp per frame:
+// conj . FFT256 . conj of the half-size inverse spectrum, x synthesis window
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void aw_ifft_role(const ApplyIstftArgs& a, const AwSmem& sm, int lo, int hi,
                                              int T_cap, bool vec_ok) {
   const int tid = (int)threadIdx.x - kAwFftThreads;
   const int lane = tid & 31, lane16 = lane & 15, iw = tid >> 5;
-  int n = 0;
+  int nbase = 0;
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) aw_fill_table(a, sm, lo, hi, T_cap, vec_ok);
     __syncthreads();
     const int cnt = sm.gen->count;
     const bool more = !sm.gen->done;
-    for (int i = 0; i < cnt; ++i, ++n) {
-      if ((n & 1) != (iw >> 1)) continue;            // the other pair's tile
+    for (int i = 0; i < cnt; ++i) {
+      const int n = nbase + i;
+      if ((n & (kAwSlots - 1)) != iw) continue;      // another warp's tile
       const int nt_m = (int)(sm.tiles[i].flags & AW_NT);
-      const int s = n & 1;
-      mbar_wait(&sm.zi_full[s], (unsigned)(n >> 1) & 1u);
-      const int j = (iw & 1) * 2 + (lane >> 4);      // frame inside the tile
+      const int s = n & (kAwSlots - 1);
+      mbar_wait(&sm.zi_full[s], (unsigned)(n >> 2) & 1u);
+      const int j = lane >> 4;                       // frame inside the tile
       {
         // a dead frame (j >= nt_m) transforms zeros: both half-warps run the same code
-        float2* zi = sm.z + (s * 16 + j * kAwC) * SETK_ZSLOT;
+        float2* zi = sm.z + (s * kAwJobs + j * kAwC) * SETK_ZSLOT;
         float2 v[16];
         const bool live = j < nt_m;
 #pragma unroll
@@ -295,7 +307,7 @@ __device__ __forceinline__ void aw_ifft_role(const ApplyIstftArgs& a, const AwSm
         __syncwarp();                                // the slot part is free: reuse it as the exchange tile
         halfwarp_fft256_a(v, sm.twtab, lane16);
         halfwarp_fft256_b(v, zi, lane16);
-        float* fo = reinterpret_cast<float*>(sm.z + (s * 16 + j * kAwC + 1) * SETK_ZSLOT);
+        float* fo = reinterpret_cast<float*>(sm.z + (s * kAwJobs + j * kAwC + 1) * SETK_ZSLOT);
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
           const int mm = lane16 + 16 * kof(q);
@@ -306,6 +318,7 @@ __device__ __forceinline__ void aw_ifft_role(const ApplyIstftArgs& a, const AwSm
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.fr_full[s]);
     }
+    nbase += cnt;
     if (!more) break;
   }
 }
@@ -364,7 +377,7 @@ __device__ __forceinline__ void aw_back_role(const ApplyIstftArgs& a, const AwSm
 
   // overlap-add, normalise, trim, write: the frames of tile (p_t0, p_nt) in slot s
   auto flush = [&](int s, int p_t0, int p_nt, const AwSeg& sg, bool carry_zero) {
-    const float* frames = reinterpret_cast<const float*>(sm.z + (s * 16 + 1) * SETK_ZSLOT);
+    const float* frames = reinterpret_cast<const float*>(sm.z + (s * kAwJobs + 1) * SETK_ZSLOT);
     constexpr int FSTRIDE = C * SETK_ZSLOT * 2;      // floats between the frames of a slot
     const int p_tile = p_t0 * hop;
     const bool last_tile = (p_t0 + p_nt == sg.T_used);
@@ -405,7 +418,7 @@ __device__ __forceinline__ void aw_back_role(const ApplyIstftArgs& a, const AwSm
           } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float wss = (t < sg.T_used ? sm.wsq[r + i] : 0.f) + (t >= 1 ? sm.wsq[kM + r + i] : 0.f);
+              const float wss = (t < sg.T_used ? a.wsq[r + i] : 0.f) + (t >= 1 ? a.wsq[kM + r + i] : 0.f);
               if (wss > SETK_TINY32) vv[i] /= wss;
             }
           }
@@ -478,9 +491,9 @@ __device__ __forceinline__ void aw_back_role(const ApplyIstftArgs& a, const AwSm
         for (int c = 0; c < C; ++c) { wk[c] = sm.w[c * kAwWPitch + k]; wm[c] = sm.w[c * kAwWPitch + km]; }
       }
       // ---- apply of tile n ----
-      const int s = n & 1;
-      mbar_wait(&sm.z_full[s], (unsigned)(n >> 1) & 1u);
-      float2* zt = sm.z + s * 16 * SETK_ZSLOT;
+      const int s = n & (kAwSlots - 1);
+      mbar_wait(&sm.z_full[s], (unsigned)(n >> 2) & 1u);
+      float2* zt = sm.z + s * kAwJobs * SETK_ZSLOT;
       const bool post = a.post_mask != nullptr;
       if (nt == TT && !post) {
 #pragma unroll
@@ -498,8 +511,8 @@ __device__ __forceinline__ void aw_back_role(const ApplyIstftArgs& a, const AwSm
       if (lane == 0) mbar_arrive(&sm.zi_full[s]);
       // ---- flush of tile n - 1 (its inverse FFT ran while we applied tile n) ----
       if (have_prev) {
-        const int sp = (n - 1) & 1;
-        mbar_wait(&sm.fr_full[sp], (unsigned)((n - 1) >> 1) & 1u);
+        const int sp = (n - 1) & (kAwSlots - 1);
+        mbar_wait(&sm.fr_full[sp], (unsigned)((n - 1) >> 2) & 1u);
         flush(sp, prev.t0, (int)(prev.flags & AW_NT), seg_prev, (prev.flags & AW_SEG_BEGIN) != 0);
         if (prev.flags & AW_SEG_END) finish_segment(seg_prev, prev.flags);
         __syncwarp();
@@ -510,8 +523,8 @@ __device__ __forceinline__ void aw_back_role(const ApplyIstftArgs& a, const AwSm
     if (!more) break;
   }
   if (have_prev) {
-    const int sp = (n - 1) & 1;
-    mbar_wait(&sm.fr_full[sp], (unsigned)((n - 1) >> 1) & 1u);
+    const int sp = (n - 1) & (kAwSlots - 1);
+    mbar_wait(&sm.fr_full[sp], (unsigned)((n - 1) >> 2) & 1u);
     flush(sp, prev.t0, (int)(prev.flags & AW_NT), seg_prev, (prev.flags & AW_SEG_BEGIN) != 0);
     if (prev.flags & AW_SEG_END) finish_segment(seg_prev, prev.flags);
   }
@@ -533,7 +546,6 @@ __global__ void __maxnreg__(SETK_AW_LAUNCH_REGS) apply_istft_ws_kernel(ApplyIstf
     const float w = a.window[n];
     sm.win[n] = 0.5f * w;
     sm.wsyn[n] = w * (1.0f / 512.0f);
-    sm.wsq[n] = a.wsq[n];
   }
   for (int n = tid; n < kM; n += kAwThreads) {
     const float s = a.wsq[n] + a.wsq[n + kM];
@@ -541,15 +553,16 @@ __global__ void __maxnreg__(SETK_AW_LAUNCH_REGS) apply_istft_ws_kernel(ApplyIstf
   }
   twiddle_table_fill(sm.twtab, tid, kAwThreads);
   if (tid == 0) {
-    mbar_init(sm.bar_audio, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&sm.z_full[s], kAwFftThreads / 32);
+    mbar_init(&sm.bar_audio[0], 1);
+    mbar_init(&sm.bar_audio[1], 1);
+    for (int s = 0; s < kAwSlots; ++s) {
+      mbar_init(&sm.z_full[s], kAwGroupThreads / 32);
       mbar_init(&sm.zi_full[s], kAwBackThreads / 32);
-      mbar_init(&sm.fr_full[s], 2);
+      mbar_init(&sm.fr_full[s], 1);
       mbar_init(&sm.z_empty[s], kAwBackThreads / 32);
     }
     AwGen g;
-    g.x = lo; g.halo_done = 0; g.done = 0; g.count = 0;
+    g.x = lo; g.halo_done = 0; g.done = 0; g.count = 0; g.avail = 0;
     *sm.gen = g;
   }
   const bool vec_ok = ((a.N & 3) == 0) && ((a.g.hop & 3) == 0) && ((a.g.pad & 3) == 0) &&
@@ -568,6 +581,7 @@ __global__ void __maxnreg__(SETK_AW_LAUNCH_REGS) apply_istft_ws_kernel(ApplyIstf
   }
 }
 
+int apply_istft_ws_tt() { return kAwTT; }
 bool apply_istft_ws_supported(const Geometry& g) {
   return g.n_fft == 512 && g.C == 4 && g.hop == kM;
 }

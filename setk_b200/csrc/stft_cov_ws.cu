@@ -601,8 +601,11 @@ cudaError_t run_stft_cov_ws(setk_plan* pl, const float* audio, const int* n_samp
     a.sched.prefix = tile_prefix;
   }
   a.window = pl->d_window;
-  const char* env_pw = getenv("SETK_WS_PAIRWIN");       // measurement knob: 0 = table window
-  a.win_pair_sum = (env_pw && env_pw[0] == '0') ? 0.f : pl->win_pair_sum;
+  // SETK_WS_PAIRWIN=1 (measurement knob): window folded into the first butterflies.  Measured
+  // SLOWER on B200 (0.436 vs 0.420 ms): the eight window pairs it keeps in registers push the
+  // 64-register FFT warps into spills, which cost more than the 16 wavefronts per warp it saves.
+  const char* env_pw = getenv("SETK_WS_PAIRWIN");
+  a.win_pair_sum = (env_pw && env_pw[0] == '1') ? pl->win_pair_sum : 0.f;
   a.partials = partials;
   a.maxabs_bits = maxabs_bits;
   const bool pw = a.win_pair_sum > 0.f;

@@ -69,6 +69,13 @@ def test_stft_cov_ws_protocol(emu, B, N, hop, center, with_mn, clip, mask_ft):
                       with_mask_n=with_mn, clip=clip, mask_ft=mask_ft)
 
 
+def test_stft_cov_ws_pair_window(emu, monkeypatch):
+    monkeypatch.setenv("SETK_WS_PAIRWIN", "1")       # opt-in: window folded into the first butterflies
+    pc.check_stft_cov(emu, np.random.default_rng(11), 2, 4, 3000)
+    pc.check_stft_cov(emu, np.random.default_rng(11), 2, 4, 3000, 512, 256, True, "hamming", with_mask_n=True)
+    pc.check_stft_cov(emu, np.random.default_rng(11), 1, 4, 3000, 400, 256, True, "hann")   # no pair sum: falls back
+
+
 def test_stft_cov_ws_long_run(emu):
     # one long utterance: every CTA refills its 8-entry tile table (CPU build) several times
     pc.check_stft_cov(emu, np.random.default_rng(10), 1, 4, 40000)

@@ -127,14 +127,14 @@ def test_apply_istft_nsamps_and_ragged(cuda):
 
 def test_opt_in_builds(cuda, monkeypatch):
     """Builds kept behind environment knobs stay correct: the warp-specialised apply+iSTFT, the
-    classic fused STFT+covariance, the table-window path of the ws kernel, CUDA-core covariance."""
+    classic fused STFT+covariance, the pair-window path of the ws kernel, CUDA-core covariance."""
     rng = np.random.default_rng(41)
     ns = torch.tensor([30000, 19000, 9000], dtype=torch.int32)
     monkeypatch.setenv("SETK_AI_IMPL", "ws")
     pc.check_apply_istft(cuda, rng, 3, 4, 30000, n_samples=ns)
     pc.check_apply_istft(cuda, rng, 2, 4, 48000, post_mask=True)
     monkeypatch.delenv("SETK_AI_IMPL")
-    for knob, val in (("SETK_SC_IMPL", "classic"), ("SETK_WS_PAIRWIN", "0")):
+    for knob, val in (("SETK_SC_IMPL", "classic"), ("SETK_WS_PAIRWIN", "1")):
         monkeypatch.setenv(knob, val)
         pc.check_stft_cov(cuda, rng, 3, 4, 30000, n_samples=ns)
         monkeypatch.delenv(knob)
