@@ -17,7 +17,13 @@
 // (forward FFT -> apply -> inverse FFT -> flush) but only TWO slots existed, so a stage could start
 // only every (sum of the four) / 2.  This build cuts tiles to 2 frames x 4 channels and rings FOUR
 // slots in the same shared memory, one per stage; the two FFT groups take alternate tiles with an
-// audio buffer each, so nothing but mbarriers couples the stages.  A slot is re-used in place:
+// audio buffer each, so nothing but mbarriers couples the stages.  MEASURED: 0.70 ms -- slower
+// again (profiles/r2_apply_istft_ws_ring4_ncu.txt): twice the tiles means twice the per-tile
+// protocol (waits, arrivals, table reads; 53 % of the issued instructions are mbarrier polls) and
+// a table refill every 128 tiles drains the four-stage pipeline.  The classic kernel therefore
+// stays the default (apply_istft_fused.cu, SETK_AI_IMPL=ws selects this one); what the three
+// builds show is that this pass has too many short stages per frame for a producer/consumer ring
+// to pay -- the next attempt should fuse apply + inverse FFT in one role.  A slot is re-used in place:
 //
 //   FFT group   audio tile (TMA bulk copy) -> forward FFT -> Z[slot]        ... arrive z_full
 //   BACK warps  wait z_full: thread k applies the weights of bin pair (k, 256-k) to the four
