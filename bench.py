@@ -299,8 +299,12 @@ def gpu_arm(args):
     glists = None
     if world > 1 and rank == 0:
         n_out = pipe.plan.istft_length(T)
-        glists = [[torch.empty((B, n_out), dtype=torch.int16, device=dev) for _ in range(world)]
+        # NCCL has no int16 type: the PCM travels as its uint8 byte view (same bytes, same count)
+        glists = [[torch.empty((B, 2 * n_out), dtype=torch.uint8, device=dev) for _ in range(world)]
                   for _ in range(RING)]
+
+    def as_bytes(w):
+        return w.view(torch.uint8)
 
     def run_steps(k):
         works, keep = [], collections.deque(maxlen=RING + 1)
@@ -311,7 +315,7 @@ def gpu_arm(args):
                 if i >= RING:
                     works[i - RING].wait()          # that ring slot's gather has drained
                 keep.append(wave)
-                works.append(dist.gather(wave, glists[i % RING] if rank == 0 else None, dst=0,
+                works.append(dist.gather(as_bytes(wave), glists[i % RING] if rank == 0 else None, dst=0,
                                          async_op=True))
         for w in works[-RING:]:
             w.wait()
@@ -343,10 +347,13 @@ def gpu_arm(args):
         barrier()
         g0.record()
         for _ in range(3):
-            dist.gather(wave, glists[0] if rank == 0 else None, dst=0)
+            dist.gather(as_bytes(wave), glists[0] if rank == 0 else None, dst=0)
         g1.record()
         barrier()
         g_ms = max_over_ranks(g0.elapsed_time(g1)) / 3
+        if rank == 0:
+            assert torch.equal(glists[0][0], as_bytes(wave)), "gather: rank 0's own slot differs"
+            assert all(int(g.any()) for g in glists[0][1:]), "gather: an empty slot arrived"
         gbytes = (world - 1) * wave.numel() * 2
         gather = {"payload": "int16 PCM, every batch of every rank -> rank 0 (dist.gather, async to the "
                              "kernels, ring of 3)",
