@@ -295,13 +295,23 @@ def gpu_arm(args):
         return pipe.run(audio, mask, pcm16_out=True)
 
     # ---- the result gather: every batch, PCM-16, asynchronous to the kernels ----
+    # First choice: peer copies into a ring on rank 0 (copy engines over NVLink, no kernel on any
+    # SM: setk_b200.distributed.PeerResultRing).  --gather nccl, or a box where the peer mapping
+    # fails, uses dist.gather on NCCL's stream instead.
     RING = 3
-    glists = None
-    if world > 1 and rank == 0:
-        n_out = pipe.plan.istft_length(T)
-        # NCCL has no int16 type: the PCM travels as its uint8 byte view (same bytes, same count)
-        glists = [[torch.empty((B, 2 * n_out), dtype=torch.uint8, device=dev) for _ in range(world)]
-                  for _ in range(RING)]
+    glists = ring = None
+    n_out = pipe.plan.istft_length(T)
+    if world > 1:
+        if args.gather == "peer":
+            from setk_b200.distributed import PeerResultRing
+            ring = PeerResultRing.create((B, n_out), torch.int16, dev, slots=RING)
+            if ring is None and rank == 0:
+                print(f"[bench] peer ring unavailable ({PeerResultRing.last_error}); NCCL gather",
+                      file=sys.stderr)
+        if ring is None and rank == 0:
+            # NCCL has no int16 type: the PCM travels as its uint8 byte view (same bytes, same count)
+            glists = [[torch.empty((B, 2 * n_out), dtype=torch.uint8, device=dev) for _ in range(world)]
+                      for _ in range(RING)]
 
     def as_bytes(w):
         return w.view(torch.uint8)
@@ -311,12 +321,16 @@ def gpu_arm(args):
         wave = status = None
         for i in range(k):
             wave, status = step()
-            if world > 1:
+            if ring is not None:
+                ring.push(wave, i)
+            elif world > 1:
                 if i >= RING:
                     works[i - RING].wait()          # that ring slot's gather has drained
                 keep.append(wave)
                 works.append(dist.gather(as_bytes(wave), glists[i % RING] if rank == 0 else None, dst=0,
                                          async_op=True))
+        if ring is not None:
+            ring.drain()
         for w in works[-RING:]:
             w.wait()
         return wave, status
@@ -343,24 +357,38 @@ def gpu_arm(args):
     # ---- the gather alone (one batch from every rank into rank 0), for the record ----
     gather = None
     if world > 1:
+        def gather_once(i):
+            if ring is not None:
+                ring.push(wave, i)
+                ring.drain()
+            else:
+                dist.gather(as_bytes(wave), glists[0] if rank == 0 else None, dst=0)
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         g0.record()
-        for _ in range(3):
-            dist.gather(as_bytes(wave), glists[0] if rank == 0 else None, dst=0)
+        for i in range(3):
+            gather_once(args.steps - 1)           # the slot the run's last batch went to
         g1.record()
         barrier()
         g_ms = max_over_ranks(g0.elapsed_time(g1)) / 3
+        # every rank's last batch must be on rank 0, bit for bit: compare checksums
+        sums = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(sums, wave.to(torch.int64).sum().reshape(1))
         if rank == 0:
-            assert torch.equal(glists[0][0], as_bytes(wave)), "gather: rank 0's own slot differs"
-            assert all(int(g.any()) for g in glists[0][1:]), "gather: an empty slot arrived"
+            got = ring.slot(args.steps - 1) if ring is not None else \
+                torch.stack([g.view(torch.int16) for g in glists[0]])
+            assert torch.equal(got[0], wave), "gather: rank 0's own slot differs"
+            for r in range(world):
+                assert int(got[r].to(torch.int64).sum()) == int(sums[r]), f"gather: rank {r}'s batch differs"
         gbytes = (world - 1) * wave.numel() * 2
-        gather = {"payload": "int16 PCM, every batch of every rank -> rank 0 (dist.gather, async to the "
-                             "kernels, ring of 3)",
+        how = ("device-to-peer copies into a ring of 3 on rank 0 (CUDA IPC mapping, copy engines over "
+               "NVLink, side stream; no collective kernel)" if ring is not None else
+               "dist.gather on NCCL's stream, ring of 3")
+        gather = {"payload": "int16 PCM, every batch of every rank -> rank 0", "how": how,
                   "bytes_into_rank0_per_step": gbytes, "gather_ms_alone": g_ms,
                   "gather_GBps": gbytes / (g_ms * 1e-3) / 1e9,
                   "needed_GBps_at_value": gbytes / ((ms / args.steps) * 1e-3) / 1e9}
-    del glists
+    del glists, ring
 
     # ---- roofline of the dominant kernel: fused STFT+cov, timed alone ----
     def timed(fn, n):
@@ -577,6 +605,8 @@ def main():
                     help="seconds of CPU work the --impl reference run may take")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--gather", choices=["peer", "nccl"], default="peer",
+                    help="N > 1: how every batch's result reaches rank 0")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

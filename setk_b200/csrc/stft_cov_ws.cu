@@ -40,6 +40,7 @@
 //
 // Algorithmic bytes per utterance: 4*C*N + 4*T*F (+4*T*F with mask_n) + 2*8*F*C^2.
 #include <cstdlib>
+#include <cstring>
 #include "common.cuh"
 #include "stft_tile.cuh"
 #include "stft_cov_args.cuh"
@@ -60,6 +61,10 @@ namespace setk {
 #define SETK_WS_COV_FIRST 0
 #endif
 
+enum { WS_MODE_TMA = 0, WS_MODE_PAIRWIN = 1, WS_MODE_DIRECT = 2 };
+#ifndef SETK_WS_L2_PREFETCH
+#define SETK_WS_L2_PREFETCH 1
+#endif
 constexpr int kWsCovThreads = 128, kWsFftThreads = 256, kWsThreads = 384;
 constexpr int kWsBarFft = 1, kWsBarCov = 2;   // named barriers (0 is __syncthreads)
 #ifndef SETK_TABLE_CHUNK
@@ -210,11 +215,12 @@ __device__ __forceinline__ void ws_stage_scalar(const WsSmem<C>& sm, const float
 // ---------------------------------------------------------------------------
 // FFT role: threads 0..255, half-warp job = thread / 16 = frame * C + channel
 // ---------------------------------------------------------------------------
-template <int C, bool HAS_MN, bool PAIRWIN>
+template <int C, bool HAS_MN, int MODE>
 __device__ __forceinline__ void ws_fft_role(const StftCovArgs& a, const WsSmem<C>& sm, int lo, int hi, int q,
                                             bool vec_ok) {
   constexpr int TT = WsShape<C>::TT;
   constexpr int NR = HAS_MN ? 2 : 1, MS = HAS_MN ? 2 : 3;
+  constexpr bool PAIRWIN = MODE == WS_MODE_PAIRWIN, DIRECT = MODE == WS_MODE_DIRECT;
   const int ftid = (int)threadIdx.x - (SETK_WS_COV_FIRST ? kWsCovThreads : 0);
   const int lane = ftid & 31, lane16 = lane & 15;
   const int job = ftid >> 4;
@@ -241,7 +247,13 @@ __device__ __forceinline__ void ws_fft_role(const StftCovArgs& a, const WsSmem<C
     if (nt <= 0) return false;
     const float* xb = a.audio + (long long)d.b * C * a.N;
     if (d.flags & WS_AUDIO_BULK) {
-      if (ftid == 0) ws_stage_bulk<C>(sm, xb, a.N, d.t0, nt, hop, pad);
+      if (DIRECT) {       // the FFT threads will read the samples themselves: warm L2 a tile ahead
+        if (SETK_WS_L2_PREFETCH && ftid < C)
+          bulk_prefetch_l2(xb + (long long)ftid * a.N + d.t0 * hop - pad,
+                           (unsigned)(((nt - 1) * hop + kNfft) * sizeof(float)));
+      } else if (ftid == 0) {
+        ws_stage_bulk<C>(sm, xb, a.N, d.t0, nt, hop, pad);
+      }
       return false;
     }
     ws_stage_scalar<C>(sm, xb, a.N, d.nb, d.t0, nt, hop, pad, ftid);
@@ -264,27 +276,38 @@ __device__ __forceinline__ void ws_fft_role(const StftCovArgs& a, const WsSmem<C
       const int nt = (int)(d.flags & WS_NT);
       float2 v[16];
       float2 w8[8];                                  // PAIRWIN: window of the first half frame
+      const bool from_global = DIRECT && (d.flags & WS_AUDIO_BULK);
       if (nt > 0) {
-        if (d.flags & WS_AUDIO_BULK) { mbar_wait(sm.bar_audio, apar); apar ^= 1u; }
+        if (!DIRECT && (d.flags & WS_AUDIO_BULK)) { mbar_wait(sm.bar_audio, apar); apar ^= 1u; }
         // a dead frame (fr >= nt, only in an utterance's last tile) re-transforms the last live
         // one: its spectrum is never read and max|x| sees nothing new
         const int fr_src = imin(fr, nt - 1);
-        const float* src = sm.audio + ch * sm.Lp + fr_src * hop + 2 * lane16;
+        // DIRECT: an interior tile's samples come straight from global memory (a half-warp reads
+        // 128 contiguous bytes per load, each sample twice across the 50 % frame overlap: L1/L2
+        // hits) and never cross shared memory; edge tiles keep the staged path
+        const float* src = from_global
+            ? a.audio + ((long long)d.b * C + ch) * a.N + ((d.t0 + fr_src) * hop - pad) + 2 * lane16
+            : sm.audio + ch * sm.Lp + fr_src * hop + 2 * lane16;
         const float* wsrc = sm.win + 2 * lane16;
+        if (from_global) {
+#pragma unroll
+          for (int m1 = 0; m1 < 16; ++m1) v[m1] = __ldg(reinterpret_cast<const float2*>(src + 32 * m1));
+        } else {
+#pragma unroll
+          for (int m1 = 0; m1 < 16; ++m1) v[m1] = *reinterpret_cast<const float2*>(src + 32 * m1);
+        }
 #pragma unroll
         for (int m1 = 0; m1 < 16; ++m1) {
-          const float2 sx = *reinterpret_cast<const float2*>(src + 32 * m1);
-          amax = fmaxf(amax, fmaxf(fabsf(sx.x), fabsf(sx.y)));
-          if (PAIRWIN) {
-            v[m1] = sx;                              // the window rides in the first butterflies
+          amax = fmaxf(amax, fmaxf(fabsf(v[m1].x), fabsf(v[m1].y)));
+          if (PAIRWIN) {                             // the window rides in the first butterflies
             if (m1 < 8) w8[m1] = *reinterpret_cast<const float2*>(wsrc + 32 * m1);
           } else {
-            const float2 w = *reinterpret_cast<const float2*>(wsrc + 32 * m1);
-            v[m1] = f2mul(sx, w);
+            v[m1] = f2mul(v[m1], *reinterpret_cast<const float2*>(wsrc + 32 * m1));
           }
         }
       }
-      named_bar_sync(kWsBarFft, kWsFftThreads);    // every FFT warp holds its samples: the buffer is free
+      // every FFT warp holds its samples: the staging buffer is free
+      if (!from_global) named_bar_sync(kWsBarFft, kWsFftThreads);
       const bool has_next = c0 + i + 1 < hi;
       bool scalar_next = false;
       if (has_next) scalar_next = stage(sm.tiles[i + 1]);
@@ -512,8 +535,9 @@ __device__ __forceinline__ void ws_cov_role(const StftCovArgs& a, const WsSmem<C
 // PAIRWIN: the window has a constant pair sum K = w[n] + w[n + 256] (Hann: 1): the FFT warps load
 // half the window (scaled by 1 / K) and fold it into the first butterflies; the spectra come out
 // scaled by 2 / K, which cov_finalize_kernel takes back (K^2 / 4 on the sums).
-template <int C, bool HAS_MN, bool PAIRWIN>
+template <int C, bool HAS_MN, int MODE>
 __global__ void __maxnreg__(SETK_WS_LAUNCH_REGS) stft_cov_ws_kernel(StftCovArgs a) {
+  constexpr bool PAIRWIN = MODE == WS_MODE_PAIRWIN;
   SETK_DYN_SMEM(float, smem);
   WsSmem<C> sm;
   sm.carve(smem, a.g.hop, HAS_MN ? 2 : 1);
@@ -544,7 +568,7 @@ __global__ void __maxnreg__(SETK_WS_LAUNCH_REGS) stft_cov_ws_kernel(StftCovArgs 
     ws_cov_role<C, HAS_MN>(a, sm, lo, hi, q, vec_ok);
   } else {
     setmaxnreg_dec<SETK_WS_FFT_REGS>();
-    ws_fft_role<C, HAS_MN, PAIRWIN>(a, sm, lo, hi, q, vec_ok);
+    ws_fft_role<C, HAS_MN, MODE>(a, sm, lo, hi, q, vec_ok);
   }
 }
 
@@ -563,17 +587,17 @@ bool stft_cov_ws_supported(const Geometry& g) {
 }
 int stft_cov_ws_tt(int C) { return 16 / C; }
 
-template <int C, bool HAS_MN, bool PAIRWIN>
+template <int C, bool HAS_MN, int MODE>
 static cudaError_t run_ws_t(StftCovArgs a, int B, int n_ctas, float2* Rs, float2* Rn, float* maxabs,
                             void* stream) {
   const size_t smem = WsSmem<C>::bytes(a.g.hop, HAS_MN ? 2 : 1);
-  cudaError_t e = cudaFuncSetAttribute(stft_cov_ws_kernel<C, HAS_MN, PAIRWIN>,
+  cudaError_t e = cudaFuncSetAttribute(stft_cov_ws_kernel<C, HAS_MN, MODE>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  e = launch(stft_cov_ws_kernel<C, HAS_MN, PAIRWIN>, dim3(n_ctas), dim3(kWsThreads), smem, stream, false,
+  e = launch(stft_cov_ws_kernel<C, HAS_MN, MODE>, dim3(n_ctas), dim3(kWsThreads), smem, stream, false,
              a);
   if (e != cudaSuccess) return e;
-  const float scale = PAIRWIN ? 0.25f * a.win_pair_sum * a.win_pair_sum : 1.0f;
+  const float scale = MODE == WS_MODE_PAIRWIN ? 0.25f * a.win_pair_sum * a.win_pair_sum : 1.0f;
   e = run_cov_finalize(C, a.partials, B, a.g.F, a.sched, n_ctas, a.slots, scale, Rs, Rn, stream);
   if (e != cudaSuccess) return e;
   if (maxabs) e = run_bits_to_float(a.maxabs_bits, B, maxabs, stream);
@@ -609,14 +633,18 @@ cudaError_t run_stft_cov_ws(setk_plan* pl, const float* audio, const int* n_samp
   a.partials = partials;
   a.maxabs_bits = maxabs_bits;
   const bool pw = a.win_pair_sum > 0.f;
-  switch (pl->geo.C) {
-    case 4:
-      if (mask_n) return pw ? run_ws_t<4, true, true>(a, B, n_ctas, Rs, Rn, maxabs, stream)
-                            : run_ws_t<4, true, false>(a, B, n_ctas, Rs, Rn, maxabs, stream);
-      return pw ? run_ws_t<4, false, true>(a, B, n_ctas, Rs, Rn, maxabs, stream)
-                : run_ws_t<4, false, false>(a, B, n_ctas, Rs, Rn, maxabs, stream);
-    default: return cudaErrorInvalidValue;
+  // SETK_WS_AUDIO=direct (measurement knob): interior tiles' samples by LDG instead of TMA staging
+  const char* env_au = getenv("SETK_WS_AUDIO");
+  const bool direct = !pw && env_au && strcmp(env_au, "direct") == 0;
+  if (pl->geo.C != 4) return cudaErrorInvalidValue;
+  if (mask_n) {
+    if (pw) return run_ws_t<4, true, WS_MODE_PAIRWIN>(a, B, n_ctas, Rs, Rn, maxabs, stream);
+    if (direct) return run_ws_t<4, true, WS_MODE_DIRECT>(a, B, n_ctas, Rs, Rn, maxabs, stream);
+    return run_ws_t<4, true, WS_MODE_TMA>(a, B, n_ctas, Rs, Rn, maxabs, stream);
   }
+  if (pw) return run_ws_t<4, false, WS_MODE_PAIRWIN>(a, B, n_ctas, Rs, Rn, maxabs, stream);
+  if (direct) return run_ws_t<4, false, WS_MODE_DIRECT>(a, B, n_ctas, Rs, Rn, maxabs, stream);
+  return run_ws_t<4, false, WS_MODE_TMA>(a, B, n_ctas, Rs, Rn, maxabs, stream);
 }
 
 }  // namespace setk

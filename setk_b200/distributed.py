@@ -1,7 +1,7 @@
 """
 setk_b200.distributed -- multi-GPU plumbing: one process per GPU, the utterance
-list sharded by rank, no collective on the data path, one gather of results at
-the end.  This is the B200 equivalent of the reference's
+list sharded by rank, no collective on the data path, results collected on rank 0
+ -- by peer copies over NVLink (`PeerResultRing`) or NCCL.  This is the B200 equivalent of the reference's
 `split_scp.pl` + `run.pl JOB=1:nj` fan-out (scripts/run_adapt_beamformer.sh:66-92):
 there every job writes its own files; here rank 0 can collect the enhanced audio
 over NCCL (NVLink 5 / NVSwitch) instead.
@@ -67,6 +67,84 @@ def gather_ragged(local_list, dst=0, group=None):
         for i in range(int(counts[r])):
             result[r + i * world] = out[r][i, :int(all_lens[r][i])].clone()
     return result
+
+
+class PeerResultRing:
+    """
+    Result collection over NVLink peer memory instead of a collective kernel.
+
+    Rank `dst` owns a ring of `slots` receive buffers, each `[world, *shape]`; every other rank
+    maps that allocation into its own address space (CUDA IPC handle, exchanged once through the
+    process group) and delivers a batch with ONE asynchronous device-to-peer copy on a side stream:
+    the copy engines move the bytes over NVLink / NVSwitch while the SMs of both GPUs keep running
+    the next batch.  `ncclGather` needs a kernel on every rank for the same transfer; the fused
+    kernels of this path are persistent (one wave of 2 x 148 CTAs) and lose their balance when a
+    collective kernel holds an SM, which is why the bench measured 0.89 weak-scaling efficiency at
+    two GPUs with the NCCL gather of every batch.
+
+    The reference has no counterpart (its jobs write their own files,
+    scripts/run_adapt_beamformer.sh:66-92); SURVEY.md section 8e defines the collective as "all
+    results to rank 0".  Flow control is the consumer's business: slot `i % slots` is overwritten
+    `slots` batches later, so whoever reads the ring on `dst` must be done by then (the bench only
+    checks the last batch).
+    """
+
+    def __init__(self, shape, dtype, device, slots=3, dst=0, group=None):
+        from torch.multiprocessing.reductions import reduce_tensor
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.dst = dst
+        self.slots = slots
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self._owned = None
+        payload = [None]
+        if self.rank == dst:
+            self._owned = torch.zeros((slots, self.world) + tuple(shape), dtype=dtype, device=self.device)
+            torch.cuda.synchronize(self.device)
+            payload = [reduce_tensor(self._owned)]
+        dist.broadcast_object_list(payload, src=dst, group=group)
+        if self.rank == dst:
+            self.ring = self._owned
+        else:
+            rebuild, rebuild_args = payload[0]
+            self.ring = rebuild(*rebuild_args)          # a tensor on dst's GPU, mapped in this process
+        self.mine = [self.ring[s, self.rank] for s in range(slots)]
+
+    @classmethod
+    def create(cls, shape, dtype, device, slots=3, dst=0, group=None):
+        """The ring, or None on every rank when any rank cannot map the peer allocation."""
+        ring, ok = None, 1
+        try:
+            ring = cls(shape, dtype, device, slots, dst, group)
+            ring.push(torch.zeros(tuple(shape), dtype=dtype, device=device), 0)
+            ring.drain()
+            torch.cuda.synchronize(device)
+        except Exception as err:     # noqa: BLE001 -- any failure means "use the collective instead"
+            ring, ok = None, 0
+            cls.last_error = repr(err)
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        return ring if int(flag.item()) == 1 else None
+
+    last_error = None
+
+    def push(self, result, step):
+        """Deliver this rank's `result` into slot `step % slots` (asynchronous, ordered after the
+        current stream's work so far)."""
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            self.mine[step % self.slots].copy_(result, non_blocking=True)
+        result.record_stream(self.stream)
+
+    def drain(self):
+        """Order the current stream after every copy pushed so far."""
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+    def slot(self, step):
+        """[world, *shape] view of the slot batch `step` landed in (meaningful on dst)."""
+        return self.ring[step % self.slots]
 
 
 def max_over_ranks(value, device):

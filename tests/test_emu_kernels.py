@@ -76,6 +76,15 @@ def test_stft_cov_ws_pair_window(emu, monkeypatch):
     pc.check_stft_cov(emu, np.random.default_rng(11), 1, 4, 3000, 400, 256, True, "hann")   # no pair sum: falls back
 
 
+def test_stft_cov_ws_direct_loads(emu, monkeypatch):
+    # opt-in: interior tiles' samples by global loads (no staging), edge tiles staged as before
+    monkeypatch.setenv("SETK_WS_AUDIO", "direct")
+    pc.check_stft_cov(emu, np.random.default_rng(12), 3, 4, 6000, clip=True)
+    pc.check_stft_cov(emu, np.random.default_rng(12), 2, 4, 5000, 512, 128, False, "hamming", with_mask_n=True)
+    ns = torch.tensor([3000, 200, 1701, 513, 2999, 256, 257, 1024], dtype=torch.int32)
+    pc.check_stft_cov(emu, np.random.default_rng(8), 8, 4, 3000, n_samples=ns)
+
+
 def test_stft_cov_ws_long_run(emu):
     # one long utterance: every CTA refills its 8-entry tile table (CPU build) several times
     pc.check_stft_cov(emu, np.random.default_rng(10), 1, 4, 40000)
