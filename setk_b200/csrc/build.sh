@@ -17,7 +17,7 @@ DEPS[weights]="common.cuh compat.cuh hermitian_solve.cuh weights_args.cuh"
 DEPS[weights_coop]="common.cuh compat.cuh hermitian_solve.cuh jacobi_coop.cuh weights_args.cuh"
 DEPS[weights_post]="common.cuh compat.cuh hermitian_solve.cuh"
 DEPS[stft_cov_fused]="common.cuh compat.cuh stft_tile.cuh fft16.cuh async_copy.cuh stft_cov_args.cuh"
-DEPS[stft_cov_ws]="common.cuh compat.cuh stft_tile.cuh fft16.cuh async_copy.cuh stft_cov_args.cuh"
+DEPS[stft_cov_ws]="common.cuh compat.cuh stft_tile.cuh fft16.cuh async_copy.cuh stft_cov_args.cuh tmem.cuh"
 DEPS[apply_istft_fused]="common.cuh compat.cuh stft_tile.cuh fft16.cuh async_copy.cuh apply_istft_args.cuh"
 DEPS[apply_istft_ws]="common.cuh compat.cuh stft_tile.cuh fft16.cuh async_copy.cuh apply_istft_args.cuh"
 DEPS[stft_spill]="common.cuh compat.cuh stft_tile.cuh fft16.cuh async_copy.cuh cov_spill_args.cuh"

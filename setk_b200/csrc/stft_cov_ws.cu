@@ -44,6 +44,7 @@
 #include "common.cuh"
 #include "stft_tile.cuh"
 #include "stft_cov_args.cuh"
+#include "tmem.cuh"
 
 namespace setk {
 
@@ -120,6 +121,10 @@ struct WsSmem {
            sizeof(float) * C * staged_len(hop) + sizeof(float2) * 2 * 16 * SETK_ZSLOT +
            sizeof(float) * mask_slots(mrows) * mrows * kWsMaskRegion +
            sizeof(float2) * WsShape<C>::ROWS128 * WsShape<C>::NPAIR;
+  }
+  // [1] base address of the CTA's tensor-memory columns (TC builds): the word behind the barriers
+  static __device__ __forceinline__ unsigned* tmem_slot(float* base) {
+    return reinterpret_cast<unsigned*>(base) + 10;
   }
   __device__ void carve(float* base, int hop, int mrows_) {
     Lp = staged_len(hop);
@@ -215,9 +220,12 @@ __device__ __forceinline__ void ws_stage_scalar(const WsSmem<C>& sm, const float
 // ---------------------------------------------------------------------------
 // FFT role: threads 0..255, half-warp job = thread / 16 = frame * C + channel
 // ---------------------------------------------------------------------------
-template <int C, bool HAS_MN, int MODE>
+// TC: the thread's window values and inter-pass twiddles come from its tensor-memory lane
+// (tmem.cuh) instead of the shared-memory tables; same values, same arithmetic.
+constexpr int kWsTmemCols = 128;              // 2 FFT warps per lane quadrant x 64 columns
+template <int C, bool HAS_MN, int MODE, bool TC>
 __device__ __forceinline__ void ws_fft_role(const StftCovArgs& a, const WsSmem<C>& sm, int lo, int hi, int q,
-                                            bool vec_ok) {
+                                            bool vec_ok, unsigned tmem_base) {
   constexpr int TT = WsShape<C>::TT;
   constexpr int NR = HAS_MN ? 2 : 1, MS = HAS_MN ? 2 : 3;
   constexpr bool PAIRWIN = MODE == WS_MODE_PAIRWIN, DIRECT = MODE == WS_MODE_DIRECT;
@@ -228,6 +236,30 @@ __device__ __forceinline__ void ws_fft_role(const StftCovArgs& a, const WsSmem<C
   const int hop = a.g.hop, pad = a.g.pad;
   float amax = 0.f;
   unsigned apar = 0;
+  unsigned tc = 0;                                 // this thread's constants: columns tc .. tc + 63
+  if (TC) {
+    // columns 0..31: window of samples 2 lane16 + 32 m1 (+1), m1 = 0..15; 32..61: twiddle of slot
+    // s = 1..15 (W256^{lane16 kof(s)}); copied from the shared-memory tables the kernel filled
+    tc = tmem_addr(tmem_base, (int)threadIdx.x >> 5, ((ftid >> 5) >> 2) * 64);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float2 t[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) t[j] = *reinterpret_cast<const float2*>(sm.win + 2 * lane16 + 32 * (4 * g + j));
+      tmem_st<4>(tc + 8 * g, t);
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float2 t[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int sl = 1 + 4 * g + j;
+        t[j] = sl < 16 ? sm.twtab[kof(sl & 15) * 16 + lane16] : make_float2(0.f, 0.f);
+      }
+      tmem_st<4>(tc + 32 + 8 * g, t);
+    }
+    tmem_wait_st();
+  }
 
   // one thread: the mask rows of tile d (local number nn) -> mask slot nn % MS, completing on
   // z_full[nn & 1] together with that tile's Z
@@ -296,13 +328,35 @@ __device__ __forceinline__ void ws_fft_role(const StftCovArgs& a, const WsSmem<C
 #pragma unroll
           for (int m1 = 0; m1 < 16; ++m1) v[m1] = *reinterpret_cast<const float2*>(src + 32 * m1);
         }
+        if (TC) {
+          float2 wa[4], wb[4];
+          tmem_ld<4>(tc, wa);
 #pragma unroll
-        for (int m1 = 0; m1 < 16; ++m1) {
-          amax = fmaxf(amax, fmaxf(fabsf(v[m1].x), fabsf(v[m1].y)));
-          if (PAIRWIN) {                             // the window rides in the first butterflies
-            if (m1 < 8) w8[m1] = *reinterpret_cast<const float2*>(wsrc + 32 * m1);
-          } else {
-            v[m1] = f2mul(v[m1], *reinterpret_cast<const float2*>(wsrc + 32 * m1));
+          for (int m1 = 0; m1 < 16; ++m1) amax = fmaxf(amax, fmaxf(fabsf(v[m1].x), fabsf(v[m1].y)));
+          tmem_wait_ld(wa);
+          tmem_ld<4>(tc + 8, wb);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = f2mul(v[j], wa[j]);
+          tmem_wait_ld(wb);
+          tmem_ld<4>(tc + 16, wa);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[4 + j] = f2mul(v[4 + j], wb[j]);
+          tmem_wait_ld(wa);
+          tmem_ld<4>(tc + 24, wb);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[8 + j] = f2mul(v[8 + j], wa[j]);
+          tmem_wait_ld(wb);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[12 + j] = f2mul(v[12 + j], wb[j]);
+        } else {
+#pragma unroll
+          for (int m1 = 0; m1 < 16; ++m1) {
+            amax = fmaxf(amax, fmaxf(fabsf(v[m1].x), fabsf(v[m1].y)));
+            if (PAIRWIN) {                             // the window rides in the first butterflies
+              if (m1 < 8) w8[m1] = *reinterpret_cast<const float2*>(wsrc + 32 * m1);
+            } else {
+              v[m1] = f2mul(v[m1], *reinterpret_cast<const float2*>(wsrc + 32 * m1));
+            }
           }
         }
       }
@@ -312,7 +366,26 @@ __device__ __forceinline__ void ws_fft_role(const StftCovArgs& a, const WsSmem<C
       bool scalar_next = false;
       if (has_next) scalar_next = stage(sm.tiles[i + 1]);
       if (nt > 0) {
-        if (PAIRWIN) halfwarp_fft256_a_pairwin(v, w8, sm.twtab, lane16);
+        if (TC) {                                    // twiddles of slots 1..15 in four loads
+          float2 ta[4], tb[4];
+          tmem_ld<4>(tc + 32, ta);
+          dft16(v);
+          tmem_wait_ld(ta);
+          tmem_ld<4>(tc + 40, tb);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[1 + j] = cmul(v[1 + j], ta[j]);
+          tmem_wait_ld(tb);
+          tmem_ld<4>(tc + 48, ta);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[5 + j] = cmul(v[5 + j], tb[j]);
+          tmem_wait_ld(ta);
+          tmem_ld<4>(tc + 56, tb);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[9 + j] = cmul(v[9 + j], ta[j]);
+          tmem_wait_ld(tb);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) v[13 + j] = cmul(v[13 + j], tb[j]);
+        } else if (PAIRWIN) halfwarp_fft256_a_pairwin(v, w8, sm.twtab, lane16);
         else halfwarp_fft256_a(v, sm.twtab, lane16);
       }
       const int s = n & 1;
@@ -353,6 +426,12 @@ __device__ __forceinline__ void ws_fft_role(const StftCovArgs& a, const WsSmem<C
       if (scalar_next) named_bar_sync(kWsBarFft, kWsFftThreads);
       m3 = (m3 == MS - 1) ? 0 : m3 + 1;
     }
+  }
+  if (TC) {                                        // every FFT warp has read its last constant
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    if (ftid < 32) tmem_dealloc_warp(tmem_base, kWsTmemCols);
   }
 }
 
@@ -443,7 +522,7 @@ __device__ __forceinline__ void ws_cov_tile(float2* ak, float2* am, float2* my12
   }
 }
 
-template <int C, bool HAS_MN>
+template <int C, bool HAS_MN, bool TC>
 __device__ __forceinline__ void ws_cov_role(const StftCovArgs& a, const WsSmem<C>& sm, int lo, int hi,
                                             int q, bool vec_ok) {
   constexpr int TT = WsShape<C>::TT, NPAIR = WsShape<C>::NPAIR, NACC = WsShape<C>::NACC;
@@ -530,12 +609,13 @@ __device__ __forceinline__ void ws_cov_role(const StftCovArgs& a, const WsSmem<C
       m3 = (m3 == MS - 1) ? 0 : m3 + 1;
     }
   }
+  if (TC) __syncthreads();                         // pairs with the FFT role's barrier before tcgen05.dealloc
 }
 
 // PAIRWIN: the window has a constant pair sum K = w[n] + w[n + 256] (Hann: 1): the FFT warps load
 // half the window (scaled by 1 / K) and fold it into the first butterflies; the spectra come out
 // scaled by 2 / K, which cov_finalize_kernel takes back (K^2 / 4 on the sums).
-template <int C, bool HAS_MN, int MODE>
+template <int C, bool HAS_MN, int MODE, bool TC>
 __global__ void __maxnreg__(SETK_WS_LAUNCH_REGS) stft_cov_ws_kernel(StftCovArgs a) {
   constexpr bool PAIRWIN = MODE == WS_MODE_PAIRWIN;
   SETK_DYN_SMEM(float, smem);
@@ -560,15 +640,21 @@ __global__ void __maxnreg__(SETK_WS_LAUNCH_REGS) stft_cov_ws_kernel(StftCovArgs 
     mbar_init(&sm.z_empty[0], kWsCovThreads / 32);
     mbar_init(&sm.z_empty[1], kWsCovThreads / 32);
   }
+  if (TC) {
+    if ((tid >> 5) == (SETK_WS_COV_FIRST ? kWsCovThreads / 32 : 0))    // the first FFT warp owns the columns
+      tmem_alloc_warp(WsSmem<C>::tmem_slot(smem), kWsTmemCols);
+    tmem_fence_before_sync();
+  }
   __syncthreads();
+  if (TC) tmem_fence_after_sync();
   const bool vec_ok = ((a.N & 3) == 0) && ((a.g.hop & 3) == 0) && ((a.g.pad & 3) == 0) &&
                       ((reinterpret_cast<uintptr_t>(a.audio) & 15) == 0);
   if (SETK_WS_COV_FIRST ? tid < kWsCovThreads : tid >= kWsFftThreads) {
     setmaxnreg_inc<SETK_WS_COV_REGS>();
-    ws_cov_role<C, HAS_MN>(a, sm, lo, hi, q, vec_ok);
+    ws_cov_role<C, HAS_MN, TC>(a, sm, lo, hi, q, vec_ok);
   } else {
     setmaxnreg_dec<SETK_WS_FFT_REGS>();
-    ws_fft_role<C, HAS_MN, MODE>(a, sm, lo, hi, q, vec_ok);
+    ws_fft_role<C, HAS_MN, MODE, TC>(a, sm, lo, hi, q, vec_ok, TC ? *WsSmem<C>::tmem_slot(smem) : 0u);
   }
 }
 
@@ -587,14 +673,14 @@ bool stft_cov_ws_supported(const Geometry& g) {
 }
 int stft_cov_ws_tt(int C) { return 16 / C; }
 
-template <int C, bool HAS_MN, int MODE>
+template <int C, bool HAS_MN, int MODE, bool TC = false>
 static cudaError_t run_ws_t(StftCovArgs a, int B, int n_ctas, float2* Rs, float2* Rn, float* maxabs,
                             void* stream) {
   const size_t smem = WsSmem<C>::bytes(a.g.hop, HAS_MN ? 2 : 1);
-  cudaError_t e = cudaFuncSetAttribute(stft_cov_ws_kernel<C, HAS_MN, MODE>,
+  cudaError_t e = cudaFuncSetAttribute(stft_cov_ws_kernel<C, HAS_MN, MODE, TC>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  e = launch(stft_cov_ws_kernel<C, HAS_MN, MODE>, dim3(n_ctas), dim3(kWsThreads), smem, stream, false,
+  e = launch(stft_cov_ws_kernel<C, HAS_MN, MODE, TC>, dim3(n_ctas), dim3(kWsThreads), smem, stream, false,
              a);
   if (e != cudaSuccess) return e;
   const float scale = MODE == WS_MODE_PAIRWIN ? 0.25f * a.win_pair_sum * a.win_pair_sum : 1.0f;
@@ -637,6 +723,17 @@ cudaError_t run_stft_cov_ws(setk_plan* pl, const float* audio, const int* n_samp
   const char* env_au = getenv("SETK_WS_AUDIO");
   const bool direct = !pw && env_au && strcmp(env_au, "direct") == 0;
   if (pl->geo.C != 4) return cudaErrorInvalidValue;
+  // SETK_WS_CONST=tmem: the FFT warps' window / twiddle constants from tensor memory
+  const char* env_tc = getenv("SETK_WS_CONST");
+  const bool tmemc = !pw && env_tc && strcmp(env_tc, "tmem") == 0;
+  if (tmemc) {
+    if (mask_n) {
+      if (direct) return run_ws_t<4, true, WS_MODE_DIRECT, true>(a, B, n_ctas, Rs, Rn, maxabs, stream);
+      return run_ws_t<4, true, WS_MODE_TMA, true>(a, B, n_ctas, Rs, Rn, maxabs, stream);
+    }
+    if (direct) return run_ws_t<4, false, WS_MODE_DIRECT, true>(a, B, n_ctas, Rs, Rn, maxabs, stream);
+    return run_ws_t<4, false, WS_MODE_TMA, true>(a, B, n_ctas, Rs, Rn, maxabs, stream);
+  }
   if (mask_n) {
     if (pw) return run_ws_t<4, true, WS_MODE_PAIRWIN>(a, B, n_ctas, Rs, Rn, maxabs, stream);
     if (direct) return run_ws_t<4, true, WS_MODE_DIRECT>(a, B, n_ctas, Rs, Rn, maxabs, stream);

@@ -10,6 +10,8 @@
 //
 // Kinds: MVDR (beamformer.py:527-539), MPDR (555-573), GEVD / PEVD (31-63, 674-682), with BAN
 // (14-28).  MPDR-whiten, PMWF and the rank-1 options stay on weights.cu.
+#include <cstdlib>
+#include <cstring>
 #include "jacobi_coop.cuh"
 #include "weights_args.cuh"
 
@@ -280,7 +282,12 @@ __global__ void __launch_bounds__(WCfg<C>::THREADS) weights_coop_kernel(WeightsA
 }
 
 bool weights_coop_supported(const WeightsArgs& a, int C) {
-  if (C <= 4) return false;                            // register-resident one-thread solve is faster
+  if (C <= 4) {
+    // register-resident one-thread solve by default; SETK_W_IMPL=coop (measurement knob, read per
+    // call) puts C = 4 on the thread-group kernels as well (4 threads per bin)
+    const char* env = getenv("SETK_W_IMPL");
+    if (C != 4 || !env || strcmp(env, "coop") != 0) return false;
+  }
   if (a.rank1 != SETK_RANK1_NONE) return false;
   return a.kind == SETK_BF_MVDR || a.kind == SETK_BF_MPDR || a.kind == SETK_BF_GEVD ||
          a.kind == SETK_BF_PEVD;
@@ -304,7 +311,7 @@ static cudaError_t weights_coop_t(const WeightsArgs& a, void* stream) {
 cudaError_t weights_coop_launch(const WeightsArgs& a, int C, void* stream) {
   switch (C) {
 #define SETK_CASE(k) case k: return weights_coop_t<k>(a, stream);
-    SETK_CASE(5) SETK_CASE(6) SETK_CASE(7) SETK_CASE(8) SETK_CASE(9) SETK_CASE(10) SETK_CASE(11) SETK_CASE(12)
+    SETK_CASE(4) SETK_CASE(5) SETK_CASE(6) SETK_CASE(7) SETK_CASE(8) SETK_CASE(9) SETK_CASE(10) SETK_CASE(11) SETK_CASE(12)
     SETK_CASE(13) SETK_CASE(14) SETK_CASE(15) SETK_CASE(16)
 #undef SETK_CASE
     default: return cudaErrorInvalidValue;

@@ -139,6 +139,8 @@ struct Ctx {
   std::vector<double> gather64;   // the same for fp64 fragments
   unsigned char* dyn = nullptr;
   bool serial = false;
+  std::vector<unsigned> tmem;     // tensor memory of the CTA: [128 lanes][512 columns], garbage until written
+  std::atomic<int> tmem_cols{0};  // columns currently allocated (tcgen05.alloc / dealloc)
 };
 
 extern thread_local Ctx* g_ctx;
@@ -193,7 +195,29 @@ void launch(dim3 grid, dim3 block, size_t smem, bool serial, F&& body) {
           for (int t = 0; t < nthr; ++t) th.emplace_back(run, t);
           for (auto& t : th) t.join();
         }
+        if (ctx.tmem_cols.load() != 0) die("CTA exited with tensor memory still allocated");
       }
+}
+// tensor memory (tcgen05.alloc / st / ld / dealloc): plain per-CTA storage; the model checks what the
+// hardware would punish silently -- access outside the allocation or outside the warp's lane quadrant,
+// a CTA that exits with columns still allocated
+inline void tmem_alloc(int ncols) {
+  if (g_tid % 32 == 0) {
+    if (g_ctx->tmem_cols.load() != 0) die("tcgen05.alloc: second allocation in one CTA (model supports one)");
+    g_ctx->tmem.assign((size_t)128 * 512, 0xCDCDCDCDu);
+    g_ctx->tmem_cols.store(ncols);
+  }
+}
+inline void tmem_free(int ncols) {
+  if (g_tid % 32 == 0) {
+    if (g_ctx->tmem_cols.load() != ncols) die("tcgen05.dealloc: column count differs from the allocation");
+    g_ctx->tmem_cols.store(0);
+  }
+}
+inline unsigned* tmem_row(unsigned lane_base, int lane_in_warp) {
+  if (g_ctx->tmem_cols.load() <= 0) die("tcgen05.ld/st without an allocation");
+  if (lane_base != (unsigned)((g_tid / 32) & 3) * 32u) die("tcgen05.ld/st outside the warp's lane quadrant");
+  return g_ctx->tmem.data() + (size_t)(lane_base + lane_in_warp) * 512;
 }
 inline void sync_cta() {
   if (g_ctx->serial) die("__syncthreads in a kernel launched as barrier-free");

@@ -85,6 +85,18 @@ def test_stft_cov_ws_direct_loads(emu, monkeypatch):
     pc.check_stft_cov(emu, np.random.default_rng(8), 8, 4, 3000, n_samples=ns)
 
 
+def test_stft_cov_ws_tmem_constants(emu, monkeypatch):
+    # opt-in: the FFT warps' window / twiddle constants parked in tensor memory (tcgen05.st / ld model:
+    # allocation, lane quadrants, dealloc before exit), alone and with direct audio loads
+    monkeypatch.setenv("SETK_WS_CONST", "tmem")
+    pc.check_stft_cov(emu, np.random.default_rng(13), 3, 4, 6000, clip=True)
+    pc.check_stft_cov(emu, np.random.default_rng(13), 2, 4, 5000, 512, 128, False, "hamming", with_mask_n=True)
+    ns = torch.tensor([3000, 200, 1701, 513, 2999, 256, 257, 1024], dtype=torch.int32)
+    pc.check_stft_cov(emu, np.random.default_rng(8), 8, 4, 3000, n_samples=ns)
+    monkeypatch.setenv("SETK_WS_AUDIO", "direct")
+    pc.check_stft_cov(emu, np.random.default_rng(14), 2, 4, 6000)
+
+
 def test_stft_cov_ws_long_run(emu):
     # one long utterance: every CTA refills its 8-entry tile table (CPU build) several times
     pc.check_stft_cov(emu, np.random.default_rng(10), 1, 4, 40000)
@@ -250,6 +262,12 @@ def test_cov_generic(emu):
 @pytest.mark.parametrize("C", [1, 2, 4, 5, 8])
 def test_weights_all_kinds(emu, C):
     pc.check_weights(emu, np.random.default_rng(10 + C), 2, 7, C)
+
+
+def test_weights_c4_thread_groups(emu, monkeypatch):
+    monkeypatch.setenv("SETK_W_IMPL", "coop")         # opt-in: 4 threads per 4 x 4 problem
+    pc.check_weights(emu, np.random.default_rng(14), 2, 7, 4)
+    pc.check_weights_status(emu)
 
 
 def test_weights_c64_and_status(emu):

@@ -134,13 +134,17 @@ def test_opt_in_builds(cuda, monkeypatch):
     pc.check_apply_istft(cuda, rng, 3, 4, 30000, n_samples=ns)
     pc.check_apply_istft(cuda, rng, 2, 4, 48000, post_mask=True)
     monkeypatch.delenv("SETK_AI_IMPL")
-    for knob, val in (("SETK_SC_IMPL", "classic"), ("SETK_WS_PAIRWIN", "1")):
+    for knob, val in (("SETK_SC_IMPL", "classic"), ("SETK_WS_PAIRWIN", "1"), ("SETK_WS_CONST", "tmem"),
+                      ("SETK_WS_AUDIO", "direct")):
         monkeypatch.setenv(knob, val)
         pc.check_stft_cov(cuda, rng, 3, 4, 30000, n_samples=ns)
         monkeypatch.delenv(knob)
     monkeypatch.setenv("SETK_COV_IMPL", "cuda")
     pc.check_stft_cov(cuda, rng, 2, 8, 20000)
     monkeypatch.delenv("SETK_COV_IMPL")
+    monkeypatch.setenv("SETK_W_IMPL", "coop")
+    pc.check_weights(cuda, rng, 3, 257, 4)
+    monkeypatch.delenv("SETK_W_IMPL")
 
 
 def test_wpe_tensor_core_correlation(cuda, monkeypatch):
