@@ -35,6 +35,7 @@
 // Algorithmic bytes per utterance: 4*C*N (audio) + 8*F*C (w) + 4*n_out (wave)
 // (+ 4*T*F with a post-mask).
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 #include "common.cuh"
 #include "stft_tile.cuh"
@@ -45,7 +46,9 @@ namespace setk {
 constexpr int kApplyThreads = 320;
 constexpr int kWPitch = 260;          // float2 pitch of the per-channel weight rows
 
-template <int C, int TT>
+// TC: the forward-FFT warps read their window / twiddle constants from tensor memory (tmem.cuh)
+constexpr int kApplyTmemCols = 128;   // 2 FFT warps per lane quadrant x 64 columns
+template <int C, int TT, bool TC>
 __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
   static_assert(TT == 4, "two inverse-FFT warps serve exactly four frames");
   constexpr int F = kBins;
@@ -95,6 +98,18 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
   }
   if (tid == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); }
   for (int k = tid; k < NPAIR; k += blockDim.x) s_tw[k] = split_twiddle(k);
+  unsigned tc = 0;
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(s_carry + 2 * carry_len);
+  if (TC) {                                          // warp 0 owns the CTA's tensor-memory columns
+    if (warp == 0) tmem_alloc_warp(tmem_slot, kApplyTmemCols);
+    tmem_fence_before_sync();
+    __syncthreads();                                 // also: sm.win is complete
+    tmem_fence_after_sync();
+    if (warp < 8) {
+      tc = tmem_addr(*tmem_slot, warp, (warp >> 2) * 64);
+      fft_constants_to_tmem(tc, sm.win, lane16);
+    }
+  }
 
   float w1s, w1c;
   sincospif((float)lane16 / 128.0f, &w1s, &w1c);
@@ -304,7 +319,7 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
       }
       // ---- phase A: forward FFT of this tile || inverse FFT of the previous one ----
       if (warp < 8) {
-        fft_tile<C, TT>(sm, buf, nt, hop, w1, amax_unused);
+        fft_tile<C, TT, false, 8, TC>(sm, buf, nt, hop, w1, amax_unused, nullptr, tc);
       } else if (prev_nt > 0) {
         ifft_tile(prev_nt);
       }
@@ -391,6 +406,12 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
     }
     cur_tile = seg_end;
   }
+  if (TC) {                                          // every FFT warp has read its last constant
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    if (warp == 0) tmem_dealloc_warp(*tmem_slot, kApplyTmemCols);
+  }
 }
 
 template <int C, int TT>
@@ -403,16 +424,17 @@ static size_t apply_istft_smem_bytes(int hop) {
   fl += 2 * (size_t)kNfft;                // s_wsyn, s_wsq
   fl += (size_t)kM;                       // s_rw
   fl += 2 * (size_t)(kNfft - hop);        // carry x2
+  fl += 4;                                // tensor-memory base address (TC builds)
   return fl * sizeof(float);
 }
 
-template <int C, int TT>
+template <int C, int TT, bool TC = false>
 static cudaError_t run_apply_istft_t(const ApplyIstftArgs& a, int n_ctas, void* stream) {
   const size_t smem = apply_istft_smem_bytes<C, TT>(a.g.hop);
-  cudaError_t e = cudaFuncSetAttribute(apply_istft_kernel<C, TT>,
+  cudaError_t e = cudaFuncSetAttribute(apply_istft_kernel<C, TT, TC>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  return launch(apply_istft_kernel<C, TT>, dim3(n_ctas), dim3(kApplyThreads), smem, stream, false, a);
+  return launch(apply_istft_kernel<C, TT, TC>, dim3(n_ctas), dim3(kApplyThreads), smem, stream, false, a);
 }
 
 bool apply_istft_fused_supported(const Geometry& g) {
@@ -473,6 +495,9 @@ cudaError_t run_apply_istft_fused(setk_plan* pl, const float* audio, const int* 
     a.c0 = 0; a.accumulate = 0; a.peak = peak;
     return run_apply_istft_ws(a, n_ctas, stream);
   }
+  // SETK_AI_CONST=tmem (measurement knob, read per call): forward-FFT constants from tensor memory
+  const char* env_tc = getenv("SETK_AI_CONST");
+  const bool tmemc = env_tc && strcmp(env_tc, "tmem") == 0;
   for (int c0 = 0; c0 < Ctot && e == cudaSuccess; c0 += 4) {
     const int cb = Ctot - c0 < 4 ? Ctot - c0 : 4;
     a.c0 = c0;
@@ -482,7 +507,10 @@ cudaError_t run_apply_istft_fused(setk_plan* pl, const float* audio, const int* 
       case 1: e = run_apply_istft_t<1, TT>(a, n_ctas, stream); break;
       case 2: e = run_apply_istft_t<2, TT>(a, n_ctas, stream); break;
       case 3: e = run_apply_istft_t<3, TT>(a, n_ctas, stream); break;
-      default: e = run_apply_istft_t<4, TT>(a, n_ctas, stream); break;
+      default:
+        e = tmemc ? run_apply_istft_t<4, TT, true>(a, n_ctas, stream)
+                  : run_apply_istft_t<4, TT>(a, n_ctas, stream);
+        break;
     }
   }
   return e;

@@ -231,8 +231,13 @@ __device__ __forceinline__ void ws_fft_role(const StftCovArgs& a, const WsSmem<C
   constexpr bool PAIRWIN = MODE == WS_MODE_PAIRWIN, DIRECT = MODE == WS_MODE_DIRECT;
   const int ftid = (int)threadIdx.x - (SETK_WS_COV_FIRST ? kWsCovThreads : 0);
   const int lane = ftid & 31, lane16 = lane & 15;
-  const int job = ftid >> 4;
-  const int fr = job / C, ch = job - fr * C;
+  // the warp index through a shuffle: the compiler then knows it is warp-uniform and keeps what
+  // depends on it (frame of the job pair, slot and tensor-memory addresses) in uniform registers
+  const int fwarp = TC ? __shfl_sync(0xffffffffu, ftid >> 5, 0) : (ftid >> 5);   // (!TC: measured builds unchanged)
+  const int half = lane >> 4;
+  const int job = 2 * fwarp + half;
+  static_assert(C % 2 == 0, "a warp's two jobs are channels (c, c + 1) of one frame");
+  const int fr = (2 * fwarp) / C, ch = (2 * fwarp) % C + half;
   const int hop = a.g.hop, pad = a.g.pad;
   float amax = 0.f;
   unsigned apar = 0;
@@ -240,7 +245,7 @@ __device__ __forceinline__ void ws_fft_role(const StftCovArgs& a, const WsSmem<C
   if (TC) {
     // columns 0..31: window of samples 2 lane16 + 32 m1 (+1), m1 = 0..15; 32..61: twiddle of slot
     // s = 1..15 (W256^{lane16 kof(s)}); copied from the shared-memory tables the kernel filled
-    tc = tmem_addr(tmem_base, (int)threadIdx.x >> 5, ((ftid >> 5) >> 2) * 64);
+    tc = tmem_addr(tmem_base, fwarp + (SETK_WS_COV_FIRST ? kWsCovThreads / 32 : 0), (fwarp >> 2) * 64);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       float2 t[4];
@@ -314,6 +319,9 @@ __device__ __forceinline__ void ws_fft_role(const StftCovArgs& a, const WsSmem<C
         // a dead frame (fr >= nt, only in an utterance's last tile) re-transforms the last live
         // one: its spectrum is never read and max|x| sees nothing new
         const int fr_src = imin(fr, nt - 1);
+        // max|x|: with hop = n_fft / 2 the first halves of the frames tile the signal, so only an
+        // utterance's last frame looks at its second half as well
+        const bool amax_full = hop != kM || ((d.flags & WS_UTT_END) && fr >= nt - 1);
         // DIRECT: an interior tile's samples come straight from global memory (a half-warp reads
         // 128 contiguous bytes per load, each sample twice across the 50 % frame overlap: L1/L2
         // hits) and never cross shared memory; edge tiles keep the staged path
@@ -332,7 +340,11 @@ __device__ __forceinline__ void ws_fft_role(const StftCovArgs& a, const WsSmem<C
           float2 wa[4], wb[4];
           tmem_ld<4>(tc, wa);
 #pragma unroll
-          for (int m1 = 0; m1 < 16; ++m1) amax = fmaxf(amax, fmaxf(fabsf(v[m1].x), fabsf(v[m1].y)));
+          for (int m1 = 0; m1 < 8; ++m1) amax = fmaxf(amax, fmaxf(fabsf(v[m1].x), fabsf(v[m1].y)));
+          if (amax_full) {
+#pragma unroll
+            for (int m1 = 8; m1 < 16; ++m1) amax = fmaxf(amax, fmaxf(fabsf(v[m1].x), fabsf(v[m1].y)));
+          }
           tmem_wait_ld(wa);
           tmem_ld<4>(tc + 8, wb);
 #pragma unroll

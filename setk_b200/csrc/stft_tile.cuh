@@ -14,6 +14,7 @@
 //                constant twiddle
 #pragma once
 #include "async_copy.cuh"
+#include "tmem.cuh"
 #include "common.cuh"
 #include "fft16.cuh"
 
@@ -165,12 +166,42 @@ __device__ __forceinline__ void stage_tile_scalar(const TileSmem<C, TT>& sm, int
   }
 }
 
+// The 62 per-thread constants of the forward FFT -> the thread's tensor-memory lane (tmem.cuh):
+// columns 0..31 the window (x 0.5, as in sm.win) of samples 2 lane16 + 32 m1 (+1), m1 = 0..15;
+// columns 32..61 the inter-pass twiddle W256^{lane16 kof(s)} of slot s = 1..15.  One call per thread
+// of the FFT warps before the first tile; win = the shared-memory window table.
+__device__ __forceinline__ void fft_constants_to_tmem(unsigned tc, const float* win, int lane16) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float2 t[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[j] = *reinterpret_cast<const float2*>(win + 2 * lane16 + 32 * (4 * g + j));
+    tmem_st<4>(tc + 8 * g, t);
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float2 t[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int sl = 1 + 4 * g + j;
+      float sn = 0.f, cs = 0.f;
+      if (sl < 16) sincospif((float)((kof(sl & 15) * lane16) & 255) / 128.0f, &sn, &cs);
+      t[j] = make_float2(cs, -sn);
+    }
+    tmem_st<4>(tc + 32 + 8 * g, t);
+  }
+  tmem_wait_st();
+}
+
 // Forward FFT of every (frame, channel) of the tile by warps 0..NW-1, reading
 // audio[buf].  All threads of those warps must call it; hop must be even.
 // amax accumulates max |sample| of everything the tile reads.
-template <int C, int TT, bool TAB = false, int NW = 8>
+// TC: the thread's window values and inter-pass twiddles come from its tensor-memory lane (columns
+// tc .. tc + 63, written by fft_constants_to_tmem) instead of shared memory / the power tree.
+template <int C, int TT, bool TAB = false, int NW = 8, bool TC = false>
 __device__ __forceinline__ void fft_tile(const TileSmem<C, TT>& sm, int buf, int nt, int hop,
-                                         float2 w1, float& amax, const float2* twtab = nullptr) {
+                                         float2 w1, float& amax, const float2* twtab = nullptr,
+                                         unsigned tc = 0) {
   constexpr int JOBS = TT * C;
   static_assert(JOBS % 2 == 0, "half-warp jobs must pair up per warp");
   constexpr int ROUNDS = (JOBS + 2 * NW - 1) / (2 * NW);       // warps 0..NW-1 call this
@@ -188,15 +219,58 @@ __device__ __forceinline__ void fft_tile(const TileSmem<C, TT>& sm, int buf, int
       float2 v[16];
       const float* src = sm.abuf(buf) + ch * sm.Lp + fr_src * hop + 2 * lane16;
       const float* wsrc = sm.win + 2 * lane16;
-#pragma unroll
-      for (int m1 = 0; m1 < 16; ++m1) {
-        const float2 s = *reinterpret_cast<const float2*>(src + 32 * m1);
-        const float2 w = *reinterpret_cast<const float2*>(wsrc + 32 * m1);
-        amax = fmaxf(amax, fmaxf(fabsf(s.x), fabsf(s.y)));
-        v[m1] = f2mul(s, w);
-      }
       float2* zs = sm.z + job * SETK_ZSLOT;
-      halfwarp_fft256<TAB>(v, zs, lane16, w1, twtab);
+      if (TC) {
+        float2 wa[4], wb[4];
+        tmem_ld<4>(tc, wa);
+#pragma unroll
+        for (int m1 = 0; m1 < 16; ++m1) {
+          v[m1] = *reinterpret_cast<const float2*>(src + 32 * m1);
+          amax = fmaxf(amax, fmaxf(fabsf(v[m1].x), fabsf(v[m1].y)));
+        }
+        tmem_wait_ld(wa);
+        tmem_ld<4>(tc + 8, wb);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = f2mul(v[j], wa[j]);
+        tmem_wait_ld(wb);
+        tmem_ld<4>(tc + 16, wa);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[4 + j] = f2mul(v[4 + j], wb[j]);
+        tmem_wait_ld(wa);
+        tmem_ld<4>(tc + 24, wb);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[8 + j] = f2mul(v[8 + j], wa[j]);
+        tmem_wait_ld(wb);
+        tmem_ld<4>(tc + 32, wa);                   // twiddles of slots 1..4, in flight during pass 1
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[12 + j] = f2mul(v[12 + j], wb[j]);
+        dft16(v);
+        tmem_wait_ld(wa);
+        tmem_ld<4>(tc + 40, wb);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[1 + j] = cmul(v[1 + j], wa[j]);
+        tmem_wait_ld(wb);
+        tmem_ld<4>(tc + 48, wa);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[5 + j] = cmul(v[5 + j], wb[j]);
+        tmem_wait_ld(wa);
+        tmem_ld<4>(tc + 56, wb);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[9 + j] = cmul(v[9 + j], wa[j]);
+        tmem_wait_ld(wb);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) v[13 + j] = cmul(v[13 + j], wb[j]);
+        halfwarp_fft256_b(v, zs, lane16);
+      } else {
+#pragma unroll
+        for (int m1 = 0; m1 < 16; ++m1) {
+          const float2 s = *reinterpret_cast<const float2*>(src + 32 * m1);
+          const float2 w = *reinterpret_cast<const float2*>(wsrc + 32 * m1);
+          amax = fmaxf(amax, fmaxf(fabsf(s.x), fabsf(s.y)));
+          v[m1] = f2mul(s, w);
+        }
+        halfwarp_fft256<TAB>(v, zs, lane16, w1, twtab);
+      }
 #pragma unroll
       for (int s = 0; s < 16; ++s) zs[lane16 + 16 * kof(s)] = v[s];
     }

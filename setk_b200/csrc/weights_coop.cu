@@ -152,19 +152,29 @@ __device__ __forceinline__ void forward_subst_coop(const cd* L, cd* B, int c, bo
   __syncwarp();
 }
 
+SETK_HD inline bool coop_two_matrices(const WeightsArgs& a) {
+  return a.kind == SETK_BF_MVDR || a.kind == SETK_BF_MPDR || (a.kind == SETK_BF_PEVD && a.Rn == nullptr);
+}
+template <int C>
+SETK_HD inline int coop_group_pitch(bool two) { return ((two ? 2 : 3) * Coop<C>::MAT + C) | 1; }
+
 template <int C>
 __global__ void __launch_bounds__(WCfg<C>::THREADS) weights_coop_kernel(WeightsArgs a) {
   using K = Coop<C>;
   constexpr int GS = K::GS, LD = K::LD, MAT = K::MAT, MPB = WCfg<C>::THREADS / GS;
-  constexpr int PER = 3 * MAT + C;                 // cd per group: A, V, M, w
+  // cd per group: A, V, M, w.  The eigenvector kinds (MVDR, MPDR, PEVD of Rs) are done with A when
+  // they fill M, so M lives on A: a third less shared memory = a third more problems resident.
+  // The pitch is odd: the groups of a warp start in different 16-byte bank groups.
+  const bool two = coop_two_matrices(a);
+  const int PER = coop_group_pitch<C>(two);
   SETK_DYN_SMEM(double, sm);
   const int tid = threadIdx.x;
   const int grp = tid / GS, r = tid - grp * GS;
   const int lane_base = (tid & 31) - r;            // first lane of this group in its warp
   cd* A = reinterpret_cast<cd*>(sm) + (size_t)grp * PER;
   cd* V = A + MAT;
-  cd* M = V + MAT;
-  cd* wv = M + MAT;
+  cd* M = two ? A : V + MAT;
+  cd* wv = (two ? V : M) + MAT;
   double* rot = sm + (size_t)MPB * PER * 2 + grp * K::ROT;
   const long long idx = (long long)blockIdx.x * MPB + grp;
   const bool active = idx < (long long)a.B * a.F;
@@ -184,6 +194,7 @@ __global__ void __launch_bounds__(WCfg<C>::THREADS) weights_coop_kernel(WeightsA
     } else {
       // denominator matrix: Rn for MVDR, Ry (all-ones mask) for MPDR (beamformer.py:555-573)
       const void* D = a.kind == SETK_BF_MPDR ? a.Ry : a.Rn;
+      __syncwarp();                                    // every lane has read A and V: M may overwrite A
       if (row) {
         for (int j = 0; j < C; ++j) M[r * LD + j] = load_c(D, a.r_dtype, idx * (C * C) + r * C + j);
         M[r * LD + C] = d;
@@ -297,7 +308,8 @@ template <int C>
 static cudaError_t weights_coop_t(const WeightsArgs& a, void* stream) {
   using K = Coop<C>;
   constexpr int MPB = WCfg<C>::THREADS / K::GS;
-  const size_t smem = sizeof(double) * ((size_t)MPB * (3 * K::MAT + C) * 2 + (size_t)MPB * K::ROT);
+  const size_t smem = sizeof(double) * ((size_t)MPB * coop_group_pitch<C>(coop_two_matrices(a)) * 2 +
+                                        (size_t)MPB * K::ROT);
 #ifndef SETK_EMU
   cudaError_t ea = cudaFuncSetAttribute(weights_coop_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem);

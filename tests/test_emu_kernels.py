@@ -287,6 +287,15 @@ def test_apply_istft_fused(emu, C, N, hop, center, pm, norm):
                          post_mask=pm, norm=norm)
 
 
+def test_apply_istft_tmem_constants(emu, monkeypatch):
+    monkeypatch.setenv("SETK_AI_CONST", "tmem")       # opt-in: forward-FFT constants from tensor memory
+    rng = np.random.default_rng(34)
+    pc.check_apply_istft(emu, rng, 2, 4, 6000, post_mask=True)
+    ns = torch.tensor([9000, 700, 5120], dtype=torch.int32)
+    pc.check_apply_istft(emu, rng, 3, 4, 9000, n_samples=ns)
+    pc.check_apply_istft(emu, rng, 1, 8, 3000)        # two channel blocks, the second accumulates
+
+
 def test_apply_istft_ws_protocol(emu, monkeypatch):
     monkeypatch.setenv("SETK_AI_IMPL", "ws")          # opt-in build (read once per process)
     # the warp-specialised build (apply_istft_ws.cu): long runs (several fills of the 8-entry

@@ -134,6 +134,10 @@ def test_opt_in_builds(cuda, monkeypatch):
     pc.check_apply_istft(cuda, rng, 3, 4, 30000, n_samples=ns)
     pc.check_apply_istft(cuda, rng, 2, 4, 48000, post_mask=True)
     monkeypatch.delenv("SETK_AI_IMPL")
+    monkeypatch.setenv("SETK_AI_CONST", "tmem")
+    pc.check_apply_istft(cuda, rng, 3, 4, 30000, n_samples=ns)
+    pc.check_apply_istft(cuda, rng, 2, 8, 48000, post_mask=True)
+    monkeypatch.delenv("SETK_AI_CONST")
     for knob, val in (("SETK_SC_IMPL", "classic"), ("SETK_WS_PAIRWIN", "1"), ("SETK_WS_CONST", "tmem"),
                       ("SETK_WS_AUDIO", "direct")):
         monkeypatch.setenv(knob, val)
