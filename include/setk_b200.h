@@ -331,6 +331,18 @@ int setk_float_to_pcm16(const float* wave, int64_t n, int16_t* pcm, void* stream
 /* int16 / 32768 -> float32: read_wav (utils.py:80-92). */
 int setk_pcm16_to_float(const int16_t* pcm, int64_t n, float* wave, void* stream);
 
+/* Kaldi CompressedMatrix masks, format "CM" (per-column percentile headers + one byte per element),
+ * expanded on the device: kaldi_io.py:248-281 uncompress() as reached by the mask ScriptReader of
+ * apply_adaptive_beamformer.py:139-142 (--mask-format kaldi), same float32 operations, bit-identical.
+ *   blobs  u8  [B][slot_bytes]  one matrix per slot exactly as it lies in the archive behind the "CM "
+ *                               token: {f32 min, f32 range, i32 rows, i32 cols}, cols x 4 u16,
+ *                               cols x rows u8 (column major); slot_bytes a multiple of 16
+ *   out    f32 [B][T][F]        rows t < rows_b decoded, the rest zero (ragged batches)
+ *   status i32 [B]              set to 1 where a header is inconsistent (cols != F, rows > T, the
+ *                               matrix does not fit its slot); that matrix decodes to zeros */
+int setk_cm_masks(const uint8_t* blobs, int64_t slot_bytes, int32_t B, int32_t T, int32_t F, float* out,
+                  int32_t* status, void* stream);
+
 /* How many kernels of this library have been launched by this process
  * (for bench.py's "gpu_launches"). */
 int64_t setk_launch_count(void);

@@ -100,6 +100,7 @@ _PROTOTYPES = {
                          c_void_p]),
     "setk_float_to_pcm16": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "setk_pcm16_to_float": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "setk_cm_masks": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)

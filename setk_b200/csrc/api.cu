@@ -24,6 +24,7 @@ cudaError_t run_peak_scale(float*, int, int, const float*, const unsigned*, void
 cudaError_t run_float_to_pcm16(const float*, long long, int16_t*, void*);
 cudaError_t run_peak_scale_pcm16(const float*, int, int, const float*, const unsigned*, int16_t*, void*);
 cudaError_t run_pcm16_to_float(const int16_t*, long long, float*, void*);
+cudaError_t run_cm_masks(const unsigned char*, long long, int, int, int, float*, int*, void*);
 
 cudaError_t run_ipd(const float2*, const float2*, long long, int, int, float*, void*);
 cudaError_t run_dirfeat(const float2*, const double2*, int, const int*, int, int, int, int, int, double*,
@@ -598,6 +599,15 @@ int setk_pcm16_to_float(const int16_t* pcm, int64_t n, float* wave, void* stream
   if (n == 0) return SETK_OK;
   cudaError_t e = run_pcm16_to_float(pcm, n, wave, stream);
   return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_pcm16_to_float");
+}
+
+int setk_cm_masks(const uint8_t* blobs, int64_t slot_bytes, int32_t B, int32_t T, int32_t F, float* out,
+                  int32_t* status, void* stream) {
+  if (!blobs || !out || !status || B < 0 || T < 0 || F < 0 || slot_bytes < 16 || (slot_bytes & 15) ||
+      (reinterpret_cast<uintptr_t>(blobs) & 15))
+    return fail(SETK_EINVAL, "setk_cm_masks: bad argument");
+  cudaError_t e = run_cm_masks(blobs, slot_bytes, B, T, F, out, status, stream);
+  return e == cudaSuccess ? SETK_OK : cuda_fail(e, "setk_cm_masks");
 }
 
 // ---- spatial features (spatial.cu) ----

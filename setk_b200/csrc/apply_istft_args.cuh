@@ -1,5 +1,5 @@
 // apply_istft_args.cuh -- launch arguments shared by the two fused apply + iSTFT kernels
-// (apply_istft_fused.cu, apply_istft_ws.cu).
+// (apply_istft_fused.cu).
 #pragma once
 #include "common.cuh"
 #include "stft_tile.cuh"

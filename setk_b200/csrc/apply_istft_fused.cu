@@ -445,16 +445,10 @@ bool apply_istft_fused_supported(const Geometry& g) {
 }
 
 void fused_schedule(const setk_plan* pl, int B, int T, int TT, int* n_ctas, int* slots, int* min_quota);
-bool apply_istft_ws_supported(const Geometry& g);
-int apply_istft_ws_tt();
-cudaError_t run_apply_istft_ws(const ApplyIstftArgs& a, int n_ctas, void* stream);
-// The warp-specialised build is opt-in (SETK_AI_IMPL=ws): measured on B200 at config 2 it is
-// still slower than this kernel (0.62 vs 0.57 ms; apply_istft_ws.cu says why)
-static bool use_apply_ws(const Geometry& g) {
-  const char* env = getenv("SETK_AI_IMPL");
-  if (!(env && env[0] == 'w')) return false;
-  return apply_istft_ws_supported(g);
-}
+// Three warp-specialised builds of this pass (FFT / apply+flush / inverse-FFT roles on mbarrier rings)
+// were measured on B200 at config 2 against this kernel's 0.57 ms: 0.79, 0.62 and 0.70 ms
+// (profiles/r2_apply_istft_ws_*_ncu.txt, DESIGN.md K4+K5) -- four short stages per frame make the
+// hand-overs cost more than the two barriers they replace.  They are not part of the library.
 cudaError_t run_tile_prefix(const int* n_samples, int B, const Geometry& g, int TT, int T_cap,
                             int* prefix, void* stream);
 
@@ -462,8 +456,7 @@ cudaError_t run_apply_istft_fused(setk_plan* pl, const float* audio, const int* 
                                   int T, const void* w, int w_dtype, const float* post_mask, int n_out,
                                   int* tile_prefix, float* wave, unsigned* peak, void* stream) {
   constexpr int TT = 4;
-  const bool ws = use_apply_ws(pl->geo);
-  const int TTs = ws ? apply_istft_ws_tt() : TT;      // frames per tile of the schedule
+  const int TTs = TT;                                 // frames per tile of the schedule
   ApplyIstftArgs a;
   a.g = pl->geo;
   a.audio = audio; a.n_samples = n_samples; a.N = N;
@@ -491,10 +484,6 @@ cudaError_t run_apply_istft_fused(setk_plan* pl, const float* audio, const int* 
   // peak is taken by the last block (it sees the complete sums)
   const int Ctot = pl->geo.C;
   a.c_total = Ctot;
-  if (ws) {                            // the warp-specialised build (opt-in) for the metric geometry
-    a.c0 = 0; a.accumulate = 0; a.peak = peak;
-    return run_apply_istft_ws(a, n_ctas, stream);
-  }
   // SETK_AI_CONST=tmem (measurement knob, read per call): forward-FFT constants from tensor memory
   const char* env_tc = getenv("SETK_AI_CONST");
   const bool tmemc = env_tc && strcmp(env_tc, "tmem") == 0;

@@ -19,14 +19,14 @@ DEPS[weights_post]="common.cuh compat.cuh hermitian_solve.cuh"
 DEPS[stft_cov_fused]="common.cuh compat.cuh stft_tile.cuh fft16.cuh async_copy.cuh tmem.cuh stft_cov_args.cuh"
 DEPS[stft_cov_ws]="common.cuh compat.cuh stft_tile.cuh fft16.cuh async_copy.cuh tmem.cuh stft_cov_args.cuh"
 DEPS[apply_istft_fused]="common.cuh compat.cuh stft_tile.cuh fft16.cuh async_copy.cuh tmem.cuh apply_istft_args.cuh"
-DEPS[apply_istft_ws]="common.cuh compat.cuh stft_tile.cuh fft16.cuh async_copy.cuh tmem.cuh apply_istft_args.cuh"
 DEPS[stft_spill]="common.cuh compat.cuh stft_tile.cuh fft16.cuh async_copy.cuh tmem.cuh cov_spill_args.cuh"
 DEPS[cov_mma]="common.cuh compat.cuh async_copy.cuh cov_spill_args.cuh mma_tf32.cuh"
 DEPS[cgmm]="common.cuh compat.cuh hermitian_solve.cuh jacobi_coop.cuh"
 DEPS[wpe]="common.cuh compat.cuh hermitian_solve.cuh"
 DEPS[spatial]="common.cuh compat.cuh"
+DEPS[cm_mask]="common.cuh compat.cuh"
 pids=()
-for f in api generic weights weights_coop weights_post stft_cov_fused stft_cov_ws apply_istft_fused apply_istft_ws stft_spill cov_mma cgmm wpe spatial; do
+for f in api generic weights weights_coop weights_post stft_cov_fused stft_cov_ws apply_istft_fused stft_spill cov_mma cgmm wpe spatial cm_mask; do
   stale=0
   [ -f "$OBJ/$f.o" ] || stale=1
   for d in "$f.cu" ${DEPS[$f]} ../../include/setk_b200.h build.sh; do
@@ -40,5 +40,5 @@ done
 rc=0
 for p in "${pids[@]}"; do wait $p || rc=1; done
 if [ $rc -ne 0 ]; then cat "$OBJ"/*.log | grep -v "^ptxas info" | head -100; exit 1; fi
-$NVCC -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT" "$OBJ"/api.o "$OBJ"/generic.o "$OBJ"/weights.o "$OBJ"/weights_coop.o "$OBJ"/weights_post.o "$OBJ"/stft_cov_fused.o "$OBJ"/stft_cov_ws.o "$OBJ"/apply_istft_fused.o "$OBJ"/apply_istft_ws.o "$OBJ"/stft_spill.o "$OBJ"/cov_mma.o "$OBJ"/cgmm.o "$OBJ"/wpe.o "$OBJ"/spatial.o
+$NVCC -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT" "$OBJ"/api.o "$OBJ"/generic.o "$OBJ"/weights.o "$OBJ"/weights_coop.o "$OBJ"/weights_post.o "$OBJ"/stft_cov_fused.o "$OBJ"/stft_cov_ws.o "$OBJ"/apply_istft_fused.o "$OBJ"/stft_spill.o "$OBJ"/cov_mma.o "$OBJ"/cgmm.o "$OBJ"/wpe.o "$OBJ"/spatial.o "$OBJ"/cm_mask.o
 echo "built $OUT"

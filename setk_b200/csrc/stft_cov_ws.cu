@@ -735,9 +735,11 @@ cudaError_t run_stft_cov_ws(setk_plan* pl, const float* audio, const int* n_samp
   const char* env_au = getenv("SETK_WS_AUDIO");
   const bool direct = !pw && env_au && strcmp(env_au, "direct") == 0;
   if (pl->geo.C != 4) return cudaErrorInvalidValue;
-  // SETK_WS_CONST=tmem: the FFT warps' window / twiddle constants from tensor memory
+  // The FFT warps' window / twiddle constants come from tensor memory (tmem.cuh; measured 0.426 ->
+  // 0.386 ms at config 2: a quarter of the kernel's shared-memory wavefronts gone);
+  // SETK_WS_CONST=smem (measurement knob, read per call) selects the shared-memory tables.
   const char* env_tc = getenv("SETK_WS_CONST");
-  const bool tmemc = !pw && env_tc && strcmp(env_tc, "tmem") == 0;
+  const bool tmemc = !pw && !(env_tc && strcmp(env_tc, "smem") == 0);
   if (tmemc) {
     if (mask_n) {
       if (direct) return run_ws_t<4, true, WS_MODE_DIRECT, true>(a, B, n_ctas, Rs, Rn, maxabs, stream);

@@ -294,10 +294,13 @@ __global__ void __launch_bounds__(WCfg<C>::THREADS) weights_coop_kernel(WeightsA
 
 bool weights_coop_supported(const WeightsArgs& a, int C) {
   if (C <= 4) {
-    // register-resident one-thread solve by default; SETK_W_IMPL=coop (measurement knob, read per
-    // call) puts C = 4 on the thread-group kernels as well (4 threads per bin)
+    // C = 4: four threads per bin for the eigenvector kinds (MVDR 0.167 -> 0.137 ms per 65 792 bins on
+    // B200: the one-thread solve is a single long fp64 dependency chain per bin with 19 % of the warp
+    // slots filled); the Cholesky kinds and C < 4 keep the register-resident one-thread solve.
+    // SETK_W_IMPL=thread / coop (measurement knob, read per call) forces either.
     const char* env = getenv("SETK_W_IMPL");
-    if (C != 4 || !env || strcmp(env, "coop") != 0) return false;
+    if (C != 4 || (env && strcmp(env, "thread") == 0)) return false;
+    if (!coop_two_matrices(a) && !(env && strcmp(env, "coop") == 0)) return false;
   }
   if (a.rank1 != SETK_RANK1_NONE) return false;
   return a.kind == SETK_BF_MVDR || a.kind == SETK_BF_MPDR || a.kind == SETK_BF_GEVD ||

@@ -138,15 +138,25 @@ class HostBatchStreamer(object):
                utils.py:80-92, happens on the device)
     pcm16_out: the result is int16 PCM (what WaveWriter writes: floor(y * 32768),
                utils.py:45-62), 2 bytes per sample over the link instead of 4
+    cm_masks:  the host masks are Kaldi "CM" compressed matrices, one per utterance in a uint8
+               [batch][cm_slot_bytes(T, F)] array exactly as they lie in the archive behind the "CM "
+               token (1 byte per TF cell over the link instead of 4); kaldi_io.py:248-281's
+               uncompress() happens on the device (setk_cm_masks), bit-identical
     A batch may be ragged (`n_samples`, host int32) and shorter than the lane (`count`).
     """
 
+    @staticmethod
+    def cm_slot_bytes(T, F):
+        """Bytes reserved per compressed mask: global header + column headers + T x F codes, rounded to 16."""
+        return (16 + F * (8 + T) + 15) & ~15
+
     def __init__(self, make_pipeline, batch, num_channels, num_samples, slots=2, pcm16=False,
-                 pcm16_out=False, device=None, run_kwargs=None):
+                 pcm16_out=False, device=None, run_kwargs=None, cm_masks=False):
         self.device = torch.device(device if device is not None else "cuda")
         self.slots = []
         self.pcm16 = bool(pcm16)
         self.pcm16_out = bool(pcm16_out)
+        self.cm_masks = bool(cm_masks)
         self.run_kwargs = dict(run_kwargs or {})
         for _ in range(slots):
             pipe = make_pipeline()
@@ -159,6 +169,9 @@ class HostBatchStreamer(object):
                                      device=self.device),
                 "mask": torch.empty((batch, T, F), dtype=torch.float32, device=self.device),
                 "mask_n": None,
+                "cm": (torch.empty((batch, self.cm_slot_bytes(T, F)), dtype=torch.uint8, device=self.device)
+                       if cm_masks else None),
+                "cm_status": None,
                 "n_samples": torch.empty((batch,), dtype=torch.int32, device=self.device),
                 "status": None,
                 "done": torch.cuda.Event(),
@@ -181,7 +194,13 @@ class HostBatchStreamer(object):
                 lane["stream"].wait_event(after)
             audio, mask = lane["audio"][:B], lane["mask"][:B]
             audio.copy_(h_audio[:B], non_blocking=True)
-            mask.copy_(h_mask[:B], non_blocking=True)
+            if self.cm_masks:
+                from .plan import cm_masks
+                cm = lane["cm"][:B]
+                cm.copy_(h_mask[:B], non_blocking=True)
+                _, lane["cm_status"] = cm_masks(cm, mask.shape[1], mask.shape[2], out=mask)
+            else:
+                mask.copy_(h_mask[:B], non_blocking=True)
             mask_n = None
             if h_mask_n is not None:
                 if lane["mask_n"] is None:

@@ -270,6 +270,37 @@ def _read_compressed_matrix(fd, token):
     return min_val + seq.reshape(num_rows, num_cols) * inc
 
 
+def compress_kaldi_cm(mat):
+    """
+    float32 matrix [rows][cols] -> the bytes of a Kaldi CompressedMatrix of format "CM" as they
+    follow the "CM " token in an archive (global header, per-column percentile headers, one byte
+    per element, column major) -- what Kaldi's copy-feats --compress=true writes and what
+    _read_compressed_matrix / setk_cm_masks expand.  The percentiles of a column are its minimum,
+    quartiles and maximum (kept strictly increasing as 16-bit codes, like Kaldi does); an element
+    becomes the nearest code of its segment.
+    """
+    mat = np.ascontiguousarray(mat, dtype=np.float32)
+    rows, cols = mat.shape
+    min_val = float(mat.min()) if mat.size else 0.0
+    prange = float(mat.max()) - min_val if mat.size else 1.0
+    if not prange > 0.0:
+        prange = 1.0
+    q = np.quantile(mat, [0.0, 0.25, 0.75, 1.0], axis=0) if rows else np.zeros((4, cols))
+    code = np.clip(np.rint((q - min_val) / prange * 65535.0), 0, 65535).astype(np.int64)
+    code[0] = np.minimum(code[0], 65532)
+    for i in (1, 2, 3):
+        code[i] = np.clip(np.maximum(code[i], code[i - 1] + 1), 0, 65532 + i)
+    pch = code.astype(np.float32) * np.float32(prange) / np.float32(65535.0) + np.float32(min_val)
+    p0, p1, p2, p3 = (pch[i][None, :] for i in range(4))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        lo = np.clip(np.rint((mat - p0) / (p1 - p0) * 64.0), 0, 64)
+        mid = np.clip(64 + np.rint((mat - p1) / (p2 - p1) * 128.0), 64, 192)
+        hi = np.clip(192 + np.rint((mat - p2) / (p3 - p2) * 63.0), 192, 255)
+    u8 = np.where(mat < p1, lo, np.where(mat < p2, mid, hi)).astype(np.uint8)
+    return (struct.pack("<ffii", min_val, prange, rows, cols) + code.T.astype("<u2").tobytes() +
+            np.ascontiguousarray(u8.T).tobytes())
+
+
 def read_kaldi_matrix(fd):
     """
     One uncompressed Kaldi float/double matrix or vector from a binary stream

@@ -434,6 +434,25 @@ def pcm16_to_float(pcm):
     return wave
 
 
+def cm_masks(blobs, T, F, out=None):
+    """
+    Kaldi "CM" compressed matrices -> float32 masks [B][T][F] on the device (kaldi_io.py:248-281).
+    blobs: uint8 [B][slot_bytes] device tensor, one matrix per slot as it lies in the archive behind
+    the "CM " token (slot_bytes a multiple of 16).  Returns (masks, status int32 [B]).
+    """
+    if blobs.dtype != torch.uint8 or blobs.dim() != 2:
+        raise ValueError("cm_masks: blobs must be uint8 [B][slot_bytes]")
+    blobs = blobs.contiguous()
+    B = blobs.shape[0]
+    if out is None:
+        out = torch.empty((B, T, F), dtype=torch.float32, device=blobs.device)
+    status = torch.zeros((B,), dtype=torch.int32, device=blobs.device)
+    with _ctx(blobs.device):
+        _lib.check(_lib.library().setk_cm_masks(_lib.ptr(blobs), blobs.shape[1], B, T, F, _lib.ptr(out),
+                                                _lib.ptr(status), _lib.current_stream(blobs.device)))
+    return out, status
+
+
 # ---------------------------------------------------------------------------
 # spatial features on explicit STFTs (libs/spatial.py of the reference; csrc/spatial.cu)
 # ---------------------------------------------------------------------------

@@ -9,7 +9,7 @@ OUT="$HERE/libsetk_b200_emu.so"
 OBJ="$HERE/obj"
 mkdir -p "$OBJ"
 pids=()
-for f in api generic weights weights_coop weights_post stft_cov_fused stft_cov_ws apply_istft_fused apply_istft_ws stft_spill cov_mma cgmm wpe spatial; do
+for f in api generic weights weights_coop weights_post stft_cov_fused stft_cov_ws apply_istft_fused stft_spill cov_mma cgmm wpe spatial cm_mask; do
   g++ -O2 -std=c++17 -DSETK_EMU -DSETK_TABLE_CHUNK=8 -fPIC -pthread -I"$HERE" -I"$ROOT/include" -x c++ -c "$SRC/$f.cu" -o "$OBJ/$f.o" &
   pids+=($!)
 done

@@ -354,6 +354,43 @@ def check_pcm(device, rng):
         assert np.array_equal(q, so.pcm16_from_float(y))
 
 
+def pack_cm_blobs(mats, T, F):
+    """Kaldi "CM" bytes of every matrix in a uint8 [B][slot] array (slot = a multiple of 16)."""
+    from setk_b200.libs.data_handler import compress_kaldi_cm
+    slot = (16 + F * (8 + T) + 15) & ~15
+    blobs = np.zeros((len(mats), slot), dtype=np.uint8)
+    for b, m in enumerate(mats):
+        raw = np.frombuffer(compress_kaldi_cm(m), dtype=np.uint8)
+        blobs[b, :raw.size] = raw
+    return blobs
+
+
+def check_cm_masks(device, rng, B=3, T=70, F=257):
+    """Kaldi CompressedMatrix masks expanded on the device == the archive reader (which the CPU tier
+    pins to the reference's own kaldi_io.uncompress): bit-exact, ragged rows zero-filled, a bad
+    header flagged and decoded to zeros."""
+    import io
+    from setk_b200.libs.data_handler import read_kaldi_matrix
+    rows = [T] + [int(rng.integers(1, T)) for _ in range(B - 1)]
+    mats = [rng.random((r, F)).astype(np.float32) ** 2 for r in rows]
+    mats[-1][:, 3] = 0.25                                 # a constant column: degenerate percentiles
+    blobs = pack_cm_blobs(mats, T, F)
+    blobs[0, 16 + 8 * F:16 + 8 * F + 4] = (64, 65, 192, 193)    # the segments' edges
+    expect = np.zeros((B, T, F), dtype=np.float32)
+    for b in range(B):
+        size = 16 + F * (8 + rows[b])
+        expect[b, :rows[b]] = read_kaldi_matrix(io.BytesIO(b"\0BCM " + blobs[b, :size].tobytes()))
+    out, st = P.cm_masks(torch.from_numpy(blobs).to(device), T, F)
+    assert not st.cpu().numpy().any()
+    assert np.array_equal(out.cpu().numpy(), expect)
+    bad = blobs.copy()
+    bad[1, 8:12] = np.frombuffer(np.int32(T + 1).tobytes(), dtype=np.uint8)     # rows > T
+    out, st = P.cm_masks(torch.from_numpy(bad).to(device), T, F)
+    assert list(st.cpu().numpy()) == [0, 1] + [0] * (B - 2)
+    o = out.cpu().numpy()
+    assert not o[1].any() and np.array_equal(o[0], expect[0])
+
+
 def check_config_fixture(device, name, tol=TOL_E2E, stft_from_oracle=False):
     """
     tests/golden/ref_configs.npz (oracle/make_golden.py): BASELINE.json configs 3 and 4

@@ -85,10 +85,14 @@ def test_stft_cov_ws_direct_loads(emu, monkeypatch):
     pc.check_stft_cov(emu, np.random.default_rng(8), 8, 4, 3000, n_samples=ns)
 
 
-def test_stft_cov_ws_tmem_constants(emu, monkeypatch):
-    # opt-in: the FFT warps' window / twiddle constants parked in tensor memory (tcgen05.st / ld model:
-    # allocation, lane quadrants, dealloc before exit), alone and with direct audio loads
-    monkeypatch.setenv("SETK_WS_CONST", "tmem")
+def test_stft_cov_ws_constants_tmem_and_smem(emu, monkeypatch):
+    # default: the FFT warps' window / twiddle constants parked in tensor memory (tcgen05.st / ld model:
+    # allocation, lane quadrants, dealloc before exit), alone and with direct audio loads;
+    # SETK_WS_CONST=smem: the shared-memory tables (the build measured before)
+    monkeypatch.setenv("SETK_WS_CONST", "smem")
+    pc.check_stft_cov(emu, np.random.default_rng(13), 3, 4, 6000, clip=True)
+    pc.check_stft_cov(emu, np.random.default_rng(13), 2, 4, 5000, 512, 128, False, "hamming", with_mask_n=True)
+    monkeypatch.delenv("SETK_WS_CONST")
     pc.check_stft_cov(emu, np.random.default_rng(13), 3, 4, 6000, clip=True)
     pc.check_stft_cov(emu, np.random.default_rng(13), 2, 4, 5000, 512, 128, False, "hamming", with_mask_n=True)
     ns = torch.tensor([3000, 200, 1701, 513, 2999, 256, 257, 1024], dtype=torch.int32)
@@ -265,9 +269,13 @@ def test_weights_all_kinds(emu, C):
 
 
 def test_weights_c4_thread_groups(emu, monkeypatch):
-    monkeypatch.setenv("SETK_W_IMPL", "coop")         # opt-in: 4 threads per 4 x 4 problem
+    # C = 4 default: eigenvector kinds on 4 threads per problem, Cholesky kinds one thread per problem
+    monkeypatch.setenv("SETK_W_IMPL", "coop")         # every supported kind on thread groups
     pc.check_weights(emu, np.random.default_rng(14), 2, 7, 4)
-    pc.check_weights_status(emu)
+    pc.check_weights_status(emu, C=4)
+    monkeypatch.setenv("SETK_W_IMPL", "thread")       # every kind on the one-thread kernels
+    pc.check_weights(emu, np.random.default_rng(14), 2, 7, 4)
+    pc.check_weights_status(emu, C=4)
 
 
 def test_weights_c64_and_status(emu):
@@ -294,19 +302,6 @@ def test_apply_istft_tmem_constants(emu, monkeypatch):
     ns = torch.tensor([9000, 700, 5120], dtype=torch.int32)
     pc.check_apply_istft(emu, rng, 3, 4, 9000, n_samples=ns)
     pc.check_apply_istft(emu, rng, 1, 8, 3000)        # two channel blocks, the second accumulates
-
-
-def test_apply_istft_ws_protocol(emu, monkeypatch):
-    monkeypatch.setenv("SETK_AI_IMPL", "ws")          # opt-in build (read once per process)
-    # the warp-specialised build (apply_istft_ws.cu): long runs (several fills of the 8-entry
-    # tile table of the CPU build, halo tiles), many short utterances (several segments per CTA),
-    # ragged lengths, post-mask, no centre padding
-    rng = np.random.default_rng(33)
-    pc.check_apply_istft(emu, rng, 1, 4, 30000)
-    pc.check_apply_istft(emu, rng, 13, 4, 1500, post_mask=True)
-    ns = torch.tensor([9000, 700, 5120, 200, 8999, 4097], dtype=torch.int32)
-    pc.check_apply_istft(emu, rng, 6, 4, 9000, n_samples=ns)
-    pc.check_apply_istft(emu, rng, 3, 4, 9000, 512, 256, False, "hamming", n_samples=ns[:3], norm=False)
 
 
 def test_apply_istft_nsamps_and_ragged(emu):
@@ -349,3 +344,8 @@ def test_argument_errors(emu):
 
 def test_pcm_conversions(emu):
     pc.check_pcm(emu, np.random.default_rng(40))
+
+
+def test_cm_masks(emu):
+    pc.check_cm_masks(emu, np.random.default_rng(41))
+    pc.check_cm_masks(emu, np.random.default_rng(42), B=2, T=33, F=40)

@@ -220,3 +220,46 @@ def test_pmwf_two_streams_do_not_share_scratch(cuda):
         for i in range(2):
             assert torch.equal(outs[i][0], ref[i][0]) and torch.equal(outs[i][2], ref[i][2])
 
+
+
+def test_streamer_compressed_masks(cuda):
+    """HostBatchStreamer(cm_masks=True): PCM-16 samples + Kaldi CompressedMatrix masks from pinned host
+    buffers.  The device expansion is bit-identical to the archive reader, so the output equals the
+    same streamer fed the expanded float32 masks bit for bit, and the oracle run on the expanded masks
+    (what the reference computes from such an archive) within the end-to-end tolerance."""
+    import io
+    from setk_b200 import synth
+    from setk_b200 import plan as P
+    from setk_b200.engine import BeamformPipeline, HostBatchStreamer
+    from setk_b200.libs.data_handler import read_kaldi_matrix
+    B, C, N = 3, 4, 24000
+    x, m = synth.make_batch(B, C, N, device=cuda, first=700)
+    pcm = P.float_to_pcm16(x)
+    T, F = m.shape[1], m.shape[2]
+    blobs = pc.pack_cm_blobs(list(m.cpu().numpy()), T, F)
+    assert blobs.shape[1] == HostBatchStreamer.cm_slot_bytes(T, F)
+    m_dec = np.stack([read_kaldi_matrix(io.BytesIO(b"\0BCM " + blobs[b, :16 + F * (8 + T)].tobytes()))
+                      for b in range(B)])
+    h_pcm = pcm.cpu().pin_memory()
+    h_cm = torch.from_numpy(blobs).pin_memory()
+    h_m = torch.from_numpy(m_dec).pin_memory()
+
+    def mk():
+        return BeamformPipeline(C, "mvdr", max_batch=B, max_samples=N, device=cuda)
+
+    n_out = mk().run(x, m)[0].shape[1]
+    outs = []
+    for cm, hm in ((True, h_cm), (False, h_m)):
+        st = HostBatchStreamer(mk, B, C, N, slots=2, pcm16=True, pcm16_out=True, device=cuda, cm_masks=cm)
+        h_out = torch.empty((B, n_out), dtype=torch.int16).pin_memory()
+        lane = st.submit(h_pcm, hm, h_out)
+        st.synchronize()
+        assert int(lane["status"].abs().sum()) == 0
+        if cm:
+            assert int(lane["cm_status"].abs().sum()) == 0
+        outs.append(h_out.clone())
+    assert torch.equal(outs[0], outs[1])
+    # against the oracle on the expanded masks (the reference's view of the archive)
+    xf = (pcm.cpu().numpy().astype(np.float32) / 32768.0)
+    err = pc.mvdr_end_to_end(cuda, xf, m_dec, kind="mvdr")
+    assert err <= pc.TOL_E2E, err

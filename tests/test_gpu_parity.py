@@ -126,19 +126,16 @@ def test_apply_istft_nsamps_and_ragged(cuda):
 
 
 def test_opt_in_builds(cuda, monkeypatch):
-    """Builds kept behind environment knobs stay correct: the warp-specialised apply+iSTFT, the
-    classic fused STFT+covariance, the pair-window path of the ws kernel, CUDA-core covariance."""
+    """Builds kept behind environment knobs stay correct: tensor-memory constants in apply+iSTFT, the
+    classic fused STFT+covariance, the pair-window / shared-memory-table / direct-load paths of the ws
+    kernel, CUDA-core covariance, both weight-solve layouts at C = 4."""
     rng = np.random.default_rng(41)
     ns = torch.tensor([30000, 19000, 9000], dtype=torch.int32)
-    monkeypatch.setenv("SETK_AI_IMPL", "ws")
-    pc.check_apply_istft(cuda, rng, 3, 4, 30000, n_samples=ns)
-    pc.check_apply_istft(cuda, rng, 2, 4, 48000, post_mask=True)
-    monkeypatch.delenv("SETK_AI_IMPL")
     monkeypatch.setenv("SETK_AI_CONST", "tmem")
     pc.check_apply_istft(cuda, rng, 3, 4, 30000, n_samples=ns)
     pc.check_apply_istft(cuda, rng, 2, 8, 48000, post_mask=True)
     monkeypatch.delenv("SETK_AI_CONST")
-    for knob, val in (("SETK_SC_IMPL", "classic"), ("SETK_WS_PAIRWIN", "1"), ("SETK_WS_CONST", "tmem"),
+    for knob, val in (("SETK_SC_IMPL", "classic"), ("SETK_WS_PAIRWIN", "1"), ("SETK_WS_CONST", "smem"),
                       ("SETK_WS_AUDIO", "direct")):
         monkeypatch.setenv(knob, val)
         pc.check_stft_cov(cuda, rng, 3, 4, 30000, n_samples=ns)
@@ -146,9 +143,10 @@ def test_opt_in_builds(cuda, monkeypatch):
     monkeypatch.setenv("SETK_COV_IMPL", "cuda")
     pc.check_stft_cov(cuda, rng, 2, 8, 20000)
     monkeypatch.delenv("SETK_COV_IMPL")
-    monkeypatch.setenv("SETK_W_IMPL", "coop")
-    pc.check_weights(cuda, rng, 3, 257, 4)
-    monkeypatch.delenv("SETK_W_IMPL")
+    for impl in ("coop", "thread"):
+        monkeypatch.setenv("SETK_W_IMPL", impl)
+        pc.check_weights(cuda, rng, 3, 257, 4)
+        monkeypatch.delenv("SETK_W_IMPL")
 
 
 def test_wpe_tensor_core_correlation(cuda, monkeypatch):
@@ -295,6 +293,12 @@ def test_golden_doc_vectors_gevd_sign_fit(cuda):
 
 def test_pcm_conversions(cuda):
     pc.check_pcm(cuda, np.random.default_rng(40))
+
+
+def test_cm_masks(cuda):
+    """Kaldi compressed-matrix masks expanded on the device (kaldi_io.py:248-281): bit-exact."""
+    pc.check_cm_masks(cuda, np.random.default_rng(41))
+    pc.check_cm_masks(cuda, np.random.default_rng(42), B=5, T=626, F=257)
 
 
 @pytest.mark.parametrize("name", ["cfg3", "cfg4"])
