@@ -192,7 +192,7 @@ def reference_arm(args):
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "timed_s": r["seconds"], "wall_s": time.time() - t0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------- NUMA binding ---
@@ -381,8 +381,8 @@ def gpu_arm(args):
             for r in range(world):
                 assert int(got[r].to(torch.int64).sum()) == int(sums[r]), f"gather: rank {r}'s batch differs"
         gbytes = (world - 1) * wave.numel() * 2
-        how = ("device-to-peer copies into a ring of 3 on rank 0 (CUDA IPC mapping, copy engines over "
-               "NVLink, side stream; no collective kernel)" if ring is not None else
+        how = (f"device-to-peer copies into a ring of 3 on rank 0 ({ring.mode} mapping of rank 0's buffer, "
+               "copy engines over NVLink, side stream; no collective kernel)" if ring is not None else
                "dist.gather on NCCL's stream, ring of 3")
         gather = {"payload": "int16 PCM, every batch of every rank -> rank 0", "how": how,
                   "bytes_into_rank0_per_step": gbytes, "gather_ms_alone": g_ms,
@@ -523,7 +523,7 @@ def gpu_arm(args):
         }
         if sampler:
             sampler.stop()
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -618,6 +618,15 @@ def other_configs(dev, world, rank, barrier, max_over_ranks, peak):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -634,6 +643,12 @@ def main():
     ap.add_argument("--gather", choices=["peer", "nccl"], default="peer",
                     help="N > 1: how every batch's result reaches rank 0")
     args = ap.parse_args()
+    # stdout carries ONE JSON line: everything else any library writes to file descriptor 1 (NCCL's
+    # version banner comes from C) goes to stderr; emit() writes the line to the real stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         reference_arm(args)
     else:

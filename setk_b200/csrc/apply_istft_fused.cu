@@ -342,8 +342,9 @@ __global__ void __maxnreg__(96) apply_istft_kernel(ApplyIstftArgs a) {
           for (int c = 0; c < C; ++c) {
             const float2* z = sm.z + (j * C + c) * SETK_ZSLOT;
             float2 xk, xm;
+            // (k = 0: zk = zn = Z[0] and tw = (-0, -1) give X[0], X[256] with imaginary parts that are
+            // exact zeros for finite data -- no special case, as in the covariance kernels)
             split_pair(z[k & (kM - 1)], z[km & (kM - 1)], tw, xk, xm);
-            if (k == 0) { xk.y = 0.f; xm.y = 0.f; }
             yk = cmad_conjw(wk[c], xk, yk);                    // += conj(w) x: two packed instructions
             ym = cmad_conjw(wm[c], xm, ym);
           }

@@ -6,6 +6,8 @@ list sharded by rank, no collective on the data path, results collected on rank 
 there every job writes its own files; here rank 0 can collect the enhanced audio
 over NCCL (NVLink 5 / NVSwitch) instead.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -89,8 +91,7 @@ class PeerResultRing:
     checks the last batch).
     """
 
-    def __init__(self, shape, dtype, device, slots=3, dst=0, group=None):
-        from torch.multiprocessing.reductions import reduce_tensor
+    def __init__(self, shape, dtype, device, slots=3, dst=0, group=None, mode=None):
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
@@ -98,37 +99,88 @@ class PeerResultRing:
         self.slots = slots
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(self.device)
-        self._owned = None
-        payload = [None]
-        if self.rank == dst:
-            self._owned = torch.zeros((slots, self.world) + tuple(shape), dtype=dtype, device=self.device)
+        self._owned = self._hdl = None
+        full = (slots, self.world) + tuple(shape)
+        mode = mode or os.environ.get("SETK_PEER_RING", "symm")
+        if mode == "symm":
+            # torch symmetric memory: every rank allocates the ring with the driver's virtual-memory
+            # API and maps its peers' copies (POSIX handles over the group's store) -- real NVLink
+            # peer mappings.  Only dst's copy is ever written.
+            import torch.distributed._symmetric_memory as symm
+            self._owned = symm.empty(full, dtype=dtype, device=self.device)
+            self._owned.zero_()
             torch.cuda.synchronize(self.device)
-            payload = [reduce_tensor(self._owned)]
-        dist.broadcast_object_list(payload, src=dst, group=group)
-        if self.rank == dst:
-            self.ring = self._owned
+            self._hdl = symm.rendezvous(self._owned, group if group is not None else dist.group.WORLD)
+            self.ring = self._owned if self.rank == dst else self._hdl.get_buffer(dst, full, dtype)
         else:
-            rebuild, rebuild_args = payload[0]
-            self.ring = rebuild(*rebuild_args)          # a tensor on dst's GPU, mapped in this process
+            # legacy CUDA IPC handle of a caching-allocator block (measured 35 GB/s between two B200s
+            # of an NVSwitch box: the mapping does not ride NVLink there; kept as a functional fallback)
+            from torch.multiprocessing.reductions import reduce_tensor
+            payload = [None]
+            if self.rank == dst:
+                self._owned = torch.zeros(full, dtype=dtype, device=self.device)
+                torch.cuda.synchronize(self.device)
+                payload = [reduce_tensor(self._owned)]
+            dist.broadcast_object_list(payload, src=dst, group=group)
+            if self.rank == dst:
+                self.ring = self._owned
+            else:
+                rebuild, rebuild_args = payload[0]
+                self.ring = rebuild(*rebuild_args)      # a tensor on dst's GPU, mapped in this process
+        self.mode = mode
         self.mine = [self.ring[s, self.rank] for s in range(slots)]
 
     @classmethod
-    def create(cls, shape, dtype, device, slots=3, dst=0, group=None):
-        """The ring, or None on every rank when any rank cannot map the peer allocation."""
-        ring, ok = None, 1
-        try:
-            ring = cls(shape, dtype, device, slots, dst, group)
-            ring.push(torch.zeros(tuple(shape), dtype=dtype, device=device), 0)
+    def create(cls, shape, dtype, device, slots=3, dst=0, group=None, min_gbps=100.0):
+        """
+        The ring, or None on EVERY rank when any rank cannot map the peer allocation or its copies
+        run below `min_gbps` (a mapping that does not ride NVLink is worse than the collective).
+        Tries the symmetric-memory mapping, then the legacy IPC handle.
+        """
+        world = dist.get_world_size(group)
+
+        def agree(ok):                       # the same decision on every rank
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            return int(flag.item()) == 1
+
+        for mode in ("symm", "ipc"):
+            ring = None
+            try:
+                ring = cls(shape, dtype, device, slots, dst, group, mode=mode)
+                probe = torch.zeros(tuple(shape), dtype=dtype, device=device)
+                ring.push(probe, 0)
+                ring.drain()
+                torch.cuda.synchronize(device)
+                ok = True
+            except Exception as err:     # noqa: BLE001 -- any failure means "try the next transport"
+                ok = False
+                cls.last_error = f"{mode}: {err!r}"
+            if not agree(ok):
+                ring = None
+                continue
+            # every rank holds a working mapping: time three deliveries
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier(group)
+            e0.record()
+            for i in range(3):
+                ring.push(probe, i)
             ring.drain()
+            e1.record()
             torch.cuda.synchronize(device)
-        except Exception as err:     # noqa: BLE001 -- any failure means "use the collective instead"
-            ring, ok = None, 0
-            cls.last_error = repr(err)
-        flag = torch.tensor([ok], dtype=torch.int32, device=device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-        return ring if int(flag.item()) == 1 else None
+            nbytes = probe.numel() * probe.element_size()
+            gbps = 3 * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+            cls.last_gbps = gbps
+            fast = ring.rank == dst or world == 1 or nbytes < (1 << 24) or gbps >= min_gbps
+            if not fast:
+                cls.last_error = f"{mode}: peer copies run at {gbps:.0f} GB/s (< {min_gbps:.0f})"
+            if agree(fast):
+                return ring
+            ring = None
+        return None
 
     last_error = None
+    last_gbps = None
 
     def push(self, result, step):
         """Deliver this rank's `result` into slot `step % slots` (asynchronous, ordered after the

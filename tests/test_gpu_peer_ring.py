@@ -1,7 +1,7 @@
 """
 PeerResultRing (setk_b200/distributed.py): results reach rank 0 by device-to-peer copies through a
-CUDA IPC mapping, no collective kernel.  Two processes on the same GPU exercise the mapping, the
-side-stream ordering and the slot arithmetic; `bench.py --gpus N` checks the same thing across
+mapping of rank 0's buffer (torch symmetric memory; legacy CUDA IPC as the fallback), no collective
+kernel.  Two processes exercise the mappings, the side-stream ordering and the slot arithmetic; `bench.py --gpus N` checks the same thing across
 GPUs (checksums of every rank's last batch).
 """
 import os
