@@ -316,45 +316,56 @@ __global__ void __maxnreg__(SETK_SC_REGS) stft_cov_kernel(StftCovArgs a) {
 }
 
 // Deterministic reduction over the segments of an utterance + normalisation + Hermitian fill.
-// One thread per (b, f).
+// One thread per (matrix, b, f) -- Rs and Rn of a bin are reduced by different threads (half the
+// dependent loads per thread, twice the threads in flight); a thread writes its C x C matrix as
+// 16-byte stores (rows of the row-major matrix are contiguous).
 template <int C>
 __global__ void cov_finalize_kernel(const float* __restrict__ partials, int B, int F, TileSched sched,
                                     int n_ctas, int slots, float scale, float2* __restrict__ Rs,
                                     float2* __restrict__ Rn) {
   constexpr int NACC = CovAcc<C>::NACC;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)B * F) return;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)B * F;
+  if (gid >= 2 * n) return;
+  const int which = gid >= n ? 1 : 0;
+  const long long idx = gid - which * n;
   const int b = (int)(idx / F), f = (int)(idx % F);
   // the CTAs of the main kernel that held tiles of utterance b wrote slots 0..n_used-1
   const int q = sched_quota(sched, n_ctas);
   const int pb = sched_prefix(sched, b), pe = sched_prefix(sched, b + 1);
   const int n_used = (pe - 1) / q - pb / q + 1;
-  float acc[2 * NACC + 2];
+  float acc[NACC + 1];                                   // this matrix's sums, then its mask sum
 #pragma unroll
-  for (int i = 0; i < 2 * NACC + 2; ++i) acc[i] = 0.f;
+  for (int i = 0; i <= NACC; ++i) acc[i] = 0.f;
   for (int ch = 0; ch < n_used; ++ch) {
     const float* pp = partials + (((long long)b * slots + ch) * (2 * NACC + 2)) * F + f;
 #pragma unroll
-    for (int i = 0; i < 2 * NACC + 2; ++i) acc[i] += pp[(long long)i * F];
+    for (int i = 0; i < NACC; ++i) acc[i] += pp[(long long)(which * NACC + i) * F];
+    acc[NACC] += pp[(long long)(2 * NACC + which) * F];
   }
+  // scale: the spectra behind the sums were scaled by 1 / sqrt(scale) (pair-sum window path)
+  const float inv = scale / fmaxf(acc[NACC], 1e-6f);
+  float2 M[C * C];
+  int o = C;
 #pragma unroll
-  for (int which = 0; which < 2; ++which) {
-    const float* A = acc + which * NACC;
-    // scale: the spectra behind the sums were scaled by 1 / sqrt(scale) (pair-sum window path)
-    const float inv = scale / fmaxf(acc[2 * NACC + which], 1e-6f);
-    float2* R = (which == 0 ? Rs : Rn) + idx * (C * C);
-    int o = C;
+  for (int i = 0; i < C; ++i) {
+    M[i * C + i] = make_float2(acc[i] * inv, 0.f);
 #pragma unroll
-    for (int i = 0; i < C; ++i) {
-      R[i * C + i] = make_float2(A[i] * inv, 0.f);
-#pragma unroll
-      for (int k = i + 1; k < C; ++k) {
-        const float re = A[o] * inv, im = A[o + 1] * inv;
-        R[i * C + k] = make_float2(re, im);
-        R[k * C + i] = make_float2(re, -im);
-        o += 2;
-      }
+    for (int k = i + 1; k < C; ++k) {
+      const float re = acc[o] * inv, im = acc[o + 1] * inv;
+      M[i * C + k] = make_float2(re, im);
+      M[k * C + i] = make_float2(re, -im);
+      o += 2;
     }
+  }
+  float2* R = (which == 0 ? Rs : Rn) + idx * (C * C);
+  if ((C * C) % 2 == 0 && (reinterpret_cast<uintptr_t>(R) & 15) == 0) {
+#pragma unroll
+    for (int e = 0; e < C * C; e += 2)
+      *reinterpret_cast<float4*>(R + e) = make_float4(M[e].x, M[e].y, M[e + 1].x, M[e + 1].y);
+  } else {
+#pragma unroll
+    for (int e = 0; e < C * C; ++e) R[e] = M[e];
   }
 }
 
@@ -364,7 +375,7 @@ template <int C>
 static cudaError_t run_cov_finalize_t(const float* partials, int B, int F, TileSched sched, int n_ctas,
                                       int slots, float scale, float2* Rs, float2* Rn, void* stream) {
   const long long n = (long long)B * F;
-  return launch(cov_finalize_kernel<C>, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, stream, true,
+  return launch(cov_finalize_kernel<C>, dim3((unsigned)((2 * n + 127) / 128)), dim3(128), 0, stream, true,
                 partials, B, F, sched, n_ctas, slots, scale, Rs, Rn);
 }
 cudaError_t run_cov_finalize(int C, const float* partials, int B, int F, TileSched sched, int n_ctas,

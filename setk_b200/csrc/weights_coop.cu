@@ -155,8 +155,16 @@ __device__ __forceinline__ void forward_subst_coop(const cd* L, cd* B, int c, bo
 SETK_HD inline bool coop_two_matrices(const WeightsArgs& a) {
   return a.kind == SETK_BF_MVDR || a.kind == SETK_BF_MPDR || (a.kind == SETK_BF_PEVD && a.Rn == nullptr);
 }
+// Pitch between the groups' matrices, in cd (16 bytes = one bank group of a 128-byte wavefront).
+// C = 4: a quarter-warp is two groups x four rows and rows sit 5 cd apart ({0, 5, 2, 7} mod 8), so
+// the second group must start 4 (mod 8) later ({4, 1, 6, 3}): conflict-free rows AND columns.
+// Otherwise an odd pitch (a group of 8 or 16 lanes fills its quarter-warps by itself).
 template <int C>
-SETK_HD inline int coop_group_pitch(bool two) { return ((two ? 2 : 3) * Coop<C>::MAT + C) | 1; }
+SETK_HD inline int coop_group_pitch(bool two) {
+  const int base = (two ? 2 : 3) * Coop<C>::MAT + C;
+  if (Coop<C>::GS == 4) return base + ((4 - base % 8) + 8) % 8;
+  return base | 1;
+}
 
 template <int C>
 __global__ void __launch_bounds__(WCfg<C>::THREADS) weights_coop_kernel(WeightsArgs a) {
@@ -164,7 +172,7 @@ __global__ void __launch_bounds__(WCfg<C>::THREADS) weights_coop_kernel(WeightsA
   constexpr int GS = K::GS, LD = K::LD, MAT = K::MAT, MPB = WCfg<C>::THREADS / GS;
   // cd per group: A, V, M, w.  The eigenvector kinds (MVDR, MPDR, PEVD of Rs) are done with A when
   // they fill M, so M lives on A: a third less shared memory = a third more problems resident.
-  // The pitch is odd: the groups of a warp start in different 16-byte bank groups.
+  // The pitch staggers the groups of a warp over the 16-byte bank groups (coop_group_pitch).
   const bool two = coop_two_matrices(a);
   const int PER = coop_group_pitch<C>(two);
   SETK_DYN_SMEM(double, sm);
