@@ -3,7 +3,7 @@
 tools/sass_histogram.py -- opcode histogram per kernel of setk_b200/libsetk_b200.so
 (`cuobjdump -sass`), the evidence of which hardware paths each kernel uses:
   HMMA = mma.sync tensor cores, UBLKCP = TMA bulk copies, SYNCS = mbarriers, LDGSTS = cp.async,
-  USETMAXREG = per-role register budgets, FFMA2/FADD2/FMUL2 = packed fp32, DFMA = fp64.
+  USETMAXREG = per-role register budgets, LDTM / STTM = tensor-memory loads / stores (tcgen05.ld / st), FFMA2/FADD2/FMUL2 = packed fp32, DFMA = fp64.
 
     python tools/sass_histogram.py [lib] > profiles/r2_sass_opcodes.txt
 """
@@ -27,7 +27,7 @@ for line in out.splitlines():
     m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
     if m and kern:
         hist[kern][m.group(1)] += 1
-KEY = ["HMMA", "UBLKCP", "SYNCS", "LDGSTS", "USETMAXREG", "FFMA2", "FADD2", "FMUL2", "FFMA", "DFMA", "DMMA",
+KEY = ["HMMA", "UBLKCP", "SYNCS", "LDGSTS", "USETMAXREG", "LDTM", "STTM", "FFMA2", "FADD2", "FMUL2", "FFMA", "DFMA", "DMMA",
        "LDS", "STS", "BAR", "STL", "LDL"]
 print(f"# opcode histogram of {os.path.relpath(lib, ROOT)} (cuobjdump -sass); static instruction counts")
 print(f"# {'kernel':70s} {'total':>7s} " + " ".join(f"{k:>7s}" for k in KEY))
