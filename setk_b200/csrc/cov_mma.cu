@@ -18,8 +18,10 @@
 //
 // Mapping: CTA = 8 warps = NB bins x one chunk of frames of one utterance; per step of 8 frames
 //   stage   8 frames x C channels x NB bins, 8-byte cp.async (zero-filled past the utterance),
-//           bin-major in shared memory (pitch 8*CP+1: conflict-free both ways), double buffered;
-//           the step's mask values (clip, 1 - m) by ordinary loads
+//           bin-major in shared memory (pitch 8*CP+1: conflict-free both ways), a ring of four
+//           steps (three in flight); the step's raw mask values by 4-byte cp.async (clip and
+//           1 - m at use) -- round 2's first build double-buffered and fetched the masks with
+//           ordinary loads: every step then waited out one DRAM latency (0.49 ms per 64 x 8 ch)
 //   mma     warp w owns bins [w*BPW, (w+1)*BPW): lane (g, q) reads channel g (and g+8) of frames
 //           q and q+4 -- exactly its A and B fragment elements -- splits them and issues
 //           12 (C <= 8) or 48 (C <= 16) HMMA per bin for both masks
@@ -39,8 +41,9 @@ struct CovMmaShape {
   static constexpr int NB = 8 * BPW;               // bins per CTA
   static constexpr int BP = 8 * CP + 1;            // float2 pitch of one bin's [8 frames][CP channels]
   static constexpr int MT = CP / 8;                // 16-row blocks of Re (and of Im) components
+  static constexpr int NS = 4;                     // cp.async ring depth: three steps in flight
   static constexpr size_t smem_bytes() {
-    return sizeof(float2) * 2 * NB * BP + sizeof(float) * 2 * 2 * 8 * NB;
+    return sizeof(float2) * NS * NB * BP + sizeof(float) * NS * 2 * 8 * NB;
   }
 };
 
@@ -48,21 +51,33 @@ struct CovMmaShape {
 __device__ inline void cp_async_8_zfill(void* dst, const void* src, bool valid) {
   if (valid) memcpy(dst, src, 8); else memset(dst, 0, 8);
 }
+__device__ inline void cp_async_4_zfill(void* dst, const void* src, bool valid) {
+  if (valid) memcpy(dst, src, 4); else memset(dst, 0, 4);
+}
+__device__ inline void cp_async_wait_group2() {}
 #else
 __device__ __forceinline__ void cp_async_8_zfill(void* dst, const void* src, bool valid) {
   const unsigned n = valid ? 8u : 0u;              // src-size 0: the 8 bytes are zero-filled
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n)
                : "memory");
 }
+__device__ __forceinline__ void cp_async_4_zfill(void* dst, const void* src, bool valid) {
+  const unsigned n = valid ? 4u : 0u;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n)
+               : "memory");
+}
+// all but the two most recently committed groups have landed
+__device__ __forceinline__ void cp_async_wait_group2() { asm volatile("cp.async.wait_group 2;" ::: "memory"); }
 #endif
 
 template <int CP>
 __global__ void __launch_bounds__(256) cov_mma_kernel(CovSpillArgs a) {
   using S = CovMmaShape<CP>;
-  constexpr int BPW = S::BPW, NB = S::NB, BP = S::BP, MT = S::MT;
+  constexpr int BPW = S::BPW, NB = S::NB, BP = S::BP, MT = S::MT, NS = S::NS;
+  static_assert(NS == 4, "the wait below leaves NS - 2 = 2 groups in flight");
   SETK_DYN_SMEM(float2, smem);
-  float2* xs = smem;                                            // [2][NB][BP]
-  float* msk = reinterpret_cast<float*>(xs + 2 * NB * BP);      // [2][2 (s, n)][8][NB]
+  float2* xs = smem;                                            // [NS][NB][BP]
+  float* msk = reinterpret_cast<float*>(xs + NS * NB * BP);     // [NS][2 (s, n)][8][NB], raw mask values
 
   const int C = a.g.C, F = a.F;
   const int nbb = (F + NB - 1) / NB;
@@ -83,27 +98,31 @@ __global__ void __launch_bounds__(256) cov_mma_kernel(CovSpillArgs a) {
   const float* msb = a.mask_s + (long long)b * a.T * F;
   const float* mnb = has_mn ? a.mask_n + (long long)b * a.T * F : nullptr;
 
+  // One step = 8 frames x CP channels x NB bins of the workspace + the step's raw mask values, all by
+  // cp.async (nothing a thread has to wait for at issue time).  A thread keeps its (bin, channel)
+  // and walks the frames: pointers advance by constants.
+  constexpr int EPT = 8 * CP * NB / 256;           // workspace elements per thread and step
+  constexpr int TSTEP = 256 / (CP * NB) > 0 ? 256 / (CP * NB) : 1;   // frames covered by one pass of the CTA
+  static_assert(EPT * TSTEP == 8 || (CP * NB >= 256 && EPT == 8), "frame walk of the staging loop");
+  const int s_bin = tid % NB, s_c = (tid / NB) % CP, s_t = tid / (NB * CP);
+  const bool s_ok = s_c < C && f0 + s_bin < F;
+  const int m_bin = tid % NB, m_t = tid / NB;                        // masks: 8 * NB <= 256 values
   auto stage = [&](int ks, int buf) {
     const int t0 = t_begin + 8 * ks;
-    float2* dst = xs + buf * NB * BP;
-    for (int e = tid; e < 8 * CP * NB; e += 256) {
-      const int bin = e % NB, c = (e / NB) % CP, tt = e / (NB * CP);
-      const bool ok = t0 + tt < t_end && c < C && f0 + bin < F;
-      const float2* src = xb + ((long long)(t0 + tt) * C + c) * pitch + bin;
-      cp_async_8_zfill(dst + bin * BP + tt * CP + c, ok ? src : a.xws, ok);
+    float2* dst = xs + buf * NB * BP + s_bin * BP + s_c;
+    const float2* src = xb + ((long long)t0 * C + s_c) * pitch + s_bin;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      const int tt = s_t + i * TSTEP;
+      const bool ok = s_ok && t0 + tt < t_end;
+      cp_async_8_zfill(dst + tt * CP, ok ? src + (long long)tt * C * pitch : a.xws, ok);
     }
-    float* md = msk + buf * 2 * 8 * NB;
-    for (int e = tid; e < 8 * NB; e += 256) {
-      const int bin = e % NB, tt = e / NB;
-      float ms = 0.f, mn = 0.f;
-      if (t0 + tt < t_end && f0 + bin < F) {
-        const long long o = (long long)(t0 + tt) * m_ts + (long long)(f0 + bin) * m_fs;
-        ms = msb[o];
-        if (clip) ms = fminf(ms, 1.0f);
-        mn = has_mn ? mnb[o] : 1.0f - ms;
-      }
-      md[tt * NB + bin] = ms;
-      md[(8 + tt) * NB + bin] = mn;
+    if (tid < 8 * NB) {
+      const bool ok = t0 + m_t < t_end && f0 + m_bin < F;
+      const long long o = (long long)(t0 + m_t) * m_ts + (long long)(f0 + m_bin) * m_fs;
+      float* md = msk + buf * 2 * 8 * NB + m_t * NB + m_bin;
+      cp_async_4_zfill(md, ok ? msb + o : a.mask_s, ok);
+      if (has_mn) cp_async_4_zfill(md + 8 * NB, ok ? mnb + o : a.mask_n, ok);
     }
   };
 
@@ -126,21 +145,30 @@ __global__ void __launch_bounds__(256) cov_mma_kernel(CovSpillArgs a) {
           for (int r = 0; r < 4; ++r) acc[i][m][mt][nt][r] = 0.f;
   }
 
-  if (nk > 0) stage(0, 0);
-  cp_async_commit();
-  for (int ks = 0; ks < nk; ++ks) {
-    cp_async_wait_all();
-    __syncthreads();                       // step ks has landed; everyone is done with step ks - 1
-    if (ks + 1 < nk) stage(ks + 1, (ks + 1) & 1);
+  // ring of NS steps: NS - 1 are in flight while one is consumed (one commit group per step, empty
+  // groups past the end keep the count uniform)
+#pragma unroll
+  for (int p = 0; p < NS - 1; ++p) {
+    if (p < nk) stage(p, p);
     cp_async_commit();
-    const float2* xt = xs + (ks & 1) * NB * BP;
-    const float* md = msk + (ks & 1) * 2 * 8 * NB;
+  }
+  for (int ks = 0; ks < nk; ++ks) {
+    cp_async_wait_group2();
+    __syncthreads();                       // step ks has landed; everyone is done with step ks - 1
+    if (ks + NS - 1 < nk) stage(ks + NS - 1, (ks + NS - 1) % NS);
+    cp_async_commit();
+    const float2* xt = xs + (ks % NS) * NB * BP;
+    const float* md = msk + (ks % NS) * 2 * 8 * NB;
+    const int live = t_end - (t_begin + 8 * ks);            // frames of this step inside the utterance
+    const bool v0 = q < live, v1 = q + 4 < live;
 #pragma unroll
     for (int i = 0; i < BPW; ++i) {
       const int bin = warp * BPW + i;
       const float2* xbin = xt + bin * BP;
-      const float s0 = md[q * NB + bin], s1 = md[(q + 4) * NB + bin];
-      const float n0 = md[(8 + q) * NB + bin], n1 = md[(12 + q) * NB + bin];
+      float s0 = md[q * NB + bin], s1 = md[(q + 4) * NB + bin];   // raw (zero past the utterance)
+      if (clip) { s0 = fminf(s0, 1.0f); s1 = fminf(s1, 1.0f); }
+      const float n0 = has_mn ? md[(8 + q) * NB + bin] : (v0 ? 1.0f - s0 : 0.f);
+      const float n1 = has_mn ? md[(12 + q) * NB + bin] : (v1 ? 1.0f - s1 : 0.f);
       if (g == 0) { sum_s[i] += s0 + s1; sum_n[i] += n0 + n1; }
       if (CP == 8) {
         const float2 x0 = xbin[q * CP + g], x1 = xbin[(q + 4) * CP + g];

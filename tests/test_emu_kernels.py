@@ -138,6 +138,9 @@ def test_many_channel_ragged_and_nocenter(emu):
     pc.check_apply_istft(emu, rng, 2, 6, 3000, n_samples=ns)
     pc.check_stft_cov(emu, rng, 1, 7, 2500, 512, 256, False, "hamming")
     pc.check_apply_istft(emu, rng, 1, 7, 2500, 512, 128, False, "hamming")
+    # longer than the covariance kernel's cp.async ring (4 steps of 8 frames): slots are re-used
+    pc.check_stft_cov(emu, rng, 1, 8, 11000, clip=True)
+    pc.check_stft_cov(emu, rng, 1, 12, 9300, with_mask_n=True)
 
 
 @pytest.mark.parametrize("C,hop,center", [(8, 256, True), (3, 512, False), (1, 128, True), (6, 340, True)])
