@@ -107,23 +107,35 @@ __global__ void __launch_bounds__(256) cov_mma_kernel(CovSpillArgs a) {
   const int s_bin = tid % NB, s_c = (tid / NB) % CP, s_t = tid / (NB * CP);
   const bool s_ok = s_c < C && f0 + s_bin < F;
   const int m_bin = tid % NB, m_t = tid / NB;                        // masks: 8 * NB <= 256 values
-  auto stage = [&](int ks, int buf) {
-    const int t0 = t_begin + 8 * ks;
-    float2* dst = xs + buf * NB * BP + s_bin * BP + s_c;
-    const float2* src = xb + ((long long)t0 * C + s_c) * pitch + s_bin;
+  // running source pointers: the steps are staged in order, so every call advances them by 8 frames
+  const long long walk = (long long)TSTEP * C * pitch;               // float2 between this thread's frames
+  const float2* src_next = xb + ((long long)(t_begin + s_t) * C + s_c) * pitch + s_bin;
+  const long long m_off = (long long)(t_begin + m_t) * m_ts + (long long)(f0 + m_bin) * m_fs;
+  const float* ms_next = msb + m_off;
+  const float* mn_next = has_mn ? mnb + m_off : nullptr;
+  const bool m_ok = tid < 8 * NB && f0 + m_bin < F;
+  float2* const dst0 = xs + s_bin * BP + s_t * CP + s_c;
+  float* const md0 = msk + m_t * NB + m_bin;
+  int t_next = t_begin;                                              // first frame of the next step
+  auto stage = [&](int buf) {
+    float2* dst = dst0 + buf * NB * BP;
+    const float2* src = src_next;
 #pragma unroll
     for (int i = 0; i < EPT; ++i) {
-      const int tt = s_t + i * TSTEP;
-      const bool ok = s_ok && t0 + tt < t_end;
-      cp_async_8_zfill(dst + tt * CP, ok ? src + (long long)tt * C * pitch : a.xws, ok);
+      const bool ok = s_ok && t_next + s_t + i * TSTEP < t_end;
+      cp_async_8_zfill(dst + i * TSTEP * CP, ok ? src : a.xws, ok);
+      src += walk;
     }
+    src_next = src;
     if (tid < 8 * NB) {
-      const bool ok = t0 + m_t < t_end && f0 + m_bin < F;
-      const long long o = (long long)(t0 + m_t) * m_ts + (long long)(f0 + m_bin) * m_fs;
-      float* md = msk + buf * 2 * 8 * NB + m_t * NB + m_bin;
-      cp_async_4_zfill(md, ok ? msb + o : a.mask_s, ok);
-      if (has_mn) cp_async_4_zfill(md + 8 * NB, ok ? mnb + o : a.mask_n, ok);
+      const bool ok = m_ok && t_next + m_t < t_end;
+      float* md = md0 + buf * 2 * 8 * NB;
+      cp_async_4_zfill(md, ok ? ms_next : a.mask_s, ok);
+      if (has_mn) cp_async_4_zfill(md + 8 * NB, ok ? mn_next : a.mask_n, ok);
     }
+    ms_next += 8 * m_ts;
+    if (has_mn) mn_next += 8 * m_ts;
+    t_next += 8;
   };
 
   // accumulators [bin of this warp][mask][m-tile: Re rows, Im rows][n-tile][4]
@@ -149,13 +161,13 @@ __global__ void __launch_bounds__(256) cov_mma_kernel(CovSpillArgs a) {
   // groups past the end keep the count uniform)
 #pragma unroll
   for (int p = 0; p < NS - 1; ++p) {
-    if (p < nk) stage(p, p);
+    if (p < nk) stage(p);
     cp_async_commit();
   }
   for (int ks = 0; ks < nk; ++ks) {
     cp_async_wait_group2();
     __syncthreads();                       // step ks has landed; everyone is done with step ks - 1
-    if (ks + NS - 1 < nk) stage(ks + NS - 1, (ks + NS - 1) % NS);
+    if (ks + NS - 1 < nk) stage((ks + NS - 1) % NS);
     cp_async_commit();
     const float2* xt = xs + (ks % NS) * NB * BP;
     const float* md = msk + (ks % NS) * 2 * 8 * NB;

@@ -22,8 +22,9 @@ __device__ inline unsigned tf32_rna(float x) {            // round to nearest, t
 __device__ inline void mma_tf32_16x8x8(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
   // every lane publishes its fragments; then each lane gathers the row / column it needs
   float mine[6], all[6 * 32];
-  for (int i = 0; i < 4; ++i) mine[i] = __uint_as_float(a[i]);
-  for (int i = 0; i < 2; ++i) mine[4 + i] = __uint_as_float(b[i]);
+  // the tensor core reads the upper 19 bits of a .tf32 operand
+  for (int i = 0; i < 4; ++i) mine[i] = __uint_as_float(a[i] & 0xffffe000u);
+  for (int i = 0; i < 2; ++i) mine[4 + i] = __uint_as_float(b[i] & 0xffffe000u);
   emu::warp_allgather(mine, 6, all);
   const int lane = emu::g_tid & 31, g = lane >> 2, q = lane & 3;
   auto A = [&](int r, int k) { return all[((r >= 8 ? 1 : 0) + (k >= 4 ? 2 : 0)) * 32 + (r & 7) * 4 + (k & 3)]; };
@@ -50,10 +51,15 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const unsigned (&
 }
 #endif
 
-// x = hi + lo in TF32
+// x = hi + lo in TF32.  hi = x with its low 13 mantissa bits cleared (one LOP3), lo = x - hi (exact,
+// one FADD) handed over as it is: the tensor core reads the upper 19 bits of a .tf32 operand, i.e.
+// truncates lo itself (|error| <= 2^-10 |lo| <= 2^-20 |x|, the size of the lo x lo term the scheme
+// drops anyway).  cvt.rna.tf32.f32 is not one instruction on sm_100a: ptxas expands it into an
+// integer add, a mask and a NaN test -- with two of them per operand, 217 M of the covariance
+// kernel's 308 M instructions were conversions (profiles/r2_cov_mma8_rna_ncu.txt).
 __device__ __forceinline__ void tf32_split(float x, unsigned& hi, unsigned& lo) {
-  hi = tf32_rna(x);
-  lo = tf32_rna(x - __uint_as_float(hi));
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
 // d += A B with both operands split: three tensor-core passes
