@@ -169,7 +169,9 @@ def test_nfft1024_ragged(emu):
 ])
 def test_cgmm_masks(emu, C, fl, K, init, alpha):
     rng = np.random.default_rng(80 + C)
-    pc.check_cgmm(emu, rng, 2, C, 4600, fl, 256, K, 3, with_init=init, update_alpha=alpha,
+    # (C = 9 on the CPU model: 256-thread CTAs of OS threads -- one utterance, two iterations)
+    B, N, iters = (1, 2800, 2) if C == 9 else (2, 4600, 3)
+    pc.check_cgmm(emu, rng, B, C, N, fl, 256, K, iters, with_init=init, update_alpha=alpha,
                   n_samples=torch.tensor([4600, 3300], dtype=torch.int32) if C == 3 else None)
 
 
@@ -195,20 +197,20 @@ def test_cgmm_argument_errors(emu):
 
 def test_wpe(emu):
     rng = np.random.default_rng(90)
-    pc.check_wpe(emu, rng, 2, 3, 3000, 256, 64, taps=4, delay=2, ctx=1, iters=2)
-    pc.check_wpe(emu, rng, 1, 2, 2500, 256, 64, taps=6, delay=1, ctx=0, iters=1)
-    pc.check_wpe(emu, rng, 1, 5, 4000, 256, 128, taps=3, delay=3, ctx=2, iters=3)   # NK = 15: ragged tiles
+    pc.check_wpe(emu, rng, 2, 3, 2000, 256, 64, taps=4, delay=2, ctx=1, iters=2)
+    pc.check_wpe(emu, rng, 1, 2, 2000, 256, 64, taps=6, delay=1, ctx=0, iters=1)
+    pc.check_wpe(emu, rng, 1, 5, 3000, 256, 128, taps=3, delay=3, ctx=2, iters=2)   # NK = 15: ragged tiles
 
 
 def test_wpe_chunked_long_utterance_path(emu, monkeypatch):
     # utterances whose bin does not fit in shared memory are walked in chunks (history +
     # context halo reloaded per chunk); forcing tiny chunks must not change a bit
     rng = np.random.default_rng(21)
-    ref = pc.check_wpe(emu, rng, 1, 3, 3000, 256, 64, taps=4, delay=2, ctx=1, iters=2, return_out=True)
-    for chunk in ("7", "40"):
+    ref = pc.check_wpe(emu, rng, 1, 3, 2000, 256, 64, taps=4, delay=2, ctx=1, iters=2, return_out=True)
+    for chunk in ("7", "20"):
         monkeypatch.setenv("SETK_WPE_CHUNK", chunk)
         rng = np.random.default_rng(21)
-        out = pc.check_wpe(emu, rng, 1, 3, 3000, 256, 64, taps=4, delay=2, ctx=1, iters=2,
+        out = pc.check_wpe(emu, rng, 1, 3, 2000, 256, 64, taps=4, delay=2, ctx=1, iters=2,
                            return_out=True)
         assert np.array_equal(out, ref)
 
