@@ -246,6 +246,8 @@ def get_parser():
                         "(0: one utterance per launch, like the reference's loop)")
     parser.add_argument("--lookahead", default=256, type=int,
                         help="[setk_b200] utterances read ahead and sorted by length before batching")
+    parser.add_argument("--reader-threads", default=8, type=int,
+                        help="[setk_b200] loader threads of the batched path (file reads in scp order)")
     return parser
 
 
