@@ -10,7 +10,7 @@ mkdir -p "$ROOT/ab"
 /usr/local/cuda/bin/nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC \
   -I"$ROOT/include" -Xptxas -v "$@" -c "$ROOT/setk_b200/csrc/$TU.cu" -o "$ROOT/ab/$TU.$NAME.o" 2> "$ROOT/ab/$TU.$NAME.log"
 objs=""
-for f in api generic weights weights_coop weights_post stft_cov_fused stft_cov_ws apply_istft_fused stft_spill cov_mma cgmm wpe spatial; do
+for f in api generic weights weights_coop weights_post stft_cov_fused stft_cov_ws apply_istft_fused stft_spill cov_mma cgmm wpe spatial cm_mask; do
   if [ "$f" = "$TU" ]; then objs="$objs $ROOT/ab/$TU.$NAME.o"; else objs="$objs $OBJ/$f.o"; fi
 done
 /usr/local/cuda/bin/nvcc -shared -gencode arch=compute_100a,code=sm_100a -o "$ROOT/ab/libsetk_b200_$NAME.so" $objs
