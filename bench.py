@@ -347,12 +347,22 @@ def gpu_arm(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
+    h0 = time.perf_counter()
     wave, status = run_steps(args.steps)
+    host_ms = (time.perf_counter() - h0) * 1e3      # host time to ENQUEUE the steps (no sync inside)
     ev1.record()
     barrier()
     launches = _lib.launch_count() - launches0
-    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    ms_mine = ev0.elapsed_time(ev1)
+    ms = max_over_ranks(ms_mine)
     value = world * B * args.steps / (ms / 1000.0)
+    # per-rank device and host-enqueue times (a rank whose host time reaches its device time is
+    # launch-bound: the GPU waits for Python)
+    per_rank = [None] * world
+    if world > 1:
+        dist.all_gather_object(per_rank, (ms_mine / args.steps, host_ms / args.steps))
+    else:
+        per_rank = [(ms_mine / args.steps, host_ms / args.steps)]
 
     # ---- the gather alone (one batch from every rank into rank 0), for the record ----
     gather = None
@@ -494,7 +504,9 @@ def gpu_arm(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (STFT/cov/apply), f64 (per-bin weight solve)", "data": "synthetic",
             "config": config_dict(world, B),
-            "run": {"unique_utterances_per_gpu": uniq, "numa": numa},
+            "run": {"unique_utterances_per_gpu": uniq, "numa": numa,
+                    "per_rank_ms_per_step": [{"device": round(a, 4), "host_enqueue": round(b, 4)}
+                                             for a, b in per_rank]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": measured_traffic(B), "peak_source": peak_src,
                          "kernel": "setk_stft_cov (stft_cov_ws_kernel<4> + finalize)",
