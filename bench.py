@@ -316,7 +316,31 @@ def gpu_arm(args):
     def as_bytes(w):
         return w.view(torch.uint8)
 
+    # Order of the peer delivery (SETK_BENCH_PUSH, measurement knob):
+    #   "after" : push batch i right behind its last kernel (default)
+    #   "inside": launch the next batch's fused STFT+covariance first, then push batch i, and let the
+    #             next apply+iSTFT wait for the copy.  Built to test whether the copy disturbs the launch
+    #             of a persistent kernel: it does not -- both orders show the same two regimes at two
+    #             GPUs (1.05-1.08 ms per step on most process starts, 2-4 ms on others).
+    push_mode = os.environ.get("SETK_BENCH_PUSH", "after")
+
+    def run_steps_inside(k):
+        wave = status = None
+        for i in range(k):
+            Rs_, Rn_, mx_ = pipe.covariances(audio, mask)
+            if wave is not None:
+                ring.push(wave, i - 1)
+            w_, status, _ = pipe.solve(Rs_, Rn_)
+            ring.drain()                            # the apply kernel is launched behind the copy
+            wave = pipe.plan.apply_istft(audio, w_, norm=mx_, pcm16=True)
+        if wave is not None:
+            ring.push(wave, k - 1)
+        ring.drain()
+        return wave, status
+
     def run_steps(k):
+        if ring is not None and push_mode == "inside":
+            return run_steps_inside(k)
         works, keep = [], collections.deque(maxlen=RING + 1)
         wave = status = None
         for i in range(k):
@@ -339,6 +363,44 @@ def gpu_arm(args):
     torch.cuda.synchronize()
     assert int(status.abs().sum()) == 0, "solver reported failures on the synthetic batch"
 
+    # ---- calibration of the peer delivery: on some process starts the host gets blocked for
+    # milliseconds per step once the ring is in use (seen at two GPUs: 1.05 ms per step on most runs,
+    # 1.3-4 ms on others, both ranks alike, host enqueue time = device time); a run that shows it
+    # falls back to the NCCL gather instead of reporting a number the kernels do not explain ----
+    ring_probe = None
+    if ring is not None:
+        def probe(k, with_push):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            w = None
+            for i in range(k):
+                w, _ = step()
+                if with_push:
+                    ring.push(w, i)
+            if with_push:
+                ring.drain()
+            e1.record()
+            barrier()
+            return max_over_ranks(e0.elapsed_time(e1)) / k
+
+        probe(4, True)
+        t_plain, t_push = probe(12, False), probe(12, True)
+        ring_probe = {"ms_per_step_without_push": round(t_plain, 4), "ms_per_step_with_push": round(t_push, 4)}
+        if t_push > 1.15 * t_plain or os.environ.get("SETK_BENCH_PROBE_FORCE_REJECT") == "1":
+            ring_probe["verdict"] = "rejected: NCCL gather used"
+            if rank == 0:
+                print(f"[bench] peer ring rejected by the calibration probe ({t_push:.3f} vs "
+                      f"{t_plain:.3f} ms per step); NCCL gather", file=sys.stderr)
+            ring = None
+            if rank == 0:
+                glists = [[torch.empty((B, 2 * n_out), dtype=torch.uint8, device=dev) for _ in range(world)]
+                          for _ in range(RING)]
+            run_steps(RING + 1)                  # warm the collective path
+            torch.cuda.synchronize()
+        else:
+            ring_probe["verdict"] = "accepted"
+
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -346,11 +408,27 @@ def gpu_arm(args):
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    def host_state():
+        st = {"cuda_mallocs": torch.cuda.memory_stats(dev).get("num_device_alloc", 0), "cpu_s": sum(os.times()[:2])}
+        try:
+            with open("/sys/fs/cgroup/cpu.stat") as fh:
+                kv = dict(l.split() for l in fh)
+            st["throttled_ms"] = int(kv.get("throttled_usec", 0)) / 1e3
+        except Exception:
+            st["throttled_ms"] = None
+        return st
+
+    hs0 = host_state()
     ev0.record()
     h0 = time.perf_counter()
     wave, status = run_steps(args.steps)
     host_ms = (time.perf_counter() - h0) * 1e3      # host time to ENQUEUE the steps (no sync inside)
     ev1.record()
+    hs1 = host_state()
+    host_diag = {"cuda_mallocs_in_region": hs1["cuda_mallocs"] - hs0["cuda_mallocs"],
+                 "process_cpu_ms_in_region": round((hs1["cpu_s"] - hs0["cpu_s"]) * 1e3, 1),
+                 "cgroup_throttled_ms_in_region": (None if hs0["throttled_ms"] is None else
+                                                   round(hs1["throttled_ms"] - hs0["throttled_ms"], 1))}
     barrier()
     launches = _lib.launch_count() - launches0
     ms_mine = ev0.elapsed_time(ev1)
@@ -360,9 +438,9 @@ def gpu_arm(args):
     # launch-bound: the GPU waits for Python)
     per_rank = [None] * world
     if world > 1:
-        dist.all_gather_object(per_rank, (ms_mine / args.steps, host_ms / args.steps))
+        dist.all_gather_object(per_rank, (ms_mine / args.steps, host_ms / args.steps, host_diag))
     else:
-        per_rank = [(ms_mine / args.steps, host_ms / args.steps)]
+        per_rank = [(ms_mine / args.steps, host_ms / args.steps, host_diag)]
 
     # ---- the gather alone (one batch from every rank into rank 0), for the record ----
     gather = None
@@ -395,6 +473,7 @@ def gpu_arm(args):
                "copy engines over NVLink, side stream; no collective kernel)" if ring is not None else
                "dist.gather on NCCL's stream, ring of 3")
         gather = {"payload": "int16 PCM, every batch of every rank -> rank 0", "how": how,
+                  "peer_ring_probe": ring_probe,
                   "bytes_into_rank0_per_step": gbytes, "gather_ms_alone": g_ms,
                   "gather_GBps": gbytes / (g_ms * 1e-3) / 1e9,
                   "needed_GBps_at_value": gbytes / ((ms / args.steps) * 1e-3) / 1e9}
@@ -505,8 +584,8 @@ def gpu_arm(args):
             "dtype": "f32 (STFT/cov/apply), f64 (per-bin weight solve)", "data": "synthetic",
             "config": config_dict(world, B),
             "run": {"unique_utterances_per_gpu": uniq, "numa": numa,
-                    "per_rank_ms_per_step": [{"device": round(a, 4), "host_enqueue": round(b, 4)}
-                                             for a, b in per_rank]},
+                    "per_rank_ms_per_step": [dict({"device": round(a, 4), "host_enqueue": round(b, 4)}, **hd)
+                                             for a, b, hd in per_rank]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": measured_traffic(B), "peak_source": peak_src,
                          "kernel": "setk_stft_cov (stft_cov_ws_kernel<4> + finalize)",
