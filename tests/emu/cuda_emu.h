@@ -92,38 +92,65 @@ template <class K> static inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAtt
 namespace emu {
 
 struct Barrier {
+  // Arrival is one compare-and-swap on {generation, arrived} (no mutex: a CTA is 128-512 OS threads
+  // and every __syncthreads / __syncwarp / named barrier of every thread used to take the same lock);
+  // the mutex + condition variable only serve threads that give up spinning.
   std::mutex m;
   std::condition_variable cv;
-  int expected = 0, waiting = 0;
-  std::atomic<unsigned> gen{0};
-  void init(int n) { expected = n; waiting = 0; gen.store(0); }
+  std::atomic<int> expected{0};
+  std::atomic<uint64_t> state{0};           // (generation << 32) | arrived
+  std::atomic<int> sleepers{0};
+  void init(int n) { expected.store(n); state.store(0); sleepers.store(0); }
+  void wake() {
+    if (sleepers.load(std::memory_order_acquire) > 0) {
+      { std::lock_guard<std::mutex> lk(m); }
+      cv.notify_all();
+    }
+  }
+  unsigned generation() const { return (unsigned)(state.load(std::memory_order_acquire) >> 32); }
   void wait() {
+    uint64_t s = state.load(std::memory_order_acquire);
     unsigned g;
-    {
-      std::unique_lock<std::mutex> lk(m);
-      g = gen.load(std::memory_order_relaxed);
-      if (++waiting >= expected) {
-        waiting = 0;
-        gen.store(g + 1, std::memory_order_release);
-        cv.notify_all();
-        return;
+    for (;;) {
+      g = (unsigned)(s >> 32);
+      const int arrived = (int)(s & 0xffffffffu) + 1;
+      const bool last = arrived >= expected.load(std::memory_order_acquire);
+      const uint64_t ns = last ? ((uint64_t)(g + 1) << 32) : (((uint64_t)g << 32) | (unsigned)arrived);
+      if (state.compare_exchange_weak(s, ns, std::memory_order_acq_rel, std::memory_order_acquire)) {
+        if (last) { wake(); return; }
+        // a thread may have dropped out between our read of `expected` and this arrival (it saw us
+        // not yet arrived and left the release to us): look again
+        if (arrived >= expected.load(std::memory_order_acquire)) {
+          uint64_t cur = ns;
+          if (state.compare_exchange_strong(cur, (uint64_t)(g + 1) << 32, std::memory_order_acq_rel)) {
+            wake();
+            return;
+          }
+        }
+        break;
       }
     }
     // spin first (kernels with many short barrier episodes), then block
     for (int i = 0; i < 4000; ++i) {
-      if (gen.load(std::memory_order_acquire) != g) return;
+      if (generation() != g) return;
       if ((i & 15) == 15) std::this_thread::yield();
     }
     std::unique_lock<std::mutex> lk(m);
-    cv.wait(lk, [&] { return gen.load(std::memory_order_acquire) != g; });
+    sleepers.fetch_add(1, std::memory_order_acq_rel);
+    cv.wait(lk, [&] { return generation() != g; });
+    sleepers.fetch_sub(1, std::memory_order_acq_rel);
   }
   void drop() {  // a thread that exited no longer participates
-    std::unique_lock<std::mutex> lk(m);
-    --expected;
-    if (expected > 0 && waiting >= expected) {
-      waiting = 0;
-      gen.fetch_add(1, std::memory_order_release);
-      cv.notify_all();
+    const int e = expected.fetch_sub(1, std::memory_order_acq_rel) - 1;
+    uint64_t s = state.load(std::memory_order_acquire);
+    for (;;) {
+      const int arrived = (int)(s & 0xffffffffu);
+      if (e <= 0 || arrived == 0 || arrived < e) return;
+      const uint64_t ns = (uint64_t)((unsigned)(s >> 32) + 1) << 32;
+      if (state.compare_exchange_weak(s, ns, std::memory_order_acq_rel, std::memory_order_acquire)) {
+        wake();
+        return;
+      }
     }
   }
 };
@@ -230,8 +257,8 @@ inline void named_sync(int id, int nthreads) {
   Barrier& b = g_ctx->named[id];
   {
     std::unique_lock<std::mutex> lk(g_ctx->named_m);
-    if (b.expected == 0) b.init(nthreads);
-    else if (b.expected != nthreads) die("named barrier used with two different thread counts");
+    if (b.expected.load() == 0) b.init(nthreads);
+    else if (b.expected.load() != nthreads) die("named barrier used with two different thread counts");
   }
   b.wait();
 }
