@@ -359,6 +359,25 @@ def gpu_arm(args):
             w.wait()
         return wave, status
 
+    # N > 1: the steps run on a HIGH-PRIORITY stream.  Delivering a batch to rank 0 is executed by
+    # copy kernels on the SMs (the ring slot is a mapping in this rank's own address space, so the
+    # runtime treats the copy as device-local; NCCL's gather is a kernel anyway).  The fused kernels are
+    # persistent with static equal runs: when a copy's CTAs get onto the SMs first at a batch
+    # boundary, CTAs of the persistent kernel cannot become resident and its time doubles -- the
+    # suspected mechanism of the slow regime seen at two GPUs.  With the compute stream at
+    # a higher priority the block scheduler places the persistent CTAs first and the copy fills what
+    # is left.  SETK_BENCH_PRIORITY=0 keeps everything on the default stream.
+    compute_ctx = None
+    if world > 1 and os.environ.get("SETK_BENCH_PRIORITY", "1") == "1":
+        try:
+            torch.cuda.synchronize()
+            compute_ctx = torch.cuda.stream(torch.cuda.Stream(device=dev, priority=-1))
+            compute_ctx.__enter__()
+        except Exception as err:     # noqa: BLE001 -- a platform without stream priorities: default stream
+            compute_ctx = None
+            if rank == 0:
+                print(f"[bench] no high-priority compute stream ({err!r})", file=sys.stderr)
+
     wave, status = run_steps(max(args.warmup, 1))
     torch.cuda.synchronize()
     assert int(status.abs().sum()) == 0, "solver reported failures on the synthetic batch"
@@ -425,6 +444,9 @@ def gpu_arm(args):
     host_ms = (time.perf_counter() - h0) * 1e3      # host time to ENQUEUE the steps (no sync inside)
     ev1.record()
     hs1 = host_state()
+    if compute_ctx is not None:
+        torch.cuda.synchronize()
+        compute_ctx.__exit__(None, None, None)
     host_diag = {"cuda_mallocs_in_region": hs1["cuda_mallocs"] - hs0["cuda_mallocs"],
                  "process_cpu_ms_in_region": round((hs1["cpu_s"] - hs0["cpu_s"]) * 1e3, 1),
                  "cgroup_throttled_ms_in_region": (None if hs0["throttled_ms"] is None else
@@ -584,6 +606,7 @@ def gpu_arm(args):
             "dtype": "f32 (STFT/cov/apply), f64 (per-bin weight solve)", "data": "synthetic",
             "config": config_dict(world, B),
             "run": {"unique_utterances_per_gpu": uniq, "numa": numa,
+                    "compute_stream": "high priority" if compute_ctx is not None else "default",
                     "per_rank_ms_per_step": [dict({"device": round(a, 4), "host_enqueue": round(b, 4)}, **hd)
                                              for a, b, hd in per_rank]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
