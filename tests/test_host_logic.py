@@ -606,6 +606,16 @@ def test_kaldi_compressed_matrix_reader(tmp_path):
         assert np.array_equal(rd[key], got)
         if ref_io is not None:
             assert np.array_equal(ref_io.read_float_mat_vec(io.BufferedReader(io.BytesIO(blob)), direct_access=True), got), key
+    # a mask through compress_kaldi_cm (what bench.py / the streamer ship to setk_cm_masks): the same
+    # bytes read by this repo's reader and by the reference's, within the format's quantisation of the input
+    from setk_b200.libs.data_handler import compress_kaldi_cm
+    m = (rng.random((37, 19)) ** 2).astype(np.float32)
+    blob = b"\0BCM " + compress_kaldi_cm(m)
+    got = read_kaldi_matrix(io.BytesIO(blob))
+    assert got.shape == m.shape and got.dtype == np.float32
+    assert np.max(np.abs(got - m)) <= 0.02 * (m.max() - m.min())
+    if ref_io is not None:
+        assert np.array_equal(ref_io.read_float_mat_vec(io.BufferedReader(io.BytesIO(blob)), direct_access=True), got)
 
 
 def test_remaining_table_readers(tmp_path):
