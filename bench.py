@@ -404,14 +404,18 @@ def gpu_arm(args):
         ring_probe = {"ms_per_step_without_push": round(t_plain, 4), "ms_per_step_with_push": round(t_push, 4)}
         use_hp = False
         if hp_stream is not None:
-            torch.cuda.synchronize()
-            with torch.cuda.stream(hp_stream):
-                probe(2, True)
-                t_hp = probe(12, True)
+            try:
                 torch.cuda.synchronize()
-            ring_probe["ms_per_step_with_push_high_priority_stream"] = round(t_hp, 4)
-            use_hp = t_hp < t_push
-            t_push = min(t_push, t_hp)
+                with torch.cuda.stream(hp_stream):
+                    probe(2, True)
+                    t_hp = probe(12, True)
+                    torch.cuda.synchronize()
+                ring_probe["ms_per_step_with_push_high_priority_stream"] = round(t_hp, 4)
+                use_hp = t_hp < t_push
+                t_push = min(t_push, t_hp)
+            except Exception as err:     # noqa: BLE001 -- the same code on every rank: all take this path
+                hp_stream = None
+                ring_probe["high_priority_stream_error"] = repr(err)
         if t_push > 1.15 * t_plain or os.environ.get("SETK_BENCH_PROBE_FORCE_REJECT") == "1":
             ring_probe["verdict"] = "rejected: NCCL gather used"
             if rank == 0:
