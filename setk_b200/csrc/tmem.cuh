@@ -37,13 +37,13 @@ __device__ inline unsigned tmem_addr(unsigned base, int warp_in_cta, int col) {
 }
 template <int NF2>
 __device__ inline void tmem_st(unsigned taddr, const float2 (&r)[NF2]) {
-  unsigned* row = emu::tmem_row(taddr >> 16, threadIdx.x & 31);
+  unsigned* row = emu::tmem_row(taddr >> 16, threadIdx.x & 31, taddr & 0xffffu, 2 * NF2);
   memcpy(row + (taddr & 0xffffu), r, sizeof(float2) * NF2);
 }
 __device__ inline void tmem_wait_st() {}
 template <int NF2>
 __device__ inline void tmem_ld(unsigned taddr, float2 (&r)[NF2]) {
-  const unsigned* row = emu::tmem_row(taddr >> 16, threadIdx.x & 31);
+  const unsigned* row = emu::tmem_row(taddr >> 16, threadIdx.x & 31, taddr & 0xffffu, 2 * NF2);
   memcpy(r, row + (taddr & 0xffffu), sizeof(float2) * NF2);
 }
 template <int NF2>

@@ -241,8 +241,9 @@ inline void tmem_free(int ncols) {
     g_ctx->tmem_cols.store(0);
   }
 }
-inline unsigned* tmem_row(unsigned lane_base, int lane_in_warp) {
+inline unsigned* tmem_row(unsigned lane_base, int lane_in_warp, unsigned col = 0, unsigned ncols = 0) {
   if (g_ctx->tmem_cols.load() <= 0) die("tcgen05.ld/st without an allocation");
+  if ((int)(col + ncols) > g_ctx->tmem_cols.load()) die("tcgen05.ld/st beyond the allocated columns");
   if (lane_base != (unsigned)((g_tid / 32) & 3) * 32u) die("tcgen05.ld/st outside the warp's lane quadrant");
   return g_ctx->tmem.data() + (size_t)(lane_base + lane_in_warp) * 512;
 }
